@@ -1,0 +1,163 @@
+"""Generate tests/golden/*.npz from the UNCHANGED reference files (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/{models,losses,utils} under oracle/shim.py, loads the deterministic synthetic weights of
+oracle/synth.py, runs forward / loss / backward on CPU fp32 and stores inputs' seeds + outputs.  The GPU box has no
+/root/reference: tests there regenerate the same weights/inputs from the seeds and compare with these files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import shim, synth, cox, cindex, model as omodel  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(8)
+
+KEEP_FULL = ["image_model.model.backbone.conv0.weight",
+             "image_model.model.backbone.norm0.weight", "image_model.model.backbone.norm0.bias",
+             "image_model.model.backbone.denseblock1.denselayer1.layers.conv1.weight",
+             "image_model.model.backbone.denseblock1.denselayer1.layers.norm2.weight",
+             "image_model.model.backbone.denseblock1.denselayer6.layers.norm1.bias",
+             "image_model.model.backbone.transition1.norm.weight",
+             "image_model.model.backbone.denseblock4.denselayer16.layers.conv2.weight",
+             "image_model.model.backbone.norm5.weight", "image_model.model.backbone.norm5.bias",
+             "image_model.model.features.feature_layer.weight", "image_model.model.features.feature_layer.bias",
+             "clinical_model.model.backbone.dense0.weight", "clinical_model.model.backbone.bn0.weight",
+             "clinical_model.model.features.dense5.weight", "clinical_model.model.features.bn5.bias",
+             "output_head.weight", "output_head.bias", "image_output_head.weight", "clinical_output_head.weight"]
+
+
+class _MaskedDropout(torch.nn.Module):
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask
+
+
+def build_reference(ns, in_channels, blend, dropout_prob, sd):
+    dn = ns.densenet.DenseNet121(spatial_dims=3, in_channels=in_channels, out_channels=2, feature_channels=12,
+                                 dropout_prob=dropout_prob)
+    mm = ns.multimodal.MultiModalModel(dn, ["x"] * 20, 2, 12, blend=blend)
+    mm.load_state_dict(sd)
+    return mm
+
+
+def inject_masks(mm, masks):
+    """Swap the reference's Dropout modules for fixed-mask multipliers (module tree otherwise untouched)."""
+    bb = mm.image_model.model.backbone
+    for (b, l), m in masks["dense"].items():
+        layers = getattr(getattr(bb, f"denseblock{b + 1}"), f"denselayer{l + 1}").layers
+        layers.dropout = _MaskedDropout(m[:, :, None, None, None])
+    mm.image_model.model.features.dropout = _MaskedDropout(masks["image_features"])
+    cm = mm.clinical_model.model
+    for i in range(5):
+        setattr(cm.backbone, f"drop{i}", _MaskedDropout(masks["mlp"][i][:, None]))
+    cm.features.drop5 = _MaskedDropout(masks["mlp"][5][:, None])
+
+
+def run_case(ns, name, *, seed_w, seed_x, batch, in_channels, spatial, blend, training, dropout, tie_free=True):
+    sd = synth.make_state_dict(seed_w, in_channels=in_channels)
+    mm = build_reference(ns, in_channels, blend, 0.2 if dropout else 0.0, sd)
+    image, clinical, events, durations = synth.make_batch(seed_x, batch, in_channels, spatial, tie_free=tie_free)
+    masks = synth.make_masks(seed_x + 1000, batch) if dropout else synth.make_masks(0, batch, 0, 0, 0)
+    mm.train(training)
+    if training:
+        inject_masks(mm, masks)
+    out = mm({"image": image, "clinical": clinical})
+    res = {"logits": out.detach().numpy()}
+    # oracle restatement on the same inputs (pins oracle/model.py against the reference)
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    coll = {}
+    out_o = omodel.multimodal_forward(sd_o, image, clinical, training, blend, masks if training else None, collect=coll)
+    res["oracle_max_abs_diff"] = np.float64((out_o - out).abs().max().item())
+    res["image_features"] = coll["image_features"].detach().numpy()
+    res["clinical_features"] = coll["clinical_features"].detach().numpy()
+    if training:
+        if blend:
+            gb = ns.blender.GradientBlender(ns.losses.CoxPH, survival=True, surv_criterion=ns.utils.surv_criterion)
+            loss, head0 = gb.computeLoss(out, events, durations)
+            res["head0_loss"] = head0.detach().numpy()
+        else:
+            loss = ns.utils.surv_criterion(ns.losses.CoxPH, out, events, durations, "cpu")
+        loss.backward()
+        res["loss"] = loss.detach().numpy()
+        norms, names = [], []
+        for k, p in mm.named_parameters():
+            names.append(k)
+            norms.append(float("nan") if p.grad is None else float(p.grad.double().norm()))
+            if k in KEEP_FULL and p.grad is not None:
+                res["grad:" + k] = p.grad.numpy()
+        res["grad_norms"] = np.array(norms)
+        res["param_names"] = np.array(names)
+        new_sd = mm.state_dict()
+        for k in ["image_model.model.backbone.norm0", "image_model.model.backbone.denseblock2.denselayer3.layers.norm2",
+                  "image_model.model.backbone.norm5", "clinical_model.model.backbone.bn0"]:
+            res["rm:" + k] = new_sd[k + ".running_mean"].numpy()
+            res["rv:" + k] = new_sd[k + ".running_var"].numpy()
+    res["meta"] = np.array([seed_w, seed_x, batch, in_channels, *spatial, int(blend), int(training), int(dropout), int(tie_free)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    print(name, "logits", res["logits"].ravel()[:4], "loss", res.get("loss"), "oracle diff", res["oracle_max_abs_diff"])
+
+
+def kats(ns):
+    res = {}
+    rng = np.random.RandomState(7)
+    # Cox through the reference's own CoxPH (as written, swapped call order) on tie-free-in-events? no: events are
+    # binary so the as-written sort key is tie-dominated; record the permutation torch used so the kernel can be
+    # driven with the identical order (SURVEY 8c tie policy iii) plus stable-order expectations from oracle/cox.py.
+    for n in (2, 4, 16, 64, 1000):
+        h = torch.tensor(rng.randn(n), dtype=torch.float32)
+        ev = torch.tensor(rng.randint(0, 2, n)); ev[0] = 1
+        du = torch.tensor(rng.permutation(3650)[:n] + 1)
+        res[f"cox{n}_h"] = h.numpy(); res[f"cox{n}_e"] = ev.numpy(); res[f"cox{n}_d"] = du.numpy()
+        hh = h.clone().requires_grad_(True)
+        l = ns.losses.CoxPH(hh, ev, du); l.backward()
+        res[f"cox{n}_aswritten_loss"] = l.detach().numpy(); res[f"cox{n}_aswritten_grad"] = hh.grad.numpy()
+        hh = h.clone().requires_grad_(True)
+        l = cox.cox_ph_loss(hh, du, ev); l.backward()     # intended order, tie-free durations
+        res[f"cox{n}_intended_loss"] = l.detach().numpy(); res[f"cox{n}_intended_grad"] = hh.grad.numpy()
+    res["katA"] = np.float64(cox.cox_ph_loss(torch.tensor([0.5, -1, 2, 0.], dtype=torch.float64), torch.tensor([4, 3, 2, 1]), torch.tensor([1, 0, 1, 1])).item())
+    res["katB"] = np.float64(ns.losses.CoxPH(torch.tensor([0.3, -0.7], dtype=torch.float64), torch.tensor([0, 1]), torch.tensor([10, 20])).item())
+    # C-index cases (lifelines restatement, cross-checked brute force vs sweep)
+    for n in (6, 64, 500):
+        t = rng.randint(1, max(4, n // 3), n); p = np.round(rng.randn(n), 1).astype(np.float32); e = rng.randint(0, 2, n)
+        c = cindex.concordance_counts(t, p, e); assert c == cindex.concordance_counts_bruteforce(t, p, e)
+        res[f"ci{n}_t"] = t; res[f"ci{n}_p"] = p; res[f"ci{n}_e"] = e; res[f"ci{n}_counts"] = np.array(c)
+    # GradientBlender KAT-E through the reference's own class
+    gb = ns.blender.GradientBlender(ns.losses.CoxPH, survival=True, surv_criterion=ns.utils.surv_criterion)
+    seq = []
+    for it in range(3):
+        tp = torch.tensor(rng.randn(3, 40, 2), dtype=torch.float32); vp = torch.tensor(rng.randn(3, 24, 2), dtype=torch.float32)
+        te = torch.tensor(rng.randint(0, 2, (40, 2))); ve = torch.tensor(rng.randint(0, 2, (24, 2)))
+        td = torch.tensor(np.stack([rng.permutation(3650)[:40] + 1 for _ in range(2)], 1)); vd = torch.tensor(np.stack([rng.permutation(3650)[:24] + 1 for _ in range(2)], 1))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if it == 0:
+                l, h0 = gb.computeLoss(tp[:, :8], te[:8], td[:8])
+                res["gb_first_loss"] = l.numpy(); res["gb_first_weights"] = gb.weights.numpy()
+            gb.updateWeights(tp, te, td, vp, ve, vd)
+        for nm, a in (("tp", tp), ("te", te), ("td", td), ("vp", vp), ("ve", ve), ("vd", vd)):
+            res[f"gb{it}_{nm}"] = a.numpy()
+        res[f"gb{it}_weights"] = gb.weights.numpy()
+    np.savez_compressed(os.path.join(OUT, "kats.npz"), **res)
+    print("kats", res["katA"], res["katB"], res["gb2_weights"])
+
+
+if __name__ == "__main__":
+    ns = shim.load_reference()
+    kats(ns)
+    run_case(ns, "tiny_blend_train", seed_w=42, seed_x=1, batch=4, in_channels=2, spatial=(32, 32, 32), blend=True, training=True, dropout=False)
+    run_case(ns, "tiny_blend_train_dropout", seed_w=42, seed_x=2, batch=4, in_channels=2, spatial=(32, 32, 32), blend=True, training=True, dropout=True)
+    run_case(ns, "tiny_eval", seed_w=42, seed_x=3, batch=3, in_channels=2, spatial=(32, 32, 32), blend=True, training=False, dropout=False)
+    run_case(ns, "cfg1_train", seed_w=42, seed_x=4, batch=4, in_channels=1, spatial=(64, 64, 32), blend=False, training=True, dropout=False)
+    run_case(ns, "cfg1_eval", seed_w=42, seed_x=5, batch=4, in_channels=1, spatial=(64, 64, 32), blend=False, training=False, dropout=False)
+    run_case(ns, "odd_train", seed_w=43, seed_x=6, batch=2, in_channels=2, spatial=(40, 48, 32), blend=True, training=True, dropout=False, tie_free=False)
