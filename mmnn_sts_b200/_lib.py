@@ -1,0 +1,74 @@
+"""ctypes binding of the C-ABI library (libmmnn_b200.so).  No CPU fallback: a missing library is a hard error."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmnn_b200.so")
+
+_lib = None
+
+
+class MMNNLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise MMNNLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+class BnSrc(C.Structure):
+    _fields_ = [("sum", C.c_void_p), ("sumsq", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("rmean", C.c_void_p), ("rvar", C.c_void_p), ("inv_count", C.c_float), ("eps", C.c_float),
+                ("use_batch", C.c_int)]
+
+
+class RowsParams(C.Structure):
+    _fields_ = [("M", C.c_int), ("NT", C.c_int), ("Ncols", C.c_int), ("Cin", C.c_int), ("kbw", C.c_int),
+                ("ntaps", C.c_int), ("tap_sign", C.c_int), ("Dz", C.c_int), ("Dy", C.c_int), ("Dx", C.c_int),
+                ("Sz", C.c_int), ("Sy", C.c_int), ("Sx", C.c_int),
+                ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
+                ("b_packed", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_longlong),
+                ("colscale", C.c_void_p), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p),
+                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("NT", C.c_int), ("Cin", C.c_int),
+                ("kbw", C.c_int), ("ntaps", C.c_int), ("mode", C.c_int), ("cin_real", C.c_int), ("pad_", C.c_int),
+                ("sn", C.c_longlong), ("sc", C.c_longlong), ("st", C.c_longlong)]
+
+
+A_LINEAR_CONV, A_STEM = 0, 1
+T_NONE, T_BNRELU = 0, 1
+EP_STORE, EP_STORE_STATS, EP_MASK_STATS = 0, 1, 2
+PACK_GENERIC, PACK_STEM = 0, 1
+
+
+def _declare(l):
+    l.mmnn_conv_rows.argtypes = [C.POINTER(RowsParams), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.mmnn_conv_rows.restype = C.c_int
+    l.mmnn_pack_weights.argtypes = [C.POINTER(PackDesc), C.c_int, C.c_void_p, C.c_void_p]
+    l.mmnn_pack_weights.restype = C.c_int
+    l.mmnn_sizeof_rows_params.restype = C.c_int
+    l.mmnn_sizeof_pack_desc.restype = C.c_int
+    assert l.mmnn_sizeof_rows_params() == C.sizeof(RowsParams), (l.mmnn_sizeof_rows_params(), C.sizeof(RowsParams))
+    assert l.mmnn_sizeof_pack_desc() == C.sizeof(PackDesc), (l.mmnn_sizeof_pack_desc(), C.sizeof(PackDesc))
+
+
+def check(code, what):
+    if code != 0:
+        raise MMNNLibraryError(f"{what} failed with status {code}")
+
+
+def packed_elems(N, NT, Cin, kbw, ntaps):
+    kb_per_tap = (Cin + kbw - 1) // kbw
+    ntile = (N + NT - 1) // NT
+    return ntile * ntaps * kb_per_tap * (kbw // 8) * NT * 8

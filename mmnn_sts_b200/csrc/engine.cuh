@@ -1,0 +1,649 @@
+// tcgen05 tile engine: implicit-GEMM kernels shared by every convolution of the DenseNet-3D trunk.
+//
+// Operand staging.  Every operand tile in shared memory is a "chunk-plane" matrix
+//        tile[chunk][row] of 16-byte cells   (cell = 8 consecutive channels of one voxel / one weight row)
+// with rows contiguous at 16 B inside a plane.  8 consecutive rows of a plane are therefore one contiguous 128-byte
+// core matrix, which is exactly the SWIZZLE_NONE canonical layout of the tcgen05 shared-memory descriptor:
+//   * as a K-major operand (fprop / dgrad: M or N = row, K = channel)  LBO = plane stride, SBO = 128 B
+//   * as an MN-major operand (wgrad: M or N = channel, K = row/voxel)  SBO = plane stride, LBO = 128 B
+// so one producer routine feeds forward, data-gradient and weight-gradient GEMMs.
+//
+// Roles (160 threads): warps 0-3 = producers (gather + BN/ReLU transform of the activation operand, 16-byte
+// vector loads, conflict-free 16-byte shared stores) and, after the K loop, the epilogue (TMEM -> registers ->
+// global, fused per-channel statistics);  warp 4 = TMEM allocator + single-thread tcgen05.mma issuer.
+// Weights arrive with one cp.async.bulk (TMA unit, 1-D) per k-block from a pre-packed image.
+// Pipelines: full[stage] (128 producer arrivals + 1 expect_tx arrival), empty[stage] (tcgen05.commit), accum (commit).
+#pragma once
+#include "common.cuh"
+
+namespace mmnn {
+
+constexpr int TILE_ROWS = 128;
+constexpr int PLANE_BYTES = TILE_ROWS * 16 + 16;  // +16 B pad: chunk planes land on distinct 16-byte bank groups
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int ENGINE_THREADS = 160;
+
+// Where a BatchNorm's per-channel scale/shift comes from (batch statistics accumulated by a producer kernel's
+// epilogue, or running statistics in eval mode).
+struct BnSrc {
+  const double* sum;    // [C] sum x      (batch mode)
+  const double* sumsq;  // [C] sum x^2
+  const float* gamma;
+  const float* beta;
+  const float* rmean;  // eval mode
+  const float* rvar;
+  float inv_count;
+  float eps;
+  int use_batch;
+};
+
+MMNN_DEVINL void bn_mean_rstd(const BnSrc& b, int c, float& mean, float& rstd) {
+  if (b.use_batch) {
+    const double m = b.sum[c] * (double)b.inv_count;
+    double var = b.sumsq[c] * (double)b.inv_count - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)b.eps));
+  } else {
+    mean = b.rmean[c];
+    rstd = rsqrtf(b.rvar[c] + b.eps);
+  }
+}
+
+enum { A_LINEAR_CONV = 0, A_STEM = 1 };
+enum { T_NONE = 0, T_BNRELU = 1 };
+enum { EP_STORE = 0, EP_STORE_STATS = 1, EP_MASK_STATS = 2 };
+
+struct RowsParams {
+  int M;       // rows (output voxels)
+  int NT;      // MMA N (tile width, multiple of 32, <= 256)
+  int Ncols;   // total valid output columns over all N tiles
+  int Cin;     // channels per tap of the A operand
+  int kbw;     // k-block width in channels (64 or 32)
+  int ntaps;   // 1 (1x1x1), 27 (3x3x3) or 16 (stem: (dz,dy) pairs of the space-to-depth 4x4x4 form)
+  int tap_sign;
+  int Dz, Dy, Dx;  // row space dims (voxels per sample = Dz*Dy*Dx)
+  int Sz, Sy, Sx;  // stem only: padded space-to-depth source dims
+  const bf16* a_src;
+  long long a_pitch;  // elements between consecutive voxels of the source
+  BnSrc bnA;
+  const bf16* b_packed;  // [n tile][k-block][chunk][NT][8]
+  bf16* out;
+  long long out_pitch;
+  const float* colscale;  // optional [batch][Ncols] multiplier (channel dropout keep-mask / (1-p))
+  double* st_sum;         // EP_STORE_STATS: sum / sumsq of the stored values;  EP_MASK_STATS: sum dy / sum dy*xhat
+  double* st_sq;
+  const bf16* e_src;  // EP_MASK_STATS: forward input of the BN whose ReLU gates the gradient
+  long long e_pitch;
+  BnSrc bnE;
+  int stages;
+};
+
+MMNN_DEVINL void apply_bnrelu8(uint4& v, const float* sc, const float* sh) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = fmaxf(fmaf(bf16_lo(w[i]), sc[2 * i], sh[2 * i]), 0.f);
+    const float b = fmaxf(fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+    w[i] = pack_bf16(a, b);
+  }
+}
+
+struct EngineSmem {
+  uint32_t full, empty, accum, tmem_ptr, rowinfo, coefA, coefE, red, stage0;
+  uint32_t stage_bytes, a_bytes;
+};
+
+// dynamic smem carve-up shared by host (size) and device (offsets)
+__host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, int stages, uint32_t* offs /*[6]*/) {
+  uint32_t o = 0;
+  offs[0] = o; o += 128;                 // barriers + tmem ptr
+  offs[1] = o; o += TILE_ROWS * 16;      // rowinfo
+  offs[2] = o; o += 2u * Cin * 4;        // coefA: scale, shift
+  offs[3] = o; o += 4u * NT * 4;         // coefE: scale, shift, mean, rstd
+  offs[4] = o; o += 8u * NT * 4;         // red[2][4][NT]
+  o = (o + 127u) & ~127u;
+  offs[5] = o;
+  const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
+  return o + stages * stage;
+}
+
+template <int AMODE, int TRANS, int EPI>
+__global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_constant__ RowsParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t offs[6];
+  rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + offs[0];
+  const uint32_t bar_empty = bar_full + 8 * 6;
+  const uint32_t bar_accum = bar_full + 8 * 12;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 13);
+  int4* rowinfo = reinterpret_cast<int4*>(smem + offs[1]);
+  float* coefA = reinterpret_cast<float*>(smem + offs[2]);
+  float* coefE = reinterpret_cast<float*>(smem + offs[3]);
+  float* red = reinterpret_cast<float*>(smem + offs[4]);
+  const int planes = p.kbw / 8;
+  const uint32_t a_bytes = planes * PLANE_BYTES;
+  const uint32_t b_bytes = planes * p.NT * 16;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage0 = sbase + offs[5];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int S = p.stages;
+  const int kb_per_tap = (p.Cin + p.kbw - 1) / p.kbw;
+  const int KB = p.ntaps * kb_per_tap;
+  const int vps = p.Dz * p.Dy * p.Dx;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
+
+  // ---------------- prologue
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS + 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+  }
+  if (TRANS == T_BNRELU) {
+    for (int c = tid; c < p.Cin; c += ENGINE_THREADS) {
+      float mean, rstd;
+      bn_mean_rstd(p.bnA, c, mean, rstd);
+      const float s = p.bnA.gamma[c] * rstd;
+      coefA[c] = s;
+      coefA[p.Cin + c] = p.bnA.beta[c] - mean * s;
+    }
+  }
+  if (EPI == EP_MASK_STATS) {
+    for (int c = tid; c < p.NT; c += ENGINE_THREADS) {
+      const int col = tile_n * p.NT + c;
+      float mean = 0.f, rstd = 0.f, s = 0.f, t = -1.f;
+      if (col < p.Ncols) {
+        bn_mean_rstd(p.bnE, col, mean, rstd);
+        s = p.bnE.gamma[col] * rstd;
+        t = p.bnE.beta[col] - mean * s;
+      }
+      coefE[c] = s; coefE[p.NT + c] = t; coefE[2 * p.NT + c] = mean; coefE[3 * p.NT + c] = rstd;
+    }
+  }
+  if (tid < TILE_ROWS) {
+    const long long m = (long long)tile_m * TILE_ROWS + tid;
+    int4 ri;
+    if (m < p.M) {
+      const int n = (int)(m / vps);
+      int rem = (int)(m - (long long)n * vps);
+      const int z = rem / (p.Dy * p.Dx);
+      rem -= z * p.Dy * p.Dx;
+      const int y = rem / p.Dx;
+      const int x = rem - y * p.Dx;
+      if (AMODE == A_STEM) {
+        ri.x = ((n * p.Sz + z) * p.Sy + y) * p.Sx + x;
+      } else {
+        ri.x = (int)m;
+      }
+      ri.y = z; ri.z = y; ri.w = x;
+    } else {
+      ri.x = 0; ri.y = -100000; ri.z = 0; ri.w = 0;
+    }
+    rowinfo[tid] = ri;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // ================= producers
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)(kb / S) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
+      const uint32_t sA = stage0 + s * stage_bytes;
+      const uint32_t sB = sA + a_bytes;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+        bulk_g2s(sB, p.b_packed + ((size_t)tile_n * KB + kb) * (size_t)(planes * p.NT * 8), b_bytes, bar_full + 8 * s);
+      }
+      const int tap = kb / kb_per_tap;
+      const int cb = kb - tap * kb_per_tap;
+      int cpl = (p.Cin - cb * p.kbw) / 8;
+      cpl = cpl > planes ? planes : cpl;
+      int dz = 0, dy = 0, dx = 0;
+      long long delta = 0;
+      if (AMODE == A_STEM) {
+        dz = tap >> 2; dy = tap & 3;
+        delta = (long long)(dz * p.Sy + dy) * p.Sx;
+      } else if (p.ntaps == 27) {
+        dz = (tap / 9 - 1) * p.tap_sign; dy = ((tap / 3) % 3 - 1) * p.tap_sign; dx = (tap % 3 - 1) * p.tap_sign;
+        delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
+      }
+      // lane -> (chunk, row sub-index): a warp-wide 16-byte load covers 32/cpl rows x (cpl*16) contiguous bytes
+      const int cshift = (cpl == 8) ? 3 : 2;
+      const int chunk = lane & (cpl == 8 ? 7 : 3);
+      const int rsub = lane >> cshift;
+      const int rpp = 32 >> cshift;
+      const int npass = 32 / rpp;
+      const int ch0 = cb * p.kbw + chunk * 8;
+      float sc[8], sh[8];
+      if (TRANS == T_BNRELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
+      }
+      const bool chunk_ok = chunk < cpl;
+#pragma unroll 4
+      for (int ps = 0; ps < npass; ++ps) {
+        const int r = warp * 32 + ps * rpp + rsub;
+        const int4 ri = rowinfo[r];
+        bool ok = chunk_ok && (ri.y > -1000);
+        if (AMODE == A_LINEAR_CONV) {
+          const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
+          ok = ok && zz >= 0 && zz < p.Dz && yy >= 0 && yy < p.Dy && xx >= 0 && xx < p.Dx;
+        }
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          v = ldg16(p.a_src + ((long long)ri.x + delta) * p.a_pitch + ch0);
+          if (TRANS == T_BNRELU) apply_bnrelu8(v, sc, sh);
+        }
+        if (chunk_ok) sts16(sA + chunk * PLANE_BYTES + r * 16, v);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ================= epilogue (same warps: TMEM lane quarter == warp index)
+    mbar_wait(bar_accum, 0, 3);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const long long m = (long long)tile_m * TILE_ROWS + r;
+    const bool row_ok = m < p.M;
+    const int nb = row_ok ? (int)(m / vps) : 0;
+    for (int cc = 0; cc < p.NT / 32; ++cc) {
+      const int col0 = tile_n * p.NT + cc * 32;
+      if (col0 >= p.Ncols) {
+        if (EPI != EP_STORE) {
+          red[(0 * 4 + warp) * p.NT + cc * 32 + lane] = 0.f;
+          red[(1 * 4 + warp) * p.NT + cc * 32 + lane] = 0.f;
+        }
+        continue;
+      }
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), v);
+      float q[32];
+      if (EPI == EP_MASK_STATS) {
+        uint4 xv[4];
+        if (row_ok) {
+          const bf16* xp = p.e_src + m * p.e_pitch + col0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = ldg16(xp + i * 8);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = (j & 1) ? bf16_hi(xw[j >> 1]) : bf16_lo(xw[j >> 1]);
+          const int c = cc * 32 + j;
+          const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
+          const float g = (row_ok && act) ? round_bf16(v[j]) : 0.f;
+          v[j] = g;
+          q[j] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
+        }
+      } else {
+        if (p.colscale != nullptr) {
+          const float* cs = p.colscale + (size_t)nb * p.Ncols + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = row_ok ? round_bf16(v[j]) : 0.f;
+          v[j] = g;
+          q[j] = g * g;
+        }
+      }
+      if (row_ok) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          op[i] = o;
+        }
+      }
+      if (EPI != EP_STORE) {
+        const float s1 = warp_transpose_sum32(v, lane);
+        const float s2 = warp_transpose_sum32(q, lane);
+        red[(0 * 4 + warp) * p.NT + cc * 32 + lane] = s1;
+        red[(1 * 4 + warp) * p.NT + cc * 32 + lane] = s2;
+      }
+    }
+    if (EPI != EP_STORE) {
+      named_bar_sync(1, NUM_PRODUCER_THREADS);
+      for (int c = tid; c < p.NT; c += NUM_PRODUCER_THREADS) {
+        const int col = tile_n * p.NT + c;
+        if (col < p.Ncols) {
+          const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
+          const float b = red[(1 * 4 + 0) * p.NT + c] + red[(1 * 4 + 1) * p.NT + c] + red[(1 * 4 + 2) * p.NT + c] + red[(1 * 4 + 3) * p.NT + c];
+          atomicAdd(p.st_sum + col, (double)a);
+          atomicAdd(p.st_sq + col, (double)b);
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer (warp 4, one elected lane)
+    const uint32_t idesc = make_idesc_bf16(TILE_ROWS, p.NT, 0, 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)(kb / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph, 2);
+      tc_fence_after();
+      if (lane == 0) {
+        const int tap = kb / kb_per_tap;
+        const int cb = kb - tap * kb_per_tap;
+        int cpl = (p.Cin - cb * p.kbw) / 8;
+        cpl = cpl > planes ? planes : cpl;
+        const uint32_t sA = stage0 + s * stage_bytes;
+        const uint32_t sB = sA + a_bytes;
+        for (int k16 = 0; k16 < cpl / 2; ++k16) {
+          const uint64_t ad = make_smem_desc(sA + k16 * 2 * PLANE_BYTES, PLANE_BYTES, 128);
+          const uint64_t bd = make_smem_desc(sB + k16 * 2 * p.NT * 16, p.NT * 16, 128);
+          tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (kb == KB - 1) tc_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+  }
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace mmnn
+
+// =====================================================================================================================
+// Weight-gradient kernel:  D_j[a][b] = sum over voxels v of  Aop[v][a] * Bop_j[v][b]        (K = voxels, split across CTAs)
+// Both operands are chunk-plane tiles of 128 voxels read as MN-major (channel-major) matrices.  A CTA walks a
+// contiguous range of voxel tiles, accumulating in TMEM, then adds its partial result into the fp32 gradient with
+// lane-contiguous atomics.
+namespace mmnn {
+
+enum { WA_LINEAR = 0, WA_STEM_PAIR = 1 };
+enum { WE_STRIDED = 0, WE_STEM = 1 };
+
+struct WgradParams {
+  int M;           // voxels
+  int CB;          // MMA N (B channels per tile), multiple of 32, <= 128
+  int NB;          // B tiles (taps) per stage: 1 or 9
+  int na_total;    // valid A channels over all z tiles (A tile = 128 channels at z*128)
+  int nb_total;    // valid B channels over all y tiles (NB == 1) -- B tile = CB channels at y*CB
+  int Dz, Dy, Dx;
+  int Sz, Sy, Sx;  // stem
+  const bf16* a_src;
+  long long a_pitch;
+  BnSrc bnA;       // used when A transform is T_BNRELU (channel index = z*128 + a)
+  const bf16* b_src;
+  long long b_pitch;
+  BnSrc bnB;       // used when B transform is T_BNRELU (channel index = y*CB + b)
+  float* dw;
+  long long so_a, so_b, so_j;  // element strides of the gradient for (a, b, tap j); tap index = y*NB + j when NB > 1
+  int cin_real;    // stem
+  int stages;
+};
+
+__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, uint32_t* offs /*[4]*/) {
+  uint32_t o = 0;
+  offs[0] = o; o += 128;                          // barriers + tmem ptr
+  offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
+  offs[2] = o; o += 2u * 128 * 4 + 2u * CB * 4;   // coefA (scale, shift) [128], coefB [CB]
+  o = (o + 127u) & ~127u;
+  offs[3] = o;
+  const uint32_t stage = 16u * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
+  return o + stages * stage;
+}
+
+// Fill `planes` chunk planes of one operand tile. lane -> (chunk within a group of G, row sub-index).
+template <int TRANS, bool SHIFTED>
+MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long long pitch, const int4* rowinfo, int warp,
+                                int lane, int dz, int dy, int dx, long long delta, int Dz, int Dy, int Dx,
+                                const float* scale, const float* shift) {
+  const int G = planes >= 8 ? 8 : 4;
+  const int gshift = planes >= 8 ? 3 : 2;
+  const int rsub = lane >> gshift;
+  const int rpp = 32 >> gshift;
+  for (int grp = 0; grp < planes / G; ++grp) {
+    const int chunk = grp * G + (lane & (G - 1));
+    float sc[8], sh[8];
+    if (TRANS == T_BNRELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sc[e] = scale[chunk * 8 + e]; sh[e] = shift[chunk * 8 + e]; }
+    }
+#pragma unroll 4
+    for (int ps = 0; ps < 32 / rpp; ++ps) {
+      const int r = warp * 32 + ps * rpp + rsub;
+      const int4 ri = rowinfo[r];
+      bool ok = ri.y > -1000;
+      if (SHIFTED) {
+        const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
+        ok = ok && zz >= 0 && zz < Dz && yy >= 0 && yy < Dy && xx >= 0 && xx < Dx;
+      }
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) {
+        v = ldg16(src + ((long long)ri.x + delta) * pitch + chunk * 8);
+        if (TRANS == T_BNRELU) apply_bnrelu8(v, sc, sh);
+      }
+      sts16(sdst + chunk * PLANE_BYTES + r * 16, v);
+    }
+  }
+}
+
+template <int AMODE, int ATRANS, int BTRANS, int EMODE>
+__global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t offs[4];
+  wgrad_smem_layout(p.CB, p.NB, p.stages, offs);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + offs[0];
+  const uint32_t bar_empty = bar_full + 8 * 6;
+  const uint32_t bar_accum = bar_full + 8 * 12;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 13);
+  int4* rowinfo_all = reinterpret_cast<int4*>(smem + offs[1]);
+  float* coefA = reinterpret_cast<float*>(smem + offs[2]);
+  float* coefB = coefA + 256;
+  const int bplanes = p.CB / 8;
+  const uint32_t a_bytes = 16u * PLANE_BYTES;
+  const uint32_t bt_bytes = (uint32_t)bplanes * PLANE_BYTES;
+  const uint32_t stage_bytes = a_bytes + p.NB * bt_bytes;
+  const uint32_t stage0 = sbase + offs[3];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int ntiles_total = (p.M + TILE_ROWS - 1) / TILE_ROWS;
+  const int split = gridDim.x;
+  const int t_begin = (int)((long long)ntiles_total * blockIdx.x / split);
+  const int t_end = (int)((long long)ntiles_total * (blockIdx.x + 1) / split);
+  const int nt = t_end - t_begin;
+  if (nt <= 0) return;
+  const int ytile = blockIdx.y, ztile = blockIdx.z;
+  const int vps = p.Dz * p.Dy * p.Dx;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.NB * p.CB) tmem_cols <<= 1;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+  }
+  if (ATRANS == T_BNRELU) {
+    for (int c = tid; c < 128; c += ENGINE_THREADS) {
+      const int ch = ztile * 128 + c;
+      float s = 0.f, t = 0.f;
+      if (ch < p.na_total) {
+        float mean, rstd;
+        bn_mean_rstd(p.bnA, ch, mean, rstd);
+        s = p.bnA.gamma[ch] * rstd;
+        t = p.bnA.beta[ch] - mean * s;
+      }
+      coefA[c] = s; coefA[128 + c] = t;
+    }
+  }
+  if (BTRANS == T_BNRELU) {
+    for (int c = tid; c < p.CB; c += ENGINE_THREADS) {
+      const int ch = ytile * p.CB + c;
+      float s = 0.f, t = 0.f;
+      if (ch < p.nb_total) {
+        float mean, rstd;
+        bn_mean_rstd(p.bnB, ch, mean, rstd);
+        s = p.bnB.gamma[ch] * rstd;
+        t = p.bnB.beta[ch] - mean * s;
+      }
+      coefB[c] = s; coefB[p.CB + c] = t;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // valid plane counts (multiples of 4) of the A / B tiles handled by this CTA
+    int aplanes = 16;
+    if (AMODE == WA_LINEAR) { int rem = (p.na_total - ztile * 128) / 8; aplanes = rem < 16 ? rem : 16; }
+    int bplanes_valid = bplanes;
+    if (p.NB == 1) { int rem = (p.nb_total - ytile * p.CB) / 8; bplanes_valid = rem < bplanes ? rem : bplanes; }
+    for (int it = 0; it < nt; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u, 11);
+      int4* rowinfo = rowinfo_all + s * TILE_ROWS;
+      {
+        const long long m = (long long)(t_begin + it) * TILE_ROWS + tid;
+        int4 ri;
+        if (m < p.M) {
+          const int n = (int)(m / vps);
+          int rem = (int)(m - (long long)n * vps);
+          const int z = rem / (p.Dy * p.Dx);
+          rem -= z * p.Dy * p.Dx;
+          const int y = rem / p.Dx;
+          const int x = rem - y * p.Dx;
+          ri.x = (int)m; ri.y = z; ri.z = y; ri.w = x;
+          if (AMODE == WA_STEM_PAIR) ri.x = ((n * p.Sz + z) * p.Sy + y) * p.Sx + x;  // A-side index; B uses m (see below)
+        } else {
+          ri.x = 0; ri.y = -100000; ri.z = 0; ri.w = 0;
+        }
+        rowinfo[tid] = ri;
+      }
+      named_bar_sync(1, NUM_PRODUCER_THREADS);
+      const uint32_t sA = stage0 + s * stage_bytes;
+      const uint32_t sB = sA + a_bytes;
+      if (AMODE == WA_LINEAR) {
+        produce_planes<ATRANS, false>(sA, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz,
+                                      p.Dy, p.Dx, coefA, coefA + 128);
+      } else {
+        for (int g = 0; g < 2; ++g) {
+          const int kb = ztile * 2 + g;
+          const long long delta = (long long)((kb >> 2) * p.Sy + (kb & 3)) * p.Sx;
+          produce_planes<T_NONE, false>(sA + g * 8 * PLANE_BYTES, 8, p.a_src, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, delta,
+                                        p.Dz, p.Dy, p.Dx, nullptr, nullptr);
+        }
+      }
+      if (AMODE == WA_STEM_PAIR) {
+        // B rows are plain output-voxel rows: rebuild the linear index for them
+        named_bar_sync(1, NUM_PRODUCER_THREADS);
+        const long long m = (long long)(t_begin + it) * TILE_ROWS + tid;
+        if (m < p.M) rowinfo[tid].x = (int)m;
+        named_bar_sync(1, NUM_PRODUCER_THREADS);
+      }
+      if (p.NB == 1) {
+        produce_planes<BTRANS, false>(sB, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0, 0,
+                                      p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
+      } else {
+        for (int j = 0; j < p.NB; ++j) {
+          const int tap = ytile * p.NB + j;
+          // B_j[v] = g[v - tap offset]
+          const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
+          const long long delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
+          produce_planes<BTRANS, true>(sB + j * bt_bytes, bplanes, p.b_src, p.b_pitch, rowinfo, warp, lane, dz, dy, dx, delta,
+                                       p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_full + 8 * s);
+    }
+    // ---- epilogue: TMEM lane = A channel
+    mbar_wait(bar_accum, 0, 13);
+    tc_fence_after();
+    const int a = warp * 32 + lane;
+    for (int j = 0; j < p.NB; ++j) {
+      for (int cc = 0; cc < p.CB / 32; ++cc) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * p.CB + cc * 32), v);
+        if (EMODE == WE_STRIDED) {
+          const int ag = ztile * 128 + a;
+          const int b0 = (p.NB == 1 ? ytile * p.CB : 0) + cc * 32;
+          const int tap = p.NB == 1 ? 0 : ytile * p.NB + j;
+          if (ag < p.na_total) {
+            float* dst = p.dw + (long long)ag * p.so_a + (long long)tap * p.so_j;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (b0 + i < p.nb_total) atomicAdd(dst + (long long)(b0 + i) * p.so_b, v[i]);
+          }
+        } else {
+          // stem: a = (g, c64) with kb = ztile*2 + g, c64 = (dx, pz, py, px, ci); b = output channel
+          const int kb = ztile * 2 + (a >> 6), c = a & 63;
+          const int kz = 2 * (kb >> 2) + ((c >> 3) & 1), ky = 2 * (kb & 3) + ((c >> 2) & 1), kx = 2 * (c >> 4) + ((c >> 1) & 1);
+          const int ci = c & 1;
+          if (kz < 7 && ky < 7 && kx < 7 && ci < p.cin_real) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = cc * 32 + i;
+              atomicAdd(p.dw + ((((long long)co * p.cin_real + ci) * 7 + kz) * 7 + ky) * 7 + kx, v[i]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const uint32_t idesc = make_idesc_bf16(128, p.CB, 1, 1);
+    for (int it = 0; it < nt; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      mbar_wait(bar_full + 8 * s, ph, 12);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sA = stage0 + s * stage_bytes;
+        const uint32_t sB = sA + a_bytes;
+        for (int j = 0; j < p.NB; ++j) {
+          for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16) {
+            const uint64_t ad = make_smem_desc(sA + k16 * 256, 128, PLANE_BYTES);
+            const uint64_t bd = make_smem_desc(sB + j * bt_bytes + k16 * 256, 128, PLANE_BYTES);
+            tc_mma_bf16(tmem_base + j * p.CB, ad, bd, idesc, (it > 0 || k16 > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(bar_empty + 8 * s);
+        if (it == nt - 1) tc_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace mmnn

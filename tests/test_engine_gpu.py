@@ -1,0 +1,149 @@
+"""GPU parity tests of the tcgen05 tile engine through the C-ABI against fp32 torch references of the same op.
+Tolerances: operands are bf16-rounded in the reference too, accumulation is fp32 on both sides, the output is
+bf16-rounded -> |diff| <= 2^-8 * |ref| + small absolute slack."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _close(a, b, rtol=1.0 / 128, atol=2e-2):
+    d = (a.float() - b.float()).abs()
+    lim = rtol * b.float().abs() + atol
+    assert bool((d <= lim).all()), f"max diff {d.max().item()} at ref {b.float().flatten()[d.argmax()].item()}"
+
+
+def test_linear_gemm_store():
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(0)
+    M, Cin, N = 1000, 96, 128
+    a = torch.randn(M, Cin, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, Cin, device="cuda") * 0.2
+    bp = H.pack(w, N, 128, Cin, 64, 1, Cin, 1, 0)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    H.rows(M, 128, N, Cin, 64, 1, (1, 1, M), a, Cin, bp, out, N)
+    torch.cuda.synchronize()
+    ref = a.float() @ _bf(w).t()
+    _close(out, ref)
+
+
+def test_linear_bnrelu_stats_ntiles_strided():
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(1)
+    M, Ctot, Cin, N = 777, 256, 160, 224
+    buf = torch.randn(M, Ctot, device="cuda").to(torch.bfloat16)
+    x = buf[:, :Cin].float()
+    w = torch.randn(N, Cin, device="cuda") * 0.1
+    gamma = torch.rand(Cin, device="cuda") + 0.5
+    beta = torch.randn(Cin, device="cuda") * 0.3
+    s1 = x.double().sum(0); s2 = (x.double() ** 2).sum(0)
+    bp = H.pack(w, N, 128, Cin, 64, 1, Cin, 1, 0)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.rows(M, 128, N, Cin, 64, 1, (1, 1, M), buf, Ctot, bp, out, N, trans=L.T_BNRELU, epi=L.EP_STORE_STATS,
+           bnA=H.bnsrc(s1, s2, gamma, beta, count=M), st_sum=st[0], st_sq=st[1])
+    torch.cuda.synchronize()
+    a = _bf(F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5)))
+    ref = a @ _bf(w).t()
+    _close(out, ref, rtol=1 / 64, atol=5e-2)
+    o = out.double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[1], (o ** 2).sum(0), rtol=1e-5, atol=1e-3)
+
+
+def test_conv3x3x3_fprop_bnrelu_dropout_slice():
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(2)
+    B, Dz, Dy, Dx, Cin, N, Ctot = 2, 5, 6, 8, 128, 32, 96
+    M = B * Dz * Dy * Dx
+    bott = torch.randn(M, Cin, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, Cin, 3, 3, 3, device="cuda") * 0.05
+    gamma = torch.rand(Cin, device="cuda") + 0.5
+    beta = torch.randn(Cin, device="cuda") * 0.3
+    rmean = torch.randn(Cin, device="cuda") * 0.2
+    rvar = torch.rand(Cin, device="cuda") + 0.5
+    keep = (torch.rand(B, N, device="cuda") > 0.3).float() / 0.7
+    bp = H.pack(w, N, 32, Cin, 64, 27, Cin * 27, 27, 1)
+    buf = torch.zeros(M, Ctot, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.rows(M, 32, N, Cin, 64, 27, (Dz, Dy, Dx), bott, Cin, bp, buf[:, 64:], Ctot, trans=L.T_BNRELU,
+           epi=L.EP_STORE_STATS, bnA=H.bnsrc(None, None, gamma, beta, rmean, rvar, use_batch=0), colscale=keep,
+           st_sum=st[0], st_sq=st[1])
+    torch.cuda.synchronize()
+    x = bott.float().view(B, Dz, Dy, Dx, Cin).permute(0, 4, 1, 2, 3)
+    a = _bf(F.relu(F.batch_norm(x, rmean, rvar, gamma, beta, False, 0.0, 1e-5)))
+    ref = F.conv3d(a, _bf(w), padding=1) * keep[:, :, None, None, None]
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(M, N)
+    _close(buf[:, 64:], ref, rtol=1 / 64, atol=5e-2)
+    assert float(buf[:, :64].abs().max()) == 0.0
+    o = buf[:, 64:].double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-5, atol=1e-3)
+
+
+def test_conv3x3x3_dgrad_mask_stats():
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(3)
+    B, Dz, Dy, Dx, Cg, N = 2, 4, 5, 8, 32, 128
+    M = B * Dz * Dy * Dx
+    g = torch.randn(M, Cg, device="cuda").to(torch.bfloat16)
+    w = torch.randn(Cg, N, 3, 3, 3, device="cuda") * 0.05      # conv2.weight [co=32][ci=128][27]
+    xb = torch.randn(M, N, device="cuda").to(torch.bfloat16)    # bottleneck (BN2 input)
+    gamma = torch.rand(N, device="cuda") + 0.5
+    beta = torch.randn(N, device="cuda") * 0.3
+    s1 = xb.double().sum(0); s2 = (xb.double() ** 2).sum(0)
+    # dgrad operand: n = ci, channel = co, tap
+    bp = H.pack(w, N, 128, Cg, 32, 27, 27, N * 27, 1)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.rows(M, 128, N, Cg, 32, 27, (Dz, Dy, Dx), g, Cg, bp, out, N, epi=L.EP_MASK_STATS, tap_sign=-1,
+           st_sum=st[0], st_sq=st[1], e_src=xb, e_pitch=N, bnE=H.bnsrc(s1, s2, gamma, beta, count=M))
+    torch.cuda.synchronize()
+    g5 = g.float().view(B, Dz, Dy, Dx, Cg).permute(0, 4, 1, 2, 3)
+    dA = F.conv_transpose3d(g5, _bf(w), padding=1).permute(0, 2, 3, 4, 1).reshape(M, N)
+    mean = xb.float().mean(0); var = xb.float().var(0, unbiased=False); rstd = (var + 1e-5).rsqrt()
+    xhat = (xb.float() - mean) * rstd
+    act = (xhat * gamma + beta) > 0
+    ref = dA * act
+    # elements whose pre-activation is within rounding of zero may flip: exclude a thin band
+    band = (xhat * gamma + beta).abs() < 1e-3
+    d = ((out.float() - ref).abs() - (ref.abs() / 64 + 5e-2)).masked_fill(band, -1)
+    assert float(d.max()) <= 0
+    o = out.double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[1], (o * xhat.double()).sum(0), rtol=1e-3, atol=5e-2)
+
+
+def test_stem_conv7_s2():
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(4)
+    for cin in (1, 2):
+        B, X, Y, Z = 2, 24, 20, 16
+        img = torch.rand(B, cin, X, Y, Z, device="cuda")
+        w = torch.randn(64, cin, 7, 7, 7, device="cuda") * 0.05
+        Dz, Dy, Dx = (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1
+        Sz, Sy, Sx = Dz + 3, Dy + 3, Dx + 3
+        # reference-side construction of the padded space-to-depth input [B][Sz][Sy][Sx][(pz,py,px,c2)]
+        pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
+        pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
+        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(torch.bfloat16)
+        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=torch.bfloat16, device="cuda")])  # tail slack for the 4-voxel rows
+        M = B * Dz * Dy * Dx
+        bp = H.pack(w, 64, 64, 64, 64, 16, 0, 0, 0, mode=L.PACK_STEM, cin_real=cin)
+        out = torch.zeros(M, 64, dtype=torch.bfloat16, device="cuda")
+        st = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
+        H.rows(M, 64, 64, 64, 64, 16, (Dz, Dy, Dx), s2d, 16, bp, out, 64, amode=L.A_STEM, epi=L.EP_STORE_STATS,
+               sdims=(Sz, Sy, Sx), st_sum=st[0], st_sq=st[1])
+        torch.cuda.synchronize()
+        ref = F.conv3d(_bf(img), _bf(w), stride=2, padding=3).permute(0, 2, 3, 4, 1).reshape(M, 64)
+        _close(out, ref, rtol=1 / 64, atol=5e-2)
+        assert torch.allclose(st[0], out.double().sum(0), rtol=1e-5, atol=1e-3)
