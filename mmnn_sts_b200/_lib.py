@@ -40,6 +40,15 @@ class RowsParams(C.Structure):
                 ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int)]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [("M", C.c_int), ("CB", C.c_int), ("NB", C.c_int), ("na_total", C.c_int), ("nb_total", C.c_int),
+                ("Dz", C.c_int), ("Dy", C.c_int), ("Dx", C.c_int), ("Sz", C.c_int), ("Sy", C.c_int), ("Sx", C.c_int),
+                ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
+                ("b_src", C.c_void_p), ("b_pitch", C.c_longlong), ("bnB", BnSrc),
+                ("dw", C.c_void_p), ("so_a", C.c_longlong), ("so_b", C.c_longlong), ("so_j", C.c_longlong),
+                ("cin_real", C.c_int), ("stages", C.c_int)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("NT", C.c_int), ("Cin", C.c_int),
                 ("kbw", C.c_int), ("ntaps", C.c_int), ("mode", C.c_int), ("cin_real", C.c_int), ("pad_", C.c_int),
@@ -57,6 +66,9 @@ def _declare(l):
     l.mmnn_conv_rows.restype = C.c_int
     l.mmnn_pack_weights.argtypes = [C.POINTER(PackDesc), C.c_int, C.c_void_p, C.c_void_p]
     l.mmnn_pack_weights.restype = C.c_int
+    l.mmnn_conv_wgrad.argtypes = [C.POINTER(WgradParams), C.c_int, C.c_int, C.c_void_p]
+    l.mmnn_conv_wgrad.restype = C.c_int
+    assert l.mmnn_sizeof_wgrad_params() == C.sizeof(WgradParams), (l.mmnn_sizeof_wgrad_params(), C.sizeof(WgradParams))
     l.mmnn_sizeof_rows_params.restype = C.c_int
     l.mmnn_sizeof_pack_desc.restype = C.c_int
     assert l.mmnn_sizeof_rows_params() == C.sizeof(RowsParams), (l.mmnn_sizeof_rows_params(), C.sizeof(RowsParams))

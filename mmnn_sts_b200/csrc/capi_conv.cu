@@ -51,9 +51,52 @@ int launch_rows(const RowsParams& p, int amode, int trans, int epi, cudaStream_t
   return -3;
 }
 
+template <int AMODE, int ATRANS, int BTRANS, int EMODE>
+int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream) {
+  uint32_t offs[4];
+  if (p.stages <= 0) {
+    p.stages = 1;
+    for (int s = 1; s <= 4; ++s)
+      if (wgrad_smem_layout(p.CB, p.NB, s, offs) <= 225 * 1024) p.stages = s;
+  }
+  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, offs);
+  auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = (p.M + TILE_ROWS - 1) / TILE_ROWS;
+  if (split <= 0) {
+    split = 148 / (gy * gz);
+    if (split < 1) split = 1;
+  }
+  if (split > ntiles) split = ntiles;
+  kern<<<dim3(split, gy, gz), ENGINE_THREADS, smem, stream>>>(p);
+  MMNN_CHECK_LAUNCH();
+  return 0;
+}
+
+// kind: 0 = conv1x1 (A = BN+ReLU(activation tile), B = raw gradient tile), 1 = conv3x3x3 (A = BN+ReLU(bottleneck),
+// B = 9 shifted raw gradient tiles per CTA), 2 = raw x raw (transition), 3 = stem (A = space-to-depth rows, B = raw)
+int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream) {
+  if (p.CB % 32 != 0 || p.CB > 128) return -2;
+  const int gz_lin = (p.na_total + 127) / 128;
+  const int gy_lin = (p.nb_total + p.CB - 1) / p.CB;
+  switch (kind) {
+    case 0: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
+    case 1: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, 3, 1, stream);
+    case 2: return launch_wgrad_t<WA_LINEAR, T_NONE, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
+    case 3: return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(p, split, 1, 8, stream);
+  }
+  return -3;
+}
+
 }  // namespace mmnn
 
 extern "C" {
+
+int mmnn_conv_wgrad(const WgradParams* p, int kind, int split, void* stream) {
+  return launch_wgrad(*p, kind, split, (cudaStream_t)stream);
+}
+int mmnn_sizeof_wgrad_params() { return (int)sizeof(WgradParams); }
 
 int mmnn_conv_rows(const RowsParams* p, int amode, int trans, int epi, void* stream) {
   return launch_rows(*p, amode, trans, epi, (cudaStream_t)stream);

@@ -1,0 +1,523 @@
+// Memory-bound kernels of the DenseNet-3D trunk (everything that is not a GEMM): layout conversion, BN+ReLU+max-pool,
+// BN+ReLU+avg-pool (transition), BatchNorm backward application, slice extraction, norm5, and their backwards.
+// Design rules: one thread owns a 16-byte cell (8 bf16 channels of one voxel); consecutive threads own consecutive
+// cells so every warp access is a run of contiguous 128-bit vectors; per-channel statistics are reduced in
+// registers -> shared memory -> one fp64 atomic per channel per block; grids are sized in multiples of the SM count.
+#pragma once
+#include "common.cuh"
+#include "engine.cuh"
+
+namespace mmnn {
+
+constexpr int EW_THREADS = 256;
+
+MMNN_DEVINL void unpack8(const uint4& v, float* f) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo(w[i]); f[2 * i + 1] = bf16_hi(w[i]); }
+}
+MMNN_DEVINL uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+// Block-level reduction of per-thread 8-channel partial sums (two quantities) followed by fp64 atomics.
+// Thread layout: tid = rowslot * cpr + chunk  (cpr = chunks per row = C/8, cpr divides EW_THREADS).
+MMNN_DEVINL void block_channel_reduce(float* red /*[EW_THREADS][16]*/, const float* s1, const float* s2, int cpr,
+                                      double* dst1, double* dst2) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[tid * 16 + e] = s1[e]; red[tid * 16 + 8 + e] = s2[e]; }
+  __syncthreads();
+  // cpr*16 outputs, each the sum of EW_THREADS/cpr entries
+  for (int o = tid; o < cpr * 16; o += EW_THREADS) {
+    const int chunk = o >> 4, e = o & 15;
+    float acc = 0.f;
+    for (int r = 0; r < EW_THREADS / cpr; ++r) acc += red[(r * cpr + chunk) * 16 + e];
+    if (e < 8) atomicAdd(dst1 + chunk * 8 + e, (double)acc);
+    else atomicAdd(dst2 + chunk * 8 + (e - 8), (double)acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- E1: input pack
+// image NCDHW fp32 [B][cin][X][Y][Z]  ->  padded space-to-depth bf16 [B][Sz][Sy][Sx][(pz,py,px,c2)]   (pad 3, stride 2)
+__global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
+                                int Sz, int Sy, int Sx) {
+  const long long total = (long long)B * Sz * Sy * Sx * 2;  // 16-byte cells (pz = cell & 1)
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long t = idx;
+    const int pz = (int)(t & 1); t >>= 1;
+    const int qx = (int)(t % Sx); t /= Sx;
+    const int qy = (int)(t % Sy); t /= Sy;
+    const int qz = (int)(t % Sz);
+    const int b = (int)(t / Sz);
+    float f[8];
+    const int iz = 2 * qz + pz - 3;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int py = e >> 2, px = (e >> 1) & 1, c = e & 1;
+      const int iy = 2 * qy + py - 3, ix = 2 * qx + px - 3;
+      float v = 0.f;
+      if (c < cin && iz >= 0 && iz < X && iy >= 0 && iy < Y && ix >= 0 && ix < Z)
+        v = img[((((long long)b * cin + c) * X + iz) * Y + iy) * Z + ix];
+      f[e] = v;
+    }
+    reinterpret_cast<uint4*>(dst)[idx] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- E2: BN0+ReLU+maxpool
+struct PoolParams {
+  int B, D0, H0, W0, D1, H1, W1;
+  const bf16* src;  // [B*D0*H0*W0][64]
+  BnSrc bn;
+  bf16* dst;        // block-1 buffer, channels [0,64)
+  long long dst_pitch;
+  uint8_t* argmax;  // [M1][64] window code 0..26 (first maximum in (dz,dy,dx) scan order, like torch)
+  double* st_sum;
+  double* st_sq;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const __grid_constant__ PoolParams p) {
+  __shared__ float red[EW_THREADS * 16];
+  __shared__ float coef[128];
+  for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float s = p.bn.gamma[c] * rstd;
+    coef[c] = s; coef[64 + c] = p.bn.beta[c] - mean * s;
+  }
+  __syncthreads();
+  const int chunk = threadIdx.x & 7;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = coef[chunk * 8 + e]; sh[e] = coef[64 + chunk * 8 + e]; }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long M1 = (long long)p.B * p.D1 * p.H1 * p.W1;
+  for (long long m = (long long)blockIdx.x * (EW_THREADS / 8) + (threadIdx.x >> 3); m < M1; m += (long long)gridDim.x * (EW_THREADS / 8)) {
+    long long t = m;
+    const int x = (int)(t % p.W1); t /= p.W1;
+    const int y = (int)(t % p.H1); t /= p.H1;
+    const int z = (int)(t % p.D1);
+    const int b = (int)(t / p.D1);
+    float best[8];
+    int code[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; code[e] = 0; }
+    for (int dz = 0; dz < 3; ++dz) {
+      const int iz = 2 * z + dz - 1;
+      if (iz < 0 || iz >= p.D0) continue;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int iy = 2 * y + dy - 1;
+        if (iy < 0 || iy >= p.H0) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int ix = 2 * x + dx - 1;
+          if (ix < 0 || ix >= p.W0) continue;
+          const uint4 v = ldg16(p.src + ((((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix) * 64 + chunk * 8);
+          float f[8];
+          unpack8(v, f);
+          const int cd = (dz * 3 + dy) * 3 + dx;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float a = fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f);
+            if (a > best[e]) { best[e] = a; code[e] = cd; }
+          }
+        }
+      }
+    }
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { r[e] = round_bf16(best[e]); s1[e] += r[e]; s2[e] += r[e] * r[e]; }
+    *reinterpret_cast<uint4*>(p.dst + m * p.dst_pitch + chunk * 8) = pack8(r);
+    uint2 cdv;
+    cdv.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+    cdv.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+    *reinterpret_cast<uint2*>(p.argmax + m * 64 + chunk * 8) = cdv;
+  }
+  block_channel_reduce(red, s1, s2, 8, p.st_sum, p.st_sq);
+}
+
+// backward of pool0+relu0: gather form. dR[m0][c] = relu'(.) * sum over windows whose argmax is m0 of dPool[o][c];
+// accumulates the BN0 backward statistics (sum dR, sum dR*xhat).
+struct PoolBwdParams {
+  int B, D0, H0, W0, D1, H1, W1;
+  const bf16* x;        // stem conv output [M0][64]
+  BnSrc bn;
+  const float* dpool;   // fp32 gradient buffer of block 1, channels [0,64)
+  long long dpool_pitch;
+  const uint8_t* argmax;
+  bf16* dr;             // [M0][64]
+  double* g_sum;
+  double* g_dot;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(const __grid_constant__ PoolBwdParams p) {
+  __shared__ float red[EW_THREADS * 16];
+  __shared__ float coef[256];
+  for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float s = p.bn.gamma[c] * rstd;
+    coef[c] = s; coef[64 + c] = p.bn.beta[c] - mean * s; coef[128 + c] = mean; coef[192 + c] = rstd;
+  }
+  __syncthreads();
+  const int chunk = threadIdx.x & 7;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long M0 = (long long)p.B * p.D0 * p.H0 * p.W0;
+  for (long long m = (long long)blockIdx.x * (EW_THREADS / 8) + (threadIdx.x >> 3); m < M0; m += (long long)gridDim.x * (EW_THREADS / 8)) {
+    long long t = m;
+    const int ix = (int)(t % p.W0); t /= p.W0;
+    const int iy = (int)(t % p.H0); t /= p.H0;
+    const int iz = (int)(t % p.D0);
+    const int b = (int)(t / p.D0);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows o with 2o-1 <= i <= 2o+1
+    for (int oz = iz >> 1; oz <= (iz + 1) >> 1; ++oz) {
+      if (oz >= p.D1) continue;
+      const int dz = iz - 2 * oz + 1;
+      for (int oy = iy >> 1; oy <= (iy + 1) >> 1; ++oy) {
+        if (oy >= p.H1) continue;
+        const int dy = iy - 2 * oy + 1;
+        for (int ox = ix >> 1; ox <= (ix + 1) >> 1; ++ox) {
+          if (ox >= p.W1) continue;
+          const int dx = ix - 2 * ox + 1;
+          const int cd = (dz * 3 + dy) * 3 + dx;
+          const long long o = (((long long)b * p.D1 + oz) * p.H1 + oy) * p.W1 + ox;
+          const uint2 cdv = *reinterpret_cast<const uint2*>(p.argmax + o * 64 + chunk * 8);
+          const float4 ga = *reinterpret_cast<const float4*>(p.dpool + o * p.dpool_pitch + chunk * 8);
+          const float4 gb = *reinterpret_cast<const float4*>(p.dpool + o * p.dpool_pitch + chunk * 8 + 4);
+          const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = (e < 4 ? (cdv.x >> (8 * e)) : (cdv.y >> (8 * (e - 4)))) & 0xff;
+            if (c == cd) g[e] += gg[e];
+          }
+        }
+      }
+    }
+    float f[8], r[8];
+    unpack8(ldg16(p.x + m * 64 + chunk * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = chunk * 8 + e;
+      const bool act = fmaf(f[e], coef[c], coef[64 + c]) > 0.f;
+      r[e] = act ? round_bf16(g[e]) : 0.f;
+      s1[e] += r[e];
+      s2[e] += r[e] * (f[e] - coef[128 + c]) * coef[192 + c];
+    }
+    *reinterpret_cast<uint4*>(p.dr + m * 64 + chunk * 8) = pack8(r);
+  }
+  block_channel_reduce(red, s1, s2, 8, p.g_sum, p.g_dot);
+}
+
+// ------------------------------------------------------------------------------------------------- E3: transition pooling
+struct AvgPoolParams {
+  int B, D, H, W;   // input dims; output dims = floor(/2)
+  int C;
+  const bf16* x;    // [M][pitch]
+  long long x_pitch;
+  BnSrc bn;
+  bf16* pooled;     // [M/8][C]   forward output: mean over 2x2x2 of relu(bn(x))
+  // backward
+  const bf16* dpooled;  // [Mout][C]
+  float* dx;            // fp32 [M][dx_pitch]   (overwritten)
+  long long dx_pitch;
+  double* g_sum;
+  double* g_dot;
+  const double* g_sum_in;  // pass 2
+  const double* g_dot_in;
+  float inv_count;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
+  extern __shared__ float coef[];  // [2][C]
+  for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float s = p.bn.gamma[c] * rstd;
+    coef[c] = s; coef[p.C + c] = p.bn.beta[c] - mean * s;
+  }
+  __syncthreads();
+  const int cpr = p.C / 8;
+  const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+  const long long total = (long long)p.B * Do * Ho * Wo * cpr;
+  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
+    const int chunk = (int)(idx % cpr);
+    long long t = idx / cpr;
+    const long long mo = t;
+    const int x = (int)(t % Wo); t /= Wo;
+    const int y = (int)(t % Ho); t /= Ho;
+    const int z = (int)(t % Do);
+    const int b = (int)(t / Do);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long mi = (((long long)b * p.D + 2 * z + (k >> 2)) * p.H + 2 * y + ((k >> 1) & 1)) * p.W + 2 * x + (k & 1);
+      float f[8];
+      unpack8(ldg16(p.x + mi * p.x_pitch + chunk * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += fmaxf(fmaf(f[e], coef[chunk * 8 + e], coef[p.C + chunk * 8 + e]), 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= 0.125f;
+    *reinterpret_cast<uint4*>(p.pooled + mo * p.C + chunk * 8) = pack8(acc);
+  }
+}
+
+// PASS == 1: accumulate sum v, sum v*xhat with v = relu'(bn(x)) * dpooled[parent]/8.   PASS == 2: dx = k (v - c1 - xhat c2)
+template <int PASS>
+__global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
+  extern __shared__ float coef[];  // [6][C]: s, t, mean, rstd, (pass2) k*c1', k*c2'
+  __shared__ float red[PASS == 1 ? EW_THREADS * 16 : 1];
+  for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float s = p.bn.gamma[c] * rstd;
+    coef[c] = s; coef[p.C + c] = p.bn.beta[c] - mean * s; coef[2 * p.C + c] = mean; coef[3 * p.C + c] = rstd;
+    if (PASS == 2) {
+      coef[4 * p.C + c] = (float)(p.g_sum_in[c] * (double)p.inv_count);
+      coef[5 * p.C + c] = (float)(p.g_dot_in[c] * (double)p.inv_count);
+    }
+  }
+  __syncthreads();
+  const int cpr = p.C / 8;
+  const int rows_per_block = EW_THREADS / cpr;
+  const int chunk = threadIdx.x % cpr;
+  const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
+  const long long M = (long long)p.B * p.D * p.H * p.W;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M; m += (long long)gridDim.x * rows_per_block) {
+    long long t = m;
+    const int x = (int)(t % p.W); t /= p.W;
+    const int y = (int)(t % p.H); t /= p.H;
+    const int z = (int)(t % p.D);
+    const int b = (int)(t / p.D);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if ((z >> 1) < Do && (y >> 1) < Ho && (x >> 1) < Wo) {
+      const long long mo = (((long long)b * Do + (z >> 1)) * Ho + (y >> 1)) * Wo + (x >> 1);
+      unpack8(ldg16(p.dpooled + mo * p.C + chunk * 8), g);
+    }
+    float f[8];
+    unpack8(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = chunk * 8 + e;
+      const bool act = fmaf(f[e], coef[c], coef[p.C + c]) > 0.f;
+      const float v = act ? g[e] * 0.125f : 0.f;
+      const float xh = (f[e] - coef[2 * p.C + c]) * coef[3 * p.C + c];
+      if (PASS == 1) { s1[e] += v; s2[e] += v * xh; }
+      else o[e] = coef[c] * (v - coef[4 * p.C + c] - xh * coef[5 * p.C + c]);
+    }
+    if (PASS == 2) {
+      float4* d = reinterpret_cast<float4*>(p.dx + m * p.dx_pitch + chunk * 8);
+      d[0] = make_float4(o[0], o[1], o[2], o[3]);
+      d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  if (PASS == 1) block_channel_reduce(red, s1, s2, cpr, p.g_sum, p.g_dot);
+}
+
+// ------------------------------------------------------------------------------------------------- E4: BN backward apply
+// out = gamma*rstd * ( v - mean(v) - xhat * mean(v*xhat) )       v: masked upstream gradient, x: forward BN input
+enum { BA_OUT_BF16 = 0, BA_OUT_F32_ADD = 1, BA_OUT_F32_STORE = 2 };
+struct BnApplyParams {
+  long long M;
+  int C;
+  const bf16* v;      // bf16 gradient (or nullptr when v32 is used)
+  const float* v32;   // fp32 gradient
+  long long v_pitch;
+  const bf16* x;
+  long long x_pitch;
+  BnSrc bn;
+  const double* g_sum;
+  const double* g_dot;
+  float inv_count;
+  void* out;
+  long long out_pitch;
+};
+
+template <int OUT>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_constant__ BnApplyParams p) {
+  extern __shared__ float coef[];  // [3][C]: a (on v), b (on x), d (const):  out = a*v + b*x + d
+  for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float k = p.bn.gamma[c] * rstd;
+    const float c1 = (float)(p.g_sum[c] * (double)p.inv_count);
+    const float c2 = (float)(p.g_dot[c] * (double)p.inv_count);
+    coef[c] = k;
+    coef[p.C + c] = -k * rstd * c2;
+    coef[2 * p.C + c] = -k * c1 + k * rstd * c2 * mean;
+  }
+  __syncthreads();
+  const int cpr = p.C / 8;
+  const long long total = p.M * cpr;
+  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
+    const int chunk = (int)(idx % cpr);
+    const long long m = idx / cpr;
+    float v[8], f[8], o[8];
+    if (p.v != nullptr) {
+      unpack8(ldg16(p.v + m * p.v_pitch + chunk * 8), v);
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8);
+      const float4 b = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    unpack8(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = chunk * 8 + e;
+      o[e] = fmaf(coef[c], v[e], fmaf(coef[p.C + c], f[e], coef[2 * p.C + c]));
+    }
+    if (OUT == BA_OUT_BF16) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + m * p.out_pitch + chunk * 8) = pack8(o);
+    } else {
+      float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.out_pitch + chunk * 8);
+      if (OUT == BA_OUT_F32_ADD) {
+        const float4 a = d[0], b = d[1];
+        d[0] = make_float4(a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3]);
+        d[1] = make_float4(b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]);
+      } else {
+        d[0] = make_float4(o[0], o[1], o[2], o[3]);
+        d[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- E5: slice extraction
+// dst bf16 [M][C] = src fp32 [M][pitch](channels [0,C) from the given pointer) * colscale[sample][C]
+__global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* __restrict__ src, long long src_pitch,
+                                                                   bf16* __restrict__ dst, long long M, int C,
+                                                                   const float* __restrict__ colscale, int vps) {
+  const int cpr = C / 8;
+  const long long total = M * cpr;
+  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
+    const int chunk = (int)(idx % cpr);
+    const long long m = idx / cpr;
+    const float4 a = *reinterpret_cast<const float4*>(src + m * src_pitch + chunk * 8);
+    const float4 b = *reinterpret_cast<const float4*>(src + m * src_pitch + chunk * 8 + 4);
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (colscale != nullptr) {
+      const float* cs = colscale + (m / vps) * C + chunk * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= __ldg(cs + e);
+    }
+    *reinterpret_cast<uint4*>(dst + m * C + chunk * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- E6: norm5
+// forward: y fp32 [M][C] = bn(x);  backward pass 1: statistics of (dy, dy*xhat) from the fp32 upstream gradient
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_f32_kernel(const bf16* __restrict__ x, long long x_pitch, BnSrc bn,
+                                                                  float* __restrict__ y, long long M, int C) {
+  extern __shared__ float coef[];
+  for (int c = threadIdx.x; c < C; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(bn, c, mean, rstd);
+    const float s = bn.gamma[c] * rstd;
+    coef[c] = s; coef[C + c] = bn.beta[c] - mean * s;
+  }
+  __syncthreads();
+  const int cpr = C / 8;
+  const long long total = M * cpr;
+  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
+    const int chunk = (int)(idx % cpr);
+    const long long m = idx / cpr;
+    float f[8];
+    unpack8(ldg16(x + m * x_pitch + chunk * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], coef[chunk * 8 + e], coef[C + chunk * 8 + e]);
+    float4* d = reinterpret_cast<float4*>(y + m * C + chunk * 8);
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_stats_f32_kernel(const float* __restrict__ dy, const bf16* __restrict__ x,
+                                                                      long long x_pitch, BnSrc bn, long long M, int C,
+                                                                      double* g_sum, double* g_dot) {
+  extern __shared__ float coef[];  // mean, rstd
+  __shared__ float red[EW_THREADS * 16];
+  for (int c = threadIdx.x; c < C; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(bn, c, mean, rstd);
+    coef[c] = mean; coef[C + c] = rstd;
+  }
+  __syncthreads();
+  const int cpr = C / 8;
+  const int rows_per_block = EW_THREADS / cpr;
+  const int chunk = threadIdx.x % cpr;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M; m += (long long)gridDim.x * rows_per_block) {
+    const float4 a = *reinterpret_cast<const float4*>(dy + m * C + chunk * 8);
+    const float4 b = *reinterpret_cast<const float4*>(dy + m * C + chunk * 8 + 4);
+    const float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float f[8];
+    unpack8(ldg16(x + m * x_pitch + chunk * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1[e] += g[e];
+      s2[e] += g[e] * (f[e] - coef[chunk * 8 + e]) * coef[C + chunk * 8 + e];
+    }
+  }
+  block_channel_reduce(red, s1, s2, cpr, g_sum, g_dot);
+}
+
+// ------------------------------------------------------------------------------------------------- E8-E10: table-driven tails
+struct BnTableEntry {
+  const double* sum;     // forward batch statistics of this BN's input channels
+  const double* sumsq;
+  const double* g_sum;   // backward statistics
+  const double* g_dot;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* grad_gamma;
+  float* grad_beta;
+  int C;
+  float count;
+};
+
+// running_mean/var momentum update (momentum 0.1, unbiased variance) for every BN of the trunk in one launch
+__global__ void bn_running_update_kernel(const BnTableEntry* __restrict__ tab, float momentum) {
+  const BnTableEntry e = tab[blockIdx.x];
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    const double mean = e.sum[c] / (double)e.count;
+    double var = e.sumsq[c] / (double)e.count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const double unbiased = e.count > 1.f ? var * (double)e.count / ((double)e.count - 1.0) : var;
+    e.running_mean[c] = (1.f - momentum) * e.running_mean[c] + momentum * (float)mean;
+    e.running_var[c] = (1.f - momentum) * e.running_var[c] + momentum * (float)unbiased;
+  }
+  if (threadIdx.x == 0 && e.num_batches_tracked != nullptr) *e.num_batches_tracked += 1;
+}
+
+// dgamma = sum dy*xhat, dbeta = sum dy
+__global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab) {
+  const BnTableEntry e = tab[blockIdx.x];
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    e.grad_gamma[c] = (float)e.g_dot[c];
+    e.grad_beta[c] = (float)e.g_sum[c];
+  }
+}
+
+// conv2 weight gradients are accumulated lane-contiguously as [tap][co][ci]; write them out as [co][ci][tap]
+struct TransposeEntry {
+  const float* src;
+  float* dst;
+};
+__global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, int Co, int Ci) {
+  const TransposeEntry e = tab[blockIdx.y];
+  const int total = Co * Ci * 27;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int tap = idx % 27;
+    const int rest = idx / 27;  // co*Ci + ci
+    e.dst[idx] = e.src[(size_t)tap * Co * Ci + rest];
+  }
+}
+
+}  // namespace mmnn

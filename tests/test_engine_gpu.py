@@ -147,3 +147,79 @@ def test_stem_conv7_s2():
         ref = F.conv3d(_bf(img), _bf(w), stride=2, padding=3).permute(0, 2, 3, 4, 1).reshape(M, 64)
         _close(out, ref, rtol=1 / 64, atol=5e-2)
         assert torch.allclose(st[0], out.double().sum(0), rtol=1e-5, atol=1e-3)
+
+
+def test_wgrad_conv1x1():
+    from tests import engine_helpers as H
+    torch.manual_seed(5)
+    M, Ctot, Cin, Co = 1300, 256, 160, 128
+    buf = torch.randn(M, Ctot, device="cuda").to(torch.bfloat16)
+    dbott = (torch.randn(M, Co, device="cuda") * 0.1).to(torch.bfloat16)
+    gamma = torch.rand(Cin, device="cuda") + 0.5
+    beta = torch.randn(Cin, device="cuda") * 0.3
+    x = buf[:, :Cin].float()
+    s1 = x.double().sum(0); s2 = (x.double() ** 2).sum(0)
+    dw = torch.zeros(Co, Cin, device="cuda")
+    for split in (1, 5):
+        dw.zero_()
+        H.wgrad(0, M, 128, 1, Cin, Co, (1, 1, M), buf, Ctot, dbott, Co, dw, 1, Cin, bnA=H.bnsrc(s1, s2, gamma, beta, count=M), split=split)
+        torch.cuda.synchronize()
+        a = _bf(F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5)))
+        ref = dbott.float().t() @ a
+        assert (dw - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw - ref).abs().max()
+
+
+def test_wgrad_conv3x3x3():
+    from tests import engine_helpers as H
+    torch.manual_seed(6)
+    B, Dz, Dy, Dx, Cb, Cg = 2, 4, 6, 8, 128, 32
+    M = B * Dz * Dy * Dx
+    bott = torch.randn(M, Cb, device="cuda").to(torch.bfloat16)
+    g = (torch.randn(M, Cg, device="cuda") * 0.1).to(torch.bfloat16)
+    gamma = torch.rand(Cb, device="cuda") + 0.5
+    beta = torch.randn(Cb, device="cuda") * 0.3
+    s1 = bott.double().sum(0); s2 = (bott.double() ** 2).sum(0)
+    dwt = torch.zeros(27, Cg, Cb, device="cuda")   # scratch layout [tap][co][ci]
+    H.wgrad(1, M, 32, 9, Cb, Cg, (Dz, Dy, Dx), bott, Cb, g, Cg, dwt, 1, Cb, Cg * Cb, bnA=H.bnsrc(s1, s2, gamma, beta, count=M))
+    torch.cuda.synchronize()
+    x5 = bott.float().view(B, Dz, Dy, Dx, Cb).permute(0, 4, 1, 2, 3)
+    a = _bf(F.relu(F.batch_norm(x5, None, None, gamma, beta, True, 0.0, 1e-5))).requires_grad_(False)
+    w = torch.zeros(Cg, Cb, 3, 3, 3, device="cuda", requires_grad=True)
+    y = F.conv3d(a, w, padding=1)
+    g5 = g.float().view(B, Dz, Dy, Dx, Cg).permute(0, 4, 1, 2, 3)
+    (ref,) = torch.autograd.grad(y, w, g5)
+    got = dwt.view(27, Cg, Cb).permute(1, 2, 0).reshape(Cg, Cb, 3, 3, 3)
+    assert (got - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (got - ref).abs().max()
+
+
+def test_wgrad_raw_and_stem():
+    from tests import engine_helpers as H
+    torch.manual_seed(7)
+    # raw x raw (transition): dW[co][ci] = sum_m g[m][co] * pooled[m][ci];  A = pooled (ci), B = g (co)
+    M, C, Co = 900, 256, 128
+    pooled = torch.randn(M, C, device="cuda").to(torch.bfloat16)
+    g = (torch.randn(M, Co, device="cuda") * 0.1).to(torch.bfloat16)
+    dw = torch.zeros(Co, C, device="cuda")
+    H.wgrad(2, M, 128, 1, C, Co, (1, 1, M), pooled, C, g, Co, dw, 1, C)
+    torch.cuda.synchronize()
+    ref = g.float().t() @ pooled.float()
+    assert (dw - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3
+    # stem
+    for cin in (1, 2):
+        B, X, Y, Z = 2, 24, 20, 16
+        img = torch.rand(B, cin, X, Y, Z, device="cuda")
+        Dz, Dy, Dx = (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1
+        Sz, Sy, Sx = Dz + 3, Dy + 3, Dx + 3
+        pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
+        pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
+        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(torch.bfloat16)
+        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=torch.bfloat16, device="cuda")])
+        M0 = B * Dz * Dy * Dx
+        dconv = (torch.randn(M0, 64, device="cuda") * 0.1).to(torch.bfloat16)
+        dw0 = torch.zeros(64, cin, 7, 7, 7, device="cuda")
+        H.wgrad(3, M0, 64, 1, 128, 64, (Dz, Dy, Dx), s2d, 16, dconv, 64, dw0, 0, 0, sdims=(Sz, Sy, Sx), cin_real=cin)
+        torch.cuda.synchronize()
+        w = torch.zeros(64, cin, 7, 7, 7, device="cuda", requires_grad=True)
+        y = F.conv3d(_bf(img), w, stride=2, padding=3)
+        (ref,) = torch.autograd.grad(y, w, dconv.float().view(B, Dz, Dy, Dx, 64).permute(0, 4, 1, 2, 3))
+        assert (dw0 - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw0 - ref).abs().max()
