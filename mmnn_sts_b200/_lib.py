@@ -69,6 +69,31 @@ def _declare(l):
     l.mmnn_conv_wgrad.argtypes = [C.POINTER(WgradParams), C.c_int, C.c_int, C.c_void_p]
     l.mmnn_conv_wgrad.restype = C.c_int
     assert l.mmnn_sizeof_wgrad_params() == C.sizeof(WgradParams), (l.mmnn_sizeof_wgrad_params(), C.sizeof(WgradParams))
+    VP, I, LL = C.c_void_p, C.c_int, C.c_longlong
+    l.mmnn_encoder_create.argtypes = [I, C.POINTER(I), I, I, I, I]
+    l.mmnn_encoder_create.restype = VP
+    l.mmnn_encoder_destroy.argtypes = [VP]
+    l.mmnn_encoder_destroy.restype = None
+    for name in ("mmnn_encoder_num_params", "mmnn_encoder_num_buffers", "mmnn_encoder_num_layers", "mmnn_encoder_out_channels"):
+        getattr(l, name).argtypes = [VP]
+        getattr(l, name).restype = I
+    l.mmnn_encoder_param_numel.argtypes = [VP, I]
+    l.mmnn_encoder_param_numel.restype = LL
+    l.mmnn_encoder_workspace_bytes.argtypes = [VP, I, I, I, I]
+    l.mmnn_encoder_workspace_bytes.restype = LL
+    l.mmnn_encoder_out_dims.argtypes = [VP, I, I, I, I, C.POINTER(I)]
+    l.mmnn_encoder_out_dims.restype = I
+    l.mmnn_encoder_forward.argtypes = [VP, I, I, I, I, VP, C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
+    l.mmnn_encoder_forward.restype = I
+    l.mmnn_encoder_backward.argtypes = [VP, I, I, I, I, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), VP, VP, VP, VP]
+    l.mmnn_encoder_backward.restype = I
+    l.mmnn_encoder_debug_offsets.argtypes = [VP, I, I, I, I, C.POINTER(LL), C.POINTER(LL)]
+    l.mmnn_encoder_debug_offsets.restype = I
+    F32P = VP
+    l.mmnn_gap_linear_fwd.argtypes = [F32P, I, I, I, F32P, F32P, F32P, I, F32P, F32P, VP]
+    l.mmnn_gap_linear_fwd.restype = I
+    l.mmnn_gap_linear_bwd.argtypes = [F32P, F32P, I, I, I, F32P, F32P, F32P, I, F32P, F32P, F32P, VP]
+    l.mmnn_gap_linear_bwd.restype = I
     l.mmnn_sizeof_rows_params.restype = C.c_int
     l.mmnn_sizeof_pack_desc.restype = C.c_int
     assert l.mmnn_sizeof_rows_params() == C.sizeof(RowsParams), (l.mmnn_sizeof_rows_params(), C.sizeof(RowsParams))

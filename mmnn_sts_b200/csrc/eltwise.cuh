@@ -30,7 +30,7 @@ MMNN_DEVINL void block_channel_reduce(float* red /*[EW_THREADS][16]*/, const flo
 #pragma unroll
   for (int e = 0; e < 8; ++e) { red[tid * 16 + e] = s1[e]; red[tid * 16 + 8 + e] = s2[e]; }
   __syncthreads();
-  // cpr*16 outputs, each the sum of EW_THREADS/cpr entries
+  // cpr*16 outputs, each the sum of floor(EW_THREADS/cpr) entries (threads beyond rows*cpr carry zeros and are skipped)
   for (int o = tid; o < cpr * 16; o += EW_THREADS) {
     const int chunk = o >> 4, e = o & 15;
     float acc = 0.f;
@@ -42,7 +42,7 @@ MMNN_DEVINL void block_channel_reduce(float* red /*[EW_THREADS][16]*/, const flo
 
 // ------------------------------------------------------------------------------------------------- E1: input pack
 // image NCDHW fp32 [B][cin][X][Y][Z]  ->  padded space-to-depth bf16 [B][Sz][Sy][Sx][(pz,py,px,c2)]   (pad 3, stride 2)
-__global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
+static __global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
                                 int Sz, int Sy, int Sx) {
   const long long total = (long long)B * Sz * Sy * Sx * 2;  // 16-byte cells (pz = cell & 1)
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -79,7 +79,7 @@ struct PoolParams {
   double* st_sq;
 };
 
-__global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const __grid_constant__ PoolParams p) {
+static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const __grid_constant__ PoolParams p) {
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[128];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -153,7 +153,7 @@ struct PoolBwdParams {
   double* g_dot;
 };
 
-__global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(const __grid_constant__ PoolBwdParams p) {
+static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(const __grid_constant__ PoolBwdParams p) {
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[256];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -231,7 +231,7 @@ struct AvgPoolParams {
   float inv_count;
 };
 
-__global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
+static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
   extern __shared__ float coef[];  // [2][C]
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid
 
 // PASS == 1: accumulate sum v, sum v*xhat with v = relu'(bn(x)) * dpooled[parent]/8.   PASS == 2: dx = k (v - c1 - xhat c2)
 template <int PASS>
-__global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
+static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
   extern __shared__ float coef[];  // [6][C]: s, t, mean, rstd, (pass2) k*c1', k*c2'
   __shared__ float red[PASS == 1 ? EW_THREADS * 16 : 1];
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __
   const int Do = p.D / 2, Ho = p.H / 2, Wo = p.W / 2;
   const long long M = (long long)p.B * p.D * p.H * p.W;
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M; m += (long long)gridDim.x * rows_per_block) {
+  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M && threadIdx.x < rows_per_block * cpr;
+       m += (long long)gridDim.x * rows_per_block) {
     long long t = m;
     const int x = (int)(t % p.W); t /= p.W;
     const int y = (int)(t % p.H); t /= p.H;
@@ -340,7 +341,7 @@ struct BnApplyParams {
 };
 
 template <int OUT>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_constant__ BnApplyParams p) {
+static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_constant__ BnApplyParams p) {
   extern __shared__ float coef[];  // [3][C]: a (on v), b (on x), d (const):  out = a*v + b*x + d
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_c
 
 // ------------------------------------------------------------------------------------------------- E5: slice extraction
 // dst bf16 [M][C] = src fp32 [M][pitch](channels [0,C) from the given pointer) * colscale[sample][C]
-__global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* __restrict__ src, long long src_pitch,
+static __global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* __restrict__ src, long long src_pitch,
                                                                    bf16* __restrict__ dst, long long M, int C,
                                                                    const float* __restrict__ colscale, int vps) {
   const int cpr = C / 8;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* 
 
 // ------------------------------------------------------------------------------------------------- E6: norm5
 // forward: y fp32 [M][C] = bn(x);  backward pass 1: statistics of (dy, dy*xhat) from the fp32 upstream gradient
-__global__ void __launch_bounds__(EW_THREADS) bn_apply_f32_kernel(const bf16* __restrict__ x, long long x_pitch, BnSrc bn,
+static __global__ void __launch_bounds__(EW_THREADS) bn_apply_f32_kernel(const bf16* __restrict__ x, long long x_pitch, BnSrc bn,
                                                                   float* __restrict__ y, long long M, int C) {
   extern __shared__ float coef[];
   for (int c = threadIdx.x; c < C; c += EW_THREADS) {
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_f32_kernel(const bf16* __
   }
 }
 
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_stats_f32_kernel(const float* __restrict__ dy, const bf16* __restrict__ x,
+static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_stats_f32_kernel(const float* __restrict__ dy, const bf16* __restrict__ x,
                                                                       long long x_pitch, BnSrc bn, long long M, int C,
                                                                       double* g_sum, double* g_dot) {
   extern __shared__ float coef[];  // mean, rstd
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_stats_f32_kernel(const floa
   const int rows_per_block = EW_THREADS / cpr;
   const int chunk = threadIdx.x % cpr;
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M; m += (long long)gridDim.x * rows_per_block) {
+  for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M && threadIdx.x < rows_per_block * cpr;
+       m += (long long)gridDim.x * rows_per_block) {
     const float4 a = *reinterpret_cast<const float4*>(dy + m * C + chunk * 8);
     const float4 b = *reinterpret_cast<const float4*>(dy + m * C + chunk * 8 + 4);
     const float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -483,7 +485,7 @@ struct BnTableEntry {
 };
 
 // running_mean/var momentum update (momentum 0.1, unbiased variance) for every BN of the trunk in one launch
-__global__ void bn_running_update_kernel(const BnTableEntry* __restrict__ tab, float momentum) {
+static __global__ void bn_running_update_kernel(const BnTableEntry* __restrict__ tab, float momentum) {
   const BnTableEntry e = tab[blockIdx.x];
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
     const double mean = e.sum[c] / (double)e.count;
@@ -497,7 +499,7 @@ __global__ void bn_running_update_kernel(const BnTableEntry* __restrict__ tab, f
 }
 
 // dgamma = sum dy*xhat, dbeta = sum dy
-__global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab) {
+static __global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab) {
   const BnTableEntry e = tab[blockIdx.x];
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
     e.grad_gamma[c] = (float)e.g_dot[c];
@@ -510,7 +512,7 @@ struct TransposeEntry {
   const float* src;
   float* dst;
 };
-__global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, int Co, int Ci) {
+static __global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, int Co, int Ci) {
   const TransposeEntry e = tab[blockIdx.y];
   const int total = Co * Ci * 27;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {

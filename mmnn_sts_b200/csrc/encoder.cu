@@ -1,0 +1,671 @@
+// Host-side orchestration of the 3-D DenseNet trunk (reference: /root/reference/models/densenet.py:196-231 backbone,
+// :46-148 dense layer / block / transition).  One C-ABI call enqueues the whole forward (or backward) on a stream:
+// no allocation, no synchronisation, no host round trip inside (CUDA-graph capturable).
+//
+// Data layout in HBM (all activations NDHWC, bf16):
+//   xs2d      padded space-to-depth image      [B][D0+3][H0+3][W0+3][16]
+//   stem_out  raw conv0 output                 [M0][64]
+//   buf[b]    ONE buffer per dense block       [M_b][Ctot_b]   layer l writes channels [c0+32l, c0+32l+32) in place
+//                                               (the reference's torch.cat copies disappear)
+//   bott[b,l] raw bottleneck (conv1 output)    [M_b][128]      kept for backward
+//   pooled[b] avgpool(relu(bn(buf[b])))        [M_b/8][Ctot_b] transition: pooling commutes with the 1x1x1 conv
+//   statistics: fp64 per-channel sum / sum-of-squares, produced by the epilogue of whichever kernel writes a channel,
+//   consumed by the prologue of every kernel that normalises it.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "eltwise.cuh"
+#include "engine.cuh"
+#include "pack.cuh"
+
+namespace mmnn {
+int launch_rows(const RowsParams& p, int amode, int trans, int epi, cudaStream_t stream);
+int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream);
+}  // namespace mmnn
+
+using namespace mmnn;
+
+namespace {
+
+constexpr int GROWTH = 32, BOTT = 128, INIT_F = 64, NUM_SMS = 148;
+
+struct BnInfo {
+  int C;
+  int fwd_off;    // channel offset in the forward statistics arena
+  int bwd_off;    // channel offset in the backward statistics arena
+  int param_idx;  // gamma; beta = +1
+  int buf_idx;    // running_mean; running_var = +1; num_batches_tracked = +2
+};
+
+struct LayerInfo {
+  int cin;
+  BnInfo n1, n2;
+  int conv1_idx, conv2_idx;
+  size_t pk_c1f, pk_c1d, pk_c2f, pk_c2d;  // packed weight offsets (elements)
+  int index;                              // global dense-layer index (dropout mask / conv2 scratch slot)
+};
+
+struct BlockInfo {
+  int c0, ctot, fwd_off;
+  std::vector<LayerInfo> layers;
+  bool has_trans;
+  BnInfo tn;
+  int tconv_idx;
+  size_t pk_tf, pk_td;
+};
+
+struct Plan {
+  int cin_real;
+  std::vector<BlockInfo> blocks;
+  BnInfo n0, n5;
+  int conv0_idx;
+  size_t pk_stem;
+  int num_params, num_buffers, num_bn, num_layers;
+  int fwd_channels, bwd_channels;
+  size_t packed_elems_total;
+  std::vector<long long> param_numel;
+  std::vector<BnInfo*> bn_order;
+  // device tables are re-uploaded only when their content (pointer sets) or destination changes: keeps the steady
+  // state free of pageable host->device copies (which synchronise the stream and cannot be graph-captured)
+  std::vector<uint8_t> cache[4];
+  const void* cache_dst[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+int upload_table(Plan* pl, int slot, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  std::vector<uint8_t>& c = pl->cache[slot];
+  if (pl->cache_dst[slot] == dst && c.size() == bytes && memcmp(c.data(), src, bytes) == 0) return 0;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  c.assign((const uint8_t*)src, (const uint8_t*)src + bytes);
+  pl->cache_dst[slot] = dst;
+  return 0;
+}
+
+struct Geo {
+  int B, X, Y, Z;
+  int D0, H0, W0, Sz, Sy, Sx;
+  long long M0;
+  int D[8], H[8], W[8];
+  long long M[8];
+  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, gslice, gout, dpooled, c2scratch, dr, total;
+  size_t buf[8], bott[8], pooled[8], dbuf[8];
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
+  g.B = B; g.X = X; g.Y = Y; g.Z = Z;
+  g.D0 = (X - 1) / 2 + 1; g.H0 = (Y - 1) / 2 + 1; g.W0 = (Z - 1) / 2 + 1;
+  g.Sz = g.D0 + 3; g.Sy = g.H0 + 3; g.Sx = g.W0 + 3;
+  g.M0 = (long long)B * g.D0 * g.H0 * g.W0;
+  int d = (g.D0 - 1) / 2 + 1, h = (g.H0 - 1) / 2 + 1, w = (g.W0 - 1) / 2 + 1;
+  const int nb = (int)pl.blocks.size();
+  for (int b = 0; b < nb; ++b) {
+    if (d < 1 || h < 1 || w < 1) return false;
+    g.D[b] = d; g.H[b] = h; g.W[b] = w;
+    g.M[b] = (long long)B * d * h * w;
+    d /= 2; h /= 2; w /= 2;
+  }
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  g.xs2d = take((size_t)B * g.Sz * g.Sy * g.Sx * 16 * 2 + 256);
+  g.stem_out = take((size_t)g.M0 * 64 * 2);
+  g.argmax = take((size_t)g.M[0] * 64);
+  size_t maxM = 0, maxMC = 0, maxMoutC = 0, maxMoutC2 = 0;
+  for (int b = 0; b < nb; ++b) {
+    const BlockInfo& bi = pl.blocks[b];
+    g.buf[b] = take((size_t)g.M[b] * bi.ctot * 2);
+    g.bott[b] = take((size_t)g.M[b] * BOTT * 2 * bi.layers.size());
+    g.dbuf[b] = take((size_t)g.M[b] * bi.ctot * 4);
+    if (bi.has_trans) {
+      g.pooled[b] = take((size_t)g.M[b + 1] * bi.ctot * 2);
+      maxMoutC = std::max(maxMoutC, (size_t)g.M[b + 1] * bi.ctot);
+      maxMoutC2 = std::max(maxMoutC2, (size_t)g.M[b + 1] * (bi.ctot / 2));
+    } else {
+      g.pooled[b] = 0;
+    }
+    maxM = std::max(maxM, (size_t)g.M[b]);
+    maxMC = std::max(maxMC, (size_t)g.M[b] * (bi.ctot - GROWTH));
+  }
+  g.fstats = take((size_t)pl.fwd_channels * 2 * sizeof(double));
+  g.bstats = take((size_t)pl.bwd_channels * 2 * sizeof(double));
+  g.packed = take(pl.packed_elems_total * 2);
+  g.tables = take(1 << 20);
+  g.dA2 = take(maxM * BOTT * 2);
+  g.dA1 = take(maxMC * 2);
+  g.gslice = take(maxM * GROWTH * 2);
+  g.gout = take(maxMoutC2 * 2 + 256);
+  g.dpooled = take(maxMoutC * 2 + 256);
+  g.c2scratch = take((size_t)pl.num_layers * 27 * GROWTH * BOTT * 4);
+  g.dr = take((size_t)g.M0 * 64 * 2);
+  g.total = o;
+  return true;
+}
+
+int ew_grid(long long work_items) {
+  long long blocks = (work_items + EW_THREADS - 1) / EW_THREADS;
+  long long cap = (long long)NUM_SMS * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+BnSrc make_bn(const BnInfo& bn, const void* const* params, void* const* buffers, const double* fstats, int fwd_channels,
+              long long count, bool batch, int ch_off = 0) {
+  BnSrc s;
+  s.sum = fstats + bn.fwd_off + ch_off;
+  s.sumsq = fstats + fwd_channels + bn.fwd_off + ch_off;
+  s.gamma = (const float*)params[bn.param_idx] + ch_off;
+  s.beta = (const float*)params[bn.param_idx + 1] + ch_off;
+  s.rmean = (const float*)buffers[bn.buf_idx] + ch_off;
+  s.rvar = (const float*)buffers[bn.buf_idx + 1] + ch_off;
+  s.inv_count = 1.0f / (float)count;
+  s.eps = 1e-5f;
+  s.use_batch = batch ? 1 : 0;
+  return s;
+}
+
+#define RET_IF(x)          \
+  do {                     \
+    int rc_ = (x);         \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+#define CUDA_RET(x)                          \
+  do {                                       \
+    cudaError_t e_ = (x);                    \
+    if (e_ != cudaSuccess) return (int)e_;   \
+  } while (0)
+#define LAUNCH_RET()                          \
+  do {                                        \
+    cudaError_t e_ = cudaGetLastError();      \
+    if (e_ != cudaSuccess) return (int)e_;    \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+void* mmnn_encoder_create(int in_channels, const int* block_config, int nblocks, int init_features, int growth_rate,
+                          int bn_size) {
+  if (in_channels < 1 || in_channels > 2 || init_features != INIT_F || growth_rate != GROWTH ||
+      bn_size * growth_rate != BOTT || nblocks < 1 || nblocks > 6)
+    return nullptr;
+  Plan* pl = new Plan();
+  pl->cin_real = in_channels;
+  int pidx = 0, bidx = 0, foff = 0, boff = 0, lidx = 0;
+  size_t pk = 0;
+  auto add_param = [&](long long numel) { pl->param_numel.push_back(numel); return pidx++; };
+  auto add_bn = [&](BnInfo& bn, int C, int fwd_off) {
+    bn.C = C; bn.fwd_off = fwd_off; bn.bwd_off = boff; boff += C;
+    bn.param_idx = add_param(C); add_param(C);
+    bn.buf_idx = bidx; bidx += 3;
+  };
+  pl->conv0_idx = add_param((long long)INIT_F * in_channels * 343);
+  pl->pk_stem = pk; pk += packed_elems(64, 64, 64, 64, 16);
+  add_bn(pl->n0, INIT_F, foff); foff += INIT_F;
+  int c = INIT_F;
+  for (int b = 0; b < nblocks; ++b) {
+    BlockInfo bi;
+    bi.c0 = c; bi.ctot = c + block_config[b] * GROWTH; bi.fwd_off = foff; foff += bi.ctot;
+    if (bi.ctot > 1024) { delete pl; return nullptr; }
+    for (int l = 0; l < block_config[b]; ++l) {
+      LayerInfo li;
+      li.cin = c + l * GROWTH; li.index = lidx++;
+      add_bn(li.n1, li.cin, bi.fwd_off);
+      li.conv1_idx = add_param((long long)BOTT * li.cin);
+      add_bn(li.n2, BOTT, foff); foff += BOTT;
+      li.conv2_idx = add_param((long long)GROWTH * BOTT * 27);
+      li.pk_c1f = pk; pk += packed_elems(BOTT, 128, li.cin, 64, 1);
+      li.pk_c1d = pk; pk += packed_elems(li.cin, 128, BOTT, 64, 1);
+      li.pk_c2f = pk; pk += packed_elems(GROWTH, 32, BOTT, 64, 27);
+      li.pk_c2d = pk; pk += packed_elems(BOTT, 128, GROWTH, 32, 27);
+      bi.layers.push_back(li);
+    }
+    c = bi.ctot;
+    bi.has_trans = b != nblocks - 1;
+    if (bi.has_trans) {
+      if (c % 64 != 0) { delete pl; return nullptr; }
+      add_bn(bi.tn, c, bi.fwd_off);
+      bi.tconv_idx = add_param((long long)(c / 2) * c);
+      bi.pk_tf = pk; pk += packed_elems(c / 2, 128, c, 64, 1);
+      bi.pk_td = pk; pk += packed_elems(c, 128, c / 2, 64, 1);
+      c /= 2;
+    }
+    pl->blocks.push_back(bi);
+  }
+  add_bn(pl->n5, c, pl->blocks.back().fwd_off);
+  pl->num_params = pidx; pl->num_buffers = bidx; pl->num_bn = bidx / 3; pl->num_layers = lidx;
+  pl->fwd_channels = foff; pl->bwd_channels = boff; pl->packed_elems_total = pk;
+  // BN order == buffer order
+  pl->bn_order.push_back(&pl->n0);
+  for (auto& bi : pl->blocks) {
+    for (auto& li : bi.layers) { pl->bn_order.push_back(&li.n1); pl->bn_order.push_back(&li.n2); }
+    if (bi.has_trans) pl->bn_order.push_back(&bi.tn);
+  }
+  pl->bn_order.push_back(&pl->n5);
+  return pl;
+}
+
+void mmnn_encoder_destroy(void* h) { delete (Plan*)h; }
+int mmnn_encoder_num_params(void* h) { return ((Plan*)h)->num_params; }
+int mmnn_encoder_num_buffers(void* h) { return ((Plan*)h)->num_buffers; }
+int mmnn_encoder_num_layers(void* h) { return ((Plan*)h)->num_layers; }
+long long mmnn_encoder_param_numel(void* h, int i) { return ((Plan*)h)->param_numel[i]; }
+int mmnn_encoder_out_channels(void* h) { return ((Plan*)h)->n5.C; }
+
+long long mmnn_encoder_workspace_bytes(void* h, int B, int X, int Y, int Z) {
+  Geo g;
+  if (!make_geo(*(Plan*)h, B, X, Y, Z, g)) return -1;
+  return (long long)g.total;
+}
+
+// out_dhw: spatial dims of the trunk output (the last block's)
+int mmnn_encoder_out_dims(void* h, int B, int X, int Y, int Z, int* out_dhw) {
+  Geo g;
+  Plan* pl = (Plan*)h;
+  if (!make_geo(*pl, B, X, Y, Z, g)) return -1;
+  const int nb = (int)pl->blocks.size();
+  out_dhw[0] = g.D[nb - 1]; out_dhw[1] = g.H[nb - 1]; out_dhw[2] = g.W[nb - 1];
+  return 0;
+}
+
+// Debug / test hook: byte offsets of the main activation buffers inside the workspace.
+// offs[0]=xs2d, [1]=stem_out, [2]=argmax, [3..3+nb)=buf[b], [3+nb..3+2nb)=bott[b], [3+2nb..3+3nb)=dbuf[b], then fstats, bstats
+int mmnn_encoder_debug_offsets(void* h, int B, int X, int Y, int Z, long long* offs, long long* dims) {
+  Geo g;
+  Plan* pl = (Plan*)h;
+  if (!make_geo(*pl, B, X, Y, Z, g)) return -1;
+  const int nb = (int)pl->blocks.size();
+  int k = 0;
+  offs[k++] = g.xs2d; offs[k++] = g.stem_out; offs[k++] = g.argmax;
+  for (int b = 0; b < nb; ++b) offs[k++] = g.buf[b];
+  for (int b = 0; b < nb; ++b) offs[k++] = g.bott[b];
+  for (int b = 0; b < nb; ++b) offs[k++] = g.dbuf[b];
+  offs[k++] = g.fstats; offs[k++] = g.bstats;
+  int d = 0;
+  dims[d++] = g.M0; dims[d++] = g.D0; dims[d++] = g.H0; dims[d++] = g.W0;
+  for (int b = 0; b < nb; ++b) { dims[d++] = g.M[b]; dims[d++] = pl->blocks[b].ctot; dims[d++] = pl->blocks[b].c0; dims[d++] = pl->blocks[b].fwd_off; }
+  dims[d++] = pl->fwd_channels;
+  return 0;
+}
+
+// image   : fp32 NCDHW [B][cin][X][Y][Z]
+// params  : device pointers in backbone.named_parameters() order;  buffers: in backbone.named_buffers() order
+// dropmask: optional fp32 [num_layers][B][32] channel keep-mask already divided by (1-p) (Dropout3d), or null
+// out     : fp32 [M_last][C_last] = norm5 output, NDHWC
+int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image, const void* const* params,
+                         void* const* buffers, const float* dropmask, void* workspace, float* out, int training,
+                         void* stream_) {
+  Plan* pl = (Plan*)h;
+  cudaStream_t st = (cudaStream_t)stream_;
+  Geo g;
+  if (!make_geo(*pl, B, X, Y, Z, g)) return -10;
+  uint8_t* ws = (uint8_t*)workspace;
+  double* fstats = (double*)(ws + g.fstats);
+  const int FC = pl->fwd_channels;
+  const bool batch = training != 0;
+  bf16* packed = (bf16*)(ws + g.packed);
+  const int nb = (int)pl->blocks.size();
+
+  CUDA_RET(cudaMemsetAsync(fstats, 0, (size_t)FC * 2 * sizeof(double), st));
+
+  // ---- 1. pack every conv weight (fprop + dgrad images) with one launch
+  {
+    std::vector<PackDesc> descs;
+    auto add = [&](const void* src, size_t off, int N, int NT, int Cin, int kbw, int ntaps, int mode, long long sn,
+                   long long sc, long long stt) {
+      PackDesc d;
+      d.src = (const float*)src; d.dst = packed + off; d.N = N; d.NT = NT; d.Cin = Cin; d.kbw = kbw; d.ntaps = ntaps;
+      d.mode = mode; d.cin_real = pl->cin_real; d.pad_ = 0; d.sn = sn; d.sc = sc; d.st = stt;
+      descs.push_back(d);
+    };
+    add(params[pl->conv0_idx], pl->pk_stem, 64, 64, 64, 64, 16, PACK_STEM, 0, 0, 0);
+    for (auto& bi : pl->blocks) {
+      for (auto& li : bi.layers) {
+        add(params[li.conv1_idx], li.pk_c1f, BOTT, 128, li.cin, 64, 1, PACK_GENERIC, li.cin, 1, 0);
+        add(params[li.conv1_idx], li.pk_c1d, li.cin, 128, BOTT, 64, 1, PACK_GENERIC, 1, li.cin, 0);
+        add(params[li.conv2_idx], li.pk_c2f, GROWTH, 32, BOTT, 64, 27, PACK_GENERIC, BOTT * 27, 27, 1);
+        add(params[li.conv2_idx], li.pk_c2d, BOTT, 128, GROWTH, 32, 27, PACK_GENERIC, 27, BOTT * 27, 1);
+      }
+      if (bi.has_trans) {
+        add(params[bi.tconv_idx], bi.pk_tf, bi.ctot / 2, 128, bi.ctot, 64, 1, PACK_GENERIC, bi.ctot, 1, 0);
+        add(params[bi.tconv_idx], bi.pk_td, bi.ctot, 128, bi.ctot / 2, 64, 1, PACK_GENERIC, 1, bi.ctot, 0);
+      }
+    }
+    if (descs.size() * sizeof(PackDesc) > (1 << 19)) return -11;
+    RET_IF(upload_table(pl, 0, ws + g.tables, descs.data(), descs.size() * sizeof(PackDesc), st));
+    pack_weights_kernel<<<dim3(16, (unsigned)descs.size()), 256, 0, st>>>((const PackDesc*)(ws + g.tables));
+    LAUNCH_RET();
+  }
+
+  // ---- 2. stem
+  bf16* xs2d = (bf16*)(ws + g.xs2d);
+  {
+    const long long cells = (long long)B * g.Sz * g.Sy * g.Sx * 2;
+    s2d_pack_kernel<<<ew_grid(cells), EW_THREADS, 0, st>>>(image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx);
+    LAUNCH_RET();
+    RowsParams p = {};
+    p.M = (int)g.M0; p.NT = 64; p.Ncols = 64; p.Cin = 64; p.kbw = 64; p.ntaps = 16; p.tap_sign = 1;
+    p.Dz = g.D0; p.Dy = g.H0; p.Dx = g.W0; p.Sz = g.Sz; p.Sy = g.Sy; p.Sx = g.Sx;
+    p.a_src = xs2d; p.a_pitch = 16;
+    p.b_packed = packed + pl->pk_stem;
+    p.out = (bf16*)(ws + g.stem_out); p.out_pitch = 64;
+    p.st_sum = fstats + pl->n0.fwd_off; p.st_sq = fstats + FC + pl->n0.fwd_off;
+    RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, st));
+    PoolParams q = {};
+    q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
+    q.src = (const bf16*)(ws + g.stem_out);
+    q.bn = make_bn(pl->n0, params, buffers, fstats, FC, g.M0, batch);
+    q.dst = (bf16*)(ws + g.buf[0]); q.dst_pitch = pl->blocks[0].ctot;
+    q.argmax = ws + g.argmax;
+    q.st_sum = fstats + pl->blocks[0].fwd_off; q.st_sq = fstats + FC + pl->blocks[0].fwd_off;
+    int blocks = (int)std::min<long long>((g.M[0] + 31) / 32, NUM_SMS * 8);
+    bnrelu_maxpool_kernel<<<blocks, EW_THREADS, 0, st>>>(q);
+    LAUNCH_RET();
+  }
+
+  // ---- 3. dense blocks + transitions
+  for (int b = 0; b < nb; ++b) {
+    const BlockInfo& bi = pl->blocks[b];
+    bf16* buf = (bf16*)(ws + g.buf[b]);
+    const long long M = g.M[b];
+    for (size_t l = 0; l < bi.layers.size(); ++l) {
+      const LayerInfo& li = bi.layers[l];
+      bf16* bott = (bf16*)(ws + g.bott[b]) + (size_t)l * M * BOTT;
+      RowsParams p = {};
+      p.M = (int)M; p.NT = 128; p.Ncols = BOTT; p.Cin = li.cin; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
+      p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
+      p.a_src = buf; p.a_pitch = bi.ctot;
+      p.bnA = make_bn(li.n1, params, buffers, fstats, FC, M, batch);
+      p.b_packed = packed + li.pk_c1f;
+      p.out = bott; p.out_pitch = BOTT;
+      p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
+      RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st));
+      RowsParams q = {};
+      q.M = (int)M; q.NT = 32; q.Ncols = GROWTH; q.Cin = BOTT; q.kbw = 64; q.ntaps = 27; q.tap_sign = 1;
+      q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b];
+      q.a_src = bott; q.a_pitch = BOTT;
+      q.bnA = make_bn(li.n2, params, buffers, fstats, FC, M, batch);
+      q.b_packed = packed + li.pk_c2f;
+      q.out = buf + li.cin; q.out_pitch = bi.ctot;
+      q.colscale = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
+      q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
+      RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st));
+    }
+    if (bi.has_trans) {
+      const BlockInfo& nx = pl->blocks[b + 1];
+      AvgPoolParams a = {};
+      a.B = B; a.D = g.D[b]; a.H = g.H[b]; a.W = g.W[b]; a.C = bi.ctot;
+      a.x = buf; a.x_pitch = bi.ctot;
+      a.bn = make_bn(bi.tn, params, buffers, fstats, FC, M, batch);
+      a.pooled = (bf16*)(ws + g.pooled[b]);
+      bnrelu_avgpool_kernel<<<ew_grid(g.M[b + 1] * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(a);
+      LAUNCH_RET();
+      RowsParams p = {};
+      p.M = (int)g.M[b + 1]; p.NT = 128; p.Ncols = bi.ctot / 2; p.Cin = bi.ctot; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
+      p.Dz = g.D[b + 1]; p.Dy = g.H[b + 1]; p.Dx = g.W[b + 1];
+      p.a_src = a.pooled; p.a_pitch = bi.ctot;
+      p.b_packed = packed + bi.pk_tf;
+      p.out = (bf16*)(ws + g.buf[b + 1]); p.out_pitch = nx.ctot;
+      p.st_sum = fstats + nx.fwd_off; p.st_sq = fstats + FC + nx.fwd_off;
+      RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE_STATS, st));
+    }
+  }
+
+  // ---- 4. norm5 -> fp32 output
+  {
+    const BlockInfo& bi = pl->blocks[nb - 1];
+    const long long M = g.M[nb - 1];
+    BnSrc bn = make_bn(pl->n5, params, buffers, fstats, FC, M, batch);
+    bn_apply_f32_kernel<<<ew_grid(M * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(
+        (const bf16*)(ws + g.buf[nb - 1]), bi.ctot, bn, out, M, bi.ctot);
+    LAUNCH_RET();
+  }
+
+  // ---- 5. running statistics (training only): one launch for all BNs
+  if (batch) {
+    std::vector<BnTableEntry> tab;
+    const long long counts0 = g.M0;
+    auto count_of = [&](const BnInfo* bn) -> long long {
+      if (bn == &pl->n0) return counts0;
+      for (int b = 0; b < nb; ++b) {
+        const BlockInfo& bi = pl->blocks[b];
+        for (auto& li : bi.layers)
+          if (bn == &li.n1 || bn == &li.n2) return g.M[b];
+        if (bi.has_trans && bn == &bi.tn) return g.M[b];
+      }
+      return g.M[nb - 1];
+    };
+    for (BnInfo* bn : pl->bn_order) {
+      BnTableEntry e = {};
+      e.sum = fstats + bn->fwd_off; e.sumsq = fstats + FC + bn->fwd_off;
+      e.running_mean = (float*)buffers[bn->buf_idx]; e.running_var = (float*)buffers[bn->buf_idx + 1];
+      e.num_batches_tracked = (long long*)buffers[bn->buf_idx + 2];
+      e.C = bn->C; e.count = (float)count_of(bn);
+      tab.push_back(e);
+    }
+    uint8_t* dtab = ws + g.tables + (1 << 19);
+    RET_IF(upload_table(pl, 1, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
+    bn_running_update_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab, 0.1f);
+    LAUNCH_RET();
+  }
+  return 0;
+}
+
+// grad_out: fp32 [M_last][C_last] gradient w.r.t. the norm5 output (NDHWC)
+// grads   : device pointers (param order) of ZERO-INITIALISED fp32 tensors shaped like the parameters
+int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const* params, void* const* buffers,
+                          void* const* grads, const float* dropmask, void* workspace, const float* grad_out,
+                          void* stream_) {
+  Plan* pl = (Plan*)h;
+  cudaStream_t st = (cudaStream_t)stream_;
+  Geo g;
+  if (!make_geo(*pl, B, X, Y, Z, g)) return -10;
+  uint8_t* ws = (uint8_t*)workspace;
+  const double* fstats = (const double*)(ws + g.fstats);
+  double* bstats = (double*)(ws + g.bstats);
+  const int FC = pl->fwd_channels, BC = pl->bwd_channels;
+  bf16* packed = (bf16*)(ws + g.packed);
+  const int nb = (int)pl->blocks.size();
+  auto gsum = [&](const BnInfo& bn) { return bstats + bn.bwd_off; };
+  auto gdot = [&](const BnInfo& bn) { return bstats + BC + bn.bwd_off; };
+
+  CUDA_RET(cudaMemsetAsync(bstats, 0, (size_t)BC * 2 * sizeof(double), st));
+  CUDA_RET(cudaMemsetAsync(ws + g.c2scratch, 0, (size_t)pl->num_layers * 27 * GROWTH * BOTT * 4, st));
+
+  auto bn_apply = [&](int out_mode, long long M, int C, const bf16* v, const float* v32, long long v_pitch, const bf16* x,
+                      long long x_pitch, const BnSrc& bn, const double* gs, const double* gd, void* outp,
+                      long long out_pitch) -> int {
+    BnApplyParams a = {};
+    a.M = M; a.C = C; a.v = v; a.v32 = v32; a.v_pitch = v_pitch; a.x = x; a.x_pitch = x_pitch; a.bn = bn;
+    a.g_sum = gs; a.g_dot = gd; a.inv_count = 1.0f / (float)M; a.out = outp; a.out_pitch = out_pitch;
+    const int grid = ew_grid(M * (C / 8));
+    const size_t sm = 3 * C * sizeof(float);
+    if (out_mode == BA_OUT_BF16) bn_bwd_apply_kernel<BA_OUT_BF16><<<grid, EW_THREADS, sm, st>>>(a);
+    else if (out_mode == BA_OUT_F32_ADD) bn_bwd_apply_kernel<BA_OUT_F32_ADD><<<grid, EW_THREADS, sm, st>>>(a);
+    else bn_bwd_apply_kernel<BA_OUT_F32_STORE><<<grid, EW_THREADS, sm, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+  };
+
+  // ---- norm5
+  {
+    const BlockInfo& bi = pl->blocks[nb - 1];
+    const long long M = g.M[nb - 1];
+    const int C = bi.ctot;
+    BnSrc bn = make_bn(pl->n5, params, buffers, fstats, FC, M, true);
+    const bf16* x = (const bf16*)(ws + g.buf[nb - 1]);
+    const int rows_per_block = EW_THREADS / (C / 8);
+    int blocks = (int)std::min<long long>((M + rows_per_block - 1) / rows_per_block, NUM_SMS * 4);
+    bn_bwd_stats_f32_kernel<<<blocks, EW_THREADS, 2 * C * sizeof(float), st>>>(grad_out, x, C, bn, M, C, gsum(pl->n5), gdot(pl->n5));
+    LAUNCH_RET();
+    RET_IF(bn_apply(BA_OUT_F32_STORE, M, C, nullptr, grad_out, C, x, C, bn, gsum(pl->n5), gdot(pl->n5), ws + g.dbuf[nb - 1], C));
+  }
+
+  for (int b = nb - 1; b >= 0; --b) {
+    const BlockInfo& bi = pl->blocks[b];
+    const long long M = g.M[b];
+    const int vps = g.D[b] * g.H[b] * g.W[b];
+    bf16* buf = (bf16*)(ws + g.buf[b]);
+    float* dbuf = (float*)(ws + g.dbuf[b]);
+    bf16* dA2 = (bf16*)(ws + g.dA2);
+    bf16* dA1 = (bf16*)(ws + g.dA1);
+    bf16* gslice = (bf16*)(ws + g.gslice);
+    for (int l = (int)bi.layers.size() - 1; l >= 0; --l) {
+      const LayerInfo& li = bi.layers[l];
+      bf16* bott = (bf16*)(ws + g.bott[b]) + (size_t)l * M * BOTT;
+      const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, true);
+      const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, true);
+      // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf)
+      extract_slice_kernel<<<ew_grid(M * 4), EW_THREADS, 0, st>>>(
+          dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps);
+      LAUNCH_RET();
+      // conv2 wgrad -> scratch [tap][co][ci]
+      {
+        WgradParams w = {};
+        w.M = (int)M; w.CB = GROWTH; w.NB = 9; w.na_total = BOTT; w.nb_total = GROWTH;
+        w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
+        w.a_src = bott; w.a_pitch = BOTT; w.bnA = bn2;
+        w.b_src = gslice; w.b_pitch = GROWTH;
+        w.dw = (float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
+        w.so_a = 1; w.so_b = BOTT; w.so_j = GROWTH * BOTT;
+        RET_IF(launch_wgrad(w, 1, 0, st));
+      }
+      // conv2 dgrad (+ ReLU mask of norm2/relu2, + BN2 backward statistics)
+      {
+        RowsParams p = {};
+        p.M = (int)M; p.NT = 128; p.Ncols = BOTT; p.Cin = GROWTH; p.kbw = 32; p.ntaps = 27; p.tap_sign = -1;
+        p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
+        p.a_src = gslice; p.a_pitch = GROWTH;
+        p.b_packed = packed + li.pk_c2d;
+        p.out = dA2; p.out_pitch = BOTT;
+        p.st_sum = gsum(li.n2); p.st_sq = gdot(li.n2);
+        p.e_src = bott; p.e_pitch = BOTT; p.bnE = bn2;
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
+      }
+      RET_IF(bn_apply(BA_OUT_BF16, M, BOTT, dA2, nullptr, BOTT, bott, BOTT, bn2, gsum(li.n2), gdot(li.n2), dA2, BOTT));
+      // conv1 wgrad: D[ci][co] -> dW1[co][ci]
+      {
+        WgradParams w = {};
+        w.M = (int)M; w.CB = 128; w.NB = 1; w.na_total = li.cin; w.nb_total = BOTT;
+        w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
+        w.a_src = buf; w.a_pitch = bi.ctot; w.bnA = bn1;
+        w.b_src = dA2; w.b_pitch = BOTT;
+        w.dw = (float*)grads[li.conv1_idx];
+        w.so_a = 1; w.so_b = li.cin; w.so_j = 0;
+        RET_IF(launch_wgrad(w, 0, 0, st));
+      }
+      // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics), then BN1 backward into dbuf[:, :cin]
+      {
+        RowsParams p = {};
+        p.M = (int)M; p.NT = 128; p.Ncols = li.cin; p.Cin = BOTT; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
+        p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
+        p.a_src = dA2; p.a_pitch = BOTT;
+        p.b_packed = packed + li.pk_c1d;
+        p.out = dA1; p.out_pitch = li.cin;
+        p.st_sum = gsum(li.n1); p.st_sq = gdot(li.n1);
+        p.e_src = buf; p.e_pitch = bi.ctot; p.bnE = bn1;
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
+      }
+      RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
+    }
+    if (b > 0) {
+      // transition b-1: buf[b][:, :c0] = avgpool(conv(relu(bn(buf[b-1]))))  ==  conv(pooled[b-1])
+      const BlockInfo& pv = pl->blocks[b - 1];
+      const long long Mp = g.M[b - 1];
+      bf16* gout = (bf16*)(ws + g.gout);
+      bf16* dpooled = (bf16*)(ws + g.dpooled);
+      const bf16* pooled = (const bf16*)(ws + g.pooled[b - 1]);
+      extract_slice_kernel<<<ew_grid(M * (bi.c0 / 8)), EW_THREADS, 0, st>>>(dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps);
+      LAUNCH_RET();
+      {
+        WgradParams w = {};
+        w.M = (int)M; w.CB = 128; w.NB = 1; w.na_total = pv.ctot; w.nb_total = bi.c0;
+        w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
+        w.a_src = pooled; w.a_pitch = pv.ctot;
+        w.b_src = gout; w.b_pitch = bi.c0;
+        w.dw = (float*)grads[pv.tconv_idx];
+        w.so_a = 1; w.so_b = pv.ctot; w.so_j = 0;
+        RET_IF(launch_wgrad(w, 2, 0, st));
+      }
+      {
+        RowsParams p = {};
+        p.M = (int)M; p.NT = 128; p.Ncols = pv.ctot; p.Cin = bi.c0; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
+        p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
+        p.a_src = gout; p.a_pitch = bi.c0;
+        p.b_packed = packed + pv.pk_td;
+        p.out = dpooled; p.out_pitch = pv.ctot;
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE, st));
+      }
+      AvgPoolParams a = {};
+      a.B = B; a.D = g.D[b - 1]; a.H = g.H[b - 1]; a.W = g.W[b - 1]; a.C = pv.ctot;
+      a.x = (const bf16*)(ws + g.buf[b - 1]); a.x_pitch = pv.ctot;
+      a.bn = make_bn(pv.tn, params, buffers, fstats, FC, Mp, true);
+      a.dpooled = dpooled;
+      a.dx = (float*)(ws + g.dbuf[b - 1]); a.dx_pitch = pv.ctot;
+      a.g_sum = gsum(pv.tn); a.g_dot = gdot(pv.tn); a.g_sum_in = gsum(pv.tn); a.g_dot_in = gdot(pv.tn);
+      a.inv_count = 1.0f / (float)Mp;
+      const int rows_per_block = EW_THREADS / (pv.ctot / 8);
+      int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
+      avgpool_bnrelu_bwd_kernel<1><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
+      LAUNCH_RET();
+      avgpool_bnrelu_bwd_kernel<2><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
+      LAUNCH_RET();
+    } else {
+      // pool0 + relu0 + norm0 + conv0
+      PoolBwdParams q = {};
+      q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
+      q.x = (const bf16*)(ws + g.stem_out);
+      q.bn = make_bn(pl->n0, params, buffers, fstats, FC, g.M0, true);
+      q.dpool = dbuf; q.dpool_pitch = bi.ctot;
+      q.argmax = ws + g.argmax;
+      q.dr = (bf16*)(ws + g.dr);
+      q.g_sum = gsum(pl->n0); q.g_dot = gdot(pl->n0);
+      int blocks = (int)std::min<long long>((g.M0 + 31) / 32, NUM_SMS * 8);
+      maxpool_bnrelu_bwd_kernel<<<blocks, EW_THREADS, 0, st>>>(q);
+      LAUNCH_RET();
+      RET_IF(bn_apply(BA_OUT_BF16, g.M0, 64, q.dr, nullptr, 64, q.x, 64, q.bn, gsum(pl->n0), gdot(pl->n0), q.dr, 64));
+      WgradParams w = {};
+      w.M = (int)g.M0; w.CB = 64; w.NB = 1; w.na_total = 128; w.nb_total = 64;
+      w.Dz = g.D0; w.Dy = g.H0; w.Dx = g.W0; w.Sz = g.Sz; w.Sy = g.Sy; w.Sx = g.Sx;
+      w.a_src = (const bf16*)(ws + g.xs2d); w.a_pitch = 16;
+      w.b_src = q.dr; w.b_pitch = 64;
+      w.dw = (float*)grads[pl->conv0_idx];
+      w.cin_real = pl->cin_real;
+      RET_IF(launch_wgrad(w, 3, 0, st));
+    }
+  }
+
+  // ---- tails: BN parameter gradients and conv2 gradient layout, one launch each
+  {
+    std::vector<BnTableEntry> tab;
+    for (BnInfo* bn : pl->bn_order) {
+      BnTableEntry e = {};
+      e.g_sum = gsum(*bn); e.g_dot = gdot(*bn);
+      e.grad_gamma = (float*)grads[bn->param_idx]; e.grad_beta = (float*)grads[bn->param_idx + 1];
+      e.C = bn->C;
+      tab.push_back(e);
+    }
+    uint8_t* dtab = ws + g.tables + (1 << 19) + (1 << 17);
+    RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
+    bn_param_grad_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab);
+    LAUNCH_RET();
+    std::vector<TransposeEntry> tt;
+    for (auto& bi : pl->blocks)
+      for (auto& li : bi.layers) {
+        TransposeEntry e;
+        e.src = (const float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
+        e.dst = (float*)grads[li.conv2_idx];
+        tt.push_back(e);
+      }
+    uint8_t* dtt = dtab + (1 << 18);
+    RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(TransposeEntry), st));
+    conv2_grad_transpose_kernel<<<dim3(16, (unsigned)tt.size()), 256, 0, st>>>((const TransposeEntry*)dtt, GROWTH, BOTT);
+    LAUNCH_RET();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -419,8 +419,9 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
   const int gshift = planes >= 8 ? 3 : 2;
   const int rsub = lane >> gshift;
   const int rpp = 32 >> gshift;
-  for (int grp = 0; grp < planes / G; ++grp) {
+  for (int grp = 0; grp < (planes + G - 1) / G; ++grp) {
     const int chunk = grp * G + (lane & (G - 1));
+    if (chunk >= planes) continue;  // planes is a multiple of 4 but not necessarily of G
     float sc[8], sh[8];
     if (TRANS == T_BNRELU) {
 #pragma unroll

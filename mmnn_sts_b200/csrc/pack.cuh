@@ -21,7 +21,7 @@ struct PackDesc {
   long long sn, sc, st;  // source strides (elements) for n, channel, tap
 };
 
-__global__ void pack_weights_kernel(const PackDesc* __restrict__ descs) {
+static __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
   const int planes = d.kbw / 8;
   const int kb_per_tap = (d.Cin + d.kbw - 1) / d.kbw;
@@ -59,7 +59,7 @@ __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs) {
   }
 }
 
-inline size_t packed_elems(int N, int NT, int Cin, int kbw, int ntaps) {
+static inline size_t packed_elems(int N, int NT, int Cin, int kbw, int ntaps) {
   const int kb_per_tap = (Cin + kbw - 1) / kbw;
   const int ntile = (N + NT - 1) / NT;
   return (size_t)ntile * ntaps * kb_per_tap * (kbw / 8) * NT * 8;

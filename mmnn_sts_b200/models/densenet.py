@@ -1,0 +1,250 @@
+"""3-D DenseNet encoder with the reference's constructor signatures and state_dict layout, running on the sm_100a
+kernels of libmmnn_b200.so.
+
+Mirrors the interface of /root/reference/models/densenet.py: `DenseNet(spatial_dims, in_channels, out_channels,
+feature_channels, init_features=64, growth_rate=32, block_config=(6,12,24,16), bn_size=4, act, norm, dropout_prob)`
+(:173-186), `DenseNet121` (:309-324), `TinyDensenet` (:333-356);  sub-modules `backbone` / `features` /
+`class_layers` keep the reference's names so `state_dict()` has the identical 779-key layout and
+`BackpropagatableFeatureExtractor` (features(backbone(x)), /root/reference/utils/utils.py:238-251) works unchanged.
+The torch.nn leaf modules below are parameter CONTAINERS only (names, shapes, initialisation law of :258-265);
+the arithmetic is done by one C-ABI call per direction (mmnn_encoder_forward / mmnn_encoder_backward).
+No CPU path: CPU tensors raise.
+"""
+import ctypes as C
+from collections import OrderedDict
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from ..ops import GapLinearDropout
+
+
+def _dense_layer(in_channels, growth_rate, bn_size, dropout_prob):
+    layer = nn.Module()
+    seq = nn.Sequential()
+    mid = bn_size * growth_rate
+    seq.add_module("norm1", nn.BatchNorm3d(in_channels))
+    seq.add_module("relu1", nn.ReLU(inplace=True))
+    seq.add_module("conv1", nn.Conv3d(in_channels, mid, kernel_size=1, bias=False))
+    seq.add_module("norm2", nn.BatchNorm3d(mid))
+    seq.add_module("relu2", nn.ReLU(inplace=True))
+    seq.add_module("conv2", nn.Conv3d(mid, growth_rate, kernel_size=3, padding=1, bias=False))
+    if dropout_prob > 0:
+        seq.add_module("dropout", nn.Dropout3d(dropout_prob))
+    layer.add_module("layers", seq)
+    return layer
+
+
+class _Workspace:
+    __slots__ = ("tensor", "busy")
+
+    def __init__(self, nbytes, device):
+        self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.busy = False
+
+
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bb, x, *params):
+        out, ws, mask = bb._run_forward(x, params)
+        ctx.bb, ctx.ws, ctx.mask, ctx.shape = bb, ws, mask, tuple(x.shape)
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        bb = ctx.bb
+        grads = bb._run_backward(ctx.shape, ctx.params, ctx.ws, ctx.mask, grad_out)
+        ctx.ws.busy = False
+        return (None, None) + tuple(grads)
+
+
+class Backbone(nn.Sequential):
+    """`backbone` of the reference (/root/reference/models/densenet.py:196-231): conv0 .. norm5, one fused call."""
+
+    def __init__(self, in_channels, init_features, growth_rate, block_config, bn_size, dropout_prob):
+        super().__init__()
+        self.add_module("conv0", nn.Conv3d(in_channels, init_features, kernel_size=7, stride=2, padding=3, bias=False))
+        self.add_module("norm0", nn.BatchNorm3d(init_features))
+        self.add_module("relu0", nn.ReLU(inplace=True))
+        self.add_module("pool0", nn.MaxPool3d(kernel_size=3, stride=2, padding=1))
+        c = init_features
+        for i, n in enumerate(block_config):
+            block = nn.Sequential()
+            for j in range(n):
+                block.add_module("denselayer%d" % (j + 1), _dense_layer(c, growth_rate, bn_size, dropout_prob))
+                c += growth_rate
+            self.add_module(f"denseblock{i + 1}", block)
+            if i == len(block_config) - 1:
+                self.add_module("norm5", nn.BatchNorm3d(c))
+            else:
+                t = nn.Sequential()
+                t.add_module("norm", nn.BatchNorm3d(c))
+                t.add_module("relu", nn.ReLU(inplace=True))
+                t.add_module("conv", nn.Conv3d(c, c // 2, kernel_size=1, bias=False))
+                t.add_module("pool", nn.AvgPool3d(kernel_size=2, stride=2))
+                self.add_module(f"transition{i + 1}", t)
+                c //= 2
+        self.out_channels = c
+        self._cfg = (in_channels, tuple(block_config), init_features, growth_rate, bn_size)
+        self.dropout_prob = float(dropout_prob)
+        self._plan = None
+        self._workspaces = {}
+        self.injected_dropmask = None  # tests: [num_layers, B, growth] keep-mask / (1-p)
+
+    # ---- C-ABI plumbing
+    def _get_plan(self):
+        if self._plan is None:
+            cin, cfg, init_f, growth, bn_size = self._cfg
+            arr = (C.c_int * len(cfg))(*cfg)
+            h = L.lib().mmnn_encoder_create(cin, arr, len(cfg), init_f, growth, bn_size)
+            if not h:
+                raise L.MMNNLibraryError(f"unsupported DenseNet configuration for the sm_100a kernels: {self._cfg}")
+            self._plan = C.c_void_p(h)
+            n_params = sum(1 for _ in self.parameters())
+            n_bufs = sum(1 for _ in self.buffers())
+            assert L.lib().mmnn_encoder_num_params(self._plan) == n_params, "parameter table mismatch"
+            assert L.lib().mmnn_encoder_num_buffers(self._plan) == n_bufs, "buffer table mismatch"
+            self._numel = [L.lib().mmnn_encoder_param_numel(self._plan, i) for i in range(n_params)]
+            assert self._numel == [p.numel() for p in self.parameters()], "parameter order mismatch"
+            self._num_layers = L.lib().mmnn_encoder_num_layers(self._plan)
+        return self._plan
+
+    def __del__(self):
+        try:
+            if self._plan is not None:
+                L.lib().mmnn_encoder_destroy(self._plan)
+        except Exception:
+            pass
+
+    def _acquire_ws(self, key, nbytes, device):
+        pool = self._workspaces.setdefault(key, [])
+        for w in pool:
+            if not w.busy:
+                return w
+        w = _Workspace(nbytes, device)
+        pool.append(w)
+        return w
+
+    @staticmethod
+    def _ptr_array(tensors):
+        return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def _run_forward(self, x, params):
+        if not x.is_cuda:
+            raise L.MMNNLibraryError("mmnn_sts_b200 has no CPU path: move the model and inputs to a CUDA device")
+        plan = self._get_plan()
+        x = x.contiguous().float()
+        B, cin, X, Y, Z = x.shape
+        assert cin == self._cfg[0], f"expected {self._cfg[0]} input channels, got {cin}"
+        lib = L.lib()
+        nbytes = lib.mmnn_encoder_workspace_bytes(plan, B, X, Y, Z)
+        if nbytes < 0:
+            raise ValueError(f"input volume {X}x{Y}x{Z} is too small for this network")
+        ws = self._acquire_ws((B, X, Y, Z, x.device.index), nbytes, x.device)
+        dims = (C.c_int * 3)()
+        lib.mmnn_encoder_out_dims(plan, B, X, Y, Z, dims)
+        out = torch.empty((B, dims[0], dims[1], dims[2], self.out_channels), dtype=torch.float32, device=x.device)
+        mask = None
+        if self.training:
+            if self.injected_dropmask is not None:
+                mask = self.injected_dropmask.to(device=x.device, dtype=torch.float32).contiguous()
+            elif self.dropout_prob > 0:
+                keep = 1.0 - self.dropout_prob
+                mask = torch.bernoulli(torch.full((self._num_layers, B, 32), keep, device=x.device)) / keep
+        bufs = list(self.buffers())
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = lib.mmnn_encoder_forward(plan, B, X, Y, Z, x.data_ptr(), self._ptr_array(params), self._ptr_array(bufs),
+                                          mask.data_ptr() if mask is not None else None, ws.tensor.data_ptr(),
+                                          out.data_ptr(), int(self.training), stream)
+        L.check(rc, "mmnn_encoder_forward")
+        ws.busy = self.training and torch.is_grad_enabled()
+        return out.permute(0, 4, 1, 2, 3), ws, mask
+
+    def _run_backward(self, xshape, params, ws, mask, grad_out):
+        B, cin, X, Y, Z = xshape
+        lib = L.lib()
+        g = grad_out.permute(0, 2, 3, 4, 1).contiguous().float()
+        flat = torch.zeros(sum(self._numel), dtype=torch.float32, device=g.device)
+        grads, off = [], 0
+        for p, n in zip(params, self._numel):
+            grads.append(flat[off:off + n].view(p.shape))
+            off += n
+        bufs = list(self.buffers())
+        with torch.cuda.device(g.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = lib.mmnn_encoder_backward(self._plan, B, X, Y, Z, self._ptr_array(params), self._ptr_array(bufs),
+                                           self._ptr_array(grads), mask.data_ptr() if mask is not None else None,
+                                           ws.tensor.data_ptr(), g.data_ptr(), stream)
+        L.check(rc, "mmnn_encoder_backward")
+        return grads
+
+    def forward(self, x):
+        params = tuple(self.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _BackboneFn.apply(self, x, *params)
+        out, ws, _ = self._run_forward(x, params)
+        ws.busy = False
+        return out
+
+
+class _Features(nn.Sequential):
+    """`features` head of the reference (:234-247): ReLU -> AdaptiveAvgPool3d(1) -> Flatten -> Linear -> Dropout."""
+
+    def __init__(self, in_channels, feature_channels, dropout_prob):
+        super().__init__(OrderedDict([
+            ("relu", nn.ReLU(inplace=True)),
+            ("pool", nn.AdaptiveAvgPool3d(1)),
+            ("flatten", nn.Flatten(1)),
+            ("feature_layer", nn.Linear(in_channels, feature_channels)),
+            ("dropout", nn.Dropout(dropout_prob)),
+        ]))
+        self.injected_mask = None  # tests: [B, F] keep-mask / (1-p)
+
+    def forward(self, x):
+        p = self.dropout.p if self.training else 0.0
+        return GapLinearDropout.run(x, self.feature_layer.weight, self.feature_layer.bias, p, self.injected_mask if self.training else None)
+
+
+class DenseNet(nn.Module):
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, feature_channels: int,
+                 init_features: int = 64, growth_rate: int = 32, block_config: Sequence[int] = (6, 12, 24, 16),
+                 bn_size: int = 4, act=("relu", {"inplace": True}), norm="batch", dropout_prob: float = 0.0) -> None:
+        super().__init__()
+        if spatial_dims != 3:
+            raise NotImplementedError("the sm_100a build implements the 3-D network only")
+        self.backbone = Backbone(in_channels, init_features, growth_rate, block_config, bn_size, dropout_prob)
+        self.features = _Features(self.backbone.out_channels, feature_channels, dropout_prob)
+        self.class_layers = nn.Sequential(OrderedDict([("out", nn.Linear(feature_channels, out_channels))]))
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight)
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.Linear):
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return self.class_layers(self.features(self.backbone(x)))
+
+
+class DenseNet121(DenseNet):
+    def __init__(self, init_features: int = 64, growth_rate: int = 32, block_config: Sequence[int] = (6, 12, 24, 16),
+                 pretrained: bool = False, progress: bool = True, **kwargs) -> None:
+        super().__init__(init_features=init_features, growth_rate=growth_rate, block_config=block_config, **kwargs)
+        if pretrained:
+            raise NotImplementedError("PyTorch Hub provides no pretrained 3-D DenseNet (same as the reference)")
+
+
+class TinyDensenet(DenseNet):
+    def __init__(self, init_features: int = 64, growth_rate: int = 32, block_config: Sequence[int] = (6, 12, 4),
+                 pretrained: bool = False, progress: bool = True, **kwargs) -> None:
+        super().__init__(init_features=init_features, growth_rate=growth_rate, block_config=block_config, **kwargs)
+
+
+Densenet = densenet = DenseNet
+Densenet121 = densenet121 = DenseNet121

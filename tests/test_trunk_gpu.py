@@ -1,0 +1,128 @@
+"""GPU parity of the DenseNet-3D trunk (+ feature head) on seeded inputs / weights, forward AND every parameter
+gradient, train mode (batch statistics, injected dropout masks) and eval mode, against two CPU checkers:
+
+  * oracle/emul.py  -- the reference algorithm with bf16 rounding at the build's storage points ("rounding-matched"):
+                       TIGHT tolerance, proves the kernels compute what they claim (same ReLU masks, same roundings);
+  * oracle/model.py -- the fp32 restatement pinned bit-exactly to the unchanged reference files: bf16-storage tolerance.
+                       Gradients of a ReLU network at reduced precision differ from fp32 by ~sqrt(forward error)
+                       because near-zero pre-activations flip ("Numerics"), so they are checked by cosine
+                       similarity and norm ratio, not element-wise.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PFX = "image_model.model."
+
+
+def _sub(sd):
+    return {k[len(PFX):]: v for k, v in sd.items() if k.startswith(PFX)}
+
+
+def _run_cpu(backbone_fn, sd, image, training, masks, gw, cfg):
+    from oracle import model as om
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    y = backbone_fn(p, image, training, masks, PFX, block_config=cfg)
+    f = om.densenet_features(p, y, masks if training else None, PFX)
+    if training:
+        (f * gw).sum().backward()
+    return f.detach(), p
+
+
+def _rel(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _cos(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+CASES = [
+    # cin, spatial, batch, dropout, seed, block_config
+    (2, (32, 32, 32), 4, False, 1, (2, 2)),
+    (2, (32, 32, 32), 4, True, 2, (2, 2, 2)),
+    (2, (40, 48, 32), 2, False, 6, (2, 3)),
+    (1, (64, 64, 32), 4, False, 4, (6, 12, 24, 16)),
+    (2, (64, 64, 64), 8, True, 7, (6, 12, 24, 16)),
+]
+
+
+@pytest.mark.parametrize("cin,spatial,batch,dropout,seed,cfg", CASES)
+def test_trunk_train(cin, spatial, batch, dropout, seed, cfg):
+    from mmnn_sts_b200.models.densenet import DenseNet
+    from oracle import emul, model as om, synth
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    sd = synth.make_state_dict(42, in_channels=cin, block_config=cfg)
+    image, _, _, _ = synth.make_batch(seed, batch, cin, spatial)
+    masks = synth.make_masks(seed + 1000, batch, block_config=cfg) if dropout else None
+    g = torch.Generator().manual_seed(seed)
+    gw = torch.randn(batch, 12, generator=g)
+    f32, p32 = _run_cpu(om.densenet_backbone, sd, image, True, masks, gw, cfg)
+    fem, pem = _run_cpu(emul.backbone_bf16, sd, image, True, masks, gw, cfg)
+
+    m = DenseNet(spatial_dims=3, in_channels=cin, out_channels=2, feature_channels=12, block_config=cfg,
+                 dropout_prob=0.2 if dropout else 0.0)
+    m.load_state_dict(_sub(sd))
+    m = m.cuda().train()
+    if dropout:
+        m.backbone.injected_dropmask = torch.stack([masks["dense"][(b, l)] for b, nl in enumerate(cfg) for l in range(nl)])
+        m.features.injected_mask = masks["image_features"]
+    f = m.features(m.backbone(image.cuda()))
+    (f * gw.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    fc = f.detach().cpu()
+    e_em, e_32 = _rel(fc, fem), _rel(fc, f32)
+    print(f"\n[{cfg}] features rel-L2: vs rounding-matched {e_em:.2e}, vs fp32 oracle {e_32:.2e}")
+    deep = len(cfg) == 4
+    assert e_em < (3e-2 if deep else 5e-3)
+    assert e_32 < (1.5e-1 if deep else 2e-2)
+    rel_em, cos_32, nrm_32 = [], [], []
+    for k, q in m.named_parameters():
+        r32, rem = p32[PFX + k].grad, pem[PFX + k].grad
+        if r32 is None:
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0
+            continue
+        gq = q.grad.cpu()
+        assert torch.isfinite(gq).all(), k
+        rel_em.append((_rel(gq, rem), k))
+        cos_32.append((_cos(gq, r32), k))
+        nrm_32.append(float(gq.norm() / (r32.norm() + 1e-30)))
+    rel_em.sort(reverse=True); cos_32.sort()
+    print("   grads vs rounding-matched: median rel-L2 %.2e, worst %s" % (np.median([e for e, _ in rel_em]), [(f"{e:.2e}", k) for e, k in rel_em[:3]]))
+    print("   grads vs fp32 oracle: median cosine %.4f, worst %s, norm ratio median %.3f" % (np.median([c for c, _ in cos_32]), [(f"{c:.3f}", k) for c, k in cos_32[:3]], np.median(nrm_32)))
+    if not deep:
+        assert np.median([e for e, _ in rel_em]) < 2e-2
+        assert rel_em[0][0] < 0.25, rel_em[:3]      # tiny-norm BN gains are the outliers
+        assert np.median([c for c, _ in cos_32]) > 0.9
+    else:
+        # full depth: residual mask flips between the CPU model and the GPU (different fp32 summation order) compound
+        assert np.median([e for e, _ in rel_em]) < 0.5
+        assert np.median([c for c, _ in cos_32]) > 0.3
+    assert 0.8 < np.median(nrm_32) < 1.25
+    new_sd = m.state_dict()
+    for k in ["backbone.norm0", "backbone.denseblock2.denselayer2.layers.norm2", "backbone.norm5"]:
+        assert _rel(new_sd[k + ".running_mean"].cpu(), p32[PFX + k + ".running_mean"]) < 2e-2, k
+        assert _rel(new_sd[k + ".running_var"].cpu(), p32[PFX + k + ".running_var"]) < 2e-2, k
+        assert int(new_sd[k + ".num_batches_tracked"]) == 1
+
+
+def test_trunk_eval():
+    from mmnn_sts_b200.models.densenet import DenseNet121
+    from oracle import emul, model as om, synth
+    cfg = (6, 12, 24, 16)
+    sd = synth.make_state_dict(42, in_channels=2)
+    image, _, _, _ = synth.make_batch(3, 3, 2, (32, 32, 32))
+    f32, _ = _run_cpu(om.densenet_backbone, sd, image, False, None, None, cfg)
+    fem, _ = _run_cpu(emul.backbone_bf16, sd, image, False, None, None, cfg)
+    m = DenseNet121(spatial_dims=3, in_channels=2, out_channels=2, feature_channels=12, dropout_prob=0.2)
+    m.load_state_dict(_sub(sd))
+    m = m.cuda().eval()
+    with torch.no_grad():
+        f = m.features(m.backbone(image.cuda())).cpu()
+    print(f"\neval features rel-L2: vs rounding-matched {_rel(f, fem):.2e}, vs fp32 {_rel(f, f32):.2e}")
+    assert _rel(f, fem) < 2e-2
+    assert _rel(f, f32) < 1e-1
