@@ -49,6 +49,33 @@ class WgradParams(C.Structure):
                 ("cin_real", C.c_int), ("stages", C.c_int)]
 
 
+_P6 = C.c_void_p * 6
+
+
+class MlpArgs(C.Structure):
+    _fields_ = [("W", _P6), ("b", _P6), ("gamma", _P6), ("beta", _P6), ("rmean", _P6), ("rvar", _P6), ("nbt", _P6),
+                ("Wo", C.c_void_p), ("bo", C.c_void_p), ("Wi", C.c_void_p), ("bi", C.c_void_p), ("Wc", C.c_void_p),
+                ("bc", C.c_void_p), ("width", C.c_int * 7), ("B", C.c_int), ("C", C.c_int), ("blend", C.c_int),
+                ("training", C.c_int), ("x", C.c_void_p), ("img_f", C.c_void_p), ("mask", C.c_void_p),
+                ("z", C.c_void_p), ("a", C.c_void_p), ("stat", C.c_void_p), ("preds", C.c_void_p),
+                ("dpreds", C.c_void_p), ("dW", _P6), ("db", _P6), ("dgamma", _P6), ("dbeta", _P6),
+                ("dWo", C.c_void_p), ("dbo", C.c_void_p), ("dWi", C.c_void_p), ("dbi", C.c_void_p),
+                ("dWc", C.c_void_p), ("dbc", C.c_void_p), ("d_img_f", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class CoxArgs(C.Structure):
+    _fields_ = [("h", C.c_void_p), ("h_seg_stride", C.c_longlong), ("h_stride", C.c_longlong),
+                ("key", C.c_void_p), ("key_seg_stride", C.c_longlong), ("key_stride", C.c_longlong),
+                ("w", C.c_void_p), ("w_seg_stride", C.c_longlong), ("w_stride", C.c_longlong),
+                ("perm", C.c_void_p), ("N", C.c_int), ("S", C.c_int), ("eps", C.c_float),
+                ("loss", C.c_void_p), ("grad", C.c_void_p)]
+
+
+class CindexArgs(C.Structure):
+    _fields_ = [("rank", C.c_void_p), ("is_death", C.c_void_p), ("group_end", C.c_void_p), ("orig", C.c_void_p),
+                ("resample", C.c_void_p), ("N", C.c_int), ("R", C.c_int), ("nranks", C.c_int), ("counts", C.c_void_p)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("NT", C.c_int), ("Cin", C.c_int),
                 ("kbw", C.c_int), ("ntaps", C.c_int), ("mode", C.c_int), ("cin_real", C.c_int), ("pad_", C.c_int),
@@ -89,6 +116,15 @@ def _declare(l):
     l.mmnn_encoder_backward.restype = I
     l.mmnn_encoder_debug_offsets.argtypes = [VP, I, I, I, I, C.POINTER(LL), C.POINTER(LL)]
     l.mmnn_encoder_debug_offsets.restype = I
+    l.mmnn_mlp_heads.argtypes = [C.POINTER(MlpArgs), I, VP]
+    l.mmnn_mlp_heads.restype = I
+    l.mmnn_cox_nll.argtypes = [C.POINTER(CoxArgs), VP]
+    l.mmnn_cox_nll.restype = I
+    l.mmnn_cindex_bootstrap.argtypes = [C.POINTER(CindexArgs), VP]
+    l.mmnn_cindex_bootstrap.restype = I
+    for nm, st in (("mmnn_sizeof_mlp_args", MlpArgs), ("mmnn_sizeof_cox_args", CoxArgs), ("mmnn_sizeof_cindex_args", CindexArgs)):
+        getattr(l, nm).restype = I
+        assert getattr(l, nm)() == C.sizeof(st), (nm, getattr(l, nm)(), C.sizeof(st))
     F32P = VP
     l.mmnn_gap_linear_fwd.argtypes = [F32P, I, I, I, F32P, F32P, F32P, I, F32P, F32P, VP]
     l.mmnn_gap_linear_fwd.restype = I

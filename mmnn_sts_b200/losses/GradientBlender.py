@@ -1,0 +1,78 @@
+"""GradientBlender with the reference's constructor, method names and update rule
+(/root/reference/losses/GradientBlender.py:9-256; survival branch :48-103,181-205).  Differences from the reference,
+all on purpose: the per-head / per-class Cox losses of one step are ONE kernel launch instead of six, and the weights
+live on the predictions' device so a step has no device->host synchronisation (quirk Q5)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+class GradientBlender:
+    def __init__(self, loss_function, survival=False, reduction="sum", device="cpu", surv_criterion=None):
+        self.loss_function = loss_function
+        self.weights = None
+        self.reduction = reduction.lower()
+        self.survival = survival
+        self.lvn = None
+        self.ltn = None
+        self.device = device
+        self.surv_criterion = surv_criterion
+        self.history = []
+
+    # ---- survival
+    def _head_losses(self, preds, events, durations):
+        from .losses import CoxPH, _coxph_columns
+        from ..utils.utils import surv_criterion as fused
+        if self.loss_function is CoxPH and self.surv_criterion is fused and preds.is_cuda:
+            return _coxph_columns(preds, events, durations).sum(dim=-1)          # [heads]
+        return torch.stack([self.surv_criterion(self.loss_function, preds[i, ...], events, durations, preds.device)
+                            for i in range(preds.shape[0])], dim=0)
+
+    def computeLossSurv(self, preds, events, durations, reduceToHeads=False):
+        head_losses = self._head_losses(preds, events, durations)
+        if self.weights is None:
+            self.weights = self.normalize(torch.ones(preds.shape[0]))
+        if reduceToHeads:
+            return head_losses
+        w = self.weights.to(device=head_losses.device, dtype=head_losses.dtype)
+        return self.reduce(w * head_losses), head_losses[0]
+
+    def updateWeightsSurv(self, train_preds, train_events, train_durations, val_preds, val_events, val_durations):
+        train_loss = self.computeLossSurv(train_preds, train_events, train_durations, reduceToHeads=True).detach()
+        val_loss = self.computeLossSurv(val_preds, val_events, val_durations, reduceToHeads=True).detach()
+        if self.lvn is None or self.ltn is None:
+            self.weights = self.normalize(torch.ones(train_preds.shape[0]))
+        else:
+            o_n = self.lvn - self.ltn
+            o_npn = val_loss - train_loss
+            delta_g = self.lvn - val_loss
+            delta_o = o_npn - o_n
+            self.weights = self.normalize(delta_g / torch.pow(delta_o, 2))
+        self.lvn, self.ltn = val_loss, train_loss
+        self.history.append(self.weights.detach().cpu().numpy())
+
+    # ---- dispatch (classification branch: SURVEY.md section 8f rank 3, not built)
+    def updateWeights(self, *args, **kwargs):
+        if not self.survival:
+            raise NotImplementedError("classification blending is outside the hot path (SURVEY.md section 8f)")
+        self.updateWeightsSurv(*args, **kwargs)
+
+    def computeLoss(self, *args, **kwargs):
+        if not self.survival:
+            raise NotImplementedError("classification blending is outside the hot path (SURVEY.md section 8f)")
+        return self.computeLossSurv(*args, **kwargs)
+
+    def reduce(self, loss):
+        if self.reduction.startswith("sum"):
+            return torch.sum(loss)
+        if self.reduction.startswith("mean"):
+            return torch.mean(loss)
+        if self.reduction.startswith("none"):
+            return loss
+        raise ValueError("Unable to reduce loss, unrecognized reduction: {}".format(self.reduction))
+
+    def normalize(self, weights):
+        return F.softmax(weights, dim=0)
+
+    def saveHistory(self):
+        np.savetxt("gblend_weights_history.csv", np.array(self.history), delimiter=",")
