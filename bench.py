@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: multimodal survival TRAINING throughput (volumes/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this build (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference's algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]): T1+T2 2x128x128x64 volumes + 20 clinical variables, batch 16 per GPU,
+3-D DenseNet-121 + clinical MLP + fusion heads, --blend (GradientBlender over 3 heads), Cox loss as the reference calls
+it, dropout 0.2 (config.yaml default), backward, SGD(nesterov, momentum 0.9, wd 1e-4) step EVERY batch.
+A "step" = one such batch.  Synthetic data (oracle/synth.py distributions), reference-law random weights.
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = same step through the public API with the
+batch in pinned HOST memory (H2D copy inside the timed region) and the loss read back to the host every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(name="configs[1]: T1+T2 2x128x128x64 + 20 clinical, blend, batch 16/GPU", cin=2, spatial=(128, 128, 64), batch=16),
+    "cfg1": dict(name="configs[0]: T1 1x64x64x32 + 20 clinical, blend, batch 4/GPU (debug size)", cin=1, spatial=(64, 64, 32), batch=4),
+}
+BLOCKS = (6, 12, 24, 16)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_flops(wl):
+    """Algorithmic FLOPs per batch of each GEMM-shaped kernel class (2*M*N*K, no credit for padding / recompute)."""
+    B = wl["batch"]; X, Y, Z = wl["spatial"]; cin = wl["cin"]
+    d0 = [(v - 1) // 2 + 1 for v in (X, Y, Z)]
+    d = [(v - 1) // 2 + 1 for v in d0]
+    M0 = B * d0[0] * d0[1] * d0[2]
+    fl = {"stem": 2.0 * M0 * 64 * 343 * cin, "conv1": 0.0, "conv2": 0.0, "trans": 0.0}
+    per_layer = {"conv1": [], "conv2": []}
+    c = 64
+    for b, nl in enumerate(BLOCKS):
+        M = B * d[0] * d[1] * d[2]
+        for l in range(nl):
+            fl["conv1"] += 2.0 * M * 128 * (c + 32 * l)
+            fl["conv2"] += 2.0 * M * 32 * 128 * 27
+        c += 32 * nl
+        if b < len(BLOCKS) - 1:
+            fl["trans"] += 2.0 * M * c * (c // 2)
+            c //= 2
+            d = [v // 2 for v in d]
+    return fl
+
+
+def build_model(wl, device, seed=42):
+    from mmnn_sts_b200.models.densenet import DenseNet121
+    from mmnn_sts_b200.models.multimodal import MultiModalModel
+    torch.manual_seed(seed)
+    m = MultiModalModel(DenseNet121(spatial_dims=3, in_channels=wl["cin"], out_channels=2, feature_channels=12, dropout_prob=0.2),
+                        ["x"] * 20, 2, 12, blend=True)
+    return m.to(device).train()
+
+
+def make_batches(wl, n, pinned=False, device=None, seed=1234):
+    """Synthetic batches with the distributions of SURVEY.md section 8d (image U[0,1), 10 N(0,1) + 10 categorical
+    clinical columns, Bernoulli events, tie-free integer-day durations)."""
+    out = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(seed + i)
+        B = wl["batch"]
+        im = torch.rand((B, wl["cin"]) + tuple(wl["spatial"]), generator=g)
+        cl = torch.cat([torch.randn((B, 10), generator=g), torch.randint(0, 5, (B, 10), generator=g).float()], 1)
+        ev = torch.randint(0, 2, (B, 2), generator=g)
+        du = torch.stack([torch.randperm(3650, generator=g)[:B] + 1 for _ in range(2)], 1)
+        t = [im, cl, ev, du]
+        if pinned:
+            t = [x.pin_memory() for x in t]
+        elif device is not None:
+            t = [x.to(device) for x in t]
+        out.append(t)
+    return out
+
+
+def run_ours(args):
+    from mmnn_sts_b200 import _lib as L, distributed as D
+    from mmnn_sts_b200.losses.GradientBlender import GradientBlender
+    from mmnn_sts_b200.losses.losses import CoxPH
+    from mmnn_sts_b200.utils.utils import surv_criterion
+    import torch.distributed as dist
+    rank, world, device = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    wl = WORKLOADS[args.workload]
+    L.lib()
+    model = build_model(wl, device)
+    opt = torch.optim.SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion)
+    sync = D.GradientAllReducer(model.parameters())
+    dev_batches = make_batches(wl, 2, device=device, seed=1234 + 100 * rank)
+    host_batches = make_batches(wl, 2, pinned=True, seed=1234 + 100 * rank)
+
+    def step(im, cl, ev, du):
+        out = model({"image": im, "clinical": cl})
+        loss, _ = blender.computeLoss(out, ev, du)
+        loss.backward()
+        sync()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(nsteps):
+            if e2e:
+                b = [t.to(device, non_blocking=True) for t in host_batches[i % 2]]
+                loss = step(*b)
+                _ = loss.item()                      # device->host read of the step's result
+            else:
+                step(*dev_batches[i % 2])
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(args.warmup):
+        step(*dev_batches[i % 2])
+    launches0 = L.lib().mmnn_launch_count()
+    with ClockSampler(device.index or 0) as cs:
+        ms = timed(args.steps, e2e=False)
+    launches = (L.lib().mmnn_launch_count() - launches0) // max(1, args.steps)
+    clocks = cs.summary()
+    ms_e2e = timed(args.steps, e2e=True)
+    vols = wl["batch"] * world * args.steps
+    value, value_e2e = vols / (ms / 1e3), vols / (ms_e2e / 1e3)
+
+    # ---- live per-kernel-class timing (CUDA events on the launch stream) for the roofline block
+    peaks = load_peaks()
+    L.lib().mmnn_profile_enable(1)
+    nprof = 2
+    for i in range(nprof):
+        step(*dev_batches[i % 2])
+    torch.cuda.synchronize()
+    prof = L.profile_collect()
+    L.lib().mmnn_profile_enable(0)
+    fl = conv_flops(wl)
+    gemm_classes = {"stem_fprop": fl["stem"], "stem_wgrad": fl["stem"], "conv1_fprop": fl["conv1"], "conv1_dgrad": fl["conv1"],
+                    "conv1_wgrad": fl["conv1"], "conv2_fprop": fl["conv2"], "conv2_dgrad": fl["conv2"], "conv2_wgrad": fl["conv2"],
+                    "trans_fprop": fl["trans"], "trans_dgrad": fl["trans"], "trans_wgrad": fl["trans"]}
+    kernels, total_ms = {}, sum(v[0] for v in prof.values()) / nprof
+    for k, (t, n) in prof.items():
+        if n == 0:
+            continue
+        e = {"ms_per_step": round(t / nprof, 4), "launches_per_step": n // nprof, "share": round(t / nprof / total_ms, 4)}
+        if k in gemm_classes:
+            e["tflops"] = round(gemm_classes[k] / (t / nprof / 1e3) / 1e12, 1)
+            e["frac_of_sustained_peak"] = round(e["tflops"] / peaks["tf_sust"], 4)
+        kernels[k] = e
+    dom = max((k for k in kernels if k in gemm_classes), key=lambda k: kernels[k]["ms_per_step"])
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                "frac": round(kernels[dom]["tflops"] / peaks["tf_sust"], 4), "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                "flops_per_launch": gemm_classes[dom] / max(1, kernels[dom]["launches_per_step"]),
+                "avg_launch_ms": round(kernels[dom]["ms_per_step"] / max(1, kernels[dom]["launches_per_step"]), 5)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_arm(wl, steps=1, warmup=1, sample_batch=2)
+    if rank == 0:
+        in_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
+        line = {"metric": "train volumes/sec", "value": round(value, 2), "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": wl["name"], "global_batch": wl["batch"] * world, "volume": list(wl["spatial"]),
+                           "in_channels": wl["cin"], "parallelism": f"dp{world}", "optimizer_step": "every batch",
+                           "l2": "inputs (134 MB/batch fp32) and activations (>1 GB) exceed the 126 MB L2; two batches alternate"},
+                "e2e": {"value": round(value_e2e, 2), "unit": "volumes/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference_arm(wl, steps, warmup, sample_batch):
+    """The reference's algorithm for one training step on the host cores: fp32 torch CPU forward of the oracle
+    restatement (bit-exact to the unchanged reference files, tests/golden), GradientBlender/Cox loss as the reference
+    calls it, backward, SGD step.  A bounded sample: `sample_batch` volumes of the workload's shape per step."""
+    from oracle import model as om, synth
+    from oracle.blender import GradientBlenderOracle
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    sd = synth.make_state_dict(42, in_channels=wl["cin"], perturb_bn=False)
+    params = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.SGD([p for p in params.values() if p.requires_grad], 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    gb = GradientBlenderOracle()
+    im, cl, ev, du = synth.make_batch(77, sample_batch, wl["cin"], wl["spatial"])
+    masks = synth.make_masks(78, sample_batch)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = om.multimodal_forward(params, im, cl, True, True, masks)
+        loss, _ = gb.computeLoss(out, ev, du)
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return {"value": round(sample_batch / t, 3), "unit": "volumes/s", "cores": ncores, "kind": "port",
+            "sample": f"{steps} timed step(s) of {sample_batch} volumes of {wl['cin']}x{'x'.join(map(str, wl['spatial']))} (same model/loss/optimizer), {warmup} warm-up",
+            "sec_per_step": round(t, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cpu = cpu_reference_arm(wl, steps=steps, warmup=warmup, sample_batch=2)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    line = {"impl": "reference", "metric": "train volumes/sec", "value": cpu["value"], "unit": "volumes/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": round(cpu["sec_per_step"] * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "note": "reference algorithm on the host CPU cores (fp32 torch CPU); each step is a bounded 2-volume sample"},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "ours":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -125,6 +125,11 @@ def _declare(l):
     for nm, st in (("mmnn_sizeof_mlp_args", MlpArgs), ("mmnn_sizeof_cox_args", CoxArgs), ("mmnn_sizeof_cindex_args", CindexArgs)):
         getattr(l, nm).restype = I
         assert getattr(l, nm)() == C.sizeof(st), (nm, getattr(l, nm)(), C.sizeof(st))
+    l.mmnn_profile_enable.argtypes = [I]
+    l.mmnn_profile_enable.restype = None
+    l.mmnn_launch_count.restype = LL
+    l.mmnn_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(I)]
+    l.mmnn_profile_collect.restype = I
     F32P = VP
     l.mmnn_gap_linear_fwd.argtypes = [F32P, I, I, I, F32P, F32P, F32P, I, F32P, F32P, VP]
     l.mmnn_gap_linear_fwd.restype = I
@@ -145,3 +150,17 @@ def packed_elems(N, NT, Cin, kbw, ntaps):
     kb_per_tap = (Cin + kbw - 1) // kbw
     ntile = (N + NT - 1) // NT
     return ntile * ntaps * kb_per_tap * (kbw // 8) * NT * 8
+
+
+PROF_CLASSES = ["pack", "s2d", "stem_fprop", "maxpool", "conv1_fprop", "conv2_fprop", "trans_pool", "trans_fprop", "norm5",
+                "bn_running", "norm5_bwd", "extract", "conv2_wgrad", "conv2_dgrad", "bn_apply", "conv1_wgrad", "conv1_dgrad",
+                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads"]
+
+
+def profile_collect():
+    n = len(PROF_CLASSES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    got = lib().mmnn_profile_collect(ms, cnt)
+    assert got == n, (got, n)
+    return {PROF_CLASSES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

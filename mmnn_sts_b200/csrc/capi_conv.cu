@@ -2,6 +2,7 @@
 // encoder orchestrator in encoder.cu).  Plain pointers and sizes only; see include/mmnn_b200.h.
 #include "engine.cuh"
 #include "pack.cuh"
+#include "prof.h"
 
 using namespace mmnn;
 
@@ -91,7 +92,31 @@ int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream)
 
 }  // namespace mmnn
 
+namespace mmnn {
+ProfState& prof_state() {
+  static ProfState s;
+  return s;
+}
+}  // namespace mmnn
+
 extern "C" {
+
+void mmnn_profile_enable(int on) { prof_state().on = on != 0; }
+long long mmnn_launch_count() { return prof_state().launches; }
+// Synchronises, sums the event-timed durations per kernel class, clears the records. ms / counts: PC_COUNT entries.
+int mmnn_profile_collect(float* ms, int* counts) {
+  ProfState& s = prof_state();
+  for (int i = 0; i < PC_COUNT; ++i) { ms[i] = 0.f; counts[i] = 0; }
+  for (auto& r : s.recs) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t; counts[r.cls] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  s.recs.clear();
+  return PC_COUNT;
+}
 
 int mmnn_conv_wgrad(const WgradParams* p, int kind, int split, void* stream) {
   return launch_wgrad(*p, kind, split, (cudaStream_t)stream);

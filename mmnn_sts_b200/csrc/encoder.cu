@@ -19,6 +19,7 @@
 #include "eltwise.cuh"
 #include "engine.cuh"
 #include "pack.cuh"
+#include "prof.h"
 
 namespace mmnn {
 int launch_rows(const RowsParams& p, int amode, int trans, int epi, cudaStream_t stream);
@@ -336,6 +337,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     }
     if (descs.size() * sizeof(PackDesc) > (1 << 19)) return -11;
     RET_IF(upload_table(pl, 0, ws + g.tables, descs.data(), descs.size() * sizeof(PackDesc), st));
+    ProfScope ps_(PC_PACK, st);
     pack_weights_kernel<<<dim3(16, (unsigned)descs.size()), 256, 0, st>>>((const PackDesc*)(ws + g.tables));
     LAUNCH_RET();
   }
@@ -344,7 +346,8 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
   bf16* xs2d = (bf16*)(ws + g.xs2d);
   {
     const long long cells = (long long)B * g.Sz * g.Sy * g.Sx * 2;
-    s2d_pack_kernel<<<ew_grid(cells), EW_THREADS, 0, st>>>(image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx);
+    { ProfScope ps_(PC_S2D, st);
+      s2d_pack_kernel<<<ew_grid(cells), EW_THREADS, 0, st>>>(image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
     LAUNCH_RET();
     RowsParams p = {};
     p.M = (int)g.M0; p.NT = 64; p.Ncols = 64; p.Cin = 64; p.kbw = 64; p.ntaps = 16; p.tap_sign = 1;
@@ -353,7 +356,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     p.b_packed = packed + pl->pk_stem;
     p.out = (bf16*)(ws + g.stem_out); p.out_pitch = 64;
     p.st_sum = fstats + pl->n0.fwd_off; p.st_sq = fstats + FC + pl->n0.fwd_off;
-    RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, st));
+    { ProfScope ps_(PC_STEM_FPROP, st); RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, st)); }
     PoolParams q = {};
     q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
     q.src = (const bf16*)(ws + g.stem_out);
@@ -362,7 +365,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     q.argmax = ws + g.argmax;
     q.st_sum = fstats + pl->blocks[0].fwd_off; q.st_sq = fstats + FC + pl->blocks[0].fwd_off;
     int blocks = (int)std::min<long long>((g.M[0] + 31) / 32, NUM_SMS * 8);
-    bnrelu_maxpool_kernel<<<blocks, EW_THREADS, 0, st>>>(q);
+    { ProfScope ps_(PC_MAXPOOL, st); bnrelu_maxpool_kernel<<<blocks, EW_THREADS, 0, st>>>(q); }
     LAUNCH_RET();
   }
 
@@ -382,7 +385,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.b_packed = packed + li.pk_c1f;
       p.out = bott; p.out_pitch = BOTT;
       p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
-      RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st));
+      { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st)); }
       RowsParams q = {};
       q.M = (int)M; q.NT = 32; q.Ncols = GROWTH; q.Cin = BOTT; q.kbw = 64; q.ntaps = 27; q.tap_sign = 1;
       q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b];
@@ -392,7 +395,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       q.out = buf + li.cin; q.out_pitch = bi.ctot;
       q.colscale = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
       q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
-      RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st));
+      { ProfScope ps_(PC_CONV2_FPROP, st); RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st)); }
     }
     if (bi.has_trans) {
       const BlockInfo& nx = pl->blocks[b + 1];
@@ -401,7 +404,8 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       a.x = buf; a.x_pitch = bi.ctot;
       a.bn = make_bn(bi.tn, params, buffers, fstats, FC, M, batch);
       a.pooled = (bf16*)(ws + g.pooled[b]);
-      bnrelu_avgpool_kernel<<<ew_grid(g.M[b + 1] * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(a);
+      { ProfScope ps_(PC_TRANS_POOL, st);
+        bnrelu_avgpool_kernel<<<ew_grid(g.M[b + 1] * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(a); }
       LAUNCH_RET();
       RowsParams p = {};
       p.M = (int)g.M[b + 1]; p.NT = 128; p.Ncols = bi.ctot / 2; p.Cin = bi.ctot; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
@@ -410,7 +414,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.b_packed = packed + bi.pk_tf;
       p.out = (bf16*)(ws + g.buf[b + 1]); p.out_pitch = nx.ctot;
       p.st_sum = fstats + nx.fwd_off; p.st_sq = fstats + FC + nx.fwd_off;
-      RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE_STATS, st));
+      { ProfScope ps_(PC_TRANS_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE_STATS, st)); }
     }
   }
 
@@ -419,6 +423,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     const BlockInfo& bi = pl->blocks[nb - 1];
     const long long M = g.M[nb - 1];
     BnSrc bn = make_bn(pl->n5, params, buffers, fstats, FC, M, batch);
+    ProfScope ps_(PC_NORM5, st);
     bn_apply_f32_kernel<<<ew_grid(M * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(
         (const bf16*)(ws + g.buf[nb - 1]), bi.ctot, bn, out, M, bi.ctot);
     LAUNCH_RET();
@@ -448,6 +453,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     }
     uint8_t* dtab = ws + g.tables + (1 << 19);
     RET_IF(upload_table(pl, 1, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
+    ProfScope ps_(PC_BN_RUNNING, st);
     bn_running_update_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab, 0.1f);
     LAUNCH_RET();
   }
@@ -483,6 +489,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     a.g_sum = gs; a.g_dot = gd; a.inv_count = 1.0f / (float)M; a.out = outp; a.out_pitch = out_pitch;
     const int grid = ew_grid(M * (C / 8));
     const size_t sm = 3 * C * sizeof(float);
+    ProfScope ps_(PC_BN_APPLY, st);
     if (out_mode == BA_OUT_BF16) bn_bwd_apply_kernel<BA_OUT_BF16><<<grid, EW_THREADS, sm, st>>>(a);
     else if (out_mode == BA_OUT_F32_ADD) bn_bwd_apply_kernel<BA_OUT_F32_ADD><<<grid, EW_THREADS, sm, st>>>(a);
     else bn_bwd_apply_kernel<BA_OUT_F32_STORE><<<grid, EW_THREADS, sm, st>>>(a);
@@ -499,7 +506,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     const bf16* x = (const bf16*)(ws + g.buf[nb - 1]);
     const int rows_per_block = EW_THREADS / (C / 8);
     int blocks = (int)std::min<long long>((M + rows_per_block - 1) / rows_per_block, NUM_SMS * 4);
-    bn_bwd_stats_f32_kernel<<<blocks, EW_THREADS, 2 * C * sizeof(float), st>>>(grad_out, x, C, bn, M, C, gsum(pl->n5), gdot(pl->n5));
+    { ProfScope ps_(PC_NORM5_BWD, st);
+      bn_bwd_stats_f32_kernel<<<blocks, EW_THREADS, 2 * C * sizeof(float), st>>>(grad_out, x, C, bn, M, C, gsum(pl->n5), gdot(pl->n5)); }
     LAUNCH_RET();
     RET_IF(bn_apply(BA_OUT_F32_STORE, M, C, nullptr, grad_out, C, x, C, bn, gsum(pl->n5), gdot(pl->n5), ws + g.dbuf[nb - 1], C));
   }
@@ -519,8 +527,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, true);
       const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, true);
       // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf)
-      extract_slice_kernel<<<ew_grid(M * 4), EW_THREADS, 0, st>>>(
-          dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps);
+      { ProfScope ps_(PC_EXTRACT, st);
+        extract_slice_kernel<<<ew_grid(M * 4), EW_THREADS, 0, st>>>(
+            dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps); }
       LAUNCH_RET();
       // conv2 wgrad -> scratch [tap][co][ci]
       {
@@ -531,6 +540,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = gslice; w.b_pitch = GROWTH;
         w.dw = (float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
         w.so_a = 1; w.so_b = BOTT; w.so_j = GROWTH * BOTT;
+        ProfScope ps_(PC_CONV2_WGRAD, st);
         RET_IF(launch_wgrad(w, 1, 0, st));
       }
       // conv2 dgrad (+ ReLU mask of norm2/relu2, + BN2 backward statistics)
@@ -543,6 +553,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.out = dA2; p.out_pitch = BOTT;
         p.st_sum = gsum(li.n2); p.st_sq = gdot(li.n2);
         p.e_src = bott; p.e_pitch = BOTT; p.bnE = bn2;
+        ProfScope ps_(PC_CONV2_DGRAD, st);
         RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
       }
       RET_IF(bn_apply(BA_OUT_BF16, M, BOTT, dA2, nullptr, BOTT, bott, BOTT, bn2, gsum(li.n2), gdot(li.n2), dA2, BOTT));
@@ -555,6 +566,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = dA2; w.b_pitch = BOTT;
         w.dw = (float*)grads[li.conv1_idx];
         w.so_a = 1; w.so_b = li.cin; w.so_j = 0;
+        ProfScope ps_(PC_CONV1_WGRAD, st);
         RET_IF(launch_wgrad(w, 0, 0, st));
       }
       // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics), then BN1 backward into dbuf[:, :cin]
@@ -567,6 +579,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.out = dA1; p.out_pitch = li.cin;
         p.st_sum = gsum(li.n1); p.st_sq = gdot(li.n1);
         p.e_src = buf; p.e_pitch = bi.ctot; p.bnE = bn1;
+        ProfScope ps_(PC_CONV1_DGRAD, st);
         RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
       }
       RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
@@ -578,7 +591,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       bf16* gout = (bf16*)(ws + g.gout);
       bf16* dpooled = (bf16*)(ws + g.dpooled);
       const bf16* pooled = (const bf16*)(ws + g.pooled[b - 1]);
-      extract_slice_kernel<<<ew_grid(M * (bi.c0 / 8)), EW_THREADS, 0, st>>>(dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps);
+      { ProfScope ps_(PC_EXTRACT, st);
+        extract_slice_kernel<<<ew_grid(M * (bi.c0 / 8)), EW_THREADS, 0, st>>>(dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps); }
       LAUNCH_RET();
       {
         WgradParams w = {};
@@ -588,6 +602,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = gout; w.b_pitch = bi.c0;
         w.dw = (float*)grads[pv.tconv_idx];
         w.so_a = 1; w.so_b = pv.ctot; w.so_j = 0;
+        ProfScope ps_(PC_TRANS_WGRAD, st);
         RET_IF(launch_wgrad(w, 2, 0, st));
       }
       {
@@ -597,6 +612,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.a_src = gout; p.a_pitch = bi.c0;
         p.b_packed = packed + pv.pk_td;
         p.out = dpooled; p.out_pitch = pv.ctot;
+        ProfScope ps_(PC_TRANS_DGRAD, st);
         RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE, st));
       }
       AvgPoolParams a = {};
@@ -609,9 +625,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       a.inv_count = 1.0f / (float)Mp;
       const int rows_per_block = EW_THREADS / (pv.ctot / 8);
       int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
-      avgpool_bnrelu_bwd_kernel<1><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
-      LAUNCH_RET();
-      avgpool_bnrelu_bwd_kernel<2><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
+      { ProfScope ps_(PC_AVGPOOL_BWD, st, 2);
+        avgpool_bnrelu_bwd_kernel<1><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
+        avgpool_bnrelu_bwd_kernel<2><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a); }
       LAUNCH_RET();
     } else {
       // pool0 + relu0 + norm0 + conv0
@@ -624,7 +640,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       q.dr = (bf16*)(ws + g.dr);
       q.g_sum = gsum(pl->n0); q.g_dot = gdot(pl->n0);
       int blocks = (int)std::min<long long>((g.M0 + 31) / 32, NUM_SMS * 8);
-      maxpool_bnrelu_bwd_kernel<<<blocks, EW_THREADS, 0, st>>>(q);
+      { ProfScope ps_(PC_MAXPOOL_BWD, st); maxpool_bnrelu_bwd_kernel<<<blocks, EW_THREADS, 0, st>>>(q); }
       LAUNCH_RET();
       RET_IF(bn_apply(BA_OUT_BF16, g.M0, 64, q.dr, nullptr, 64, q.x, 64, q.bn, gsum(pl->n0), gdot(pl->n0), q.dr, 64));
       WgradParams w = {};
@@ -634,6 +650,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       w.b_src = q.dr; w.b_pitch = 64;
       w.dw = (float*)grads[pl->conv0_idx];
       w.cin_real = pl->cin_real;
+      ProfScope ps_(PC_STEM_WGRAD, st);
       RET_IF(launch_wgrad(w, 3, 0, st));
     }
   }
@@ -650,6 +667,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     }
     uint8_t* dtab = ws + g.tables + (1 << 19) + (1 << 17);
     RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
+    ProfScope ps_(PC_TAILS, st, 2);
     bn_param_grad_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab);
     LAUNCH_RET();
     std::vector<TransposeEntry> tt;

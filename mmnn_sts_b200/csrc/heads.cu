@@ -4,6 +4,7 @@
 // /root/reference/models/multimodal.py:51-80, /root/reference/losses/losses.py:6-9 (pycox CoxPHLoss),
 // /root/reference/main.py:106-123 (lifelines concordance_index).
 #include "common.cuh"
+#include "prof.h"
 
 using namespace mmnn;
 
@@ -507,6 +508,7 @@ extern "C" {
 
 int mmnn_gap_linear_fwd(const float* y, int B, int V, int C, const float* W, const float* bias, const float* mask, int F,
                         float* pooled, float* out, void* stream) {
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream, 1);
   gap_linear_fwd_kernel<<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(y, V, C, W, bias, mask, F, pooled, out);
   LAUNCH_RET();
   return 0;
@@ -514,6 +516,7 @@ int mmnn_gap_linear_fwd(const float* y, int B, int V, int C, const float* W, con
 
 int mmnn_gap_linear_bwd(const float* y, const float* pooled, int B, int V, int C, const float* W, const float* dout,
                         const float* mask, int F, float* dy, float* dW, float* db, void* stream) {
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream, 2);
   gap_linear_bwd_dy_kernel<<<B, 256, F * sizeof(float), (cudaStream_t)stream>>>(y, V, C, W, dout, mask, F, dy);
   LAUNCH_RET();
   gap_linear_bwd_w_kernel<<<(F * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pooled, dout, mask, B, C, F, dW, db);
@@ -526,6 +529,7 @@ int mmnn_mlp_heads(const MlpArgs* args, int backward, void* stream) {
   if (args->B < 1 || args->B > 1024) return -2;
   for (int i = 1; i <= MLP_LAYERS; ++i)
     if (args->width[i] > 32) return -3;
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream);
   if (backward) mlp_heads_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*args);
   else mlp_heads_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*args);
   LAUNCH_RET();
@@ -545,6 +549,7 @@ int mmnn_cox_nll(const CoxArgs* a, void* stream) {
   if (smem > 220 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(cox_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream, 1);
   cox_nll_kernel<<<a->S, COX_THREADS, smem, (cudaStream_t)stream>>>(*a);
   LAUNCH_RET();
   return 0;
@@ -556,6 +561,7 @@ int mmnn_cindex_bootstrap(const CindexArgs* a, void* stream) {
   if (smem > 220 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(cindex_bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream, 1);
   cindex_bootstrap_kernel<<<a->R, 32, smem, (cudaStream_t)stream>>>(*a);
   LAUNCH_RET();
   return 0;

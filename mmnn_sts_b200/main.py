@@ -1,0 +1,148 @@
+"""Train / inference drivers mirroring the hot-path bodies of the reference's main.py (which cannot itself be imported:
+/root/reference/main.py:1 imports a non-existent CLASS_FREQUENCIES):
+
+  getCIndices          /root/reference/main.py:106-123   (lifelines concordance_index per class)
+  train_survival       /root/reference/main.py:385-601   (SGD nesterov + OneCycleLR, gradient accumulation to 64 samples,
+                                                          GradientBlender, per-epoch C-index, validation, weight update)
+  inference_survival   /root/reference/main.py:750-887   (forward + bootstrap C-index; idiomatic form: every patient is
+                                                          forwarded ONCE, resamples are index multisets)
+Data arrives as an iterable of batches `({'image': ..., 'clinical': ...}, events, durations)` -- what the reference's
+multimodal_collate_fn_surv yields -- so the file/S3 datasets of the reference stay out of scope.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .losses.GradientBlender import GradientBlender
+from .losses.losses import CoxPH
+from .ops import concordance_counts
+from .utils.utils import surv_criterion
+
+NUM_CLASSES = 2                 # /root/reference/data/constants.py:95
+NUM_BOOTSTRAP_ITERATIONS = 50   # /root/reference/main.py:61
+SUPER_BATCH_SIZE = 64           # /root/reference/main.py:62
+
+
+def _cindex_from_counts(correct, tied, pairs):
+    if pairs == 0:
+        raise ZeroDivisionError("No admissable pairs in the dataset.")
+    return (correct + tied / 2) / pairs
+
+
+def getCIndices(preds, events, durations, num_classes=NUM_CLASSES):
+    """List of per-class Harrell C-indices, `concordance_index(durations[:, i], preds[:, i], events[:, i])`.
+    Accepts CUDA tensors (counted on the GPU, exact in int64) ; numpy / CPU tensors are moved to the current device."""
+    dev = preds.device if torch.is_tensor(preds) and preds.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    preds, events, durations = (torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t).to(dev) for t in (preds, events, durations))
+    out = []
+    for i in range(num_classes):
+        c, t, p = (int(v) for v in concordance_counts(durations[:, i], preds[:, i], events[:, i])[0].cpu())
+        out.append(_cindex_from_counts(c, t, p))
+    return out
+
+
+def bootstrap_cindices(preds, events, durations, resample_indices, num_classes=NUM_CLASSES):
+    """Per-resample, per-class C-index [R, C] (NaN where a resample has no admissible pair: the reference skips it,
+    /root/reference/main.py:856-858), plus mean and std (ddof 0) over the kept resamples (:883-887)."""
+    counts = torch.stack([concordance_counts(durations[:, i], preds[:, i], events[:, i], resample_indices)
+                          for i in range(num_classes)], dim=1).cpu().numpy()      # [R, C, 3] int64
+    correct, tied, pairs = counts[..., 0], counts[..., 1], counts[..., 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c = (correct + tied / 2) / pairs
+    c[pairs == 0] = np.nan
+    ok = ~np.isnan(c).any(axis=1)
+    return c, c[ok].mean(axis=0), c[ok].std(axis=0), counts
+
+
+def _to_device(batch, device):
+    inputs, events, durations = batch
+    inputs = {k: v.to(device, non_blocking=True) for k, v in inputs.items()}
+    return inputs, events.to(device, non_blocking=True), durations.to(device, non_blocking=True)
+
+
+def train_survival(model, train_batches, val_batches, args, device, grad_sync=None, log=None):
+    """args: lr, momentum, weight_decay, epochs, batch_size, blend, blend_update_interval, num_train (patients).
+    grad_sync: optional callable(model) run right before each optimizer.step (data-parallel gradient all-reduce)."""
+    model = model.to(device)
+    n_train = args.num_train
+    super_batch_interval = SUPER_BATCH_SIZE / args.batch_size
+    steps_per_epoch = n_train // SUPER_BATCH_SIZE if n_train % SUPER_BATCH_SIZE == 0 else 1 + n_train // SUPER_BATCH_SIZE
+    optimizer = torch.optim.SGD(model.parameters(), args.lr, momentum=args.momentum, nesterov=True, weight_decay=args.weight_decay)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=args.lr, steps_per_epoch=steps_per_epoch, epochs=args.epochs)
+    blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion) if args.blend else None
+    hist = SimpleNamespace(train_loss=[], val_loss=[], train_c=[], val_c=[], best_loss=math.inf, best_state=None, blender=blender)
+    for epoch in range(args.epochs):
+        model.train()
+        train_batches = list(train_batches)
+        losses, c_pred, c_events, c_durations = [], [], [], []
+        for i, batch in enumerate(train_batches):
+            inputs, events, durations = _to_device(batch, device)
+            outputs = model(inputs)
+            if args.blend:
+                loss, _ = blender.computeLoss(outputs, events, durations)
+            else:
+                loss = surv_criterion(CoxPH, outputs, events, durations, device)
+            loss.backward()
+            losses.append(loss.detach())            # no per-step .item(): one sync per epoch instead of one per step
+            if (i + 1) % super_batch_interval == 0 or i == len(train_batches) - 1:
+                if grad_sync is not None:
+                    grad_sync(model)
+                optimizer.step()
+                scheduler.step()
+                optimizer.zero_grad()
+            c_pred.append(outputs.detach()); c_events.append(events); c_durations.append(durations)
+        c_pred = torch.cat(c_pred, dim=1 if args.blend else 0)
+        c_events, c_durations = torch.cat(c_events), torch.cat(c_durations)
+        hist.train_c.append(getCIndices(c_pred[0] if args.blend else c_pred, c_events, c_durations))
+        hist.train_loss.append(float(torch.stack(losses).sum()) / n_train)
+        if val_batches is not None:
+            model.eval()
+            with torch.no_grad():
+                y_pred, y_events, y_durations, vloss, sel = [], [], [], 0.0, None
+                for batch in val_batches:
+                    inputs, events, durations = _to_device(batch, device)
+                    preds = model(inputs)
+                    if args.blend:
+                        loss, sel = blender.computeLoss(preds, events, durations)
+                    else:
+                        loss = sel = surv_criterion(CoxPH, preds, events, durations, device)
+                    vloss += float(loss)
+                    y_pred.append(preds); y_events.append(events); y_durations.append(durations)
+                y_pred = torch.cat(y_pred, dim=1 if args.blend else 0)
+                y_events, y_durations = torch.cat(y_events), torch.cat(y_durations)
+                hist.val_c.append(getCIndices(y_pred[0] if args.blend else y_pred, y_events, y_durations))
+                hist.val_loss.append(vloss / max(1, y_events.shape[0]))
+                if float(sel) < hist.best_loss:
+                    hist.best_loss = float(sel)
+                    hist.best_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            if args.blend and (epoch + 1) % args.blend_update_interval == 0:
+                blender.updateWeights(c_pred, c_events, c_durations, y_pred, y_events, y_durations)
+        if log is not None:
+            log(f"epoch {epoch + 1}: train loss {hist.train_loss[-1]:.4f} train C {hist.train_c[-1]}")
+    return hist
+
+
+@torch.no_grad()
+def predict_risks(model, batches, device):
+    """Eval-mode forward of every patient once (batched). Returns (preds [N,C], events [N,C], durations [N,C])."""
+    model = model.to(device).eval()
+    preds, ev, du = [], [], []
+    for batch in batches:
+        inputs, events, durations = _to_device(batch, device)
+        out = model(inputs)
+        preds.append(out[0] if out.dim() == 3 else out); ev.append(events); du.append(durations)
+    return torch.cat(preds), torch.cat(ev), torch.cat(du)
+
+
+def inference_survival(model, batches, device, bootstrap=True, num_resamples=NUM_BOOTSTRAP_ITERATIONS, seed=None):
+    preds, events, durations = predict_risks(model, batches, device)
+    n = preds.shape[0]
+    if not bootstrap:
+        return getCIndices(preds, events, durations), preds
+    # sklearn.utils.resample(uids) == uids[RandomState.randint(0, n, n)]  
+    rng = np.random.RandomState(seed) if seed is not None else np.random
+    idx = np.stack([rng.randint(0, n, n) for _ in range(num_resamples)])
+    c, mean, std, _ = bootstrap_cindices(preds, events, durations, torch.as_tensor(idx, device=preds.device))
+    return SimpleNamespace(per_resample=c, mean=mean, std=std, preds=preds)
