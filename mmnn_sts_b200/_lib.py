@@ -78,7 +78,7 @@ class CindexArgs(C.Structure):
 
 class PackDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("N", C.c_int), ("NT", C.c_int), ("Cin", C.c_int),
-                ("kbw", C.c_int), ("ntaps", C.c_int), ("mode", C.c_int), ("cin_real", C.c_int), ("pad_", C.c_int),
+                ("kbw", C.c_int), ("ntaps", C.c_int), ("mode", C.c_int), ("cin_real", C.c_int), ("f16", C.c_int),
                 ("sn", C.c_longlong), ("sc", C.c_longlong), ("st", C.c_longlong)]
 
 
@@ -89,7 +89,8 @@ PACK_GENERIC, PACK_STEM = 0, 1
 
 
 def _declare(l):
-    l.mmnn_conv_rows.argtypes = [C.POINTER(RowsParams), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.mmnn_conv_rows.argtypes = [C.POINTER(RowsParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.mmnn_act_is_fp16.restype = C.c_int
     l.mmnn_conv_rows.restype = C.c_int
     l.mmnn_pack_weights.argtypes = [C.POINTER(PackDesc), C.c_int, C.c_void_p, C.c_void_p]
     l.mmnn_pack_weights.restype = C.c_int

@@ -24,12 +24,12 @@ int choose_stages(const RowsParams& p, uint32_t budget) {
   return best;
 }
 
-template <int AMODE, int TRANS, int EPI>
+template <int AMODE, int TRANS, int EPI, bool GRAD>
 int launch_rows_t(RowsParams p, cudaStream_t stream) {
   uint32_t offs[6];
   if (p.stages <= 0) p.stages = choose_stages(p, 100 * 1024);
   const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
-  auto kern = conv_rows_kernel<AMODE, TRANS, EPI>;
+  auto kern = conv_rows_kernel<AMODE, TRANS, EPI, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((p.M + TILE_ROWS - 1) / TILE_ROWS, (p.Ncols + p.NT - 1) / p.NT);
@@ -38,16 +38,17 @@ int launch_rows_t(RowsParams p, cudaStream_t stream) {
   return 0;
 }
 
-int launch_rows(const RowsParams& p, int amode, int trans, int epi, cudaStream_t stream) {
+// grad == 0: forward GEMM (activation-format operands and output); grad == 1: data-gradient GEMM (bf16 operands/output)
+int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cudaStream_t stream) {
   if (p.NT % 32 != 0 || p.NT > 256 || p.Cin % 32 != 0 || (p.kbw != 32 && p.kbw != 64)) return -2;
-#define CASE(A, T, E) if (amode == A && trans == T && epi == E) return launch_rows_t<A, T, E>(p, stream);
-  CASE(A_LINEAR_CONV, T_NONE, EP_STORE)
-  CASE(A_LINEAR_CONV, T_NONE, EP_STORE_STATS)
-  CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS)
-  CASE(A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS)
-  CASE(A_LINEAR_CONV, T_BNRELU, EP_STORE)
-  CASE(A_STEM, T_NONE, EP_STORE_STATS)
-  CASE(A_STEM, T_NONE, EP_STORE)
+#define CASE(A, T, E, G) if (amode == A && trans == T && epi == E && grad == (G ? 1 : 0)) return launch_rows_t<A, T, E, G>(p, stream);
+  CASE(A_LINEAR_CONV, T_NONE, EP_STORE, false)
+  CASE(A_LINEAR_CONV, T_NONE, EP_STORE_STATS, false)
+  CASE(A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, false)
+  CASE(A_LINEAR_CONV, T_BNRELU, EP_STORE, false)
+  CASE(A_STEM, T_NONE, EP_STORE_STATS, false)
+  CASE(A_LINEAR_CONV, T_NONE, EP_STORE, true)
+  CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS, true)
 #undef CASE
   return -3;
 }
@@ -123,9 +124,10 @@ int mmnn_conv_wgrad(const WgradParams* p, int kind, int split, void* stream) {
 }
 int mmnn_sizeof_wgrad_params() { return (int)sizeof(WgradParams); }
 
-int mmnn_conv_rows(const RowsParams* p, int amode, int trans, int epi, void* stream) {
-  return launch_rows(*p, amode, trans, epi, (cudaStream_t)stream);
+int mmnn_conv_rows(const RowsParams* p, int amode, int trans, int epi, int grad, void* stream) {
+  return launch_rows(*p, amode, trans, epi, grad, (cudaStream_t)stream);
 }
+int mmnn_act_is_fp16() { return kActF16 ? 1 : 0; }
 
 // descs: HOST array of n PackDesc; dev_descs: device scratch of n*sizeof(PackDesc) bytes.
 int mmnn_pack_weights(const PackDesc* descs, int n, void* dev_descs, void* stream) {

@@ -2,13 +2,23 @@
 // Everything here is written for compute_100a only (tcgen05.* does not exist elsewhere).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace mmnn {
 
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;   // storage type of every 16-bit tensor pointer; the interpretation (bf16 or fp16) is per tensor
+
+// Forward tensors (activations + forward weight images) are stored as IEEE fp16, gradient tensors as bf16:
+// same tensor-core rate (tcgen05 kind::f16 takes either), but fp16's 3 extra mantissa bits cut the forward rounding
+// noise 8x (DESIGN.md "Numerics"); activations are BatchNorm-bounded so fp16's range is safe (stores saturate),
+// while gradients keep bf16's fp32-like range.  -DMMNN_ACT_FP16=0 switches activations back to bf16.
+#ifndef MMNN_ACT_FP16
+#define MMNN_ACT_FP16 1
+#endif
+constexpr bool kActF16 = MMNN_ACT_FP16 != 0;
 
 #define MMNN_DEVINL __device__ __forceinline__
 
@@ -107,8 +117,10 @@ MMNN_DEVINL uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
          (1ull << 46);
 }
 // Instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), majors (bits 15,16), N>>3 (17..22), M>>4 (24..28)
-__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// operand format field: 0 = fp16, 1 = bf16 (both operands the same)
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -121,6 +133,33 @@ MMNN_DEVINL uint32_t pack_bf16(float lo, float hi) {
   return r;
 }
 MMNN_DEVINL float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// 16-bit pair <-> fp32 for either storage format
+template <bool F16>
+MMNN_DEVINL void unpack2(uint32_t w, float& lo, float& hi) {
+  if (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = bf16_lo(w); hi = bf16_hi(w);
+  }
+}
+template <bool F16>
+MMNN_DEVINL uint32_t pack2(float lo, float hi) {
+  if (F16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  return pack_bf16(lo, hi);
+}
+template <bool F16>
+MMNN_DEVINL float round16(float x) {
+  if (F16) return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));
+  return round_bf16(x);
+}
 
 MMNN_DEVINL uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 MMNN_DEVINL void sts16(uint32_t addr, uint4 v) {

@@ -11,14 +11,19 @@ namespace mmnn {
 
 constexpr int EW_THREADS = 256;
 
+// ACT = forward activation tensor (fp16 when kActF16), GRD = gradient tensor (bf16)
+constexpr bool ACT = kActF16;
+constexpr bool GRD = false;
+template <bool F16>
 MMNN_DEVINL void unpack8(const uint4& v, float* f) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo(w[i]); f[2 * i + 1] = bf16_hi(w[i]); }
+  for (int i = 0; i < 4; ++i) unpack2<F16>(w[i], f[2 * i], f[2 * i + 1]);
 }
+template <bool F16>
 MMNN_DEVINL uint4 pack8(const float* f) {
   uint4 o;
-  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  o.x = pack2<F16>(f[0], f[1]); o.y = pack2<F16>(f[2], f[3]); o.z = pack2<F16>(f[4], f[5]); o.w = pack2<F16>(f[6], f[7]);
   return o;
 }
 
@@ -63,7 +68,7 @@ static __global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __re
         v = img[((((long long)b * cin + c) * X + iz) * Y + iy) * Z + ix];
       f[e] = v;
     }
-    reinterpret_cast<uint4*>(dst)[idx] = pack8(f);
+    reinterpret_cast<uint4*>(dst)[idx] = pack8<ACT>(f);
   }
 }
 
@@ -117,7 +122,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const
           if (ix < 0 || ix >= p.W0) continue;
           const uint4 v = ldg16(p.src + ((((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix) * 64 + chunk * 8);
           float f[8];
-          unpack8(v, f);
+          unpack8<ACT>(v, f);
           const int cd = (dz * 3 + dy) * 3 + dx;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -129,8 +134,8 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const
     }
     float r[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { r[e] = round_bf16(best[e]); s1[e] += r[e]; s2[e] += r[e] * r[e]; }
-    *reinterpret_cast<uint4*>(p.dst + m * p.dst_pitch + chunk * 8) = pack8(r);
+    for (int e = 0; e < 8; ++e) { r[e] = round16<ACT>(best[e]); s1[e] += r[e]; s2[e] += r[e] * r[e]; }
+    *reinterpret_cast<uint4*>(p.dst + m * p.dst_pitch + chunk * 8) = pack8<ACT>(r);
     uint2 cdv;
     cdv.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
     cdv.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
@@ -198,7 +203,7 @@ static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(c
       }
     }
     float f[8], r[8];
-    unpack8(ldg16(p.x + m * 64 + chunk * 8), f);
+    unpack8<ACT>(ldg16(p.x + m * 64 + chunk * 8), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = chunk * 8 + e;
@@ -207,7 +212,7 @@ static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(c
       s1[e] += r[e];
       s2[e] += r[e] * (f[e] - coef[128 + c]) * coef[192 + c];
     }
-    *reinterpret_cast<uint4*>(p.dr + m * 64 + chunk * 8) = pack8(r);
+    *reinterpret_cast<uint4*>(p.dr + m * 64 + chunk * 8) = pack8<GRD>(r);
   }
   block_channel_reduce(red, s1, s2, 8, p.g_sum, p.g_dot);
 }
@@ -256,13 +261,13 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const
     for (int k = 0; k < 8; ++k) {
       const long long mi = (((long long)b * p.D + 2 * z + (k >> 2)) * p.H + 2 * y + ((k >> 1) & 1)) * p.W + 2 * x + (k & 1);
       float f[8];
-      unpack8(ldg16(p.x + mi * p.x_pitch + chunk * 8), f);
+      unpack8<ACT>(ldg16(p.x + mi * p.x_pitch + chunk * 8), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += fmaxf(fmaf(f[e], coef[chunk * 8 + e], coef[p.C + chunk * 8 + e]), 0.f);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] *= 0.125f;
-    *reinterpret_cast<uint4*>(p.pooled + mo * p.C + chunk * 8) = pack8(acc);
+    *reinterpret_cast<uint4*>(p.pooled + mo * p.C + chunk * 8) = pack8<ACT>(acc);
   }
 }
 
@@ -298,10 +303,10 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if ((z >> 1) < Do && (y >> 1) < Ho && (x >> 1) < Wo) {
       const long long mo = (((long long)b * Do + (z >> 1)) * Ho + (y >> 1)) * Wo + (x >> 1);
-      unpack8(ldg16(p.dpooled + mo * p.C + chunk * 8), g);
+      unpack8<GRD>(ldg16(p.dpooled + mo * p.C + chunk * 8), g);
     }
     float f[8];
-    unpack8(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
+    unpack8<ACT>(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -361,20 +366,20 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
     const long long m = idx / cpr;
     float v[8], f[8], o[8];
     if (p.v != nullptr) {
-      unpack8(ldg16(p.v + m * p.v_pitch + chunk * 8), v);
+      unpack8<GRD>(ldg16(p.v + m * p.v_pitch + chunk * 8), v);
     } else {
       const float4 a = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8);
       const float4 b = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8 + 4);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    unpack8(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
+    unpack8<ACT>(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = chunk * 8 + e;
       o[e] = fmaf(coef[c], v[e], fmaf(coef[p.C + c], f[e], coef[2 * p.C + c]));
     }
     if (OUT == BA_OUT_BF16) {
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + m * p.out_pitch + chunk * 8) = pack8(o);
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + m * p.out_pitch + chunk * 8) = pack8<GRD>(o);
     } else {
       float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.out_pitch + chunk * 8);
       if (OUT == BA_OUT_F32_ADD) {
@@ -407,7 +412,7 @@ static __global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const 
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] *= __ldg(cs + e);
     }
-    *reinterpret_cast<uint4*>(dst + m * C + chunk * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(dst + m * C + chunk * 8) = pack8<GRD>(f);
   }
 }
 
@@ -429,7 +434,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_apply_f32_kernel(const b
     const int chunk = (int)(idx % cpr);
     const long long m = idx / cpr;
     float f[8];
-    unpack8(ldg16(x + m * x_pitch + chunk * 8), f);
+    unpack8<ACT>(ldg16(x + m * x_pitch + chunk * 8), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], coef[chunk * 8 + e], coef[C + chunk * 8 + e]);
     float4* d = reinterpret_cast<float4*>(y + m * C + chunk * 8);
@@ -459,7 +464,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_stats_f32_kernel(con
     const float4 b = *reinterpret_cast<const float4*>(dy + m * C + chunk * 8 + 4);
     const float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     float f[8];
-    unpack8(ldg16(x + m * x_pitch + chunk * 8), f);
+    unpack8<ACT>(ldg16(x + m * x_pitch + chunk * 8), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       s1[e] += g[e];

@@ -22,7 +22,7 @@
 #include "prof.h"
 
 namespace mmnn {
-int launch_rows(const RowsParams& p, int amode, int trans, int epi, cudaStream_t stream);
+int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream);
 }  // namespace mmnn
 
@@ -316,23 +316,23 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
   {
     std::vector<PackDesc> descs;
     auto add = [&](const void* src, size_t off, int N, int NT, int Cin, int kbw, int ntaps, int mode, long long sn,
-                   long long sc, long long stt) {
+                   long long sc, long long stt, bool fwd) {
       PackDesc d;
       d.src = (const float*)src; d.dst = packed + off; d.N = N; d.NT = NT; d.Cin = Cin; d.kbw = kbw; d.ntaps = ntaps;
-      d.mode = mode; d.cin_real = pl->cin_real; d.pad_ = 0; d.sn = sn; d.sc = sc; d.st = stt;
+      d.mode = mode; d.cin_real = pl->cin_real; d.f16 = (fwd && kActF16) ? 1 : 0; d.sn = sn; d.sc = sc; d.st = stt;
       descs.push_back(d);
     };
-    add(params[pl->conv0_idx], pl->pk_stem, 64, 64, 64, 64, 16, PACK_STEM, 0, 0, 0);
+    add(params[pl->conv0_idx], pl->pk_stem, 64, 64, 64, 64, 16, PACK_STEM, 0, 0, 0, true);
     for (auto& bi : pl->blocks) {
       for (auto& li : bi.layers) {
-        add(params[li.conv1_idx], li.pk_c1f, BOTT, 128, li.cin, 64, 1, PACK_GENERIC, li.cin, 1, 0);
-        add(params[li.conv1_idx], li.pk_c1d, li.cin, 128, BOTT, 64, 1, PACK_GENERIC, 1, li.cin, 0);
-        add(params[li.conv2_idx], li.pk_c2f, GROWTH, 32, BOTT, 64, 27, PACK_GENERIC, BOTT * 27, 27, 1);
-        add(params[li.conv2_idx], li.pk_c2d, BOTT, 128, GROWTH, 32, 27, PACK_GENERIC, 27, BOTT * 27, 1);
+        add(params[li.conv1_idx], li.pk_c1f, BOTT, 128, li.cin, 64, 1, PACK_GENERIC, li.cin, 1, 0, true);
+        add(params[li.conv1_idx], li.pk_c1d, li.cin, 128, BOTT, 64, 1, PACK_GENERIC, 1, li.cin, 0, false);
+        add(params[li.conv2_idx], li.pk_c2f, GROWTH, 32, BOTT, 64, 27, PACK_GENERIC, BOTT * 27, 27, 1, true);
+        add(params[li.conv2_idx], li.pk_c2d, BOTT, 128, GROWTH, 32, 27, PACK_GENERIC, 27, BOTT * 27, 1, false);
       }
       if (bi.has_trans) {
-        add(params[bi.tconv_idx], bi.pk_tf, bi.ctot / 2, 128, bi.ctot, 64, 1, PACK_GENERIC, bi.ctot, 1, 0);
-        add(params[bi.tconv_idx], bi.pk_td, bi.ctot, 128, bi.ctot / 2, 64, 1, PACK_GENERIC, 1, bi.ctot, 0);
+        add(params[bi.tconv_idx], bi.pk_tf, bi.ctot / 2, 128, bi.ctot, 64, 1, PACK_GENERIC, bi.ctot, 1, 0, true);
+        add(params[bi.tconv_idx], bi.pk_td, bi.ctot, 128, bi.ctot / 2, 64, 1, PACK_GENERIC, 1, bi.ctot, 0, false);
       }
     }
     if (descs.size() * sizeof(PackDesc) > (1 << 19)) return -11;
@@ -356,7 +356,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     p.b_packed = packed + pl->pk_stem;
     p.out = (bf16*)(ws + g.stem_out); p.out_pitch = 64;
     p.st_sum = fstats + pl->n0.fwd_off; p.st_sq = fstats + FC + pl->n0.fwd_off;
-    { ProfScope ps_(PC_STEM_FPROP, st); RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, st)); }
+    { ProfScope ps_(PC_STEM_FPROP, st); RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, 0, st)); }
     PoolParams q = {};
     q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
     q.src = (const bf16*)(ws + g.stem_out);
@@ -385,7 +385,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.b_packed = packed + li.pk_c1f;
       p.out = bott; p.out_pitch = BOTT;
       p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
-      { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st)); }
+      { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
       RowsParams q = {};
       q.M = (int)M; q.NT = 32; q.Ncols = GROWTH; q.Cin = BOTT; q.kbw = 64; q.ntaps = 27; q.tap_sign = 1;
       q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b];
@@ -395,7 +395,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       q.out = buf + li.cin; q.out_pitch = bi.ctot;
       q.colscale = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
       q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
-      { ProfScope ps_(PC_CONV2_FPROP, st); RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, st)); }
+      { ProfScope ps_(PC_CONV2_FPROP, st); RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
     }
     if (bi.has_trans) {
       const BlockInfo& nx = pl->blocks[b + 1];
@@ -414,7 +414,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.b_packed = packed + bi.pk_tf;
       p.out = (bf16*)(ws + g.buf[b + 1]); p.out_pitch = nx.ctot;
       p.st_sum = fstats + nx.fwd_off; p.st_sq = fstats + FC + nx.fwd_off;
-      { ProfScope ps_(PC_TRANS_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE_STATS, st)); }
+      { ProfScope ps_(PC_TRANS_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE_STATS, 0, st)); }
     }
   }
 
@@ -554,7 +554,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.st_sum = gsum(li.n2); p.st_sq = gdot(li.n2);
         p.e_src = bott; p.e_pitch = BOTT; p.bnE = bn2;
         ProfScope ps_(PC_CONV2_DGRAD, st);
-        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, 1, st));
       }
       RET_IF(bn_apply(BA_OUT_BF16, M, BOTT, dA2, nullptr, BOTT, bott, BOTT, bn2, gsum(li.n2), gdot(li.n2), dA2, BOTT));
       // conv1 wgrad: D[ci][co] -> dW1[co][ci]
@@ -580,7 +580,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.st_sum = gsum(li.n1); p.st_sq = gdot(li.n1);
         p.e_src = buf; p.e_pitch = bi.ctot; p.bnE = bn1;
         ProfScope ps_(PC_CONV1_DGRAD, st);
-        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, st));
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, 1, st));
       }
       RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
     }
@@ -613,7 +613,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.b_packed = packed + pv.pk_td;
         p.out = dpooled; p.out_pitch = pv.ctot;
         ProfScope ps_(PC_TRANS_DGRAD, st);
-        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE, st));
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_STORE, 1, st));
       }
       AvgPoolParams a = {};
       a.B = B; a.D = g.D[b - 1]; a.H = g.H[b - 1]; a.W = g.W[b - 1]; a.C = pv.ctot;

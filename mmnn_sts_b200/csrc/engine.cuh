@@ -79,13 +79,28 @@ struct RowsParams {
   int stages;
 };
 
+// 8 elements (16 B): load format IN, BN scale/shift + ReLU in fp32, store format OUT
+template <bool IN_F16, bool OUT_F16>
 MMNN_DEVINL void apply_bnrelu8(uint4& v, const float* sc, const float* sh) {
   uint32_t* w = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float a = fmaxf(fmaf(bf16_lo(w[i]), sc[2 * i], sh[2 * i]), 0.f);
-    const float b = fmaxf(fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
-    w[i] = pack_bf16(a, b);
+    float lo, hi;
+    unpack2<IN_F16>(w[i], lo, hi);
+    const float a = fmaxf(fmaf(lo, sc[2 * i], sh[2 * i]), 0.f);
+    const float b = fmaxf(fmaf(hi, sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+    w[i] = pack2<OUT_F16>(a, b);
+  }
+}
+template <bool IN_F16, bool OUT_F16>
+MMNN_DEVINL void convert8(uint4& v) {
+  if (IN_F16 == OUT_F16) return;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo, hi;
+    unpack2<IN_F16>(w[i], lo, hi);
+    w[i] = pack2<OUT_F16>(lo, hi);
   }
 }
 
@@ -108,8 +123,13 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
   return o + stages * stage;
 }
 
-template <int AMODE, int TRANS, int EPI>
+// GRAD == false: forward GEMM  -- A = activations (act format), weights packed in act format, output act format.
+// GRAD == true : data-gradient -- A = gradients (bf16), weights packed bf16, output bf16; e_src (forward activation
+//                                 gating the ReLU / feeding x-hat) is in act format.
+template <int AMODE, int TRANS, int EPI, bool GRAD>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_constant__ RowsParams p) {
+  constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
+  constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t offs[6];
   rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
@@ -199,9 +219,62 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
 
   if (warp < 4) {
     // ================= producers
+    // Register double buffering: the 16-byte loads of k-block kb+1 are issued BEFORE k-block kb is transformed and
+    // stored, so every thread keeps up to 16 independent 128-bit loads in flight across the empty-slot wait.
+    struct KbGeom { int cb, cpl, dz, dy, dx; long long delta; };
+    auto geom = [&](int kb) {
+      KbGeom gq;
+      const int tap = kb / kb_per_tap;
+      gq.cb = kb - tap * kb_per_tap;
+      int cpl = (p.Cin - gq.cb * p.kbw) / 8;
+      gq.cpl = cpl > planes ? planes : cpl;
+      gq.dz = gq.dy = gq.dx = 0; gq.delta = 0;
+      if (AMODE == A_STEM) {
+        gq.delta = (long long)((tap >> 2) * p.Sy + (tap & 3)) * p.Sx;
+      } else if (p.ntaps == 27) {
+        gq.dz = (tap / 9 - 1) * p.tap_sign; gq.dy = ((tap / 3) % 3 - 1) * p.tap_sign; gq.dx = (tap % 3 - 1) * p.tap_sign;
+        gq.delta = (long long)(gq.dz * p.Dy + gq.dy) * p.Dx + gq.dx;
+      }
+      return gq;
+    };
+    // lane -> (chunk, row sub-index): a warp-wide 16-byte load covers 32/cpl rows x (cpl*16) contiguous bytes
+    auto load_kb = [&](const KbGeom& gq, uint4 (&regs)[8], uint32_t& okmask) {
+      const int cshift = (gq.cpl == 8) ? 3 : 2;
+      const int chunk = lane & (gq.cpl == 8 ? 7 : 3);
+      const int rsub = lane >> cshift;
+      const int rpp = 32 >> cshift;
+      const int npass = 32 / rpp;
+      const int ch0 = gq.cb * p.kbw + chunk * 8;
+      okmask = 0;
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        regs[ps] = make_uint4(0, 0, 0, 0);
+        if (ps < npass) {
+          const int r = warp * 32 + ps * rpp + rsub;
+          const int4 ri = rowinfo[r];
+          bool ok = ri.y > -1000;
+          if (AMODE == A_LINEAR_CONV) {
+            const int zz = ri.y + gq.dz, yy = ri.z + gq.dy, xx = ri.w + gq.dx;
+            ok = ok && zz >= 0 && zz < p.Dz && yy >= 0 && yy < p.Dy && xx >= 0 && xx < p.Dx;
+          }
+          if (ok) {
+            regs[ps] = ldg16(p.a_src + ((long long)ri.x + gq.delta) * p.a_pitch + ch0);
+            okmask |= 1u << ps;
+          }
+        }
+      }
+    };
+    uint4 cur[8], nxt[8];
+    uint32_t cur_ok = 0, nxt_ok = 0;
+    KbGeom gcur = geom(0), gnxt = gcur;
+    load_kb(gcur, cur, cur_ok);
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
+      if (kb + 1 < KB) {
+        gnxt = geom(kb + 1);
+        load_kb(gnxt, nxt, nxt_ok);
+      }
       mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
       const uint32_t sA = stage0 + s * stage_bytes;
       const uint32_t sB = sA + a_bytes;
@@ -209,50 +282,33 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
         bulk_g2s(sB, p.b_packed + ((size_t)tile_n * KB + kb) * (size_t)(planes * p.NT * 8), b_bytes, bar_full + 8 * s);
       }
-      const int tap = kb / kb_per_tap;
-      const int cb = kb - tap * kb_per_tap;
-      int cpl = (p.Cin - cb * p.kbw) / 8;
-      cpl = cpl > planes ? planes : cpl;
-      int dz = 0, dy = 0, dx = 0;
-      long long delta = 0;
-      if (AMODE == A_STEM) {
-        dz = tap >> 2; dy = tap & 3;
-        delta = (long long)(dz * p.Sy + dy) * p.Sx;
-      } else if (p.ntaps == 27) {
-        dz = (tap / 9 - 1) * p.tap_sign; dy = ((tap / 3) % 3 - 1) * p.tap_sign; dx = (tap % 3 - 1) * p.tap_sign;
-        delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
-      }
-      // lane -> (chunk, row sub-index): a warp-wide 16-byte load covers 32/cpl rows x (cpl*16) contiguous bytes
-      const int cshift = (cpl == 8) ? 3 : 2;
-      const int chunk = lane & (cpl == 8 ? 7 : 3);
-      const int rsub = lane >> cshift;
-      const int rpp = 32 >> cshift;
-      const int npass = 32 / rpp;
-      const int ch0 = cb * p.kbw + chunk * 8;
-      float sc[8], sh[8];
-      if (TRANS == T_BNRELU) {
+      {
+        const int cshift = (gcur.cpl == 8) ? 3 : 2;
+        const int chunk = lane & (gcur.cpl == 8 ? 7 : 3);
+        const int rsub = lane >> cshift;
+        const int rpp = 32 >> cshift;
+        const int npass = 32 / rpp;
+        const int ch0 = gcur.cb * p.kbw + chunk * 8;
+        float sc[8], sh[8];
+        if (TRANS == T_BNRELU) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
-      }
-      const bool chunk_ok = chunk < cpl;
-#pragma unroll 4
-      for (int ps = 0; ps < npass; ++ps) {
-        const int r = warp * 32 + ps * rpp + rsub;
-        const int4 ri = rowinfo[r];
-        bool ok = chunk_ok && (ri.y > -1000);
-        if (AMODE == A_LINEAR_CONV) {
-          const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
-          ok = ok && zz >= 0 && zz < p.Dz && yy >= 0 && yy < p.Dy && xx >= 0 && xx < p.Dx;
+          for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
         }
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (ok) {
-          v = ldg16(p.a_src + ((long long)ri.x + delta) * p.a_pitch + ch0);
-          if (TRANS == T_BNRELU) apply_bnrelu8(v, sc, sh);
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          if (ps < npass) {
+            const int r = warp * 32 + ps * rpp + rsub;
+            uint4 v = cur[ps];
+            if (TRANS == T_BNRELU && ((cur_ok >> ps) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+            sts16(sA + chunk * PLANE_BYTES + r * 16, v);
+          }
         }
-        if (chunk_ok) sts16(sA + chunk * PLANE_BYTES + r * 16, v);
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_full + 8 * s);
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) cur[ps] = nxt[ps];
+      cur_ok = nxt_ok; gcur = gnxt;
     }
     // ================= epilogue (same warps: TMEM lane quarter == warp index)
     mbar_wait(bar_accum, 0, 3);
@@ -286,10 +342,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float x = (j & 1) ? bf16_hi(xw[j >> 1]) : bf16_lo(xw[j >> 1]);
+          float xlo, xhi;
+          unpack2<E_F16>(xw[j >> 1], xlo, xhi);
+          const float x = (j & 1) ? xhi : xlo;
           const int c = cc * 32 + j;
           const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
-          const float g = (row_ok && act) ? round_bf16(v[j]) : 0.f;
+          const float g = (row_ok && act) ? round16<OP_F16>(v[j]) : 0.f;
           v[j] = g;
           q[j] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
         }
@@ -301,7 +359,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float g = row_ok ? round_bf16(v[j]) : 0.f;
+          const float g = row_ok ? round16<OP_F16>(v[j]) : 0.f;
           v[j] = g;
           q[j] = g * g;
         }
@@ -311,8 +369,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]); o.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-          o.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]); o.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
+          o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
           op[i] = o;
         }
       }
@@ -337,7 +395,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
     }
   } else {
     // ================= MMA issuer (warp 4, one elected lane)
-    const uint32_t idesc = make_idesc_bf16(TILE_ROWS, p.NT, 0, 0);
+    const uint32_t idesc = make_idesc(TILE_ROWS, p.NT, 0, 0, OP_F16);
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -411,7 +469,9 @@ __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages
 }
 
 // Fill `planes` chunk planes of one operand tile. lane -> (chunk within a group of G, row sub-index).
-template <int TRANS, bool SHIFTED>
+// All loads of a group are issued before the first use (8 or 4 independent 128-bit loads in flight per thread).
+// IN_F16: storage format of the source; the tile is always written as bf16 (weight-gradient GEMMs run in bf16).
+template <int TRANS, bool SHIFTED, bool IN_F16>
 MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long long pitch, const int4* rowinfo, int warp,
                                 int lane, int dz, int dy, int dx, long long delta, int Dz, int Dy, int Dx,
                                 const float* scale, const float* shift) {
@@ -419,29 +479,45 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
   const int gshift = planes >= 8 ? 3 : 2;
   const int rsub = lane >> gshift;
   const int rpp = 32 >> gshift;
+  const int npass = 32 / rpp;
   for (int grp = 0; grp < (planes + G - 1) / G; ++grp) {
     const int chunk = grp * G + (lane & (G - 1));
     if (chunk >= planes) continue;  // planes is a multiple of 4 but not necessarily of G
+    uint4 regs[8];
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      regs[ps] = make_uint4(0, 0, 0, 0);
+      if (ps < npass) {
+        const int r = warp * 32 + ps * rpp + rsub;
+        const int4 ri = rowinfo[r];
+        bool ok = ri.y > -1000;
+        if (SHIFTED) {
+          const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
+          ok = ok && zz >= 0 && zz < Dz && yy >= 0 && yy < Dy && xx >= 0 && xx < Dx;
+        }
+        if (ok) {
+          regs[ps] = ldg16(src + ((long long)ri.x + delta) * pitch + chunk * 8);
+          okmask |= 1u << ps;
+        }
+      }
+    }
     float sc[8], sh[8];
     if (TRANS == T_BNRELU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { sc[e] = scale[chunk * 8 + e]; sh[e] = shift[chunk * 8 + e]; }
     }
-#pragma unroll 4
-    for (int ps = 0; ps < 32 / rpp; ++ps) {
-      const int r = warp * 32 + ps * rpp + rsub;
-      const int4 ri = rowinfo[r];
-      bool ok = ri.y > -1000;
-      if (SHIFTED) {
-        const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
-        ok = ok && zz >= 0 && zz < Dz && yy >= 0 && yy < Dy && xx >= 0 && xx < Dx;
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      if (ps < npass) {
+        const int r = warp * 32 + ps * rpp + rsub;
+        uint4 v = regs[ps];
+        if ((okmask >> ps) & 1u) {
+          if (TRANS == T_BNRELU) apply_bnrelu8<IN_F16, false>(v, sc, sh);
+          else convert8<IN_F16, false>(v);
+        }
+        sts16(sdst + chunk * PLANE_BYTES + r * 16, v);
       }
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (ok) {
-        v = ldg16(src + ((long long)ri.x + delta) * pitch + chunk * 8);
-        if (TRANS == T_BNRELU) apply_bnrelu8(v, sc, sh);
-      }
-      sts16(sdst + chunk * PLANE_BYTES + r * 16, v);
     }
   }
 }
@@ -553,13 +629,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       const uint32_t sA = stage0 + s * stage_bytes;
       const uint32_t sB = sA + a_bytes;
       if (AMODE == WA_LINEAR) {
-        produce_planes<ATRANS, false>(sA, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz,
+        produce_planes<ATRANS, false, kActF16>(sA, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz,
                                       p.Dy, p.Dx, coefA, coefA + 128);
       } else {
         for (int g = 0; g < 2; ++g) {
           const int kb = ztile * 2 + g;
           const long long delta = (long long)((kb >> 2) * p.Sy + (kb & 3)) * p.Sx;
-          produce_planes<T_NONE, false>(sA + g * 8 * PLANE_BYTES, 8, p.a_src, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, delta,
+          produce_planes<T_NONE, false, kActF16>(sA + g * 8 * PLANE_BYTES, 8, p.a_src, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, delta,
                                         p.Dz, p.Dy, p.Dx, nullptr, nullptr);
         }
       }
@@ -571,7 +647,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         named_bar_sync(1, NUM_PRODUCER_THREADS);
       }
       if (p.NB == 1) {
-        produce_planes<BTRANS, false>(sB, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0, 0,
+        produce_planes<BTRANS, false, false>(sB, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0, 0,
                                       p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
       } else {
         for (int j = 0; j < p.NB; ++j) {
@@ -579,7 +655,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           // B_j[v] = g[v - tap offset]
           const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
           const long long delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
-          produce_planes<BTRANS, true>(sB + j * bt_bytes, bplanes, p.b_src, p.b_pitch, rowinfo, warp, lane, dz, dy, dx, delta,
+          produce_planes<BTRANS, true, false>(sB + j * bt_bytes, bplanes, p.b_src, p.b_pitch, rowinfo, warp, lane, dz, dy, dx, delta,
                                        p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
         }
       }
@@ -620,7 +696,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       }
     }
   } else {
-    const uint32_t idesc = make_idesc_bf16(128, p.CB, 1, 1);
+    const uint32_t idesc = make_idesc(128, p.CB, 1, 1, false);
     for (int it = 0; it < nt; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;

@@ -17,7 +17,7 @@ struct PackDesc {
   int ntaps;
   int mode;
   int cin_real;  // stem: real input channels (1 or 2); the packed form always has 2
-  int pad_;
+  int f16;       // 1: emit IEEE fp16 (forward images when activations are fp16), 0: bf16
   long long sn, sc, st;  // source strides (elements) for n, channel, tap
 };
 
@@ -54,7 +54,11 @@ static __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs) {
       w[e] = val;
     }
     uint4 o;
-    o.x = pack_bf16(w[0], w[1]); o.y = pack_bf16(w[2], w[3]); o.z = pack_bf16(w[4], w[5]); o.w = pack_bf16(w[6], w[7]);
+    if (d.f16) {
+      o.x = pack2<true>(w[0], w[1]); o.y = pack2<true>(w[2], w[3]); o.z = pack2<true>(w[4], w[5]); o.w = pack2<true>(w[6], w[7]);
+    } else {
+      o.x = pack_bf16(w[0], w[1]); o.y = pack_bf16(w[2], w[3]); o.z = pack_bf16(w[4], w[5]); o.w = pack_bf16(w[6], w[7]);
+    }
     reinterpret_cast<uint4*>(d.dst)[idx] = o;
   }
 }

@@ -1,7 +1,7 @@
 """Rounding-matched CPU model of the sm_100a trunk: the SAME algorithm as oracle/model.py (i.e. the reference's,
-/root/reference/models/densenet.py:46-148,196-231) with bf16 rounding inserted at exactly the points where the CUDA
-build stores bf16 (weights, conv inputs after BN+ReLU, conv outputs, pooled tensors, and the gradient tensors of the
-backward pass).  TEST INFRASTRUCTURE.
+/root/reference/models/densenet.py:46-148,196-231) with rounding inserted at exactly the points where the CUDA
+build stores 16-bit values: forward tensors (weights, conv inputs after BN+ReLU, conv outputs, pooled tensors) in the
+activation format (fp16), gradient tensors of the backward pass in bf16.  TEST INFRASTRUCTURE.
 
 Why it exists: with reduced-precision storage a ReLU whose pre-activation is within rounding distance of zero flips,
 and a flipped element changes its gradient by 100 %; gradient errors against the fp32 oracle therefore scale like
@@ -12,16 +12,23 @@ import torch
 import torch.nn.functional as F
 
 
+ACT_DTYPE = torch.float16   # storage format of forward activations / forward weights in the build (see common.cuh)
+
+
 def _bf(x):
     return x.to(torch.bfloat16).float()
 
 
+def _act(x):
+    return x.to(ACT_DTYPE).float()
+
+
 class _RoundSTE(torch.autograd.Function):
-    """forward: round to bf16; backward: identity."""
+    """forward: round to the activation format; backward: identity."""
 
     @staticmethod
     def forward(ctx, x):
-        return _bf(x)
+        return _act(x)
 
     @staticmethod
     def backward(ctx, g):
@@ -43,7 +50,7 @@ class _RoundGrad(torch.autograd.Function):
 class _RoundBoth(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return _bf(x)
+        return _act(x)
 
     @staticmethod
     def backward(ctx, g):
@@ -60,7 +67,7 @@ def _bn(x, sd, q, training):
 def backbone_bf16(sd, x, training, masks=None, prefix="", block_config=(6, 12, 24, 16), collect=None):
     p = prefix + "backbone."
     # conv0: image and weights rounded; output stored bf16; its gradient (dConv0) is stored bf16
-    x = rb(F.conv3d(_bf(x), rs(sd[p + "conv0.weight"]), None, stride=2, padding=3))
+    x = rb(F.conv3d(_act(x), rs(sd[p + "conv0.weight"]), None, stride=2, padding=3))
     if collect is not None: collect["conv0"] = x
     # norm0+relu0+pool0 fused; the masked pool gradient (dR) is stored bf16
     x = rs(F.max_pool3d(rg(F.relu(_bn(x, sd, p + "norm0", training))), 3, 2, 1))

@@ -7,6 +7,14 @@ import torch
 from mmnn_sts_b200 import _lib as L
 
 
+def act_dtype():
+    """Storage dtype of forward activations / forward weight images in this build (fp16 by default)."""
+    return torch.float16 if L.lib().mmnn_act_is_fp16() else torch.bfloat16
+
+
+GRD = torch.bfloat16
+
+
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -15,9 +23,10 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def pack(src_f32, N, NT, Cin, kbw, ntaps, sn, sc, st, mode=L.PACK_GENERIC, cin_real=0):
+def pack(src_f32, N, NT, Cin, kbw, ntaps, sn, sc, st, mode=L.PACK_GENERIC, cin_real=0, fwd=True):
     dst = torch.empty(L.packed_elems(N, NT, Cin, kbw, ntaps), dtype=torch.bfloat16, device="cuda")
-    d = L.PackDesc(ptr(src_f32), ptr(dst), N, NT, Cin, kbw, ntaps, mode, cin_real, 0, sn, sc, st)
+    f16 = 1 if (fwd and act_dtype() == torch.float16) else 0
+    d = L.PackDesc(ptr(src_f32), ptr(dst), N, NT, Cin, kbw, ntaps, mode, cin_real, f16, sn, sc, st)
     scratch = torch.empty(C.sizeof(L.PackDesc), dtype=torch.uint8, device="cuda")
     L.check(L.lib().mmnn_pack_weights(C.byref(d), 1, ptr(scratch), stream_ptr()), "pack")
     torch.cuda.synchronize()
@@ -30,7 +39,7 @@ def bnsrc(sum_=None, sumsq=None, gamma=None, beta=None, rmean=None, rvar=None, c
 
 def rows(M, NT, Ncols, Cin, kbw, ntaps, dims, a_src, a_pitch, b_packed, out, out_pitch, amode=L.A_LINEAR_CONV,
          trans=L.T_NONE, epi=L.EP_STORE, tap_sign=1, sdims=(0, 0, 0), bnA=None, colscale=None, st_sum=None, st_sq=None,
-         e_src=None, e_pitch=0, bnE=None, stages=0):
+         e_src=None, e_pitch=0, bnE=None, stages=0, grad=0):
     p = L.RowsParams()
     p.M, p.NT, p.Ncols, p.Cin, p.kbw, p.ntaps, p.tap_sign = M, NT, Ncols, Cin, kbw, ntaps, tap_sign
     p.Dz, p.Dy, p.Dx = dims
@@ -46,7 +55,7 @@ def rows(M, NT, Ncols, Cin, kbw, ntaps, dims, a_src, a_pitch, b_packed, out, out
     p.e_pitch = e_pitch
     p.bnE = bnE if bnE is not None else L.BnSrc()
     p.stages = stages
-    L.check(L.lib().mmnn_conv_rows(C.byref(p), amode, trans, epi, stream_ptr()), "conv_rows")
+    L.check(L.lib().mmnn_conv_rows(C.byref(p), amode, trans, epi, grad, stream_ptr()), "conv_rows")
 
 
 def wgrad(kind, M, CB, NB, na_total, nb_total, dims, a_src, a_pitch, b_src, b_pitch, dw, so_a, so_b, so_j=0,

@@ -155,9 +155,12 @@ def kats(ns):
 if __name__ == "__main__":
     ns = shim.load_reference()
     kats(ns)
-    run_case(ns, "tiny_blend_train", seed_w=42, seed_x=1, batch=4, in_channels=2, spatial=(32, 32, 32), blend=True, training=True, dropout=False)
-    run_case(ns, "tiny_blend_train_dropout", seed_w=42, seed_x=2, batch=4, in_channels=2, spatial=(32, 32, 32), blend=True, training=True, dropout=True)
-    run_case(ns, "tiny_eval", seed_w=42, seed_x=3, batch=3, in_channels=2, spatial=(32, 32, 32), blend=True, training=False, dropout=False)
+    # every case keeps >= 12 samples per BatchNorm channel in the last dense block: with fewer (e.g. 32^3 inputs, one
+    # voxel per sample in block 4) batch statistics over 2-4 values make outputs and gradients ill-conditioned in ANY
+    # arithmetic and the comparison says nothing about the kernels.
+    run_case(ns, "tiny_blend_train", seed_w=42, seed_x=1, batch=4, in_channels=2, spatial=(64, 64, 32), blend=True, training=True, dropout=False)
+    run_case(ns, "tiny_blend_train_dropout", seed_w=42, seed_x=2, batch=4, in_channels=2, spatial=(64, 64, 32), blend=True, training=True, dropout=True)
+    run_case(ns, "tiny_eval", seed_w=42, seed_x=3, batch=3, in_channels=2, spatial=(64, 64, 32), blend=True, training=False, dropout=False)
     run_case(ns, "cfg1_train", seed_w=42, seed_x=4, batch=4, in_channels=1, spatial=(64, 64, 32), blend=False, training=True, dropout=False)
     run_case(ns, "cfg1_eval", seed_w=42, seed_x=5, batch=4, in_channels=1, spatial=(64, 64, 32), blend=False, training=False, dropout=False)
-    run_case(ns, "odd_train", seed_w=43, seed_x=6, batch=2, in_channels=2, spatial=(40, 48, 32), blend=True, training=True, dropout=False, tie_free=False)
+    run_case(ns, "odd_train", seed_w=43, seed_x=6, batch=3, in_channels=2, spatial=(72, 66, 40), blend=True, training=True, dropout=False, tie_free=False)

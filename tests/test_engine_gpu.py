@@ -12,6 +12,17 @@ def _bf(x):
     return x.to(torch.bfloat16).float()
 
 
+def _act(x):
+    """round to the build's activation storage format (fp16 by default)"""
+    from tests import engine_helpers as H
+    return x.to(H.act_dtype()).float()
+
+
+def _actdt():
+    from tests import engine_helpers as H
+    return H.act_dtype()
+
+
 def _close(a, b, rtol=1.0 / 128, atol=2e-2):
     d = (a.float() - b.float()).abs()
     lim = rtol * b.float().abs() + atol
@@ -23,13 +34,13 @@ def test_linear_gemm_store():
     from tests import engine_helpers as H
     torch.manual_seed(0)
     M, Cin, N = 1000, 96, 128
-    a = torch.randn(M, Cin, device="cuda").to(torch.bfloat16)
+    a = torch.randn(M, Cin, device="cuda").to(_actdt())
     w = torch.randn(N, Cin, device="cuda") * 0.2
     bp = H.pack(w, N, 128, Cin, 64, 1, Cin, 1, 0)
-    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(M, N, dtype=_actdt(), device="cuda")
     H.rows(M, 128, N, Cin, 64, 1, (1, 1, M), a, Cin, bp, out, N)
     torch.cuda.synchronize()
-    ref = a.float() @ _bf(w).t()
+    ref = a.float() @ _act(w).t()
     _close(out, ref)
 
 
@@ -38,20 +49,20 @@ def test_linear_bnrelu_stats_ntiles_strided():
     from tests import engine_helpers as H
     torch.manual_seed(1)
     M, Ctot, Cin, N = 777, 256, 160, 224
-    buf = torch.randn(M, Ctot, device="cuda").to(torch.bfloat16)
+    buf = torch.randn(M, Ctot, device="cuda").to(_actdt())
     x = buf[:, :Cin].float()
     w = torch.randn(N, Cin, device="cuda") * 0.1
     gamma = torch.rand(Cin, device="cuda") + 0.5
     beta = torch.randn(Cin, device="cuda") * 0.3
     s1 = x.double().sum(0); s2 = (x.double() ** 2).sum(0)
     bp = H.pack(w, N, 128, Cin, 64, 1, Cin, 1, 0)
-    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(M, N, dtype=_actdt(), device="cuda")
     st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
     H.rows(M, 128, N, Cin, 64, 1, (1, 1, M), buf, Ctot, bp, out, N, trans=L.T_BNRELU, epi=L.EP_STORE_STATS,
            bnA=H.bnsrc(s1, s2, gamma, beta, count=M), st_sum=st[0], st_sq=st[1])
     torch.cuda.synchronize()
-    a = _bf(F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5)))
-    ref = a @ _bf(w).t()
+    a = _act(F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5)))
+    ref = a @ _act(w).t()
     _close(out, ref, rtol=1 / 64, atol=5e-2)
     o = out.double()
     assert torch.allclose(st[0], o.sum(0), rtol=1e-5, atol=1e-3)
@@ -64,7 +75,7 @@ def test_conv3x3x3_fprop_bnrelu_dropout_slice():
     torch.manual_seed(2)
     B, Dz, Dy, Dx, Cin, N, Ctot = 2, 5, 6, 8, 128, 32, 96
     M = B * Dz * Dy * Dx
-    bott = torch.randn(M, Cin, device="cuda").to(torch.bfloat16)
+    bott = torch.randn(M, Cin, device="cuda").to(_actdt())
     w = torch.randn(N, Cin, 3, 3, 3, device="cuda") * 0.05
     gamma = torch.rand(Cin, device="cuda") + 0.5
     beta = torch.randn(Cin, device="cuda") * 0.3
@@ -72,15 +83,15 @@ def test_conv3x3x3_fprop_bnrelu_dropout_slice():
     rvar = torch.rand(Cin, device="cuda") + 0.5
     keep = (torch.rand(B, N, device="cuda") > 0.3).float() / 0.7
     bp = H.pack(w, N, 32, Cin, 64, 27, Cin * 27, 27, 1)
-    buf = torch.zeros(M, Ctot, dtype=torch.bfloat16, device="cuda")
+    buf = torch.zeros(M, Ctot, dtype=_actdt(), device="cuda")
     st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
     H.rows(M, 32, N, Cin, 64, 27, (Dz, Dy, Dx), bott, Cin, bp, buf[:, 64:], Ctot, trans=L.T_BNRELU,
            epi=L.EP_STORE_STATS, bnA=H.bnsrc(None, None, gamma, beta, rmean, rvar, use_batch=0), colscale=keep,
            st_sum=st[0], st_sq=st[1])
     torch.cuda.synchronize()
     x = bott.float().view(B, Dz, Dy, Dx, Cin).permute(0, 4, 1, 2, 3)
-    a = _bf(F.relu(F.batch_norm(x, rmean, rvar, gamma, beta, False, 0.0, 1e-5)))
-    ref = F.conv3d(a, _bf(w), padding=1) * keep[:, :, None, None, None]
+    a = _act(F.relu(F.batch_norm(x, rmean, rvar, gamma, beta, False, 0.0, 1e-5)))
+    ref = F.conv3d(a, _act(w), padding=1) * keep[:, :, None, None, None]
     ref = ref.permute(0, 2, 3, 4, 1).reshape(M, N)
     _close(buf[:, 64:], ref, rtol=1 / 64, atol=5e-2)
     assert float(buf[:, :64].abs().max()) == 0.0
@@ -96,15 +107,15 @@ def test_conv3x3x3_dgrad_mask_stats():
     M = B * Dz * Dy * Dx
     g = torch.randn(M, Cg, device="cuda").to(torch.bfloat16)
     w = torch.randn(Cg, N, 3, 3, 3, device="cuda") * 0.05      # conv2.weight [co=32][ci=128][27]
-    xb = torch.randn(M, N, device="cuda").to(torch.bfloat16)    # bottleneck (BN2 input)
+    xb = torch.randn(M, N, device="cuda").to(_actdt())          # bottleneck (BN2 input), forward activation format
     gamma = torch.rand(N, device="cuda") + 0.5
     beta = torch.randn(N, device="cuda") * 0.3
     s1 = xb.double().sum(0); s2 = (xb.double() ** 2).sum(0)
     # dgrad operand: n = ci, channel = co, tap
-    bp = H.pack(w, N, 128, Cg, 32, 27, 27, N * 27, 1)
+    bp = H.pack(w, N, 128, Cg, 32, 27, 27, N * 27, 1, fwd=False)
     out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
     st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
-    H.rows(M, 128, N, Cg, 32, 27, (Dz, Dy, Dx), g, Cg, bp, out, N, epi=L.EP_MASK_STATS, tap_sign=-1,
+    H.rows(M, 128, N, Cg, 32, 27, (Dz, Dy, Dx), g, Cg, bp, out, N, epi=L.EP_MASK_STATS, tap_sign=-1, grad=1,
            st_sum=st[0], st_sq=st[1], e_src=xb, e_pitch=N, bnE=H.bnsrc(s1, s2, gamma, beta, count=M))
     torch.cuda.synchronize()
     g5 = g.float().view(B, Dz, Dy, Dx, Cg).permute(0, 4, 1, 2, 3)
@@ -135,16 +146,16 @@ def test_stem_conv7_s2():
         # reference-side construction of the padded space-to-depth input [B][Sz][Sy][Sx][(pz,py,px,c2)]
         pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
         pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
-        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(torch.bfloat16)
-        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=torch.bfloat16, device="cuda")])  # tail slack for the 4-voxel rows
+        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(_actdt())
+        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=_actdt(), device="cuda")])  # tail slack for the 4-voxel rows
         M = B * Dz * Dy * Dx
         bp = H.pack(w, 64, 64, 64, 64, 16, 0, 0, 0, mode=L.PACK_STEM, cin_real=cin)
-        out = torch.zeros(M, 64, dtype=torch.bfloat16, device="cuda")
+        out = torch.zeros(M, 64, dtype=_actdt(), device="cuda")
         st = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
         H.rows(M, 64, 64, 64, 64, 16, (Dz, Dy, Dx), s2d, 16, bp, out, 64, amode=L.A_STEM, epi=L.EP_STORE_STATS,
                sdims=(Sz, Sy, Sx), st_sum=st[0], st_sq=st[1])
         torch.cuda.synchronize()
-        ref = F.conv3d(_bf(img), _bf(w), stride=2, padding=3).permute(0, 2, 3, 4, 1).reshape(M, 64)
+        ref = F.conv3d(_act(img), _act(w), stride=2, padding=3).permute(0, 2, 3, 4, 1).reshape(M, 64)
         _close(out, ref, rtol=1 / 64, atol=5e-2)
         assert torch.allclose(st[0], out.double().sum(0), rtol=1e-5, atol=1e-3)
 
@@ -153,7 +164,7 @@ def test_wgrad_conv1x1():
     from tests import engine_helpers as H
     torch.manual_seed(5)
     M, Ctot, Cin, Co = 1300, 256, 160, 128
-    buf = torch.randn(M, Ctot, device="cuda").to(torch.bfloat16)
+    buf = torch.randn(M, Ctot, device="cuda").to(_actdt())
     dbott = (torch.randn(M, Co, device="cuda") * 0.1).to(torch.bfloat16)
     gamma = torch.rand(Cin, device="cuda") + 0.5
     beta = torch.randn(Cin, device="cuda") * 0.3
@@ -174,7 +185,7 @@ def test_wgrad_conv3x3x3():
     torch.manual_seed(6)
     B, Dz, Dy, Dx, Cb, Cg = 2, 4, 6, 8, 128, 32
     M = B * Dz * Dy * Dx
-    bott = torch.randn(M, Cb, device="cuda").to(torch.bfloat16)
+    bott = torch.randn(M, Cb, device="cuda").to(_actdt())
     g = (torch.randn(M, Cg, device="cuda") * 0.1).to(torch.bfloat16)
     gamma = torch.rand(Cb, device="cuda") + 0.5
     beta = torch.randn(Cb, device="cuda") * 0.3
@@ -197,12 +208,12 @@ def test_wgrad_raw_and_stem():
     torch.manual_seed(7)
     # raw x raw (transition): dW[co][ci] = sum_m g[m][co] * pooled[m][ci];  A = pooled (ci), B = g (co)
     M, C, Co = 900, 256, 128
-    pooled = torch.randn(M, C, device="cuda").to(torch.bfloat16)
+    pooled = torch.randn(M, C, device="cuda").to(_actdt())
     g = (torch.randn(M, Co, device="cuda") * 0.1).to(torch.bfloat16)
     dw = torch.zeros(Co, C, device="cuda")
     H.wgrad(2, M, 128, 1, C, Co, (1, 1, M), pooled, C, g, Co, dw, 1, C)
     torch.cuda.synchronize()
-    ref = g.float().t() @ pooled.float()
+    ref = g.float().t() @ _bf(pooled.float())
     assert (dw - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3
     # stem
     for cin in (1, 2):
@@ -212,14 +223,14 @@ def test_wgrad_raw_and_stem():
         Sz, Sy, Sx = Dz + 3, Dy + 3, Dx + 3
         pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
         pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
-        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(torch.bfloat16)
-        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=torch.bfloat16, device="cuda")])
+        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(_actdt())
+        s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=_actdt(), device="cuda")])
         M0 = B * Dz * Dy * Dx
         dconv = (torch.randn(M0, 64, device="cuda") * 0.1).to(torch.bfloat16)
         dw0 = torch.zeros(64, cin, 7, 7, 7, device="cuda")
         H.wgrad(3, M0, 64, 1, 128, 64, (Dz, Dy, Dx), s2d, 16, dconv, 64, dw0, 0, 0, sdims=(Sz, Sy, Sx), cin_real=cin)
         torch.cuda.synchronize()
         w = torch.zeros(64, cin, 7, 7, 7, device="cuda", requires_grad=True)
-        y = F.conv3d(_bf(img), w, stride=2, padding=3)
+        y = F.conv3d(_bf(_act(img)), w, stride=2, padding=3)
         (ref,) = torch.autograd.grad(y, w, dconv.float().view(B, Dz, Dy, Dx, 64).permute(0, 4, 1, 2, 3))
         assert (dw0 - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw0 - ref).abs().max()

@@ -1,6 +1,7 @@
 """End-to-end GPU parity of MultiModalModel + Cox / GradientBlender loss against the committed golden vectors
-(generated from the UNCHANGED reference files, tests/golden/make_golden.py) and the fp32 oracle.
-Tolerances are the measured bf16-storage envelope of DESIGN.md "Numerics" (logits relative to the logit range)."""
+(generated from the UNCHANGED reference files, tests/golden/make_golden.py).
+Tolerances: BASELINE.json north star -- logits within 2e-2 of the logit range, loss within 1e-3 (configs[0]);
+fp16 activation storage / bf16 gradient storage / fp32 accumulation vs the fp32 reference (DESIGN.md "Numerics")."""
 import os
 
 import numpy as np
@@ -45,8 +46,8 @@ def test_against_reference_golden(name):
     scale = float(ref.abs().max())
     err = float((out.detach().cpu() - ref).abs().max()) / scale
     print(f"\n{name}: logits max-abs err / max|logit| = {err:.3e}")
-    # tiny 32^3 inputs leave 4 samples per BatchNorm channel in block 4 -> the worst conditioned case
-    assert err < (0.25 if sx == 32 and training else 0.12)
+    # north star: rel 2e-2 on logits
+    assert err < (2e-2 if training else 1e-2)
     if training:
         if blend:
             loss, _ = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion).computeLoss(out, events.cuda(), durations.cuda())
@@ -54,7 +55,9 @@ def test_against_reference_golden(name):
             loss = surv_criterion(CoxPH, out, events.cuda(), durations.cuda(), "cuda")
         rel = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
         print(f"{name}: loss {loss.item():.5f} vs reference {float(g['loss']):.5f} (rel {rel:.3e})")
-        assert rel < 0.1
+        assert rel < 2e-3      # north star: 1e-3 on the loss at configs[0] (asserted below for cfg1)
+        if name.startswith('cfg1'):
+            assert rel < 1e-3
         loss.backward()
         names = [str(s) for s in g["param_names"]]
         norms = dict(zip(names, g["grad_norms"]))
@@ -67,13 +70,13 @@ def test_against_reference_golden(name):
                 if norms[k] > 1e-8:
                     ratios.append(float(p.grad.double().norm()) / norms[k])
         print(f"{name}: gradient-norm ratio median {np.median(ratios):.3f}  [p5 {np.percentile(ratios, 5):.3f}, p95 {np.percentile(ratios, 95):.3f}]")
-        assert 0.7 < np.median(ratios) < 1.4
+        assert 0.9 < np.median(ratios) < 1.1
         for k in ("output_head.weight", "clinical_model.model.backbone.dense0.weight", "image_model.model.features.feature_layer.weight"):
             a = p_grad = dict(m.named_parameters())[k].grad.cpu().double().flatten()
             b = torch.tensor(g["grad:" + k]).double().flatten()
             cos = float(a @ b / (a.norm() * b.norm()))
             print(f"   cosine({k}) = {cos:.4f}")
-            assert cos > 0.9, k
+            assert cos > 0.98, k
 
 
 def test_cindex_of_risks_bit_exact_and_bootstrap():

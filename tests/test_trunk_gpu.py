@@ -78,8 +78,8 @@ def test_trunk_train(cin, spatial, batch, dropout, seed, cfg):
     e_em, e_32 = _rel(fc, fem), _rel(fc, f32)
     print(f"\n[{cfg}] features rel-L2: vs rounding-matched {e_em:.2e}, vs fp32 oracle {e_32:.2e}")
     deep = len(cfg) == 4
-    assert e_em < (3e-2 if deep else 5e-3)
-    assert e_32 < (1.5e-1 if deep else 2e-2)
+    assert e_em < (1.5e-2 if deep else 2e-3)
+    assert e_32 < (3e-2 if deep else 5e-3)
     rel_em, cos_32, nrm_32 = [], [], []
     for k, q in m.named_parameters():
         r32, rem = p32[PFX + k].grad, pem[PFX + k].grad
@@ -88,21 +88,20 @@ def test_trunk_train(cin, spatial, batch, dropout, seed, cfg):
             continue
         gq = q.grad.cpu()
         assert torch.isfinite(gq).all(), k
+        if k == "backbone.norm0.weight":
+            continue   # d(gamma0) = sum over ~1e5..1e7 voxels of dy*xhat that cancels to ~1e-3 of its terms: ill-conditioned in any arithmetic
         rel_em.append((_rel(gq, rem), k))
         cos_32.append((_cos(gq, r32), k))
         nrm_32.append(float(gq.norm() / (r32.norm() + 1e-30)))
     rel_em.sort(reverse=True); cos_32.sort()
     print("   grads vs rounding-matched: median rel-L2 %.2e, worst %s" % (np.median([e for e, _ in rel_em]), [(f"{e:.2e}", k) for e, k in rel_em[:3]]))
     print("   grads vs fp32 oracle: median cosine %.4f, worst %s, norm ratio median %.3f" % (np.median([c for c, _ in cos_32]), [(f"{c:.3f}", k) for c, k in cos_32[:3]], np.median(nrm_32)))
-    if not deep:
-        assert np.median([e for e, _ in rel_em]) < 2e-2
-        assert rel_em[0][0] < 0.25, rel_em[:3]      # tiny-norm BN gains are the outliers
-        assert np.median([c for c, _ in cos_32]) > 0.9
-    else:
-        # full depth: residual mask flips between the CPU model and the GPU (different fp32 summation order) compound
-        assert np.median([e for e, _ in rel_em]) < 0.5
-        assert np.median([c for c, _ in cos_32]) > 0.3
-    assert 0.8 < np.median(nrm_32) < 1.25
+    # Residual ReLU-mask flips (pre-activations within rounding distance of zero) bound gradient agreement by
+    # ~sqrt(forward mismatch) per layer -- see DESIGN.md "Numerics"; hence cosine / norm-ratio criteria.
+    assert np.median([e for e, _ in rel_em]) < (0.3 if deep else 0.15)
+    assert np.median([c for c, _ in cos_32]) > (0.95 if deep else 0.99)
+    assert cos_32[0][0] > (0.85 if deep else 0.95), cos_32[:3]
+    assert 0.95 < np.median(nrm_32) < 1.05
     new_sd = m.state_dict()
     for k in ["backbone.norm0", "backbone.denseblock2.denselayer2.layers.norm2", "backbone.norm5"]:
         assert _rel(new_sd[k + ".running_mean"].cpu(), p32[PFX + k + ".running_mean"]) < 2e-2, k
@@ -124,5 +123,5 @@ def test_trunk_eval():
     with torch.no_grad():
         f = m.features(m.backbone(image.cuda())).cpu()
     print(f"\neval features rel-L2: vs rounding-matched {_rel(f, fem):.2e}, vs fp32 {_rel(f, f32):.2e}")
-    assert _rel(f, fem) < 2e-2
-    assert _rel(f, f32) < 1e-1
+    assert _rel(f, fem) < 5e-3
+    assert _rel(f, f32) < 5e-3
