@@ -1,0 +1,99 @@
+/* mmnn_b200.h -- C ABI of libmmnn_b200.so (sm_100a kernels for the MMNN_STS training / inference step).
+ *
+ * Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless it says HOST.  `stream` is a cudaStream_t
+ * passed as void*.  Every function that launches work returns 0 on success, a cudaError_t value (> 0) on a CUDA
+ * failure or a negative code for an argument the kernels do not support; nothing here allocates or synchronises
+ * (except mmnn_profile_collect).  The reference has no FFI of its own (it is a pure PyTorch repository): each entry
+ * point below names the reference code it replaces; the Python binding the reference side would use is
+ * mmnn_sts_b200/_lib.py (ctypes) and is shown in INTEGRATION.md.
+ *
+ * Storage formats: forward activations and forward weight images are IEEE fp16 (mmnn_act_is_fp16() == 1),
+ * gradient tensors bf16, accumulation / statistics / parameters / losses fp32 (statistics arena fp64).
+ */
+#ifndef MMNN_B200_H
+#define MMNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ trunk (coarse)
+ * Replaces DenseNet.backbone: conv0/norm0/relu0/pool0, _DenseBlock x4 of _DenseLayer, _Transition x3, norm5
+ * (/root/reference/models/densenet.py:46-148,196-231) and its autograd backward.
+ * params / buffers / grads are HOST arrays of device pointers in backbone.named_parameters() / named_buffers() order. */
+void* mmnn_encoder_create(int in_channels, const int* block_config /*HOST*/, int nblocks, int init_features,
+                          int growth_rate, int bn_size);
+void mmnn_encoder_destroy(void* plan);
+int mmnn_encoder_num_params(void* plan);
+int mmnn_encoder_num_buffers(void* plan);
+int mmnn_encoder_num_layers(void* plan);
+long long mmnn_encoder_param_numel(void* plan, int index);
+int mmnn_encoder_out_channels(void* plan);
+long long mmnn_encoder_workspace_bytes(void* plan, int B, int X, int Y, int Z);
+int mmnn_encoder_out_dims(void* plan, int B, int X, int Y, int Z, int* out_dhw /*HOST [3]*/);
+int mmnn_encoder_debug_offsets(void* plan, int B, int X, int Y, int Z, long long* offs /*HOST*/, long long* dims /*HOST*/);
+/* image fp32 NCDHW [B][cin][X][Y][Z];  dropmask fp32 [layers][B][32] keep/(1-p) or NULL;  out fp32 [B*d*h*w][C] NDHWC */
+int mmnn_encoder_forward(void* plan, int B, int X, int Y, int Z, const float* image, const void* const* params /*HOST*/,
+                         void* const* buffers /*HOST*/, const float* dropmask, void* workspace, float* out, int training,
+                         void* stream);
+/* grad_out fp32 [B*d*h*w][C];  grads: zero-initialised fp32 tensors shaped like the parameters */
+int mmnn_encoder_backward(void* plan, int B, int X, int Y, int Z, const void* const* params /*HOST*/,
+                          void* const* buffers /*HOST*/, void* const* grads /*HOST*/, const float* dropmask, void* workspace,
+                          const float* grad_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ trunk (fine-grained)
+ * The tcgen05 tile engine behind the trunk, exposed for per-kernel parity tests.
+ * mmnn_conv_rows  : implicit-GEMM forward / data-gradient of nn.Conv3d 1x1x1, 3x3x3 (pad 1), 7x7x7 (stride 2, pad 3)
+ *                   (/root/reference/models/densenet.py:78,82,147,199) with fused BN+ReLU prologue, fused
+ *                   per-channel statistics / ReLU-mask epilogue.  amode 0 linear/3x3x3, 1 stem;  trans 0 none,
+ *                   1 BN+ReLU;  epi 0 store, 1 store+stats, 2 relu-mask+BN-backward stats;  grad 0 fwd, 1 dgrad.
+ * mmnn_conv_wgrad : weight gradient of the same convolutions (kind 0 1x1x1, 1 3x3x3, 2 raw x raw, 3 stem).
+ * mmnn_pack_weights: fp32 master weights -> 16-bit k-block images (descs is a HOST array).
+ * struct layouts: mmnn_sts_b200/csrc/engine.cuh (RowsParams, WgradParams), pack.cuh (PackDesc); sizes are checked by
+ * the mmnn_sizeof_* functions against the ctypes mirrors in mmnn_sts_b200/_lib.py. */
+struct RowsParams;
+struct WgradParams;
+struct PackDesc;
+int mmnn_conv_rows(const struct RowsParams* p /*HOST*/, int amode, int trans, int epi, int grad, void* stream);
+int mmnn_conv_wgrad(const struct WgradParams* p /*HOST*/, int kind, int split, void* stream);
+int mmnn_pack_weights(const struct PackDesc* descs /*HOST*/, int n, void* dev_descs, void* stream);
+int mmnn_sizeof_rows_params(void);
+int mmnn_sizeof_wgrad_params(void);
+int mmnn_sizeof_pack_desc(void);
+int mmnn_act_is_fp16(void);
+
+/* ------------------------------------------------------------------------------------------------ heads
+ * mmnn_gap_linear_* : DenseNet.features = ReLU -> AdaptiveAvgPool3d(1) -> Flatten -> Linear -> Dropout
+ *                     (/root/reference/models/densenet.py:234-247).  y fp32 [B][V][C]; mask [B][F] keep/(1-p) or NULL. */
+int mmnn_gap_linear_fwd(const float* y, int B, int V, int C, const float* W, const float* bias, const float* mask, int F,
+                        float* pooled, float* out, void* stream);
+int mmnn_gap_linear_bwd(const float* y, const float* pooled, int B, int V, int C, const float* W, const float* dout,
+                        const float* mask, int F, float* dy, float* dW, float* db, void* stream);
+/* mmnn_mlp_heads    : MLP.backbone + MLP.features (/root/reference/models/mlp.py:19-51) and the three output heads of
+ *                     MultiModalModel.forward (/root/reference/models/multimodal.py:61-77), forward (backward = 0) or
+ *                     backward (1).  MlpArgs: mmnn_sts_b200/csrc/heads.cu. */
+struct MlpArgs;
+int mmnn_mlp_heads(const struct MlpArgs* args /*HOST*/, int backward, void* stream);
+int mmnn_sizeof_mlp_args(void);
+/* mmnn_cox_nll      : pycox CoxPHLoss as called from CoxPH (/root/reference/losses/losses.py:6-9), S segments
+ *                     (head x class) per launch: loss [S] and dloss/dlog_h [S][N].  CoxArgs: heads.cu. */
+struct CoxArgs;
+int mmnn_cox_nll(const struct CoxArgs* args /*HOST*/, void* stream);
+int mmnn_sizeof_cox_args(void);
+/* mmnn_cindex_bootstrap : lifelines concordance_index pair counts as used by getCIndices and the bootstrap loop
+ *                     (/root/reference/main.py:106-123,768-887): int64 (correct, tied, pairs) per resample. */
+struct CindexArgs;
+int mmnn_cindex_bootstrap(const struct CindexArgs* args /*HOST*/, void* stream);
+int mmnn_sizeof_cindex_args(void);
+
+/* ------------------------------------------------------------------------------------------------ instrumentation */
+void mmnn_profile_enable(int on);
+long long mmnn_launch_count(void);
+int mmnn_profile_collect(float* ms /*HOST*/, int* counts /*HOST*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMNN_B200_H */

@@ -8,9 +8,9 @@
 //   * as an MN-major operand (wgrad: M or N = channel, K = row/voxel)  SBO = plane stride, LBO = 128 B
 // so one producer routine feeds forward, data-gradient and weight-gradient GEMMs.
 //
-// Roles (160 threads): warps 0-3 = producers (gather + BN/ReLU transform of the activation operand, 16-byte
-// vector loads, conflict-free 16-byte shared stores) and, after the K loop, the epilogue (TMEM -> registers ->
-// global, fused per-channel statistics);  warp 4 = TMEM allocator + single-thread tcgen05.mma issuer.
+// Roles (288 threads): warps 0-7 = producers (gather + BN/ReLU transform of the activation operand, 16-byte
+// vector loads, conflict-free 16-byte shared stores); warps 0-3 additionally run the epilogue after the K loop
+// (TMEM -> registers -> global, fused per-channel statistics);  warp 8 = TMEM allocator + single-thread tcgen05.mma issuer.
 // Weights arrive with one cp.async.bulk (TMA unit, 1-D) per k-block from a pre-packed image.
 // Pipelines: full[stage] (128 producer arrivals + 1 expect_tx arrival), empty[stage] (tcgen05.commit), accum (commit).
 #pragma once
@@ -20,8 +20,12 @@ namespace mmnn {
 
 constexpr int TILE_ROWS = 128;
 constexpr int PLANE_BYTES = TILE_ROWS * 16 + 16;  // +16 B pad: chunk planes land on distinct 16-byte bank groups
-constexpr int NUM_PRODUCER_THREADS = 128;
-constexpr int ENGINE_THREADS = 160;
+constexpr int PRODUCER_WARPS = 8;   // a lone warp per scheduler cannot hide its own ALU/LDS latency: 8 warps share a k-block
+constexpr int NUM_PRODUCER_THREADS = PRODUCER_WARPS * 32;
+constexpr int EPILOGUE_THREADS = 128;  // warps 0-3: one TMEM lane quarter each
+constexpr int MMA_WARP = PRODUCER_WARPS;
+constexpr int ENGINE_THREADS = NUM_PRODUCER_THREADS + 32;
+constexpr int MAX_PASSES = 32 / PRODUCER_WARPS;
 
 // Where a BatchNorm's per-channel scale/shift comes from (batch statistics accumulated by a producer kernel's
 // epilogue, or running statistics in eval mode).
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
   while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
 
   // ---------------- prologue
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS + 1);
@@ -217,40 +221,40 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
+  if (warp < PRODUCER_WARPS) {
     // ================= producers
-    // Register double buffering: the 16-byte loads of k-block kb+1 are issued BEFORE k-block kb is transformed and
-    // stored, so every thread keeps up to 16 independent 128-bit loads in flight across the empty-slot wait.
+    // A k-block is 128 rows x cpl 16-byte cells.  One warp-wide 128-bit load covers rpp = 32/cpl rows x (cpl*16)
+    // contiguous bytes ("group"); warp w owns groups w, w+8, ...  Register double buffering: the loads of k-block
+    // kb+1 are issued BEFORE k-block kb is transformed and stored, so loads stay in flight across the slot wait.
     struct KbGeom { int cb, cpl, dz, dy, dx; long long delta; };
-    auto geom = [&](int kb) {
+    auto geom = [&](int tap, int cb) {
       KbGeom gq;
-      const int tap = kb / kb_per_tap;
-      gq.cb = kb - tap * kb_per_tap;
-      int cpl = (p.Cin - gq.cb * p.kbw) / 8;
+      gq.cb = cb;
+      int cpl = (p.Cin - cb * p.kbw) / 8;
       gq.cpl = cpl > planes ? planes : cpl;
       gq.dz = gq.dy = gq.dx = 0; gq.delta = 0;
       if (AMODE == A_STEM) {
         gq.delta = (long long)((tap >> 2) * p.Sy + (tap & 3)) * p.Sx;
       } else if (p.ntaps == 27) {
-        gq.dz = (tap / 9 - 1) * p.tap_sign; gq.dy = ((tap / 3) % 3 - 1) * p.tap_sign; gq.dx = (tap % 3 - 1) * p.tap_sign;
+        const int t9 = tap / 9, t3 = (tap - t9 * 9) / 3;
+        gq.dz = (t9 - 1) * p.tap_sign; gq.dy = (t3 - 1) * p.tap_sign; gq.dx = (tap - t9 * 9 - t3 * 3 - 1) * p.tap_sign;
         gq.delta = (long long)(gq.dz * p.Dy + gq.dy) * p.Dx + gq.dx;
       }
       return gq;
     };
-    // lane -> (chunk, row sub-index): a warp-wide 16-byte load covers 32/cpl rows x (cpl*16) contiguous bytes
-    auto load_kb = [&](const KbGeom& gq, uint4 (&regs)[8], uint32_t& okmask) {
+    auto load_kb = [&](const KbGeom& gq, uint4 (&regs)[MAX_PASSES], uint32_t& okmask) {
       const int cshift = (gq.cpl == 8) ? 3 : 2;
       const int chunk = lane & (gq.cpl == 8 ? 7 : 3);
       const int rsub = lane >> cshift;
       const int rpp = 32 >> cshift;
-      const int npass = 32 / rpp;
+      const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
       const int ch0 = gq.cb * p.kbw + chunk * 8;
       okmask = 0;
 #pragma unroll
-      for (int ps = 0; ps < 8; ++ps) {
+      for (int ps = 0; ps < MAX_PASSES; ++ps) {
         regs[ps] = make_uint4(0, 0, 0, 0);
         if (ps < npass) {
-          const int r = warp * 32 + ps * rpp + rsub;
+          const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
           const int4 ri = rowinfo[r];
           bool ok = ri.y > -1000;
           if (AMODE == A_LINEAR_CONV) {
@@ -264,16 +268,19 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         }
       }
     };
-    uint4 cur[8], nxt[8];
+    uint4 cur[MAX_PASSES], nxt[MAX_PASSES];
     uint32_t cur_ok = 0, nxt_ok = 0;
-    KbGeom gcur = geom(0), gnxt = gcur;
+    int tap_n = 0, cb_n = 0;   // (tap, cb) of the NEXT k-block to load
+    KbGeom gcur = geom(0, 0), gnxt = gcur;
     load_kb(gcur, cur, cur_ok);
+    if (++cb_n == kb_per_tap) { cb_n = 0; ++tap_n; }
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % S;
-      const uint32_t ph = (uint32_t)(kb / S) & 1u;
       if (kb + 1 < KB) {
-        gnxt = geom(kb + 1);
+        gnxt = geom(tap_n, cb_n);
         load_kb(gnxt, nxt, nxt_ok);
+        if (++cb_n == kb_per_tap) { cb_n = 0; ++tap_n; }
       }
       mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
       const uint32_t sA = stage0 + s * stage_bytes;
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         const int chunk = lane & (gcur.cpl == 8 ? 7 : 3);
         const int rsub = lane >> cshift;
         const int rpp = 32 >> cshift;
-        const int npass = 32 / rpp;
+        const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
         const int ch0 = gcur.cb * p.kbw + chunk * 8;
         float sc[8], sh[8];
         if (TRANS == T_BNRELU) {
@@ -295,9 +302,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
           for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
         }
 #pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
+        for (int ps = 0; ps < MAX_PASSES; ++ps) {
           if (ps < npass) {
-            const int r = warp * 32 + ps * rpp + rsub;
+            const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
             uint4 v = cur[ps];
             if (TRANS == T_BNRELU && ((cur_ok >> ps) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
             sts16(sA + chunk * PLANE_BYTES + r * 16, v);
@@ -307,9 +314,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
       fence_proxy_async_smem();
       mbar_arrive(bar_full + 8 * s);
 #pragma unroll
-      for (int ps = 0; ps < 8; ++ps) cur[ps] = nxt[ps];
+      for (int ps = 0; ps < MAX_PASSES; ++ps) cur[ps] = nxt[ps];
       cur_ok = nxt_ok; gcur = gnxt;
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
+  }
+  if (warp < 4) {
     // ================= epilogue (same warps: TMEM lane quarter == warp index)
     mbar_wait(bar_accum, 0, 3);
     tc_fence_after();
@@ -382,8 +392,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
       }
     }
     if (EPI != EP_STORE) {
-      named_bar_sync(1, NUM_PRODUCER_THREADS);
-      for (int c = tid; c < p.NT; c += NUM_PRODUCER_THREADS) {
+      named_bar_sync(1, EPILOGUE_THREADS);
+      for (int c = tid; c < p.NT; c += EPILOGUE_THREADS) {
         const int col = tile_n * p.NT + c;
         if (col < p.Ncols) {
           const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
@@ -393,8 +403,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         }
       }
     }
-  } else {
-    // ================= MMA issuer (warp 4, one elected lane)
+  } else if (warp == MMA_WARP) {
+    // ================= MMA issuer (one elected lane)
     const uint32_t idesc = make_idesc(TILE_ROWS, p.NT, 0, 0, OP_F16);
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % S;
@@ -422,7 +432,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 }  // namespace mmnn
@@ -479,17 +489,17 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
   const int gshift = planes >= 8 ? 3 : 2;
   const int rsub = lane >> gshift;
   const int rpp = 32 >> gshift;
-  const int npass = 32 / rpp;
+  const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
   for (int grp = 0; grp < (planes + G - 1) / G; ++grp) {
     const int chunk = grp * G + (lane & (G - 1));
     if (chunk >= planes) continue;  // planes is a multiple of 4 but not necessarily of G
-    uint4 regs[8];
+    uint4 regs[MAX_PASSES];
     uint32_t okmask = 0;
 #pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
+    for (int ps = 0; ps < MAX_PASSES; ++ps) {
       regs[ps] = make_uint4(0, 0, 0, 0);
       if (ps < npass) {
-        const int r = warp * 32 + ps * rpp + rsub;
+        const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
         const int4 ri = rowinfo[r];
         bool ok = ri.y > -1000;
         if (SHIFTED) {
@@ -508,9 +518,9 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
       for (int e = 0; e < 8; ++e) { sc[e] = scale[chunk * 8 + e]; sh[e] = shift[chunk * 8 + e]; }
     }
 #pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
+    for (int ps = 0; ps < MAX_PASSES; ++ps) {
       if (ps < npass) {
-        const int r = warp * 32 + ps * rpp + rsub;
+        const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
         uint4 v = regs[ps];
         if ((okmask >> ps) & 1u) {
           if (TRANS == T_BNRELU) apply_bnrelu8<IN_F16, false>(v, sc, sh);
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < p.NB * p.CB) tmem_cols <<= 1;
 
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS);
@@ -597,7 +607,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
+  if (warp < PRODUCER_WARPS) {
     // valid plane counts (multiples of 4) of the A / B tiles handled by this CTA
     int aplanes = 16;
     if (AMODE == WA_LINEAR) { int rem = (p.na_total - ztile * 128) / 8; aplanes = rem < 16 ? rem : 16; }
@@ -608,7 +618,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(bar_empty + 8 * s, ph ^ 1u, 11);
       int4* rowinfo = rowinfo_all + s * TILE_ROWS;
-      {
+      if (tid < TILE_ROWS) {
         const long long m = (long long)(t_begin + it) * TILE_ROWS + tid;
         int4 ri;
         if (m < p.M) {
@@ -643,7 +653,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         // B rows are plain output-voxel rows: rebuild the linear index for them
         named_bar_sync(1, NUM_PRODUCER_THREADS);
         const long long m = (long long)(t_begin + it) * TILE_ROWS + tid;
-        if (m < p.M) rowinfo[tid].x = (int)m;
+        if (tid < TILE_ROWS && m < p.M) rowinfo[tid].x = (int)m;
         named_bar_sync(1, NUM_PRODUCER_THREADS);
       }
       if (p.NB == 1) {
@@ -662,6 +672,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       fence_proxy_async_smem();
       mbar_arrive(bar_full + 8 * s);
     }
+  }
+  if (warp < 4) {
     // ---- epilogue: TMEM lane = A channel
     mbar_wait(bar_accum, 0, 13);
     tc_fence_after();
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         }
       }
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     const uint32_t idesc = make_idesc(128, p.CB, 1, 1, false);
     for (int it = 0; it < nt; ++it) {
       const int s = it % S;
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 }  // namespace mmnn

@@ -16,11 +16,12 @@ class MultiModalModel(nn.Module):
         self.num_classes = num_classes
         self.num_features = num_features
         self.num_clinical_inputs = len(clinical_predictors)
-        clinical = MLP(self.num_clinical_inputs, self.num_classes, self.num_features)
+        # registration order = the reference's (image_model, clinical_model, output_head, clinical_output_head,
+        # image_output_head) so that state_dict() enumerates the 779 keys in the same order
+        self.image_model = BackpropagatableFeatureExtractor(image_model)
+        self.clinical_model = BackpropagatableFeatureExtractor(MLP(self.num_clinical_inputs, self.num_classes, self.num_features))
         self.output_head = nn.Linear(self.num_features * 2, self.num_classes)
         self.blend = blend
-        self.image_model = BackpropagatableFeatureExtractor(image_model)
-        self.clinical_model = BackpropagatableFeatureExtractor(clinical)
         self.clinical_output_head = nn.Linear(self.num_features, self.num_classes)
         self.image_output_head = nn.Linear(self.num_features, self.num_classes)
 
