@@ -54,9 +54,14 @@ int mmnn_encoder_backward(void* plan, int B, int X, int Y, int Z, const void* co
  * struct layouts: mmnn_sts_b200/csrc/engine.cuh (RowsParams, WgradParams), pack.cuh (PackDesc); sizes are checked by
  * the mmnn_sizeof_* functions against the ctypes mirrors in mmnn_sts_b200/_lib.py. */
 struct RowsParams;
+struct BrickParams;
 struct WgradParams;
 struct PackDesc;
 int mmnn_conv_rows(const struct RowsParams* p /*HOST*/, int amode, int trans, int epi, int grad, void* stream);
+/* mmnn_conv3_brick: the 3x3x3 forward / data-gradient in "brick mode" (halo brick of a 1x16x8 tile staged once in
+ *                   shared memory, taps = descriptor start addresses); used when the spatial dims are >= 8. */
+int mmnn_conv3_brick(const struct BrickParams* p /*HOST*/, int grad, void* stream);
+int mmnn_sizeof_brick_params(void);
 int mmnn_conv_wgrad(const struct WgradParams* p /*HOST*/, int kind, int split, void* stream);
 int mmnn_pack_weights(const struct PackDesc* descs /*HOST*/, int n, void* dev_descs, void* stream);
 int mmnn_sizeof_rows_params(void);

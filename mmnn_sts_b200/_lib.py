@@ -40,6 +40,14 @@ class RowsParams(C.Structure):
                 ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int)]
 
 
+class BrickParams(C.Structure):
+    _fields_ = [("B", C.c_int), ("Dz", C.c_int), ("Dy", C.c_int), ("Dx", C.c_int), ("CH", C.c_int), ("NT", C.c_int),
+                ("tap_sign", C.c_int), ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
+                ("b_packed", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_longlong), ("colscale", C.c_void_p),
+                ("st_sum", C.c_void_p), ("st_sq", C.c_void_p), ("e_src", C.c_void_p), ("e_pitch", C.c_longlong),
+                ("bnE", BnSrc)]
+
+
 class WgradParams(C.Structure):
     _fields_ = [("M", C.c_int), ("CB", C.c_int), ("NB", C.c_int), ("na_total", C.c_int), ("nb_total", C.c_int),
                 ("Dz", C.c_int), ("Dy", C.c_int), ("Dx", C.c_int), ("Sz", C.c_int), ("Sy", C.c_int), ("Sx", C.c_int),
@@ -94,6 +102,9 @@ def _declare(l):
     l.mmnn_conv_rows.restype = C.c_int
     l.mmnn_pack_weights.argtypes = [C.POINTER(PackDesc), C.c_int, C.c_void_p, C.c_void_p]
     l.mmnn_pack_weights.restype = C.c_int
+    l.mmnn_conv3_brick.argtypes = [C.POINTER(BrickParams), C.c_int, C.c_void_p]
+    l.mmnn_conv3_brick.restype = C.c_int
+    assert l.mmnn_sizeof_brick_params() == C.sizeof(BrickParams), (l.mmnn_sizeof_brick_params(), C.sizeof(BrickParams))
     l.mmnn_conv_wgrad.argtypes = [C.POINTER(WgradParams), C.c_int, C.c_int, C.c_void_p]
     l.mmnn_conv_wgrad.restype = C.c_int
     assert l.mmnn_sizeof_wgrad_params() == C.sizeof(WgradParams), (l.mmnn_sizeof_wgrad_params(), C.sizeof(WgradParams))

@@ -1,0 +1,327 @@
+// Brick-mode 3x3x3 convolution (forward and data-gradient) for the large dense blocks.
+//
+// The gather engine (engine.cuh) rebuilds the A operand once per tap: 27 loads + 27 BN/ReLU transforms per input
+// element -- it is instruction-issue bound (ncu: 71 % issue slots busy, 4.6 % tensor pipe; profiles/r01_*).
+// Here a persistent CTA stages the input HALO BRICK of one output tile (1 x 16 x 8 voxels -> 3 x 18 x 10 voxel slots)
+// in shared memory ONCE (one load + one transform per element, 4.2x the tile instead of 27x) in the chunk-plane layout
+//      brick[chunk][slot]  (16-byte cells, slot = (z'*18 + y')*10 + x')
+// and every tap is just a different START ADDRESS of the same SWIZZLE_NONE K-major descriptor:
+//      start = plane0 + ((dz*18 + dy)*10 + dx)*16,  SBO (next 8-row group = next y) = 10*16 B,  LBO = plane stride.
+// Warp roles (448 threads): 0-7 producers, 8 MMA issuer + TMEM owner, 9 weight loader (cp.async.bulk ring),
+// 10-13 epilogue (TMEM double-buffered, so the epilogue of tile t overlaps the MMAs of tile t+1).
+#pragma once
+#include "engine.cuh"
+
+namespace mmnn {
+
+constexpr int BR_TY = 16, BR_TX = 8, BR_HY = BR_TY + 2, BR_HX = BR_TX + 2;
+constexpr int BR_SLOTS = 3 * BR_HY * BR_HX;            // 540
+constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple of 16 -> conflict-free chunk planes
+constexpr int BR_THREADS = 448;
+constexpr int BR_MMA_WARP = 8, BR_LOAD_WARP = 9, BR_EPI_WARP0 = 10;
+constexpr int BR_BSTAGES = 4;
+
+struct BrickParams {
+  int B, Dz, Dy, Dx;
+  int CH;        // A channels per tap: 128 (fprop) or 32 (dgrad)
+  int NT;        // output columns: 32 (fprop) or 128 (dgrad)
+  int tap_sign;
+  const bf16* a_src;
+  long long a_pitch;
+  BnSrc bnA;
+  const bf16* b_packed;   // [tap*NH + h][planes][NT][8]
+  bf16* out;
+  long long out_pitch;
+  const float* colscale;
+  double* st_sum;
+  double* st_sq;
+  const bf16* e_src;
+  long long e_pitch;
+  BnSrc bnE;
+};
+
+__host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* offs /*[6]*/) {
+  const int PH = CH >= 64 ? 8 : CH / 8;
+  uint32_t o = 0;
+  offs[0] = o; o += 256;                       // barriers + tmem ptr
+  offs[1] = o; o += 2u * CH * 4;               // coefA
+  offs[2] = o; o += 4u * NT * 4;               // coefE
+  offs[3] = o; o += 8u * NT * 4;               // red
+  o = (o + 127u) & ~127u;
+  offs[4] = o; o += 2u * PH * BR_PLANE;        // two brick buffers
+  o = (o + 127u) & ~127u;
+  offs[5] = o; o += BR_BSTAGES * (uint32_t)PH * NT * 16;
+  return o;
+}
+
+template <int TRANS, int EPI, bool GRAD>
+__global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid_constant__ BrickParams p) {
+  constexpr bool OP_F16 = !GRAD && kActF16;
+  constexpr bool E_F16 = kActF16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint32_t offs[6];
+  brick_smem_layout(p.CH, p.NT, offs);
+  const uint32_t sbase = smem_u32(smem);
+  // barrier map (8 B each): brick_full[2] 0,1 | brick_empty[2] 2,3 | b_full[4] 4..7 | b_empty[4] 8..11 | acc_full[2] 12,13 | acc_empty[2] 14,15
+  const uint32_t bars = sbase + offs[0];
+  auto BAR = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 16);
+  float* coefA = reinterpret_cast<float*>(smem + offs[1]);
+  float* coefE = reinterpret_cast<float*>(smem + offs[2]);
+  float* red = reinterpret_cast<float*>(smem + offs[3]);
+  const int PH = p.CH >= 64 ? 8 : p.CH / 8;      // planes per brick buffer
+  const int NH = p.CH >= 64 ? p.CH / 64 : 1;     // brick buffers ("halves") per tile
+  const uint32_t brick0 = sbase + offs[4];
+  const uint32_t brick_bytes = (uint32_t)PH * BR_PLANE;
+  const uint32_t bst0 = sbase + offs[5];
+  const uint32_t b_bytes = (uint32_t)PH * p.NT * 16;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_y = (p.Dy + BR_TY - 1) / BR_TY, tiles_x = (p.Dx + BR_TX - 1) / BR_TX;
+  const int ntiles = p.B * p.Dz * tiles_y * tiles_x;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int vps = p.Dz * p.Dy * p.Dx;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
+
+  if (warp == BR_MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), NUM_PRODUCER_THREADS); mbar_init(BAR(2 + i), 1); }
+      for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(8 + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(12 + i), 1); mbar_init(BAR(14 + i), EPILOGUE_THREADS); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+  }
+  if (TRANS == T_BNRELU) {
+    for (int c = tid; c < p.CH; c += BR_THREADS) {
+      float mean, rstd;
+      bn_mean_rstd(p.bnA, c, mean, rstd);
+      const float s = p.bnA.gamma[c] * rstd;
+      coefA[c] = s;
+      coefA[p.CH + c] = p.bnA.beta[c] - mean * s;
+    }
+  }
+  if (EPI == EP_MASK_STATS) {
+    for (int c = tid; c < p.NT; c += BR_THREADS) {
+      float mean, rstd;
+      bn_mean_rstd(p.bnE, c, mean, rstd);
+      const float s = p.bnE.gamma[c] * rstd;
+      coefE[c] = s; coefE[p.NT + c] = p.bnE.beta[c] - mean * s; coefE[2 * p.NT + c] = mean; coefE[3 * p.NT + c] = rstd;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_coords = [&](int t, int& n, int& z, int& y0, int& x0) {
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y; t /= tiles_y;
+    z = t % p.Dz; n = t / p.Dz;
+    y0 = ty * BR_TY; x0 = tx * BR_TX;
+  };
+
+  if (warp < PRODUCER_WARPS) {
+    // ================= producers: one load + one transform per brick cell
+    const int cells = BR_SLOTS * PH;
+    for (int it = 0; it < my_tiles; ++it) {
+      int n, z, y0, x0;
+      tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+      for (int h = 0; h < NH; ++h) {
+        const int seq = it * NH + h;
+        const int q = seq & 1;
+        const uint32_t par = (uint32_t)(seq >> 1) & 1u;
+        mbar_wait(BAR(2 + q), par ^ 1u, 21);
+        const uint32_t dst = brick0 + q * brick_bytes;
+        // 8 (or 4) consecutive threads = the chunks of one voxel slot = PH*16 contiguous source bytes.
+        // NUM_PRODUCER_THREADS is a multiple of PH, so a thread keeps the same chunk for all its cells.
+        const int chunk = (PH == 8) ? (tid & 7) : (tid & 3);
+        const int ch0 = h * 64 + chunk * 8;
+        float sc[8], sh[8];
+        if (TRANS == T_BNRELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.CH + ch0 + e]; }
+        }
+        for (int c0 = 0; c0 < cells; c0 += NUM_PRODUCER_THREADS * 4) {
+          uint4 regs[4];
+          uint32_t okmask = 0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * NUM_PRODUCER_THREADS + tid;
+            regs[u] = make_uint4(0, 0, 0, 0);
+            if (c < cells) {
+              const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
+              const int xx = slot % BR_HX;
+              const int r2 = slot / BR_HX;
+              const int yy = r2 % BR_HY, zz = r2 / BR_HY;
+              // slot (zz,yy,xx) holds the source voxel (z + zz-1, y0 + yy-1, x0 + xx-1); zeros outside the volume
+              const int sz = z + (zz - 1), sy = y0 + (yy - 1), sx = x0 + (xx - 1);
+              if (sz >= 0 && sz < p.Dz && sy >= 0 && sy < p.Dy && sx >= 0 && sx < p.Dx) {
+                const long long m = (((long long)n * p.Dz + sz) * p.Dy + sy) * p.Dx + sx;
+                regs[u] = ldg16(p.a_src + m * p.a_pitch + ch0);
+                okmask |= 1u << u;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * NUM_PRODUCER_THREADS + tid;
+            if (c < cells) {
+              const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
+              uint4 v = regs[u];
+              if (TRANS == T_BNRELU && ((okmask >> u) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+              sts16(dst + chunk * BR_PLANE + slot * 16, v);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(BAR(q));
+      }
+    }
+  } else if (warp == BR_LOAD_WARP) {
+    // ================= weight loader: ring of BR_BSTAGES k-block images
+    if (lane == 0) {
+      int j = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int h = 0; h < NH; ++h)
+          for (int tap = 0; tap < 27; ++tap, ++j) {
+            const int s = j % BR_BSTAGES;
+            const uint32_t par = (uint32_t)(j / BR_BSTAGES) & 1u;
+            mbar_wait(BAR(8 + s), par ^ 1u, 22);
+            mbar_arrive_expect_tx(BAR(4 + s), b_bytes);
+            bulk_g2s(bst0 + s * b_bytes, p.b_packed + (size_t)(tap * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
+          }
+    }
+  } else if (warp == BR_MMA_WARP) {
+    // ================= MMA issuer
+    const uint32_t idesc = make_idesc(TILE_ROWS, p.NT, 0, 0, OP_F16);
+    int j = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int abuf = it & 1;
+      const uint32_t apar = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(BAR(14 + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
+      tc_fence_after();
+      for (int h = 0; h < NH; ++h) {
+        const int seq = it * NH + h;
+        const int q = seq & 1;
+        mbar_wait(BAR(q), (uint32_t)(seq >> 1) & 1u, 24);
+        tc_fence_after();
+        const uint32_t src = brick0 + q * brick_bytes;
+        for (int tap = 0; tap < 27; ++tap, ++j) {
+          const int s = j % BR_BSTAGES;
+          mbar_wait(BAR(4 + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
+          tc_fence_after();
+          if (lane == 0) {
+            const int t9 = tap / 9, t3 = (tap - t9 * 9) / 3, t1 = tap - t9 * 9 - t3 * 3;
+            // tap offset d = (t-1)*tap_sign; the window of slots read for output (y,x) is (d+1, y+d+1, x+d+1)
+            const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
+            const uint32_t a0 = src + (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u;
+            const uint32_t b0 = bst0 + s * b_bytes;
+            for (int k16 = 0; k16 < PH / 2; ++k16) {
+              const uint64_t ad = make_smem_desc(a0 + k16 * 2 * BR_PLANE, BR_PLANE, BR_HX * 16);
+              const uint64_t bd = make_smem_desc(b0 + k16 * 2 * p.NT * 16, p.NT * 16, 128);
+              tc_mma_bf16(tmem_base + abuf * p.NT, ad, bd, idesc, (h > 0 || tap > 0 || k16 > 0) ? 1u : 0u);
+            }
+            tc_commit(BAR(8 + s));
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          tc_commit(BAR(2 + q));
+          if (h == NH - 1) tc_commit(BAR(12 + abuf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= BR_EPI_WARP0) {
+    // ================= epilogue (TMEM lane quarter = warp % 4)
+    const int qd = warp & 3;
+    const int etid = (warp - BR_EPI_WARP0) * 32 + lane;
+    const int r = qd * 32 + lane;
+    const int ry = r >> 3, rx = r & 7;
+    float acc1[4] = {0, 0, 0, 0}, acc2[4] = {0, 0, 0, 0};   // per-lane column partials, NT/32 <= 4 chunks
+    for (int it = 0; it < my_tiles; ++it) {
+      int n, z, y0, x0;
+      tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+      const int abuf = it & 1;
+      mbar_wait(BAR(12 + abuf), (uint32_t)(it >> 1) & 1u, 26);
+      tc_fence_after();
+      const bool row_ok = (y0 + ry < p.Dy) && (x0 + rx < p.Dx);
+      const long long m = (((long long)n * p.Dz + z) * p.Dy + (y0 + ry)) * p.Dx + (x0 + rx);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 32 >= p.NT) break;
+        float v[32], qv[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * p.NT + cc * 32), v);
+        if (EPI == EP_MASK_STATS) {
+          uint4 xv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = row_ok ? ldg16(p.e_src + m * p.e_pitch + cc * 32 + i * 8) : make_uint4(0, 0, 0, 0);
+          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float xlo, xhi;
+            unpack2<E_F16>(xw[jj >> 1], xlo, xhi);
+            const float x = (jj & 1) ? xhi : xlo;
+            const int c = cc * 32 + jj;
+            const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
+            const float g = (row_ok && act) ? round16<OP_F16>(v[jj]) : 0.f;
+            v[jj] = g;
+            qv[jj] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
+          }
+        } else {
+          if (p.colscale != nullptr) {
+            const float* cs = p.colscale + (size_t)n * p.NT + cc * 32;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] *= __ldg(cs + jj);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float g = row_ok ? round16<OP_F16>(v[jj]) : 0.f;
+            v[jj] = g;
+            qv[jj] = g * g;
+          }
+        }
+        if (row_ok) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
+            o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
+            op[i] = o;
+          }
+        }
+        if (EPI != EP_STORE) {
+          acc1[cc] += warp_transpose_sum32(v, lane);
+          acc2[cc] += warp_transpose_sum32(qv, lane);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(14 + abuf));
+    }
+    if (EPI != EP_STORE) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 32 < p.NT) {
+          red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = acc1[cc];
+          red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = acc2[cc];
+        }
+      }
+      named_bar_sync(1, EPILOGUE_THREADS);
+      for (int c = etid; c < p.NT; c += EPILOGUE_THREADS) {
+        const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
+        const float b = red[(1 * 4 + 0) * p.NT + c] + red[(1 * 4 + 1) * p.NT + c] + red[(1 * 4 + 2) * p.NT + c] + red[(1 * 4 + 3) * p.NT + c];
+        atomicAdd(p.st_sum + c, (double)a);
+        atomicAdd(p.st_sq + c, (double)b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == BR_MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace mmnn

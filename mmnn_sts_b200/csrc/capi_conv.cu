@@ -1,5 +1,6 @@
 // C-ABI entry points for the tcgen05 tile engine (fine-grained: used by the per-kernel parity tests and by the
 // encoder orchestrator in encoder.cu).  Plain pointers and sizes only; see include/mmnn_b200.h.
+#include "brick.cuh"
 #include "engine.cuh"
 #include "pack.cuh"
 #include "prof.h"
@@ -51,6 +52,31 @@ int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cu
   CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS, true)
 #undef CASE
   return -3;
+}
+
+template <int TRANS, int EPI, bool GRAD>
+int launch_brick_t(const BrickParams& p, cudaStream_t stream) {
+  uint32_t offs[6];
+  const uint32_t smem = brick_smem_layout(p.CH, p.NT, offs);
+  auto kern = conv3_brick_kernel<TRANS, EPI, GRAD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int ntiles = p.B * p.Dz * ((p.Dy + BR_TY - 1) / BR_TY) * ((p.Dx + BR_TX - 1) / BR_TX);
+  const int grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
+  kern<<<grid, BR_THREADS, smem, stream>>>(p);
+  MMNN_CHECK_LAUNCH();
+  return 0;
+}
+
+// 3x3x3 convolution in brick mode: grad == 0 forward (BN+ReLU prologue, store + statistics), grad == 1 data gradient
+// (raw gradient operand, ReLU mask + BN-backward statistics epilogue)
+int launch_brick(const BrickParams& p, int grad, cudaStream_t stream) {
+  if (grad == 0) {
+    if (p.CH != 128 || p.NT != 32) return -2;
+    return launch_brick_t<T_BNRELU, EP_STORE_STATS, false>(p, stream);
+  }
+  if (p.CH != 32 || p.NT != 128) return -2;
+  return launch_brick_t<T_NONE, EP_MASK_STATS, true>(p, stream);
 }
 
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
@@ -118,6 +144,9 @@ int mmnn_profile_collect(float* ms, int* counts) {
   s.recs.clear();
   return PC_COUNT;
 }
+
+int mmnn_conv3_brick(const BrickParams* p, int grad, void* stream) { return launch_brick(*p, grad, (cudaStream_t)stream); }
+int mmnn_sizeof_brick_params() { return (int)sizeof(BrickParams); }
 
 int mmnn_conv_wgrad(const WgradParams* p, int kind, int split, void* stream) {
   return launch_wgrad(*p, kind, split, (cudaStream_t)stream);

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "brick.cuh"
 #include "eltwise.cuh"
 #include "engine.cuh"
 #include "pack.cuh"
@@ -24,6 +25,7 @@
 namespace mmnn {
 int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream);
+int launch_brick(const BrickParams& p, int grad, cudaStream_t stream);
 }  // namespace mmnn
 
 using namespace mmnn;
@@ -386,16 +388,32 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.out = bott; p.out_pitch = BOTT;
       p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
       { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
-      RowsParams q = {};
-      q.M = (int)M; q.NT = 32; q.Ncols = GROWTH; q.Cin = BOTT; q.kbw = 64; q.ntaps = 27; q.tap_sign = 1;
-      q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b];
-      q.a_src = bott; q.a_pitch = BOTT;
-      q.bnA = make_bn(li.n2, params, buffers, fstats, FC, M, batch);
-      q.b_packed = packed + li.pk_c2f;
-      q.out = buf + li.cin; q.out_pitch = bi.ctot;
-      q.colscale = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
-      q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
-      { ProfScope ps_(PC_CONV2_FPROP, st); RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
+      const float* cs = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
+      if (g.H[b] >= 8 && g.W[b] >= 8) {
+        // large blocks: halo brick staged once per tile, taps are descriptor offsets (brick.cuh)
+        BrickParams q = {};
+        q.B = B; q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b]; q.CH = BOTT; q.NT = GROWTH; q.tap_sign = 1;
+        q.a_src = bott; q.a_pitch = BOTT;
+        q.bnA = make_bn(li.n2, params, buffers, fstats, FC, M, batch);
+        q.b_packed = packed + li.pk_c2f;
+        q.out = buf + li.cin; q.out_pitch = bi.ctot;
+        q.colscale = cs;
+        q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
+        ProfScope ps_(PC_CONV2_FPROP, st);
+        RET_IF(launch_brick(q, 0, st));
+      } else {
+        RowsParams q = {};
+        q.M = (int)M; q.NT = 32; q.Ncols = GROWTH; q.Cin = BOTT; q.kbw = 64; q.ntaps = 27; q.tap_sign = 1;
+        q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b];
+        q.a_src = bott; q.a_pitch = BOTT;
+        q.bnA = make_bn(li.n2, params, buffers, fstats, FC, M, batch);
+        q.b_packed = packed + li.pk_c2f;
+        q.out = buf + li.cin; q.out_pitch = bi.ctot;
+        q.colscale = cs;
+        q.st_sum = fstats + bi.fwd_off + li.cin; q.st_sq = fstats + FC + bi.fwd_off + li.cin;
+        ProfScope ps_(PC_CONV2_FPROP, st);
+        RET_IF(launch_rows(q, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st));
+      }
     }
     if (bi.has_trans) {
       const BlockInfo& nx = pl->blocks[b + 1];
@@ -544,7 +562,17 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         RET_IF(launch_wgrad(w, 1, 0, st));
       }
       // conv2 dgrad (+ ReLU mask of norm2/relu2, + BN2 backward statistics)
-      {
+      if (g.H[b] >= 8 && g.W[b] >= 8) {
+        BrickParams q = {};
+        q.B = B; q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b]; q.CH = GROWTH; q.NT = BOTT; q.tap_sign = -1;
+        q.a_src = gslice; q.a_pitch = GROWTH;
+        q.b_packed = packed + li.pk_c2d;
+        q.out = dA2; q.out_pitch = BOTT;
+        q.st_sum = gsum(li.n2); q.st_sq = gdot(li.n2);
+        q.e_src = bott; q.e_pitch = BOTT; q.bnE = bn2;
+        ProfScope ps_(PC_CONV2_DGRAD, st);
+        RET_IF(launch_brick(q, 1, st));
+      } else {
         RowsParams p = {};
         p.M = (int)M; p.NT = 128; p.Ncols = BOTT; p.Cin = GROWTH; p.kbw = 32; p.ntaps = 27; p.tap_sign = -1;
         p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];

@@ -71,3 +71,22 @@ def wgrad(kind, M, CB, NB, na_total, nb_total, dims, a_src, a_pitch, b_src, b_pi
     p.dw, p.so_a, p.so_b, p.so_j = dw.data_ptr(), so_a, so_b, so_j
     p.cin_real, p.stages = cin_real, stages
     L.check(L.lib().mmnn_conv_wgrad(C.byref(p), kind, split, stream_ptr()), "conv_wgrad")
+
+
+def brick(B, dims, CH, NT, a_src, a_pitch, b_packed, out, out_pitch, grad=0, tap_sign=1, bnA=None, colscale=None,
+          st_sum=None, st_sq=None, e_src=None, e_pitch=0, bnE=None):
+    p = L.BrickParams()
+    p.B = B
+    p.Dz, p.Dy, p.Dx = dims
+    p.CH, p.NT, p.tap_sign = CH, NT, tap_sign
+    p.a_src, p.a_pitch = a_src.data_ptr(), a_pitch
+    p.bnA = bnA if bnA is not None else L.BnSrc()
+    p.b_packed = b_packed.data_ptr()
+    p.out, p.out_pitch = out.data_ptr(), out_pitch
+    p.colscale = colscale.data_ptr() if colscale is not None else None
+    p.st_sum = st_sum.data_ptr() if st_sum is not None else None
+    p.st_sq = st_sq.data_ptr() if st_sq is not None else None
+    p.e_src = e_src.data_ptr() if e_src is not None else None
+    p.e_pitch = e_pitch
+    p.bnE = bnE if bnE is not None else L.BnSrc()
+    L.check(L.lib().mmnn_conv3_brick(C.byref(p), grad, stream_ptr()), "conv3_brick")

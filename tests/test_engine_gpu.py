@@ -234,3 +234,70 @@ def test_wgrad_raw_and_stem():
         y = F.conv3d(_bf(_act(img)), w, stride=2, padding=3)
         (ref,) = torch.autograd.grad(y, w, dconv.float().view(B, Dz, Dy, Dx, 64).permute(0, 4, 1, 2, 3))
         assert (dw0 - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw0 - ref).abs().max()
+
+
+@pytest.mark.parametrize("dims,B", [((3, 20, 12), 2), ((4, 16, 8), 3), ((2, 32, 16), 40)])
+def test_brick_conv3_fprop(dims, B):
+    """Brick-mode 3x3x3 forward (BN+ReLU prologue, dropout scale, statistics) incl. partial tiles and a grid with
+    more tiles than SMs (persistent loop, TMEM double buffering)."""
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(8)
+    Dz, Dy, Dx = dims
+    Cin, N, Ctot = 128, 32, 96
+    M = B * Dz * Dy * Dx
+    bott = torch.randn(M, Cin, device="cuda").to(_actdt())
+    w = torch.randn(N, Cin, 3, 3, 3, device="cuda") * 0.05
+    gamma = torch.rand(Cin, device="cuda") + 0.5
+    beta = torch.randn(Cin, device="cuda") * 0.3
+    x = bott.float()
+    s1 = x.double().sum(0); s2 = (x.double() ** 2).sum(0)
+    keep = (torch.rand(B, N, device="cuda") > 0.3).float() / 0.7
+    bp = H.pack(w, N, 32, Cin, 64, 27, Cin * 27, 27, 1)
+    buf = torch.zeros(M, Ctot, dtype=_actdt(), device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.brick(B, dims, Cin, N, bott, Cin, bp, buf[:, 64:], Ctot, bnA=H.bnsrc(s1, s2, gamma, beta, count=M), colscale=keep,
+            st_sum=st[0], st_sq=st[1])
+    torch.cuda.synchronize()
+    x5 = x.view(B, Dz, Dy, Dx, Cin).permute(0, 4, 1, 2, 3)
+    a = _act(F.relu(F.batch_norm(x5, None, None, gamma, beta, True, 0.0, 1e-5)))
+    ref = (F.conv3d(a, _act(w), padding=1) * keep[:, :, None, None, None]).permute(0, 2, 3, 4, 1).reshape(M, N)
+    _close(buf[:, 64:], ref, rtol=1 / 128, atol=2e-2)
+    assert float(buf[:, :64].abs().max()) == 0.0
+    o = buf[:, 64:].double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[1], (o ** 2).sum(0), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("dims,B", [((3, 20, 12), 2), ((2, 32, 16), 40)])
+def test_brick_conv3_dgrad(dims, B):
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(9)
+    Dz, Dy, Dx = dims
+    Cg, N = 32, 128
+    M = B * Dz * Dy * Dx
+    g = torch.randn(M, Cg, device="cuda").to(torch.bfloat16)
+    w = torch.randn(Cg, N, 3, 3, 3, device="cuda") * 0.05
+    xb = torch.randn(M, N, device="cuda").to(_actdt())
+    gamma = torch.rand(N, device="cuda") + 0.5
+    beta = torch.randn(N, device="cuda") * 0.3
+    s1 = xb.double().sum(0); s2 = (xb.double() ** 2).sum(0)
+    bp = H.pack(w, N, 128, Cg, 32, 27, 27, N * 27, 1, fwd=False)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.brick(B, dims, Cg, N, g, Cg, bp, out, N, grad=1, tap_sign=-1, st_sum=st[0], st_sq=st[1], e_src=xb, e_pitch=N,
+            bnE=H.bnsrc(s1, s2, gamma, beta, count=M))
+    torch.cuda.synchronize()
+    g5 = g.float().view(B, Dz, Dy, Dx, Cg).permute(0, 4, 1, 2, 3)
+    dA = F.conv_transpose3d(g5, _bf(w), padding=1).permute(0, 2, 3, 4, 1).reshape(M, N)
+    mean = xb.float().mean(0); var = xb.float().var(0, unbiased=False); rstd = (var + 1e-5).rsqrt()
+    xhat = (xb.float() - mean) * rstd
+    pre = xhat * gamma + beta
+    ref = dA * (pre > 0)
+    band = pre.abs() < 1e-3
+    d = ((out.float() - ref).abs() - (ref.abs() / 64 + 5e-2)).masked_fill(band, -1)
+    assert float(d.max()) <= 0
+    o = out.double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[1], (o * xhat.double()).sum(0), rtol=1e-3, atol=5e-2)
