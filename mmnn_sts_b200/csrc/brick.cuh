@@ -20,6 +20,7 @@ constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple o
 constexpr int BR_THREADS = 448;
 constexpr int BR_MMA_WARP = 8, BR_LOAD_WARP = 9, BR_EPI_WARP0 = 10;
 constexpr int BR_BSTAGES = 4;
+constexpr int BR_BTAPS = 3;     // taps per weight-ring stage (one dx row): 9 waits per brick buffer instead of 27
 
 struct BrickParams {
   int B, Dz, Dy, Dx;
@@ -50,7 +51,7 @@ __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* 
   o = (o + 127u) & ~127u;
   offs[4] = o; o += 2u * PH * BR_PLANE;        // two brick buffers
   o = (o + 127u) & ~127u;
-  offs[5] = o; o += BR_BSTAGES * (uint32_t)PH * NT * 16;
+  offs[5] = o; o += BR_BSTAGES * BR_BTAPS * (uint32_t)PH * NT * 16;
   return o;
 }
 
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   const uint32_t brick0 = sbase + offs[4];
   const uint32_t brick_bytes = (uint32_t)PH * BR_PLANE;
   const uint32_t bst0 = sbase + offs[5];
-  const uint32_t b_bytes = (uint32_t)PH * p.NT * 16;
+  const uint32_t b_bytes = (uint32_t)PH * p.NT * 16;              // one tap
+  const uint32_t bs_bytes = BR_BTAPS * b_bytes;                  // one ring stage
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_y = (p.Dy + BR_TY - 1) / BR_TY, tiles_x = (p.Dx + BR_TX - 1) / BR_TX;
@@ -144,35 +146,34 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
 #pragma unroll
           for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.CH + ch0 + e]; }
         }
-        for (int c0 = 0; c0 < cells; c0 += NUM_PRODUCER_THREADS * 4) {
-          uint4 regs[4];
-          uint32_t okmask = 0;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * NUM_PRODUCER_THREADS + tid;
-            regs[u] = make_uint4(0, 0, 0, 0);
-            if (c < cells) {
+        // every cell of this buffer goes out as one asynchronous 16-byte copy (zero-fill outside the volume): all
+        // ~17-34 loads of a thread are in flight together; the BN/ReLU transform then runs in place on the
+        // thread's own cells once they have landed.
+        unsigned long long okmask = 0ull;
+        int u = 0;
+        for (int c = tid; c < cells; c += NUM_PRODUCER_THREADS, ++u) {
+          const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
+          const int xx = slot % BR_HX;
+          const int r2 = slot / BR_HX;
+          const int yy = r2 % BR_HY, zz = r2 / BR_HY;
+          // slot (zz,yy,xx) holds the source voxel (z + zz-1, y0 + yy-1, x0 + xx-1); zeros outside the volume
+          const int sz = z + (zz - 1), sy = y0 + (yy - 1), sx = x0 + (xx - 1);
+          const bool ok = sz >= 0 && sz < p.Dz && sy >= 0 && sy < p.Dy && sx >= 0 && sx < p.Dx;
+          const long long m = ok ? (((long long)n * p.Dz + sz) * p.Dy + sy) * p.Dx + sx : 0;
+          cp_async16(dst + chunk * BR_PLANE + slot * 16, p.a_src + m * p.a_pitch + ch0, ok ? 16u : 0u);
+          okmask |= (unsigned long long)ok << u;
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        if (TRANS == T_BNRELU) {
+          u = 0;
+          for (int c = tid; c < cells; c += NUM_PRODUCER_THREADS, ++u) {
+            if ((okmask >> u) & 1ull) {
               const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
-              const int xx = slot % BR_HX;
-              const int r2 = slot / BR_HX;
-              const int yy = r2 % BR_HY, zz = r2 / BR_HY;
-              // slot (zz,yy,xx) holds the source voxel (z + zz-1, y0 + yy-1, x0 + xx-1); zeros outside the volume
-              const int sz = z + (zz - 1), sy = y0 + (yy - 1), sx = x0 + (xx - 1);
-              if (sz >= 0 && sz < p.Dz && sy >= 0 && sy < p.Dy && sx >= 0 && sx < p.Dx) {
-                const long long m = (((long long)n * p.Dz + sz) * p.Dy + sy) * p.Dx + sx;
-                regs[u] = ldg16(p.a_src + m * p.a_pitch + ch0);
-                okmask |= 1u << u;
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * NUM_PRODUCER_THREADS + tid;
-            if (c < cells) {
-              const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
-              uint4 v = regs[u];
-              if (TRANS == T_BNRELU && ((okmask >> u) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
-              sts16(dst + chunk * BR_PLANE + slot * 16, v);
+              const uint32_t addr = dst + chunk * BR_PLANE + slot * 16;
+              uint4 v = lds16(addr);
+              apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+              sts16(addr, v);
             }
           }
         }
@@ -181,17 +182,19 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
       }
     }
   } else if (warp == BR_LOAD_WARP) {
-    // ================= weight loader: ring of BR_BSTAGES k-block images
+    // ================= weight loader: ring of BR_BSTAGES stages of BR_BTAPS tap images each
     if (lane == 0) {
       int j = 0;
       for (int it = 0; it < my_tiles; ++it)
         for (int h = 0; h < NH; ++h)
-          for (int tap = 0; tap < 27; ++tap, ++j) {
+          for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
             const int s = j % BR_BSTAGES;
             const uint32_t par = (uint32_t)(j / BR_BSTAGES) & 1u;
             mbar_wait(BAR(8 + s), par ^ 1u, 22);
-            mbar_arrive_expect_tx(BAR(4 + s), b_bytes);
-            bulk_g2s(bst0 + s * b_bytes, p.b_packed + (size_t)(tap * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
+            mbar_arrive_expect_tx(BAR(4 + s), bs_bytes);
+            for (int u = 0; u < BR_BTAPS; ++u)
+              bulk_g2s(bst0 + s * bs_bytes + u * b_bytes,
+                       p.b_packed + (size_t)((tg * BR_BTAPS + u) * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
           }
     }
   } else if (warp == BR_MMA_WARP) {
@@ -208,21 +211,27 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         const int q = seq & 1;
         mbar_wait(BAR(q), (uint32_t)(seq >> 1) & 1u, 24);
         tc_fence_after();
-        const uint32_t src = brick0 + q * brick_bytes;
-        for (int tap = 0; tap < 27; ++tap, ++j) {
+        const uint64_t ad_base = make_smem_desc(brick0 + q * brick_bytes, BR_PLANE, BR_HX * 16);
+        const uint32_t td = tmem_base + abuf * p.NT;
+        for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
           const int s = j % BR_BSTAGES;
           mbar_wait(BAR(4 + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
           tc_fence_after();
           if (lane == 0) {
-            const int t9 = tap / 9, t3 = (tap - t9 * 9) / 3, t1 = tap - t9 * 9 - t3 * 3;
-            // tap offset d = (t-1)*tap_sign; the window of slots read for output (y,x) is (d+1, y+d+1, x+d+1)
-            const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
-            const uint32_t a0 = src + (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u;
-            const uint32_t b0 = bst0 + s * b_bytes;
-            for (int k16 = 0; k16 < PH / 2; ++k16) {
-              const uint64_t ad = make_smem_desc(a0 + k16 * 2 * BR_PLANE, BR_PLANE, BR_HX * 16);
-              const uint64_t bd = make_smem_desc(b0 + k16 * 2 * p.NT * 16, p.NT * 16, 128);
-              tc_mma_bf16(tmem_base + abuf * p.NT, ad, bd, idesc, (h > 0 || tap > 0 || k16 > 0) ? 1u : 0u);
+            // taps tg*3 + u, u = 0..2: (t9, t3) fixed, t1 = u.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
+            const int t9 = tg / 3, t3 = tg - t9 * 3;
+            const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1;
+            uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
+#pragma unroll
+            for (int u = 0; u < BR_BTAPS; ++u) {
+              const int ox = (u - 1) * p.tap_sign + 1;
+              const uint64_t ad = desc_advance(ad_base, (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u);
+              tc_mma_bf16(td, ad, bd, idesc, (h > 0 || tg > 0 || u > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k16 = 1; k16 < 4; ++k16)
+                if (k16 < PH / 2)
+                  tc_mma_bf16(td, desc_advance(ad, k16 * 2 * BR_PLANE), desc_advance(bd, k16 * 2 * p.NT * 16), idesc, 1u);
+              bd = desc_advance(bd, b_bytes);
             }
             tc_commit(BAR(8 + s));
           }

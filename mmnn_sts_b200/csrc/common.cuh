@@ -116,6 +116,9 @@ MMNN_DEVINL uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
 }
+// Advancing a descriptor's start address by `bytes` (multiple of 16) is an add on the low word: the 14-bit field never
+// carries because shared-memory addresses stay below 256 KB.
+MMNN_DEVINL uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), majors (bits 15,16), N>>3 (17..22), M>>4 (24..28)
 // operand format field: 0 = fp16, 1 = bf16 (both operands the same)
 __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool f16) {
@@ -164,6 +167,29 @@ MMNN_DEVINL float round16(float x) {
 MMNN_DEVINL uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 MMNN_DEVINL void sts16(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// Ampere-style asynchronous 16-byte copy global -> shared (LDGSTS); src_bytes == 0 writes 16 zero bytes.
+// Used by every producer: all loads of a stage are in flight at once without occupying registers.
+MMNN_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+MMNN_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+MMNN_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+MMNN_DEVINL void cp_async_wait_dyn(int n) {   // at most n groups still pending
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    default: cp_async_wait<5>(); break;
+  }
+}
+MMNN_DEVINL uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 MMNN_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 

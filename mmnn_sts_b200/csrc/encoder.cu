@@ -389,7 +389,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
       { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
       const float* cs = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
-      if (g.H[b] >= 8 && g.W[b] >= 8) {
+      if (true) {  // brick mode for every spatial size: partial tiles only cost idle MMA rows, tiny layers are latency-bound anyway
         // large blocks: halo brick staged once per tile, taps are descriptor offsets (brick.cuh)
         BrickParams q = {};
         q.B = B; q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b]; q.CH = BOTT; q.NT = GROWTH; q.tap_sign = 1;
@@ -562,7 +562,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         RET_IF(launch_wgrad(w, 1, 0, st));
       }
       // conv2 dgrad (+ ReLU mask of norm2/relu2, + BN2 backward statistics)
-      if (g.H[b] >= 8 && g.W[b] >= 8) {
+      if (true) {  // brick mode for every spatial size: partial tiles only cost idle MMA rows, tiny layers are latency-bound anyway
         BrickParams q = {};
         q.B = B; q.Dz = g.D[b]; q.Dy = g.H[b]; q.Dx = g.W[b]; q.CH = GROWTH; q.NT = BOTT; q.tap_sign = -1;
         q.a_src = gslice; q.a_pitch = GROWTH;

@@ -417,12 +417,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         int cpl = (p.Cin - cb * p.kbw) / 8;
         cpl = cpl > planes ? planes : cpl;
         const uint32_t sA = stage0 + s * stage_bytes;
-        const uint32_t sB = sA + a_bytes;
-        for (int k16 = 0; k16 < cpl / 2; ++k16) {
-          const uint64_t ad = make_smem_desc(sA + k16 * 2 * PLANE_BYTES, PLANE_BYTES, 128);
-          const uint64_t bd = make_smem_desc(sB + k16 * 2 * p.NT * 16, p.NT * 16, 128);
-          tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
-        }
+        const uint64_t ad0 = make_smem_desc(sA, PLANE_BYTES, 128);
+        const uint64_t bd0 = make_smem_desc(sA + a_bytes, p.NT * 16, 128);
+        const uint32_t a_step = 2 * PLANE_BYTES, b_step = 2 * p.NT * 16;
+        tc_mma_bf16(tmem_base, ad0, bd0, idesc, kb > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 1; k16 < 4; ++k16)
+          if (k16 < cpl / 2) tc_mma_bf16(tmem_base, desc_advance(ad0, k16 * a_step), desc_advance(bd0, k16 * b_step), idesc, 1u);
         tc_commit(bar_empty + 8 * s);
         if (kb == KB - 1) tc_commit(bar_accum);
       }
@@ -716,13 +717,16 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sA = stage0 + s * stage_bytes;
-        const uint32_t sB = sA + a_bytes;
+        const uint64_t ad0 = make_smem_desc(sA, 128, PLANE_BYTES);
+        uint64_t bd0 = make_smem_desc(sA + a_bytes, 128, PLANE_BYTES);
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
         for (int j = 0; j < p.NB; ++j) {
-          for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16) {
-            const uint64_t ad = make_smem_desc(sA + k16 * 256, 128, PLANE_BYTES);
-            const uint64_t bd = make_smem_desc(sB + j * bt_bytes + k16 * 256, 128, PLANE_BYTES);
-            tc_mma_bf16(tmem_base + j * p.CB, ad, bd, idesc, (it > 0 || k16 > 0) ? 1u : 0u);
-          }
+          const uint32_t td = tmem_base + j * p.CB;
+          tc_mma_bf16(td, ad0, bd0, idesc, acc0);
+#pragma unroll
+          for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
+            tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd0, k16 * 256), idesc, 1u);
+          bd0 = desc_advance(bd0, bt_bytes);
         }
         tc_commit(bar_empty + 8 * s);
         if (it == nt - 1) tc_commit(bar_accum);
