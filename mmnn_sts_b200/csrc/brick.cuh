@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           const int s = j % BR_BSTAGES;
           mbar_wait(BAR(4 + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             // taps tg*3 + u, u = 0..2: (t9, t3) fixed, t1 = u.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
             const int t9 = tg / 3, t3 = tg - t9 * 3;
             const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           }
           __syncwarp();
         }
-        if (lane == 0) {
+        if (elect_one()) {
           tc_commit(BAR(2 + q));
           if (h == NH - 1) tc_commit(BAR(12 + abuf));
         }

@@ -70,6 +70,16 @@ MMNN_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, ui
                : "memory");
 }
 
+// One lane of a fully converged warp, chosen by the hardware (elect.sync).  Guarding the tcgen05.mma / commit block
+// with THIS predicate (instead of `lane == 0`) lets ptxas emit the uniform-datapath instructions straight-line; with
+// an ordinary divergent predicate every UTCHMMA is wrapped in an ELECT / PLOP3 / BRA.U.ANY loop (~130 cycles each,
+// measured with ncu source counters: profiles/r01_brick_fprop_sass_mma_loop.txt).
+MMNN_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 MMNN_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
       mbar_wait(bar_full + 8 * s, ph, 2);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const int tap = kb / kb_per_tap;
         const int cb = kb - tap * kb_per_tap;
         int cpl = (p.Cin - cb * p.kbw) / 8;
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       const uint32_t ph = (uint32_t)(it / S) & 1u;
       mbar_wait(bar_full + 8 * s, ph, 12);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sA = stage0 + s * stage_bytes;
         const uint64_t ad0 = make_smem_desc(sA, 128, PLANE_BYTES);
         uint64_t bd0 = make_smem_desc(sA + a_bytes, 128, PLANE_BYTES);
