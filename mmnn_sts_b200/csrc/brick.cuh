@@ -255,10 +255,18 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
       int n, z, y0, x0;
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
       const int abuf = it & 1;
-      mbar_wait(BAR(12 + abuf), (uint32_t)(it >> 1) & 1u, 26);
-      tc_fence_after();
       const bool row_ok = (y0 + ry < p.Dy) && (x0 + rx < p.Dx);
       const long long m = (((long long)n * p.Dz + z) * p.Dy + (y0 + ry)) * p.Dx + (x0 + rx);
+      uint4 xpre[4][4];   // gating activations of this row: fetched before the accumulator is ready
+      if (EPI == EP_MASK_STATS) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            xpre[cc][i] = (row_ok && cc * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + cc * 32 + i * 8) : make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(BAR(12 + abuf), (uint32_t)(it >> 1) & 1u, 26);
+      tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         if (cc * 32 >= p.NT) break;
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         if (EPI == EP_MASK_STATS) {
           uint4 xv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = row_ok ? ldg16(p.e_src + m * p.e_pitch + cc * 32 + i * 8) : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 4; ++i) xv[i] = xpre[cc][i];
           const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {

@@ -47,7 +47,10 @@ MMNN_DEVINL void bn_mean_rstd(const BnSrc& b, int c, float& mean, float& rstd) {
     double var = b.sumsq[c] * (double)b.inv_count - m * m;
     var = var < 0.0 ? 0.0 : var;
     mean = (float)m;
-    rstd = (float)(1.0 / sqrt(var + (double)b.eps));
+    // fp64 only where cancellation matters (E[x^2] - E[x]^2); the reciprocal square root in fp32 + one Newton step
+    const float vf = (float)var + b.eps;
+    float r0 = rsqrtf(vf);
+    rstd = r0 * (1.5f - 0.5f * vf * r0 * r0);
   } else {
     mean = b.rmean[c];
     rstd = rsqrtf(b.rvar[c] + b.eps);
@@ -319,36 +322,48 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
       if (++s == S) { s = 0; ph ^= 1u; }
     }
   }
-  if (warp < 4) {
-    // ================= epilogue (same warps: TMEM lane quarter == warp index)
-    mbar_wait(bar_accum, 0, 3);
-    tc_fence_after();
-    const int r = warp * 32 + lane;
+  if (warp < PRODUCER_WARPS) {
+    // ================= epilogue on all 8 producer warps: warps w and w+4 share TMEM lane quarter w%4 and split the
+    // 32-column chunks between them (the epilogue, not the MMA, bounds the thin-K GEMMs: ncu, profiles/)
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
     const long long m = (long long)tile_m * TILE_ROWS + r;
     const bool row_ok = m < p.M;
     const int nb = row_ok ? (int)(m / vps) : 0;
-    for (int cc = 0; cc < p.NT / 32; ++cc) {
+    // the forward activations that gate the gradient do not depend on the MMA: fetch this row's (up to 128 columns)
+    // before waiting for the accumulator so their latency hides behind the tail of the K loop
+    uint4 xpre[2][4];
+    if (EPI == EP_MASK_STATS) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int cc = (warp >> 2) + 2 * k;
+        const int col0 = tile_n * p.NT + cc * 32;
+        const bool on = row_ok && cc * 32 < p.NT && col0 < p.Ncols;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xpre[k][i] = on ? ldg16(p.e_src + m * p.e_pitch + col0 + i * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    mbar_wait(bar_accum, 0, 3);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int cc = (warp >> 2) + 2 * k;
+      if (cc >= p.NT / 32) break;
       const int col0 = tile_n * p.NT + cc * 32;
       if (col0 >= p.Ncols) {
         if (EPI != EP_STORE) {
-          red[(0 * 4 + warp) * p.NT + cc * 32 + lane] = 0.f;
-          red[(1 * 4 + warp) * p.NT + cc * 32 + lane] = 0.f;
+          red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = 0.f;
+          red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = 0.f;
         }
         continue;
       }
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), v);
+      tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cc * 32), v);
       float q[32];
       if (EPI == EP_MASK_STATS) {
         uint4 xv[4];
-        if (row_ok) {
-          const bf16* xp = p.e_src + m * p.e_pitch + col0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = ldg16(xp + i * 8);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = make_uint4(0, 0, 0, 0);
-        }
+        for (int i = 0; i < 4; ++i) xv[i] = xpre[k < 2 ? k : 1][i];
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -387,13 +402,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
       if (EPI != EP_STORE) {
         const float s1 = warp_transpose_sum32(v, lane);
         const float s2 = warp_transpose_sum32(q, lane);
-        red[(0 * 4 + warp) * p.NT + cc * 32 + lane] = s1;
-        red[(1 * 4 + warp) * p.NT + cc * 32 + lane] = s2;
+        red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = s1;
+        red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = s2;
       }
     }
     if (EPI != EP_STORE) {
-      named_bar_sync(1, EPILOGUE_THREADS);
-      for (int c = tid; c < p.NT; c += EPILOGUE_THREADS) {
+      named_bar_sync(1, NUM_PRODUCER_THREADS);
+      for (int c = tid; c < p.NT; c += NUM_PRODUCER_THREADS) {
         const int col = tile_n * p.NT + c;
         if (col < p.Ncols) {
           const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
@@ -660,10 +675,33 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       if (p.NB == 1) {
         produce_planes<BTRANS, false, false>(sB, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0, 0,
                                       p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
+      } else if (p.NB == 9 && bplanes == 4) {
+        // 9 shifted raw gradient tiles of 4 planes: B_j[v] = g[v - tap offset].  All 18 loads of this thread are
+        // issued before the first store (one L2 round trip instead of nine).
+        const int chunk = lane & 3, rsub = lane >> 2;
+        uint4 regs[9][2];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int tap = ytile * 9 + j;
+          const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
+          const long long delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const int r = (warp + ps * PRODUCER_WARPS) * 8 + rsub;
+            const int4 ri = rowinfo[r];
+            const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
+            const bool ok = ri.y > -1000 && zz >= 0 && zz < p.Dz && yy >= 0 && yy < p.Dy && xx >= 0 && xx < p.Dx;
+            regs[j][ps] = ok ? ldg16(p.b_src + ((long long)ri.x + delta) * p.b_pitch + chunk * 8) : make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps)
+            sts16(sB + j * bt_bytes + chunk * PLANE_BYTES + ((warp + ps * PRODUCER_WARPS) * 8 + rsub) * 16, regs[j][ps]);
       } else {
         for (int j = 0; j < p.NB; ++j) {
           const int tap = ytile * p.NB + j;
-          // B_j[v] = g[v - tap offset]
           const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
           const long long delta = (long long)(dz * p.Dy + dy) * p.Dx + dx;
           produce_planes<BTRANS, true, false>(sB + j * bt_bytes, bplanes, p.b_src, p.b_pitch, rowinfo, warp, lane, dz, dy, dx, delta,
