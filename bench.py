@@ -245,6 +245,41 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_inference(args):
+    """BASELINE.json configs[4]: --inference --bootstrap --no_gradcam on synthetic patients: every patient is forwarded
+    ONCE in eval mode (batched), then 1000 bootstrap resamples of the per-class C-index are counted on the GPU.
+    Extra mode (not the driver's headline line): prints its own JSON line."""
+    import numpy as np
+    from mmnn_sts_b200 import main as M
+    dev = torch.device("cuda", 0)
+    wl = WORKLOADS[args.workload]
+    model = build_model(wl, dev).eval()
+    n, bs, R = args.patients, wl["batch"], args.resamples
+    g = torch.Generator(device=dev).manual_seed(7)
+    preds, ev, du = [], [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for w in range(2):   # warm-up
+            model({"image": torch.rand((bs, wl["cin"]) + tuple(wl["spatial"]), device=dev, generator=g), "clinical": torch.randn(bs, 20, device=dev, generator=g)})
+        torch.cuda.synchronize(); e0.record()
+        for i in range(0, n, bs):
+            b = min(bs, n - i)
+            out = model({"image": torch.rand((b, wl["cin"]) + tuple(wl["spatial"]), device=dev, generator=g), "clinical": torch.randn(b, 20, device=dev, generator=g)})
+            preds.append(out[0])
+        e1.record(); torch.cuda.synchronize()
+    fwd_ms = e0.elapsed_time(e1)
+    preds = torch.cat(preds)
+    events = torch.randint(0, 2, (n, 2), device=dev, generator=g)
+    durations = torch.randint(1, 3651, (n, 2), device=dev, generator=g)
+    idx = torch.as_tensor(np.stack([np.random.RandomState(42 + r).randint(0, n, n) for r in range(R)]), device=dev)
+    torch.cuda.synchronize(); e0.record()
+    c, mean, std, _ = M.bootstrap_cindices(preds, events, durations, idx)
+    e1.record(); torch.cuda.synchronize()
+    print(json.dumps({"mode": "inference+bootstrap", "patients": n, "resamples": R, "forward_volumes_per_s": round(n / (fwd_ms / 1e3), 1),
+                      "forward_ms": round(fwd_ms, 1), "bootstrap_ms": round(e0.elapsed_time(e1), 2), "cindex_mean": [float(v) for v in mean],
+                      "cindex_std": [float(v) for v in std], "workload": wl["name"], "note": "inputs generated on the device per batch (random volumes)"}), flush=True)
+
+
 def cpu_reference_arm(wl, steps, warmup, sample_batch):
     """The reference's algorithm for one training step on the host cores: fp32 torch CPU forward of the oracle
     restatement (bit-exact to the unchanged reference files, tests/golden), GradientBlender/Cox loss as the reference
@@ -298,10 +333,15 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "inference"])
+    ap.add_argument("--patients", type=int, default=10000)
+    ap.add_argument("--resamples", type=int, default=1000)
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3
-    if a.impl == "reference":
+    if a.mode == "inference":
+        run_inference(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

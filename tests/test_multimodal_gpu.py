@@ -121,3 +121,25 @@ def test_train_survival_driver_runs_and_accumulates():
     assert any(not torch.equal(before[k].cuda(), after[k]) for k in before if "conv" in k)
     res = M.inference_survival(m, batches, torch.device("cuda"), bootstrap=True, num_resamples=10, seed=1)
     assert res.per_resample.shape == (10, 2)
+
+
+def test_bootstrap_cindex_config5_scale():
+    """BASELINE configs[4] scale: 10 000 patients, 1000 resamples (indices np.random.RandomState(42+r).randint).
+    The GPU counts of a sample of resamples are compared bit-exactly with the CPU oracle sweep."""
+    import time
+    from mmnn_sts_b200.ops import concordance_counts
+    from oracle import cindex
+    rng = np.random.RandomState(0)
+    n, R = 10000, 1000
+    risks = np.round(rng.randn(n), 3).astype(np.float32)
+    t = rng.randint(1, 3651, n); e = rng.randint(0, 2, n)
+    idx = np.stack([np.random.RandomState(42 + r).randint(0, n, n) for r in range(R)])
+    args = [torch.tensor(v, device="cuda") for v in (t, risks, e)]
+    concordance_counts(*args, torch.tensor(idx[:4], device="cuda"))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    counts = concordance_counts(*args, torch.tensor(idx, device="cuda")).cpu().numpy()
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"\n10k patients x 1000 resamples on the GPU: {dt * 1e3:.1f} ms")
+    for r in (0, 1, 499, 999):
+        assert tuple(counts[r]) == cindex.concordance_counts(t[idx[r]], risks[idx[r]], e[idx[r]]), r
+    assert (counts[:, 2] > 0).all()
