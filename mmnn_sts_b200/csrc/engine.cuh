@@ -548,6 +548,74 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
   }
 }
 
+// Two-phase variant of produce_planes for tiles of up to 16 planes: load_planes issues every 128-bit load of the tile
+// into registers (up to 8 per thread), store_planes transforms and stores them.  The weight-gradient kernel issues the
+// loads of ALL operands of a stage before the first store: one L2 round trip per voxel tile instead of one per group.
+template <bool SHIFTED>
+MMNN_DEVINL uint32_t load_planes(uint4 (&regs)[2 * MAX_PASSES], int planes, const bf16* src, long long pitch, const int4* rowinfo,
+                                 int warp, int lane, int dz, int dy, int dx, long long delta, int Dz, int Dy, int Dx) {
+  const int G = planes >= 8 ? 8 : 4;
+  const int gshift = planes >= 8 ? 3 : 2;
+  const int rsub = lane >> gshift;
+  const int rpp = 32 >> gshift;
+  const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp) {
+    const int chunk = grp * G + (lane & (G - 1));
+#pragma unroll
+    for (int ps = 0; ps < MAX_PASSES; ++ps) {
+      regs[grp * MAX_PASSES + ps] = make_uint4(0, 0, 0, 0);
+      if (ps < npass && chunk < planes) {
+        const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
+        const int4 ri = rowinfo[r];
+        bool ok = ri.y > -1000;
+        if (SHIFTED) {
+          const int zz = ri.y + dz, yy = ri.z + dy, xx = ri.w + dx;
+          ok = ok && zz >= 0 && zz < Dz && yy >= 0 && yy < Dy && xx >= 0 && xx < Dx;
+        }
+        if (ok) {
+          regs[grp * MAX_PASSES + ps] = ldg16(src + ((long long)ri.x + delta) * pitch + chunk * 8);
+          okmask |= 1u << (grp * MAX_PASSES + ps);
+        }
+      }
+    }
+  }
+  return okmask;
+}
+
+template <int TRANS, bool IN_F16>
+MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okmask, uint32_t sdst, int planes, int warp, int lane,
+                              const float* scale, const float* shift) {
+  const int G = planes >= 8 ? 8 : 4;
+  const int gshift = planes >= 8 ? 3 : 2;
+  const int rsub = lane >> gshift;
+  const int rpp = 32 >> gshift;
+  const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp) {
+    const int chunk = grp * G + (lane & (G - 1));
+    if (chunk >= planes) continue;
+    float sc[8], sh[8];
+    if (TRANS == T_BNRELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sc[e] = scale[chunk * 8 + e]; sh[e] = shift[chunk * 8 + e]; }
+    }
+#pragma unroll
+    for (int ps = 0; ps < MAX_PASSES; ++ps) {
+      if (ps < npass) {
+        const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
+        uint4 v = regs[grp * MAX_PASSES + ps];
+        if ((okmask >> (grp * MAX_PASSES + ps)) & 1u) {
+          if (TRANS == T_BNRELU) apply_bnrelu8<IN_F16, false>(v, sc, sh);
+          else convert8<IN_F16, false>(v);
+        }
+        sts16(sdst + chunk * PLANE_BYTES + r * 16, v);
+      }
+    }
+  }
+}
+
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -654,9 +722,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       named_bar_sync(1, NUM_PRODUCER_THREADS);
       const uint32_t sA = stage0 + s * stage_bytes;
       const uint32_t sB = sA + a_bytes;
+      uint4 aregs[2 * MAX_PASSES];
+      uint32_t aok = 0;
       if (AMODE == WA_LINEAR) {
-        produce_planes<ATRANS, false, kActF16>(sA, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz,
-                                      p.Dy, p.Dx, coefA, coefA + 128);
+        // loads of the A tile are issued now and consumed after the B loads have been issued as well
+        aok = load_planes<false>(aregs, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz, p.Dy, p.Dx);
       } else {
         for (int g = 0; g < 2; ++g) {
           const int kb = ztile * 2 + g;
@@ -673,8 +743,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         named_bar_sync(1, NUM_PRODUCER_THREADS);
       }
       if (p.NB == 1) {
-        produce_planes<BTRANS, false, false>(sB, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0, 0,
-                                      p.Dz, p.Dy, p.Dx, coefB, coefB + p.CB);
+        uint4 bregs[2 * MAX_PASSES];
+        const uint32_t bok = load_planes<false>(bregs, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0,
+                                                0, p.Dz, p.Dy, p.Dx);
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        store_planes<T_NONE, false>(bregs, bok, sB, bplanes_valid, warp, lane, nullptr, nullptr);
       } else if (p.NB == 9 && bplanes == 4) {
         // 9 shifted raw gradient tiles of 4 planes: B_j[v] = g[v - tap offset].  All 18 loads of this thread are
         // issued before the first store (one L2 round trip instead of nine).
@@ -694,12 +767,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             regs[j][ps] = ok ? ldg16(p.b_src + ((long long)ri.x + delta) * p.b_pitch + chunk * 8) : make_uint4(0, 0, 0, 0);
           }
         }
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
 #pragma unroll
         for (int j = 0; j < 9; ++j)
 #pragma unroll
           for (int ps = 0; ps < 2; ++ps)
             sts16(sB + j * bt_bytes + chunk * PLANE_BYTES + ((warp + ps * PRODUCER_WARPS) * 8 + rsub) * 16, regs[j][ps]);
       } else {
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
         for (int j = 0; j < p.NB; ++j) {
           const int tap = ytile * p.NB + j;
           const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
