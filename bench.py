@@ -179,7 +179,7 @@ def run_ours(args):
     model = build_model(wl, device)
     opt = torch.optim.SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion)
-    sync = D.GradientAllReducer(model.parameters())
+    sync = D.GradientAllReducer(model.parameters(), model=model)
     dev_batches = make_batches(wl, 2, device=device, seed=1234 + 100 * rank)
     host_batches = make_batches(wl, 2, pinned=True, seed=1234 + 100 * rank)
 

@@ -37,17 +37,25 @@ class GradientAllReducer:
     Buckets are launched in reverse parameter order (the order backward produces them) on NCCL's own stream via
     async_op, so the reduction of the late layers overlaps whatever the caller still has queued."""
 
-    def __init__(self, params, bucket_bytes=64 << 20, average=False, group=None):
+    def __init__(self, params, bucket_bytes=64 << 20, average=False, group=None, model=None):
         self.params = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.average = average
         self.group = group
+        # modules that keep their gradients in one flat buffer (the DenseNet trunk) are reduced in place, without packing
+        self.flat_modules = [m for m in model.modules() if hasattr(m, "flat_grad_buffer")] if model is not None else []
 
     def __call__(self, *_):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
         world = dist.get_world_size(self.group)
-        grads = [p.grad for p in reversed(self.params) if p.grad is not None]
+        pending_flat, covered = [], set()
+        for m in self.flat_modules:
+            flat = m.flat_grad_buffer()
+            if flat is not None:
+                pending_flat.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+                covered.update(id(p) for p in m.parameters())
+        grads = [p.grad for p in reversed(self.params) if p.grad is not None and id(p) not in covered]
         buckets, cur, size = [], [], 0
         for g in grads:
             cur.append(g); size += g.numel() * g.element_size()
@@ -60,6 +68,10 @@ class GradientAllReducer:
             flat = torch.cat([g.reshape(-1) for g in b])
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             pending.append((work, flat, b))
+        for work, flat in pending_flat:
+            work.wait()
+            if self.average:
+                flat.div_(world)
         for work, flat, b in pending:
             work.wait()
             if self.average:
