@@ -25,18 +25,25 @@ int choose_stages(const RowsParams& p, uint32_t budget) {
   return best;
 }
 
-template <int AMODE, int TRANS, int EPI, bool GRAD>
-int launch_rows_t(RowsParams p, cudaStream_t stream) {
+template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
+int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   uint32_t offs[6];
   if (p.stages <= 0) p.stages = choose_stages(p, 100 * 1024);
   const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
-  auto kern = conv_rows_kernel<AMODE, TRANS, EPI, GRAD>;
+  auto kern = conv_rows_kernel<AMODE, TRANS, EPI, GRAD, PF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((p.M + TILE_ROWS - 1) / TILE_ROWS, (p.Ncols + p.NT - 1) / p.NT);
   kern<<<grid, ENGINE_THREADS, smem, stream>>>(p);
   MMNN_CHECK_LAUNCH();
   return 0;
+}
+
+template <int AMODE, int TRANS, int EPI, bool GRAD>
+int launch_rows_t(const RowsParams& p, cudaStream_t stream) {
+  const long long tiles = (long long)((p.M + TILE_ROWS - 1) / TILE_ROWS) * ((p.Ncols + p.NT - 1) / p.NT);
+  if (tiles <= 148) return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 2>(p, stream);   // latency-bound small grids
+  return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 1>(p, stream);
 }
 
 // grad == 0: forward GEMM (activation-format operands and output); grad == 1: data-gradient GEMM (bf16 operands/output)

@@ -133,7 +133,9 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
 // GRAD == false: forward GEMM  -- A = activations (act format), weights packed in act format, output act format.
 // GRAD == true : data-gradient -- A = gradients (bf16), weights packed bf16, output bf16; e_src (forward activation
 //                                 gating the ReLU / feeding x-hat) is in act format.
-template <int AMODE, int TRANS, int EPI, bool GRAD>
+// PF = register prefetch distance in k-blocks: 1 for grids of many tiles (registers -> occupancy), 2 for grids that do not
+// fill the GPU (tiny late-block layers are bound by the serial chain of K iterations, not by occupancy).
+template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_constant__ RowsParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
@@ -271,55 +273,67 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_
         }
       }
     };
-    uint4 cur[MAX_PASSES], nxt[MAX_PASSES];
-    uint32_t cur_ok = 0, nxt_ok = 0;
+    // PF+1 rotating register sets: the loads of k-blocks kb+1 .. kb+PF are in flight while kb is transformed and stored
+    uint4 R[PF + 1][MAX_PASSES];
+    uint32_t OK[PF + 1];
+    KbGeom G[PF + 1];
     int tap_n = 0, cb_n = 0;   // (tap, cb) of the NEXT k-block to load
-    KbGeom gcur = geom(0, 0), gnxt = gcur;
-    load_kb(gcur, cur, cur_ok);
-    if (++cb_n == kb_per_tap) { cb_n = 0; ++tap_n; }
+    auto next_geom = [&]() {
+      const KbGeom gq = geom(tap_n, cb_n);
+      if (++cb_n == kb_per_tap) { cb_n = 0; ++tap_n; }
+      return gq;
+    };
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = 0; kb < KB; ++kb) {
-      if (kb + 1 < KB) {
-        gnxt = geom(tap_n, cb_n);
-        load_kb(gnxt, nxt, nxt_ok);
-        if (++cb_n == kb_per_tap) { cb_n = 0; ++tap_n; }
-      }
+    auto process = [&](int kb, const KbGeom& gq, uint4 (&regs)[MAX_PASSES], uint32_t okm) {
       mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1);
       const uint32_t sA = stage0 + s * stage_bytes;
-      const uint32_t sB = sA + a_bytes;
       if (tid == 0) {
         mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-        bulk_g2s(sB, p.b_packed + ((size_t)tile_n * KB + kb) * (size_t)(planes * p.NT * 8), b_bytes, bar_full + 8 * s);
+        bulk_g2s(sA + a_bytes, p.b_packed + ((size_t)tile_n * KB + kb) * (size_t)(planes * p.NT * 8), b_bytes, bar_full + 8 * s);
       }
-      {
-        const int cshift = (gcur.cpl == 8) ? 3 : 2;
-        const int chunk = lane & (gcur.cpl == 8 ? 7 : 3);
-        const int rsub = lane >> cshift;
-        const int rpp = 32 >> cshift;
-        const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
-        const int ch0 = gcur.cb * p.kbw + chunk * 8;
-        float sc[8], sh[8];
-        if (TRANS == T_BNRELU) {
+      const int cshift = (gq.cpl == 8) ? 3 : 2;
+      const int chunk = lane & (gq.cpl == 8 ? 7 : 3);
+      const int rsub = lane >> cshift;
+      const int rpp = 32 >> cshift;
+      const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
+      const int ch0 = gq.cb * p.kbw + chunk * 8;
+      float sc[8], sh[8];
+      if (TRANS == T_BNRELU) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
-        }
+        for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
+      }
 #pragma unroll
-        for (int ps = 0; ps < MAX_PASSES; ++ps) {
-          if (ps < npass) {
-            const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
-            uint4 v = cur[ps];
-            if (TRANS == T_BNRELU && ((cur_ok >> ps) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
-            sts16(sA + chunk * PLANE_BYTES + r * 16, v);
-          }
+      for (int ps = 0; ps < MAX_PASSES; ++ps) {
+        if (ps < npass) {
+          const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
+          uint4 v = regs[ps];
+          if (TRANS == T_BNRELU && ((okm >> ps) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+          sts16(sA + chunk * PLANE_BYTES + r * 16, v);
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_full + 8 * s);
-#pragma unroll
-      for (int ps = 0; ps < MAX_PASSES; ++ps) cur[ps] = nxt[ps];
-      cur_ok = nxt_ok; gcur = gnxt;
       if (++s == S) { s = 0; ph ^= 1u; }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      OK[u] = 0;
+      if (u < KB) { G[u] = next_geom(); load_kb(G[u], R[u], OK[u]); }
+    }
+    for (int kb = 0; kb < KB; kb += PF + 1) {
+#pragma unroll
+      for (int u = 0; u <= PF; ++u) {
+        const int k = kb + u;
+        if (k < KB) {
+          constexpr int dummy = 0; (void)dummy;
+          if (k + PF < KB) {
+            G[(u + PF) % (PF + 1)] = next_geom();
+            load_kb(G[(u + PF) % (PF + 1)], R[(u + PF) % (PF + 1)], OK[(u + PF) % (PF + 1)]);
+          }
+          process(k, G[u], R[u], OK[u]);
+        }
+      }
     }
   }
   if (warp < PRODUCER_WARPS) {
@@ -797,14 +811,25 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * p.CB + cc * 32), v);
         if (EMODE == WE_STRIDED) {
-          const int ag = ztile * 128 + a;
+          // Transpose the 128(a) x 32(b) chunk through shared memory (the operand stages are free once the accumulator
+          // is final) so that every warp instruction adds one 512-byte contiguous run of the gradient with 128-bit
+          // vector atomics: 4x fewer atomic instructions than one RED per element.
+          float* stg = reinterpret_cast<float*>(smem + offs[3]);      // [32][132]
           const int b0 = (p.NB == 1 ? ytile * p.CB : 0) + cc * 32;
           const int tap = p.NB == 1 ? 0 : ytile * p.NB + j;
-          if (ag < p.na_total) {
-            float* dst = p.dw + (long long)ag * p.so_a + (long long)tap * p.so_j;
+          named_bar_sync(2, EPILOGUE_THREADS);                          // previous chunk fully drained
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (b0 + i < p.nb_total) atomicAdd(dst + (long long)(b0 + i) * p.so_b, v[i]);
+          for (int i = 0; i < 32; ++i) stg[i * 132 + a] = v[i];
+          named_bar_sync(2, EPILOGUE_THREADS);
+          const int ag4 = ztile * 128 + lane * 4;
+          if (ag4 < p.na_total) {
+            for (int i = warp; i < 32; i += 4) {
+              if (b0 + i < p.nb_total) {
+                const float4 val = *reinterpret_cast<const float4*>(stg + i * 132 + lane * 4);
+                float* dst = p.dw + (long long)ag4 + (long long)tap * p.so_j + (long long)(b0 + i) * p.so_b;
+                atomicAdd(reinterpret_cast<float4*>(dst), val);
+              }
+            }
           }
         } else {
           // stem: a = (g, c64) with kb = ztile*2 + g, c64 = (dx, pz, py, px, ci); b = output channel
