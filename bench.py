@@ -197,17 +197,41 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream(device=device)
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
     def timed(nsteps, e2e):
+        """e2e: every step's batch comes from pinned HOST memory (copy of batch i+1 is prefetched on a copy stream while
+        step i computes, as an input pipeline would) and every step's loss is read back to the host (asynchronously into
+        pinned memory, consumed one step later so the launch queue never drains)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for i in range(nsteps):
-            if e2e:
-                b = [t.to(device, non_blocking=True) for t in host_batches[i % 2]]
-                loss = step(*b)
-                _ = loss.item()                      # device->host read of the step's result
-            else:
+        if not e2e:
+            for i in range(nsteps):
                 step(*dev_batches[i % 2])
+        else:
+            cur = torch.cuda.current_stream()
+            def fetch(i):
+                with torch.cuda.stream(copy_stream):
+                    b = [t.to(device, non_blocking=True) for t in host_batches[i % 2]]
+                    e = torch.cuda.Event(); e.record(copy_stream)
+                return b, e
+            nxt = fetch(0)
+            loss_ev, seen = None, 0.0
+            for i in range(nsteps):
+                b, e = nxt
+                cur.wait_event(e)
+                if i + 1 < nsteps:
+                    nxt = fetch(i + 1)
+                loss = step(*b)
+                for t in b:
+                    t.record_stream(cur)
+                if loss_ev is not None:
+                    loss_ev.synchronize(); seen += float(loss_host[(i - 1) % 2])   # previous step's loss is on the host
+                loss_host[i % 2].copy_(loss.detach(), non_blocking=True)
+                loss_ev = torch.cuda.Event(); loss_ev.record(cur)
+            loss_ev.synchronize(); seen += float(loss_host[(nsteps - 1) % 2])
         ev1.record()
         barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)

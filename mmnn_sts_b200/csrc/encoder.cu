@@ -74,6 +74,19 @@ struct Plan {
   // state free of pageable host->device copies (which synchronise the stream and cannot be graph-captured)
   std::vector<uint8_t> cache[4];
   const void* cache_dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
+  // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t ev_next = 0;
+  cudaEvent_t next_event() {
+    if (ev_next == events.size()) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      events.push_back(e);
+    }
+    return events[ev_next++];
+  }
 };
 
 int upload_table(Plan* pl, int slot, void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -93,6 +106,7 @@ struct Geo {
   int D[8], H[8], W[8];
   long long M[8];
   size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, gslice, gout, dpooled, c2scratch, dr, total;
+  size_t maxM_;
   size_t buf[8], bott[8], pooled[8], dbuf[8];
 };
 
@@ -132,13 +146,14 @@ bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
     maxM = std::max(maxM, (size_t)g.M[b]);
     maxMC = std::max(maxMC, (size_t)g.M[b] * (bi.ctot - GROWTH));
   }
+  g.maxM_ = maxM;
   g.fstats = take((size_t)pl.fwd_channels * 2 * sizeof(double));
   g.bstats = take((size_t)pl.bwd_channels * 2 * sizeof(double));
   g.packed = take(pl.packed_elems_total * 2);
   g.tables = take(1 << 20);
-  g.dA2 = take(maxM * BOTT * 2);
+  g.dA2 = take(2 * maxM * BOTT * 2);          // x2: layer parity (the side-stream wgrad of layer l reads it while l+1 runs)
   g.dA1 = take(maxMC * 2);
-  g.gslice = take(maxM * GROWTH * 2);
+  g.gslice = take(2 * maxM * GROWTH * 2);
   g.gout = take(maxMoutC2 * 2 + 256);
   g.dpooled = take(maxMoutC * 2 + 256);
   g.c2scratch = take((size_t)pl.num_layers * 27 * GROWTH * BOTT * 4);
@@ -498,6 +513,18 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
 
   CUDA_RET(cudaMemsetAsync(bstats, 0, (size_t)BC * 2 * sizeof(double), st));
   CUDA_RET(cudaMemsetAsync(ws + g.c2scratch, 0, (size_t)pl->num_layers * 27 * GROWTH * BOTT * 4, st));
+  if (pl->side == nullptr) CUDA_RET(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+  // while bench.py's per-kernel profiling is on, everything stays on one stream so that class times are not overlapped
+  cudaStream_t sd = prof_state().on ? st : pl->side;
+  pl->ev_next = 0;
+  {  // fork: the side stream starts after everything already queued on the caller's stream (zeroed gradients etc.)
+    cudaEvent_t e = pl->next_event();
+    CUDA_RET(cudaEventRecord(e, st));
+    CUDA_RET(cudaStreamWaitEvent(sd, e, 0));
+  }
+  cudaEvent_t side_done[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [parity][0: conv2 wgrad read gslice, 1: conv1 wgrad read dA2]
+  int parity = 0;
+  cudaEvent_t trans_done = nullptr;
 
   auto bn_apply = [&](int out_mode, long long M, int C, const bf16* v, const float* v32, long long v_pitch, const bf16* x,
                       long long x_pitch, const BnSrc& bn, const double* gs, const double* gd, void* outp,
@@ -536,11 +563,14 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     const int vps = g.D[b] * g.H[b] * g.W[b];
     bf16* buf = (bf16*)(ws + g.buf[b]);
     float* dbuf = (float*)(ws + g.dbuf[b]);
-    bf16* dA2 = (bf16*)(ws + g.dA2);
     bf16* dA1 = (bf16*)(ws + g.dA1);
-    bf16* gslice = (bf16*)(ws + g.gslice);
-    for (int l = (int)bi.layers.size() - 1; l >= 0; --l) {
+    for (int l = (int)bi.layers.size() - 1; l >= 0; --l, parity ^= 1) {
       const LayerInfo& li = bi.layers[l];
+      bf16* dA2 = (bf16*)(ws + g.dA2) + (size_t)parity * g.maxM_ * BOTT;
+      bf16* gslice = (bf16*)(ws + g.gslice) + (size_t)parity * g.maxM_ * GROWTH;
+      // the buffers of this parity were last read by the side-stream wgrads of two layers ago
+      if (side_done[parity][0]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity][0], 0));
+      if (side_done[parity][1]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity][1], 0));
       bf16* bott = (bf16*)(ws + g.bott[b]) + (size_t)l * M * BOTT;
       const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, true);
       const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, true);
@@ -558,8 +588,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = gslice; w.b_pitch = GROWTH;
         w.dw = (float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
         w.so_a = 1; w.so_b = BOTT; w.so_j = GROWTH * BOTT;
-        ProfScope ps_(PC_CONV2_WGRAD, st);
-        RET_IF(launch_wgrad(w, 1, 0, st));
+        cudaEvent_t ready = pl->next_event();
+        CUDA_RET(cudaEventRecord(ready, st));          // gslice written
+        CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
+        {
+          ProfScope ps_(PC_CONV2_WGRAD, sd);
+          RET_IF(launch_wgrad(w, 1, 0, sd));
+        }
+        side_done[parity][0] = pl->next_event();
+        CUDA_RET(cudaEventRecord(side_done[parity][0], sd));
       }
       // conv2 dgrad (+ ReLU mask of norm2/relu2, + BN2 backward statistics)
       if (true) {  // brick mode for every spatial size: partial tiles only cost idle MMA rows, tiny layers are latency-bound anyway
@@ -594,8 +631,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = dA2; w.b_pitch = BOTT;
         w.dw = (float*)grads[li.conv1_idx];
         w.so_a = 1; w.so_b = li.cin; w.so_j = 0;
-        ProfScope ps_(PC_CONV1_WGRAD, st);
-        RET_IF(launch_wgrad(w, 0, 0, st));
+        cudaEvent_t ready = pl->next_event();
+        CUDA_RET(cudaEventRecord(ready, st));          // dA2 holds dBott
+        CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
+        {
+          ProfScope ps_(PC_CONV1_WGRAD, sd);
+          RET_IF(launch_wgrad(w, 0, 0, sd));
+        }
+        side_done[parity][1] = pl->next_event();
+        CUDA_RET(cudaEventRecord(side_done[parity][1], sd));
       }
       // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics), then BN1 backward into dbuf[:, :cin]
       {
@@ -619,6 +663,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       bf16* gout = (bf16*)(ws + g.gout);
       bf16* dpooled = (bf16*)(ws + g.dpooled);
       const bf16* pooled = (const bf16*)(ws + g.pooled[b - 1]);
+      if (trans_done) CUDA_RET(cudaStreamWaitEvent(st, trans_done, 0));   // previous transition's wgrad still reads gout
       { ProfScope ps_(PC_EXTRACT, st);
         extract_slice_kernel<<<ew_grid(M * (bi.c0 / 8)), EW_THREADS, 0, st>>>(dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps); }
       LAUNCH_RET();
@@ -630,8 +675,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.b_src = gout; w.b_pitch = bi.c0;
         w.dw = (float*)grads[pv.tconv_idx];
         w.so_a = 1; w.so_b = pv.ctot; w.so_j = 0;
-        ProfScope ps_(PC_TRANS_WGRAD, st);
-        RET_IF(launch_wgrad(w, 2, 0, st));
+        cudaEvent_t ready = pl->next_event();
+        CUDA_RET(cudaEventRecord(ready, st));
+        CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
+        {
+          ProfScope ps_(PC_TRANS_WGRAD, sd);
+          RET_IF(launch_wgrad(w, 2, 0, sd));
+        }
+        trans_done = pl->next_event();
+        CUDA_RET(cudaEventRecord(trans_done, sd));
       }
       {
         RowsParams p = {};
@@ -683,6 +735,11 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     }
   }
 
+  {  // join: everything queued on the side stream becomes a dependency of the caller's stream
+    cudaEvent_t e = pl->next_event();
+    CUDA_RET(cudaEventRecord(e, sd));
+    CUDA_RET(cudaStreamWaitEvent(st, e, 0));
+  }
   // ---- tails: BN parameter gradients and conv2 gradient layout, one launch each
   {
     std::vector<BnTableEntry> tab;
