@@ -343,6 +343,12 @@ struct BnApplyParams {
   float inv_count;
   void* out;
   long long out_pitch;
+  // optional fused slice extraction (BA_OUT_F32_ADD only): the 32 channels [slice_c0, slice_c0+32) of the updated fp32
+  // accumulator are final after this pass; emit them as the next layer's bf16 gradient operand (x dropout keep-scale)
+  bf16* slice_out;          // [M][32] or null
+  int slice_c0;
+  const float* slice_scale; // [samples][32] or null
+  int vps;
 };
 
 template <int OUT>
@@ -384,8 +390,18 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
       float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.out_pitch + chunk * 8);
       if (OUT == BA_OUT_F32_ADD) {
         const float4 a = d[0], b = d[1];
-        d[0] = make_float4(a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3]);
-        d[1] = make_float4(b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]);
+        float nv[8] = {a.x + o[0], a.y + o[1], a.z + o[2], a.w + o[3], b.x + o[4], b.y + o[5], b.z + o[6], b.w + o[7]};
+        d[0] = make_float4(nv[0], nv[1], nv[2], nv[3]);
+        d[1] = make_float4(nv[4], nv[5], nv[6], nv[7]);
+        const int sc0 = chunk * 8 - p.slice_c0;
+        if (p.slice_out != nullptr && sc0 >= 0 && sc0 < 32) {
+          if (p.slice_scale != nullptr) {
+            const float* cs = p.slice_scale + (m / p.vps) * 32 + sc0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) nv[e] *= __ldg(cs + e);
+          }
+          *reinterpret_cast<uint4*>(p.slice_out + m * 32 + sc0) = pack8<GRD>(nv);
+        }
       } else {
         d[0] = make_float4(o[0], o[1], o[2], o[3]);
         d[1] = make_float4(o[4], o[5], o[6], o[7]);

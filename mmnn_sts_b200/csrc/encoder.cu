@@ -528,8 +528,10 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
 
   auto bn_apply = [&](int out_mode, long long M, int C, const bf16* v, const float* v32, long long v_pitch, const bf16* x,
                       long long x_pitch, const BnSrc& bn, const double* gs, const double* gd, void* outp,
-                      long long out_pitch) -> int {
+                      long long out_pitch, bf16* slice_out = nullptr, int slice_c0 = 0, const float* slice_scale = nullptr,
+                      int vps_ = 1) -> int {
     BnApplyParams a = {};
+    a.slice_out = slice_out; a.slice_c0 = slice_c0; a.slice_scale = slice_scale; a.vps = vps_;
     a.M = M; a.C = C; a.v = v; a.v32 = v32; a.v_pitch = v_pitch; a.x = x; a.x_pitch = x_pitch; a.bn = bn;
     a.g_sum = gs; a.g_dot = gd; a.inv_count = 1.0f / (float)M; a.out = outp; a.out_pitch = out_pitch;
     const int grid = ew_grid(M * (C / 8));
@@ -574,11 +576,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       bf16* bott = (bf16*)(ws + g.bott[b]) + (size_t)l * M * BOTT;
       const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, true);
       const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, true);
-      // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf)
-      { ProfScope ps_(PC_EXTRACT, st);
+      // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf): for the top
+      // layer of a block it is extracted here; for every other layer the previous iteration's BN-backward pass already
+      // emitted it while it had the final values in registers (fused slice extraction).
+      if (l == (int)bi.layers.size() - 1) {
+        ProfScope ps_(PC_EXTRACT, st);
         extract_slice_kernel<<<ew_grid(M * 4), EW_THREADS, 0, st>>>(
-            dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps); }
-      LAUNCH_RET();
+            dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps);
+        LAUNCH_RET();
+      }
       // conv2 wgrad -> scratch [tap][co][ci]
       {
         WgradParams w = {};
@@ -654,7 +660,17 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         ProfScope ps_(PC_CONV1_DGRAD, st);
         RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, 1, st));
       }
-      RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
+      if (l > 0) {
+        // this pass finalises channels [cin-32, cin) = the new channels of layer l-1: emit that layer's gradient slice
+        // into the other parity's buffer (after the side-stream wgrad that last read it has finished)
+        const LayerInfo& lp = bi.layers[l - 1];
+        if (side_done[parity ^ 1][0]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity ^ 1][0], 0));
+        bf16* gnext = (bf16*)(ws + g.gslice) + (size_t)(parity ^ 1) * g.maxM_ * GROWTH;
+        RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot,
+                        gnext, lp.cin, dropmask ? dropmask + (size_t)lp.index * B * GROWTH : nullptr, vps));
+      } else {
+        RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
+      }
     }
     if (b > 0) {
       // transition b-1: buf[b][:, :c0] = avgpool(conv(relu(bn(buf[b-1]))))  ==  conv(pooled[b-1])

@@ -34,14 +34,16 @@ class GradientBlender:
             self.weights = self.normalize(torch.ones(preds.shape[0]))
         if reduceToHeads:
             return head_losses
-        w = self.weights.to(device=head_losses.device, dtype=head_losses.dtype)
-        return self.reduce(w * head_losses), head_losses[0]
+        if self.weights.device != head_losses.device or self.weights.dtype != head_losses.dtype:
+            # one-time move: a host->device copy of a pageable tensor every step would synchronise the stream (quirk Q5)
+            self.weights = self.weights.to(device=head_losses.device, dtype=head_losses.dtype)
+        return self.reduce(self.weights * head_losses), head_losses[0]
 
     def updateWeightsSurv(self, train_preds, train_events, train_durations, val_preds, val_events, val_durations):
         train_loss = self.computeLossSurv(train_preds, train_events, train_durations, reduceToHeads=True).detach()
         val_loss = self.computeLossSurv(val_preds, val_events, val_durations, reduceToHeads=True).detach()
         if self.lvn is None or self.ltn is None:
-            self.weights = self.normalize(torch.ones(train_preds.shape[0]))
+            self.weights = self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device))
         else:
             o_n = self.lvn - self.ltn
             o_npn = val_loss - train_loss
