@@ -19,7 +19,7 @@ constexpr int BR_SLOTS = 3 * BR_HY * BR_HX;            // 540
 constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple of 16 -> conflict-free chunk planes
 constexpr int BR_THREADS = 448;
 constexpr int BR_MMA_WARP = 8, BR_LOAD_WARP = 9, BR_EPI_WARP0 = 10;
-constexpr int BR_BSTAGES = 4;
+constexpr int BR_BSTAGES = 6;
 constexpr int BR_BTAPS = 3;     // taps per weight-ring stage (one dx row): 9 waits per brick buffer instead of 27
 
 struct BrickParams {
@@ -45,7 +45,7 @@ __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* 
   const int PH = CH >= 64 ? 8 : CH / 8;
   uint32_t o = 0;
   offs[0] = o; o += 256;                       // barriers + tmem ptr
-  offs[1] = o; o += 2u * CH * 4;               // coefA
+  offs[1] = o; o += 2u * CH * 4 + 8u * CH;    // coefA (fp32 scale, shift) + packed half2 hi/lo table (16 B per channel pair)
   offs[2] = o; o += 4u * NT * 4;               // coefE
   offs[3] = o; o += 8u * NT * 4;               // red
   o = (o + 127u) & ~127u;
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, offs);
   const uint32_t sbase = smem_u32(smem);
-  // barrier map (8 B each): brick_full[2] 0,1 | brick_empty[2] 2,3 | b_full[4] 4..7 | b_empty[4] 8..11 | acc_full[2] 12,13 | acc_empty[2] 14,15
+  // barrier map (8 B each): brick_full[2] 0,1 | brick_empty[2] 2,3 | b_full[6] 4..9 | b_empty[6] 10..15 | acc_full[2] 16,17 | acc_empty[2] 18,19
   const uint32_t bars = sbase + offs[0];
   auto BAR = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 16);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * (8 + 2 * BR_BSTAGES));
   float* coefA = reinterpret_cast<float*>(smem + offs[1]);
   float* coefE = reinterpret_cast<float*>(smem + offs[2]);
   float* red = reinterpret_cast<float*>(smem + offs[3]);
@@ -82,15 +82,15 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   const int tiles_y = (p.Dy + BR_TY - 1) / BR_TY, tiles_x = (p.Dx + BR_TX - 1) / BR_TX;
   const int ntiles = p.B * p.Dz * tiles_y * tiles_x;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int vps = p.Dz * p.Dy * p.Dx;
+  const int rot = (int)(blockIdx.x % (27 / BR_BTAPS));   // per-CTA rotation of the tap-group order
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
 
   if (warp == BR_MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), NUM_PRODUCER_THREADS); mbar_init(BAR(2 + i), 1); }
-      for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(8 + i), 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(BAR(12 + i), 1); mbar_init(BAR(14 + i), EPILOGUE_THREADS); }
+      for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(4 + BR_BSTAGES + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(4 + 2 * BR_BSTAGES + i), 1); mbar_init(BAR(6 + 2 * BR_BSTAGES + i), EPILOGUE_THREADS); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -113,6 +113,11 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
       coefE[c] = s; coefE[p.NT + c] = p.bnE.beta[c] - mean * s; coefE[2 * p.NT + c] = mean; coefE[3 * p.NT + c] = rstd;
     }
   }
+  H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA + 2 * p.CH);
+  if (TRANS == T_BNRELU && OP_F16) {
+    __syncthreads();
+    fill_h2coef(coefH, coefA, coefA + p.CH, p.CH, tid, BR_THREADS);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,54 +133,77 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   if (warp < PRODUCER_WARPS) {
     // ================= producers: one load + one transform per brick cell
     const int cells = BR_SLOTS * PH;
+    // A thread owns the same brick cells for every tile: cell c = tid + u*256 -> chunk = c % PH (constant per thread),
+    // slot = c / PH.  The slot's halo coordinates are decoded ONCE (packed z|y|x) instead of per tile.
+    constexpr int MAXU = (BR_SLOTS * 8 + NUM_PRODUCER_THREADS - 1) / NUM_PRODUCER_THREADS;   // 17
+    const int chunk = (PH == 8) ? (tid & 7) : (tid & 3);
+    int pk[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int c = tid + u * NUM_PRODUCER_THREADS;
+      const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
+      const int xx = slot % BR_HX, r2 = slot / BR_HX;
+      pk[u] = (c < cells) ? (((r2 / BR_HY) << 16) | ((r2 % BR_HY) << 8) | xx) : -1;
+    }
     for (int it = 0; it < my_tiles; ++it) {
       int n, z, y0, x0;
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+      const long long nbase = (long long)n * p.Dz;
       for (int h = 0; h < NH; ++h) {
         const int seq = it * NH + h;
         const int q = seq & 1;
         const uint32_t par = (uint32_t)(seq >> 1) & 1u;
         mbar_wait(BAR(2 + q), par ^ 1u, 21);
-        const uint32_t dst = brick0 + q * brick_bytes;
-        // 8 (or 4) consecutive threads = the chunks of one voxel slot = PH*16 contiguous source bytes.
-        // NUM_PRODUCER_THREADS is a multiple of PH, so a thread keeps the same chunk for all its cells.
-        const int chunk = (PH == 8) ? (tid & 7) : (tid & 3);
+        const uint32_t dst = brick0 + q * brick_bytes + chunk * BR_PLANE;
         const int ch0 = h * 64 + chunk * 8;
-        float sc[8], sh[8];
-        if (TRANS == T_BNRELU) {
+        const bf16* src = p.a_src + ch0;
+        // every cell of this buffer goes out as one asynchronous 16-byte copy (zero-fill outside the volume): all loads
+        // of a thread are in flight together; the BN/ReLU transform then runs in place on the thread's own cells.
+        uint32_t okmask = 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.CH + ch0 + e]; }
-        }
-        // every cell of this buffer goes out as one asynchronous 16-byte copy (zero-fill outside the volume): all
-        // ~17-34 loads of a thread are in flight together; the BN/ReLU transform then runs in place on the
-        // thread's own cells once they have landed.
-        unsigned long long okmask = 0ull;
-        int u = 0;
-        for (int c = tid; c < cells; c += NUM_PRODUCER_THREADS, ++u) {
-          const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
-          const int xx = slot % BR_HX;
-          const int r2 = slot / BR_HX;
-          const int yy = r2 % BR_HY, zz = r2 / BR_HY;
-          // slot (zz,yy,xx) holds the source voxel (z + zz-1, y0 + yy-1, x0 + xx-1); zeros outside the volume
-          const int sz = z + (zz - 1), sy = y0 + (yy - 1), sx = x0 + (xx - 1);
-          const bool ok = sz >= 0 && sz < p.Dz && sy >= 0 && sy < p.Dy && sx >= 0 && sx < p.Dx;
-          const long long m = ok ? (((long long)n * p.Dz + sz) * p.Dy + sy) * p.Dx + sx : 0;
-          cp_async16(dst + chunk * BR_PLANE + slot * 16, p.a_src + m * p.a_pitch + ch0, ok ? 16u : 0u);
-          okmask |= (unsigned long long)ok << u;
+        for (int u = 0; u < MAXU; ++u) {
+          if (pk[u] >= 0) {
+            const int sz = z + (pk[u] >> 16) - 1, sy = y0 + ((pk[u] >> 8) & 0xff) - 1, sx = x0 + (pk[u] & 0xff) - 1;
+            const bool ok = (unsigned)sz < (unsigned)p.Dz && (unsigned)sy < (unsigned)p.Dy && (unsigned)sx < (unsigned)p.Dx;
+            const long long m = ok ? ((nbase + sz) * p.Dy + sy) * p.Dx + sx : 0;
+            const int slot = ((PH == 8) ? (tid >> 3) : (tid >> 2)) + u * (NUM_PRODUCER_THREADS / ((PH == 8) ? 8 : 4));
+            cp_async16(dst + slot * 16, src + m * p.a_pitch, ok ? 16u : 0u);
+            okmask |= (uint32_t)ok << u;
+          }
         }
         cp_async_commit();
-        cp_async_wait<0>();
         if (TRANS == T_BNRELU) {
-          u = 0;
-          for (int c = tid; c < cells; c += NUM_PRODUCER_THREADS, ++u) {
-            if ((okmask >> u) & 1ull) {
-              const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
-              const uint32_t addr = dst + chunk * BR_PLANE + slot * 16;
-              uint4 v = lds16(addr);
-              apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
-              sts16(addr, v);
+          if (OP_F16) {
+            H2Coef hc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hc[i] = coefH[ch0 / 2 + i];
+            cp_async_wait<0>();
+#pragma unroll
+            for (int u = 0; u < MAXU; ++u) {
+              if ((okmask >> u) & 1u) {
+                const int slot = (tid >> 3) + u * (NUM_PRODUCER_THREADS / 8);
+                uint4 v = lds16(dst + slot * 16);
+                apply_bnrelu8_h2(v, hc);
+                sts16(dst + slot * 16, v);
+              }
+            }
+          } else {
+            float sc[8], sh[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.CH + ch0 + e]; }
+            cp_async_wait<0>();
+#pragma unroll
+            for (int u = 0; u < MAXU; ++u) {
+              if ((okmask >> u) & 1u) {
+                const int slot = (tid >> 3) + u * (NUM_PRODUCER_THREADS / 8);
+                uint4 v = lds16(dst + slot * 16);
+                apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+                sts16(dst + slot * 16, v);
+              }
             }
           }
+        } else {
+          cp_async_wait<0>();
         }
         fence_proxy_async_smem();
         mbar_arrive(BAR(q));
@@ -190,11 +218,14 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
             const int s = j % BR_BSTAGES;
             const uint32_t par = (uint32_t)(j / BR_BSTAGES) & 1u;
-            mbar_wait(BAR(8 + s), par ^ 1u, 22);
+            mbar_wait(BAR(4 + BR_BSTAGES + s), par ^ 1u, 22);
             mbar_arrive_expect_tx(BAR(4 + s), bs_bytes);
+            // every CTA walks the 9 tap groups in a different rotation: otherwise all 148 SMs request the same 12-24 KB of
+            // weights at the same moment and the few L2 slices holding those lines serialise them
+            const int tgr = (tg + rot) % (27 / BR_BTAPS);
             for (int u = 0; u < BR_BTAPS; ++u)
               bulk_g2s(bst0 + s * bs_bytes + u * b_bytes,
-                       p.b_packed + (size_t)((tg * BR_BTAPS + u) * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
+                       p.b_packed + (size_t)((tgr * BR_BTAPS + u) * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
           }
     }
   } else if (warp == BR_MMA_WARP) {
@@ -204,7 +235,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
       const uint32_t apar = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(BAR(14 + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
+      mbar_wait(BAR(6 + 2 * BR_BSTAGES + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
       tc_fence_after();
       for (int h = 0; h < NH; ++h) {
         const int seq = it * NH + h;
@@ -219,7 +250,8 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           tc_fence_after();
           if (elect_one()) {
             // taps tg*3 + u, u = 0..2: (t9, t3) fixed, t1 = u.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
-            const int t9 = tg / 3, t3 = tg - t9 * 3;
+            const int tgr = (tg + rot) % (27 / BR_BTAPS);
+            const int t9 = tgr / 3, t3 = tgr - t9 * 3;
             const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1;
             uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
 #pragma unroll
@@ -233,13 +265,13 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
                   tc_mma_bf16(td, desc_advance(ad, k16 * 2 * BR_PLANE), desc_advance(bd, k16 * 2 * p.NT * 16), idesc, 1u);
               bd = desc_advance(bd, b_bytes);
             }
-            tc_commit(BAR(8 + s));
+            tc_commit(BAR(4 + BR_BSTAGES + s));
           }
           __syncwarp();
         }
         if (elect_one()) {
           tc_commit(BAR(2 + q));
-          if (h == NH - 1) tc_commit(BAR(12 + abuf));
+          if (h == NH - 1) tc_commit(BAR(4 + 2 * BR_BSTAGES + abuf));
         }
         __syncwarp();
       }
@@ -265,7 +297,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           for (int i = 0; i < 4; ++i)
             xpre[cc][i] = (row_ok && cc * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + cc * 32 + i * 8) : make_uint4(0, 0, 0, 0);
       }
-      mbar_wait(BAR(12 + abuf), (uint32_t)(it >> 1) & 1u, 26);
+      mbar_wait(BAR(4 + 2 * BR_BSTAGES + abuf), (uint32_t)(it >> 1) & 1u, 26);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
@@ -317,7 +349,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(14 + abuf));
+      mbar_arrive(BAR(6 + 2 * BR_BSTAGES + abuf));
     }
     if (EPI != EP_STORE) {
 #pragma unroll

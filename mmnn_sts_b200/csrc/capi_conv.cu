@@ -78,6 +78,10 @@ int launch_brick_t(const BrickParams& p, cudaStream_t stream) {
 // 3x3x3 convolution in brick mode: grad == 0 forward (BN+ReLU prologue, store + statistics), grad == 1 data gradient
 // (raw gradient operand, ReLU mask + BN-backward statistics epilogue)
 int launch_brick(const BrickParams& p, int grad, cudaStream_t stream) {
+  if (grad == 2) {   // ablation (microbenchmarks only): forward shape without the BN/ReLU transform
+    if (p.CH != 128 || p.NT != 32) return -2;
+    return launch_brick_t<T_NONE, EP_STORE_STATS, false>(p, stream);
+  }
   if (grad == 0) {
     if (p.CH != 128 || p.NT != 32) return -2;
     return launch_brick_t<T_BNRELU, EP_STORE_STATS, false>(p, stream);
