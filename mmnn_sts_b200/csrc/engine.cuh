@@ -164,7 +164,7 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
 // PF = register prefetch distance in k-blocks: 1 for grids of many tiles (registers -> occupancy), 2 for grids that do not
 // fill the GPU (tiny late-block layers are bound by the serial chain of K iterations, not by occupancy).
 template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
-__global__ void __launch_bounds__(ENGINE_THREADS) conv_rows_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __grid_constant__ RowsParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
