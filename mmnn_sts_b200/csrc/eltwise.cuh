@@ -499,8 +499,8 @@ struct BnTableEntry {
   float* running_mean;
   float* running_var;
   long long* num_batches_tracked;
-  float* grad_gamma;
-  float* grad_beta;
+  long long grad_gamma_off;   // element offsets from the gradient base pointer passed to the kernel: with the
+  long long grad_beta_off;    // gradients laid out in one flat buffer the table is identical every step (graph-safe)
   int C;
   float count;
 };
@@ -520,26 +520,27 @@ static __global__ void bn_running_update_kernel(const BnTableEntry* __restrict__
 }
 
 // dgamma = sum dy*xhat, dbeta = sum dy
-static __global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab) {
+static __global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab, float* __restrict__ gbase) {
   const BnTableEntry e = tab[blockIdx.x];
   for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
-    e.grad_gamma[c] = (float)e.g_dot[c];
-    e.grad_beta[c] = (float)e.g_sum[c];
+    gbase[e.grad_gamma_off + c] = (float)e.g_dot[c];
+    gbase[e.grad_beta_off + c] = (float)e.g_sum[c];
   }
 }
 
 // conv2 weight gradients are accumulated lane-contiguously as [tap][co][ci]; write them out as [co][ci][tap]
 struct TransposeEntry {
   const float* src;
-  float* dst;
+  long long dst_off;   // element offset from the gradient base pointer
 };
-static __global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, int Co, int Ci) {
+static __global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, float* __restrict__ gbase, int Co,
+                                                   int Ci) {
   const TransposeEntry e = tab[blockIdx.y];
   const int total = Co * Ci * 27;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int tap = idx % 27;
     const int rest = idx / 27;  // co*Ci + ci
-    e.dst[idx] = e.src[(size_t)tap * Co * Ci + rest];
+    gbase[e.dst_off + idx] = e.src[(size_t)tap * Co * Ci + rest];
   }
 }
 

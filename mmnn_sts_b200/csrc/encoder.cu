@@ -74,6 +74,8 @@ struct Plan {
   // state free of pageable host->device copies (which synchronise the stream and cannot be graph-captured)
   std::vector<uint8_t> cache[4];
   const void* cache_dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t pinned_bytes[4] = {0, 0, 0, 0};
   // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
   // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
   cudaStream_t side = nullptr;
@@ -92,7 +94,16 @@ struct Plan {
 int upload_table(Plan* pl, int slot, void* dst, const void* src, size_t bytes, cudaStream_t st) {
   std::vector<uint8_t>& c = pl->cache[slot];
   if (pl->cache_dst[slot] == dst && c.size() == bytes && memcmp(c.data(), src, bytes) == 0) return 0;
-  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  // the copy is sourced from a pinned staging buffer owned by the plan: asynchronous, and still valid if the copy was
+  // captured into a CUDA graph and is replayed later
+  if (pl->pinned[slot] == nullptr || pl->pinned_bytes[slot] < bytes) {
+    if (pl->pinned[slot] != nullptr) cudaFreeHost(pl->pinned[slot]);
+    const size_t cap = bytes < (1u << 16) ? (1u << 16) : bytes;
+    if (cudaMallocHost(&pl->pinned[slot], cap) != cudaSuccess) return -20;
+    pl->pinned_bytes[slot] = cap;
+  }
+  memcpy(pl->pinned[slot], src, bytes);
+  cudaError_t e = cudaMemcpyAsync(dst, pl->pinned[slot], bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
   c.assign((const uint8_t*)src, (const uint8_t*)src + bytes);
   pl->cache_dst[slot] = dst;
@@ -758,30 +769,31 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   }
   // ---- tails: BN parameter gradients and conv2 gradient layout, one launch each
   {
+    float* gbase = (float*)grads[0];
     std::vector<BnTableEntry> tab;
     for (BnInfo* bn : pl->bn_order) {
       BnTableEntry e = {};
       e.g_sum = gsum(*bn); e.g_dot = gdot(*bn);
-      e.grad_gamma = (float*)grads[bn->param_idx]; e.grad_beta = (float*)grads[bn->param_idx + 1];
+      e.grad_gamma_off = (float*)grads[bn->param_idx] - gbase; e.grad_beta_off = (float*)grads[bn->param_idx + 1] - gbase;
       e.C = bn->C;
       tab.push_back(e);
     }
     uint8_t* dtab = ws + g.tables + (1 << 19) + (1 << 17);
     RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
     ProfScope ps_(PC_TAILS, st, 2);
-    bn_param_grad_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab);
+    bn_param_grad_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab, gbase);
     LAUNCH_RET();
     std::vector<TransposeEntry> tt;
     for (auto& bi : pl->blocks)
       for (auto& li : bi.layers) {
         TransposeEntry e;
         e.src = (const float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
-        e.dst = (float*)grads[li.conv2_idx];
+        e.dst_off = (float*)grads[li.conv2_idx] - gbase;
         tt.push_back(e);
       }
     uint8_t* dtt = dtab + (1 << 18);
     RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(TransposeEntry), st));
-    conv2_grad_transpose_kernel<<<dim3(16, (unsigned)tt.size()), 256, 0, st>>>((const TransposeEntry*)dtt, GROWTH, BOTT);
+    conv2_grad_transpose_kernel<<<dim3(16, (unsigned)tt.size()), 256, 0, st>>>((const TransposeEntry*)dtt, gbase, GROWTH, BOTT);
     LAUNCH_RET();
   }
   return 0;
