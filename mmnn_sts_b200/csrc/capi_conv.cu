@@ -96,9 +96,9 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   if (p.stages <= 0) {
     p.stages = 1;
     for (int s = 1; s <= 4; ++s)
-      if (wgrad_smem_layout(p.CB, p.NB, s, offs) <= 225 * 1024) p.stages = s;
+      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs) <= 225 * 1024) p.stages = s;
   }
-  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, offs);
+  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs);
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -123,7 +123,11 @@ int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream)
     case 0: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
     case 1: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, 3, 1, stream);
     case 2: return launch_wgrad_t<WA_LINEAR, T_NONE, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
-    case 3: return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(p, split, 1, 8, stream);
+    case 3: {
+      WgradParams q = p;
+      if (q.NP != 1 && q.NP != 2) q.NP = 2;   // two k-block pairs per CTA share one gradient tile
+      return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(q, split, 1, 8 / q.NP, stream);
+    }
   }
   return -3;
 }

@@ -523,16 +523,17 @@ struct WgradParams {
   long long so_a, so_b, so_j;  // element strides of the gradient for (a, b, tap j); tap index = y*NB + j when NB > 1
   int cin_real;    // stem
   int stages;
+  int NP;          // stem: k-block PAIRS handled per CTA (A tile = NP x 128 "channels", NP accumulators); else 1
 };
 
-__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, uint32_t* offs /*[4]*/) {
+__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/) {
   uint32_t o = 0;
   offs[0] = o; o += 128;                          // barriers + tmem ptr
   offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
   offs[2] = o; o += 2u * 128 * 4 + 2u * CB * 4;   // coefA (scale, shift) [128], coefB [CB]
   o = (o + 127u) & ~127u;
   offs[3] = o;
-  const uint32_t stage = 16u * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
+  const uint32_t stage = 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
   return o + stages * stage;
 }
 
@@ -595,7 +596,8 @@ MMNN_DEVINL void produce_planes(uint32_t sdst, int planes, const bf16* src, long
 // loads of ALL operands of a stage before the first store: one L2 round trip per voxel tile instead of one per group.
 template <bool SHIFTED>
 MMNN_DEVINL uint32_t load_planes(uint4 (&regs)[2 * MAX_PASSES], int planes, const bf16* src, long long pitch, const int4* rowinfo,
-                                 int warp, int lane, int dz, int dy, int dx, long long delta, int Dz, int Dy, int Dx) {
+                                 int warp, int lane, int dz, int dy, int dx, long long delta, int Dz, int Dy, int Dx,
+                                 long long linear_base = -1) {
   const int G = planes >= 8 ? 8 : 4;
   const int gshift = planes >= 8 ? 3 : 2;
   const int rsub = lane >> gshift;
@@ -617,7 +619,8 @@ MMNN_DEVINL uint32_t load_planes(uint4 (&regs)[2 * MAX_PASSES], int planes, cons
           ok = ok && zz >= 0 && zz < Dz && yy >= 0 && yy < Dy && xx >= 0 && xx < Dx;
         }
         if (ok) {
-          regs[grp * MAX_PASSES + ps] = ldg16(src + ((long long)ri.x + delta) * pitch + chunk * 8);
+          const long long vox = linear_base >= 0 ? linear_base + r : (long long)ri.x;
+          regs[grp * MAX_PASSES + ps] = ldg16(src + (vox + delta) * pitch + chunk * 8);
           okmask |= 1u << (grp * MAX_PASSES + ps);
         }
       }
@@ -662,7 +665,8 @@ template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t offs[4];
-  wgrad_smem_layout(p.CB, p.NB, p.stages, offs);
+  const int NP = p.NP < 1 ? 1 : p.NP;
+  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   float* coefA = reinterpret_cast<float*>(smem + offs[2]);
   float* coefB = coefA + 256;
   const int bplanes = p.CB / 8;
-  const uint32_t a_bytes = 16u * PLANE_BYTES;
+  const uint32_t a_bytes = 16u * NP * PLANE_BYTES;
   const uint32_t bt_bytes = (uint32_t)bplanes * PLANE_BYTES;
   const uint32_t stage_bytes = a_bytes + p.NB * bt_bytes;
   const uint32_t stage0 = sbase + offs[3];
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const int ytile = blockIdx.y, ztile = blockIdx.z;
   const int vps = p.Dz * p.Dy * p.Dx;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.NB * p.CB) tmem_cols <<= 1;
+  while ((int)tmem_cols < (p.NB > NP ? p.NB : NP) * p.CB) tmem_cols <<= 1;
 
   if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -769,26 +773,49 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       if (AMODE == WA_LINEAR) {
         // loads of the A tile are issued now and consumed after the B loads have been issued as well
         aok = load_planes<false>(aregs, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz, p.Dy, p.Dx);
-      } else {
-        for (int g = 0; g < 2; ++g) {
-          const int kb = ztile * 2 + g;
-          const long long delta = (long long)((kb >> 2) * p.Sy + (kb & 3)) * p.Sx;
-          produce_planes<T_NONE, false, kActF16>(sA + g * 8 * PLANE_BYTES, 8, p.a_src, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, delta,
-                                        p.Dz, p.Dy, p.Dx, nullptr, nullptr);
-        }
       }
+      uint4 sregs[4][MAX_PASSES];   // stem: up to 2 pairs = 4 k-blocks of 8 planes, all loads in flight before the stores
+      uint32_t sok = 0;
       if (AMODE == WA_STEM_PAIR) {
-        // B rows are plain output-voxel rows: rebuild the linear index for them
-        named_bar_sync(1, NUM_PRODUCER_THREADS);
-        const long long m = (long long)(t_begin + it) * TILE_ROWS + tid;
-        if (tid < TILE_ROWS && m < p.M) rowinfo[tid].x = (int)m;
-        named_bar_sync(1, NUM_PRODUCER_THREADS);
+        const int chunk = lane & 7, rsub = lane >> 3;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < 2 * NP) {
+            const int kb = ztile * 2 * NP + g;
+            const long long delta = (long long)((kb >> 2) * p.Sy + (kb & 3)) * p.Sx;
+#pragma unroll
+            for (int ps = 0; ps < MAX_PASSES; ++ps) {
+              const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
+              const int4 ri = rowinfo[r];
+              const bool ok = ri.y > -1000;
+              sregs[g][ps] = ok ? ldg16(p.a_src + ((long long)ri.x + delta) * p.a_pitch + chunk * 8) : make_uint4(0, 0, 0, 0);
+              sok |= (uint32_t)ok << (g * MAX_PASSES + ps);
+            }
+          }
+        }
       }
       if (p.NB == 1) {
         uint4 bregs[2 * MAX_PASSES];
+        // stem: the rowinfo index is the space-to-depth row; the B rows are plain output voxels (linear index)
         const uint32_t bok = load_planes<false>(bregs, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0,
-                                                0, p.Dz, p.Dy, p.Dx);
+                                                0, p.Dz, p.Dy, p.Dx,
+                                                AMODE == WA_STEM_PAIR ? (long long)(t_begin + it) * TILE_ROWS : -1);
         if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        if (AMODE == WA_STEM_PAIR) {
+          const int chunk = lane & 7, rsub = lane >> 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < 2 * NP) {
+#pragma unroll
+              for (int ps = 0; ps < MAX_PASSES; ++ps) {
+                const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
+                uint4 v = sregs[g][ps];
+                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, false>(v);
+                sts16(sA + (g * 8 + chunk) * PLANE_BYTES + r * 16, v);
+              }
+            }
+          }
+        }
         store_planes<T_NONE, false>(bregs, bok, sB, bplanes_valid, warp, lane, nullptr, nullptr);
       } else if (p.NB == 9 && bplanes == 4) {
         // 9 shifted raw gradient tiles of 4 planes: B_j[v] = g[v - tap offset].  All 18 loads of this thread are
@@ -834,7 +861,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     mbar_wait(bar_accum, 0, 13);
     tc_fence_after();
     const int a = warp * 32 + lane;
-    for (int j = 0; j < p.NB; ++j) {
+    const int nacc = (EMODE == WE_STEM) ? NP : p.NB;
+    for (int j = 0; j < nacc; ++j) {
       for (int cc = 0; cc < p.CB / 32; ++cc) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * p.CB + cc * 32), v);
@@ -861,7 +889,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           }
         } else {
           // stem: a = (g, c64) with kb = ztile*2 + g, c64 = (dx, pz, py, px, ci); b = output channel
-          const int kb = ztile * 2 + (a >> 6), c = a & 63;
+          const int kb = (ztile * NP + j) * 2 + (a >> 6), c = a & 63;
           const int kz = 2 * (kb >> 2) + ((c >> 3) & 1), ky = 2 * (kb & 3) + ((c >> 2) & 1), kx = 2 * (c >> 4) + ((c >> 1) & 1);
           const int ci = c & 1;
           if (kz < 7 && ky < 7 && kx < 7 && ci < p.cin_real) {
@@ -886,6 +914,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         const uint64_t ad0 = make_smem_desc(sA, 128, PLANE_BYTES);
         uint64_t bd0 = make_smem_desc(sA + a_bytes, 128, PLANE_BYTES);
         const uint32_t acc0 = it > 0 ? 1u : 0u;
+        if (AMODE == WA_STEM_PAIR) {
+          // NP pairs share the B tile; pair pi reads its own 16 A planes and owns accumulator pi
+          for (int pi = 0; pi < NP; ++pi) {
+            const uint64_t ad = desc_advance(ad0, pi * 16 * PLANE_BYTES);
+            const uint32_t td = tmem_base + pi * p.CB;
+            tc_mma_bf16(td, ad, bd0, idesc, acc0);
+#pragma unroll
+            for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
+              tc_mma_bf16(td, desc_advance(ad, k16 * 256), desc_advance(bd0, k16 * 256), idesc, 1u);
+          }
+        } else
         for (int j = 0; j < p.NB; ++j) {
           const uint32_t td = tmem_base + j * p.CB;
           tc_mma_bf16(td, ad0, bd0, idesc, acc0);
