@@ -290,6 +290,12 @@ def run_ours(args):
                 "flops_per_launch": gemm_classes[dom] / max(1, kernels[dom]["launches_per_step"]),
                 "avg_launch_ms": round(kernels[dom]["ms_per_step"] / max(1, kernels[dom]["launches_per_step"]), 5)}
 
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj:        # DRAM bytes of the class's largest launch (ncu --set full), next to that launch's algorithmic bytes
+            roofline["traffic"] = tj[dom]["traffic_bytes"]
+            roofline["traffic_note"] = {k: tj[dom][k] for k in ("launch", "algorithmic_bytes", "duration_us")}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_arm(wl, steps=1, warmup=1, sample_batch=2)
