@@ -169,6 +169,7 @@ def run_ours(args):
     from mmnn_sts_b200 import _lib as L, distributed as D
     from mmnn_sts_b200.losses.GradientBlender import GradientBlender
     from mmnn_sts_b200.losses.losses import CoxPH
+    from mmnn_sts_b200.optim import SGD
     from mmnn_sts_b200.utils.utils import surv_criterion
     import torch.distributed as dist
     rank, world, device = D.init_from_env()
@@ -177,7 +178,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     L.lib()
     model = build_model(wl, device)
-    opt = torch.optim.SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    opt = SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)   # one-launch torch.optim.SGD subclass
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion)
     sync = D.GradientAllReducer(model.parameters(), model=model)
     dev_batches = make_batches(wl, 2, device=device, seed=1234 + 100 * rank)

@@ -93,6 +93,19 @@ struct CindexArgs;
 int mmnn_cindex_bootstrap(const struct CindexArgs* args /*HOST*/, void* stream);
 int mmnn_sizeof_cindex_args(void);
 
+/* ------------------------------------------------------------------------------------------------ optimiser
+ * mmnn_sgd_step     : torch.optim.SGD(momentum, nesterov, weight_decay, dampening 0) as the reference builds it
+ *                     (/root/reference/main.py:410-414) and steps it (:479-481), for ALL parameter tensors in one
+ *                     launch (one per mmnn_sgd_max_tensors() tensors).  p / g / m: HOST arrays of device pointers to
+ *                     the fp32 parameter, gradient and momentum buffer of each tensor, n: HOST array of element counts;
+ *                     the table travels as the kernel's parameter, one thread block per mmnn_sgd_chunk_elems() elements.
+ *                     Momentum buffers start at zero (== torch's first-step clone). */
+int mmnn_sgd_step(void* const* p /*HOST*/, const void* const* g /*HOST*/, void* const* m /*HOST*/,
+                  const long long* n /*HOST*/, int ntensors, float lr, float momentum, float weight_decay, int nesterov,
+                  void* stream);
+int mmnn_sgd_chunk_elems(void);
+int mmnn_sgd_max_tensors(void);
+
 /* ------------------------------------------------------------------------------------------------ instrumentation */
 void mmnn_profile_enable(int on);
 long long mmnn_launch_count(void);

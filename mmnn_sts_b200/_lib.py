@@ -137,6 +137,10 @@ def _declare(l):
     for nm, st in (("mmnn_sizeof_mlp_args", MlpArgs), ("mmnn_sizeof_cox_args", CoxArgs), ("mmnn_sizeof_cindex_args", CindexArgs)):
         getattr(l, nm).restype = I
         assert getattr(l, nm)() == C.sizeof(st), (nm, getattr(l, nm)(), C.sizeof(st))
+    l.mmnn_sgd_step.argtypes = [C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), C.POINTER(LL), I, C.c_float, C.c_float, C.c_float, I, VP]
+    l.mmnn_sgd_step.restype = I
+    l.mmnn_sgd_chunk_elems.restype = I
+    l.mmnn_sgd_max_tensors.restype = I
     l.mmnn_profile_enable.argtypes = [I]
     l.mmnn_profile_enable.restype = None
     l.mmnn_launch_count.restype = LL
@@ -166,7 +170,7 @@ def packed_elems(N, NT, Cin, kbw, ntaps):
 
 PROF_CLASSES = ["pack", "s2d", "stem_fprop", "maxpool", "conv1_fprop", "conv2_fprop", "trans_pool", "trans_fprop", "norm5",
                 "bn_running", "norm5_bwd", "extract", "conv2_wgrad", "conv2_dgrad", "bn_apply", "conv1_wgrad", "conv1_dgrad",
-                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads"]
+                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd"]
 
 
 def profile_collect():

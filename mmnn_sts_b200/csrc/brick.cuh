@@ -7,8 +7,11 @@
 //      brick[chunk][slot]  (16-byte cells, slot = (z'*18 + y')*10 + x')
 // and every tap is just a different START ADDRESS of the same SWIZZLE_NONE K-major descriptor:
 //      start = plane0 + ((dz*18 + dy)*10 + dx)*16,  SBO (next 8-row group = next y) = 10*16 B,  LBO = plane stride.
-// Warp roles (448 threads): 0-7 producers, 8 MMA issuer + TMEM owner, 9 weight loader (cp.async.bulk ring),
-// 10-13 epilogue (TMEM double-buffered, so the epilogue of tile t overlaps the MMAs of tile t+1).
+// Warp roles (448 threads = 14 warps), fprop: 0-7 producers, 8 MMA issuer + TMEM owner, 9 weight loader (cp.async.bulk
+// ring), 10-13 epilogue (TMEM double-buffered, so the epilogue of tile t overlaps the MMAs of tile t+1).
+// dgrad (32 input channels, 128 output columns): the producer is light and the mask + statistics epilogue is the
+// critical path (ncu r01f: MMA warp waits on acc_empty, 4 epilogue warps 87 % busy at 16 % issue rate), so the roles
+// are 0-3 producers, 4 MMA, 5 loader, 6-13 epilogue: two warps per TMEM lane quarter, each taking half the columns.
 #pragma once
 #include "engine.cuh"
 
@@ -18,7 +21,6 @@ constexpr int BR_TY = 16, BR_TX = 8, BR_HY = BR_TY + 2, BR_HX = BR_TX + 2;
 constexpr int BR_SLOTS = 3 * BR_HY * BR_HX;            // 540
 constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple of 16 -> conflict-free chunk planes
 constexpr int BR_THREADS = 448;
-constexpr int BR_MMA_WARP = 8, BR_LOAD_WARP = 9, BR_EPI_WARP0 = 10;
 constexpr int BR_BSTAGES = 6;
 constexpr int BR_BTAPS = 3;     // taps per weight-ring stage (one dx row): 9 waits per brick buffer instead of 27
 
@@ -59,6 +61,12 @@ template <int TRANS, int EPI, bool GRAD>
 __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid_constant__ BrickParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;
   constexpr bool E_F16 = kActF16;
+  constexpr int NPW = GRAD ? 4 : 8;                    // producer warps
+  constexpr int NPT = NPW * 32;                        // producer threads
+  constexpr int NEW = GRAD ? 8 : 4;                    // epilogue warps
+  constexpr int NET = NEW * 32;
+  constexpr int BR_MMA_WARP = NPW, BR_LOAD_WARP = NPW + 1, BR_EPI_WARP0 = NPW + 2;
+  static_assert(BR_EPI_WARP0 + NEW == BR_THREADS / 32, "warp roles must fill the CTA");
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, offs);
@@ -88,9 +96,9 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
 
   if (warp == BR_MMA_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), NUM_PRODUCER_THREADS); mbar_init(BAR(2 + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), NPT); mbar_init(BAR(2 + i), 1); }
       for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(4 + BR_BSTAGES + i), 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(BAR(4 + 2 * BR_BSTAGES + i), 1); mbar_init(BAR(6 + 2 * BR_BSTAGES + i), EPILOGUE_THREADS); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(4 + 2 * BR_BSTAGES + i), 1); mbar_init(BAR(6 + 2 * BR_BSTAGES + i), NET); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -130,17 +138,17 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     y0 = ty * BR_TY; x0 = tx * BR_TX;
   };
 
-  if (warp < PRODUCER_WARPS) {
+  if (warp < NPW) {
     // ================= producers: one load + one transform per brick cell
     const int cells = BR_SLOTS * PH;
     // A thread owns the same brick cells for every tile: cell c = tid + u*256 -> chunk = c % PH (constant per thread),
     // slot = c / PH.  The slot's halo coordinates are decoded ONCE (packed z|y|x) instead of per tile.
-    constexpr int MAXU = (BR_SLOTS * 8 + NUM_PRODUCER_THREADS - 1) / NUM_PRODUCER_THREADS;   // 17
+    constexpr int MAXU = (BR_SLOTS * (GRAD ? 4 : 8) + NPT - 1) / NPT;   // 17 (dgrad launches always have PH = 4)
     const int chunk = (PH == 8) ? (tid & 7) : (tid & 3);
     int pk[MAXU];
 #pragma unroll
     for (int u = 0; u < MAXU; ++u) {
-      const int c = tid + u * NUM_PRODUCER_THREADS;
+      const int c = tid + u * NPT;
       const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
       const int xx = slot % BR_HX, r2 = slot / BR_HX;
       pk[u] = (c < cells) ? (((r2 / BR_HY) << 16) | ((r2 % BR_HY) << 8) | xx) : -1;
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
             const int sz = z + (pk[u] >> 16) - 1, sy = y0 + ((pk[u] >> 8) & 0xff) - 1, sx = x0 + (pk[u] & 0xff) - 1;
             const bool ok = (unsigned)sz < (unsigned)p.Dz && (unsigned)sy < (unsigned)p.Dy && (unsigned)sx < (unsigned)p.Dx;
             const long long m = ok ? ((nbase + sz) * p.Dy + sy) * p.Dx + sx : 0;
-            const int slot = ((PH == 8) ? (tid >> 3) : (tid >> 2)) + u * (NUM_PRODUCER_THREADS / ((PH == 8) ? 8 : 4));
+            const int slot = ((PH == 8) ? (tid >> 3) : (tid >> 2)) + u * (NPT / ((PH == 8) ? 8 : 4));
             cp_async16(dst + slot * 16, src + m * p.a_pitch, ok ? 16u : 0u);
             okmask |= (uint32_t)ok << u;
           }
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
               if ((okmask >> u) & 1u) {
-                const int slot = (tid >> 3) + u * (NUM_PRODUCER_THREADS / 8);
+                const int slot = (tid >> 3) + u * (NPT / 8);
                 uint4 v = lds16(dst + slot * 16);
                 apply_bnrelu8_h2(v, hc);
                 sts16(dst + slot * 16, v);
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
               if ((okmask >> u) & 1u) {
-                const int slot = (tid >> 3) + u * (NUM_PRODUCER_THREADS / 8);
+                const int slot = (tid >> 3) + u * (NPT / 8);
                 uint4 v = lds16(dst + slot * 16);
                 apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
                 sts16(dst + slot * 16, v);
@@ -277,37 +285,43 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
       }
     }
   } else if (warp >= BR_EPI_WARP0) {
-    // ================= epilogue (TMEM lane quarter = warp % 4)
+    // ================= epilogue (TMEM lane quarter = warp % 4; with 8 warps, warp e and e+4 share a quarter and split
+    // the 32-column chunks: CCW chunks per warp starting at cc0)
+    constexpr int CCW = GRAD ? 2 : 4;
     const int qd = warp & 3;
     const int etid = (warp - BR_EPI_WARP0) * 32 + lane;
+    const int cc0 = ((warp - BR_EPI_WARP0) >> 2) * CCW;
     const int r = qd * 32 + lane;
     const int ry = r >> 3, rx = r & 7;
-    float acc1[4] = {0, 0, 0, 0}, acc2[4] = {0, 0, 0, 0};   // per-lane column partials, NT/32 <= 4 chunks
+    float acc1[CCW], acc2[CCW];   // per-lane column partials
+#pragma unroll
+    for (int k = 0; k < CCW; ++k) { acc1[k] = 0.f; acc2[k] = 0.f; }
     for (int it = 0; it < my_tiles; ++it) {
       int n, z, y0, x0;
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
       const int abuf = it & 1;
       const bool row_ok = (y0 + ry < p.Dy) && (x0 + rx < p.Dx);
       const long long m = (((long long)n * p.Dz + z) * p.Dy + (y0 + ry)) * p.Dx + (x0 + rx);
-      uint4 xpre[4][4];   // gating activations of this row: fetched before the accumulator is ready
+      uint4 xpre[CCW][4];   // gating activations of this row: fetched before the accumulator is ready
       if (EPI == EP_MASK_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
+        for (int k = 0; k < CCW; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            xpre[cc][i] = (row_ok && cc * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + cc * 32 + i * 8) : make_uint4(0, 0, 0, 0);
+            xpre[k][i] = (row_ok && (cc0 + k) * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + (cc0 + k) * 32 + i * 8) : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(BAR(4 + 2 * BR_BSTAGES + abuf), (uint32_t)(it >> 1) & 1u, 26);
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int k = 0; k < CCW; ++k) {
+        const int cc = cc0 + k;
         if (cc * 32 >= p.NT) break;
         float v[32], qv[32];
         tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * p.NT + cc * 32), v);
         if (EPI == EP_MASK_STATS) {
           uint4 xv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = xpre[cc][i];
+          for (int i = 0; i < 4; ++i) xv[i] = xpre[k][i];
           const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
@@ -344,8 +358,8 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           }
         }
         if (EPI != EP_STORE) {
-          acc1[cc] += warp_transpose_sum32(v, lane);
-          acc2[cc] += warp_transpose_sum32(qv, lane);
+          acc1[k] += warp_transpose_sum32(v, lane);
+          acc2[k] += warp_transpose_sum32(qv, lane);
         }
       }
       tc_fence_before();
@@ -353,14 +367,15 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     }
     if (EPI != EP_STORE) {
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int k = 0; k < CCW; ++k) {
+        const int cc = cc0 + k;
         if (cc * 32 < p.NT) {
-          red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = acc1[cc];
-          red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = acc2[cc];
+          red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = acc1[k];
+          red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = acc2[k];
         }
       }
-      named_bar_sync(1, EPILOGUE_THREADS);
-      for (int c = etid; c < p.NT; c += EPILOGUE_THREADS) {
+      named_bar_sync(1, NET);
+      for (int c = etid; c < p.NT; c += NET) {
         const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
         const float b = red[(1 * 4 + 0) * p.NT + c] + red[(1 * 4 + 1) * p.NT + c] + red[(1 * 4 + 2) * p.NT + c] + red[(1 * 4 + 3) * p.NT + c];
         atomicAdd(p.st_sum + c, (double)a);

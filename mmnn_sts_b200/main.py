@@ -18,6 +18,7 @@ import torch
 from .losses.GradientBlender import GradientBlender
 from .losses.losses import CoxPH
 from .ops import concordance_counts
+from .optim import SGD
 from .utils.utils import surv_criterion
 
 NUM_CLASSES = 2                 # /root/reference/data/constants.py:95
@@ -69,7 +70,7 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
     n_train = args.num_train
     super_batch_interval = SUPER_BATCH_SIZE / args.batch_size
     steps_per_epoch = n_train // SUPER_BATCH_SIZE if n_train % SUPER_BATCH_SIZE == 0 else 1 + n_train // SUPER_BATCH_SIZE
-    optimizer = torch.optim.SGD(model.parameters(), args.lr, momentum=args.momentum, nesterov=True, weight_decay=args.weight_decay)
+    optimizer = SGD(model.parameters(), args.lr, momentum=args.momentum, nesterov=True, weight_decay=args.weight_decay)
     scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=args.lr, steps_per_epoch=steps_per_epoch, epochs=args.epochs)
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion) if args.blend else None
     hist = SimpleNamespace(train_loss=[], val_loss=[], train_c=[], val_c=[], best_loss=math.inf, best_state=None, blender=blender)

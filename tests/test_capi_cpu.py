@@ -79,6 +79,10 @@ def test_no_cpu_fallback():
         m.backbone(torch.rand(2, 1, 32, 32, 32))
     with pytest.raises(L.MMNNLibraryError):
         CoxPH(torch.randn(4), torch.ones(4), torch.arange(4))
+    from mmnn_sts_b200.optim import SGD
+    p = torch.nn.Parameter(torch.ones(4)); p.grad = torch.ones(4)
+    with pytest.raises(L.MMNNLibraryError):
+        SGD([p], 0.1, momentum=0.9, nesterov=True).step()
 
 
 def test_bench_reference_arm_runs_on_cpu():

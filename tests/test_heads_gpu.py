@@ -173,3 +173,37 @@ def test_cindex_counts_bit_exact():
     # all censored -> no admissible pair
     c = concordance_counts(torch.tensor(t, device="cuda"), torch.tensor(p, device="cuda"), torch.zeros(n, device="cuda"))
     assert int(c[0, 2]) == 0
+
+
+@pytest.mark.gpu
+def test_fused_sgd_matches_torch_sgd():
+    """mmnn_sts_b200.optim.SGD (one launch) against torch.optim.SGD (the reference's optimiser, main.py:410-414) over
+    three steps with OneCycleLR cycling lr and momentum, odd sizes and unaligned gradient views."""
+    from mmnn_sts_b200.optim import SGD
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    shapes = [(128, 64, 1, 1, 1), (64,), (32, 128, 3, 3, 3), (3,), (17, 5), (100003,), (12,)]
+    pa = [torch.randn(s, device=dev, generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.SGD(pa, 5e-2, momentum=0.9, nesterov=True, weight_decay=1e-2)
+    ob = SGD(pb, 5e-2, momentum=0.9, nesterov=True, weight_decay=1e-2)
+    sa = torch.optim.lr_scheduler.OneCycleLR(oa, max_lr=5e-2, total_steps=4)
+    sb = torch.optim.lr_scheduler.OneCycleLR(ob, max_lr=5e-2, total_steps=4)
+    for step in range(3):
+        total = sum(p.numel() for p in pa)
+        flat = torch.randn(total + 1, device=dev, generator=g)[1:]        # 4-byte aligned only: scalar path for every view
+        off = 0
+        for a, b in zip(pa, pb):
+            gr = flat[off:off + a.numel()].view(a.shape) if step == 1 else torch.randn(a.shape, device=dev, generator=g)
+            off += a.numel()
+            if a is pa[3] and step == 0:
+                a.grad = None; b.grad = None                                 # a parameter without gradient is skipped
+                continue
+            a.grad = gr.clone(); b.grad = gr if step == 1 else gr.clone()
+        oa.step(); ob.step(); sa.step(); sb.step()
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-6)
+    for a, b in zip(pa, pb):
+        if "momentum_buffer" in oa.state[a]:
+            torch.testing.assert_close(ob.state[b]["momentum_buffer"], oa.state[a]["momentum_buffer"], rtol=2e-6, atol=2e-6)
+    assert set(ob.state_dict()["param_groups"][0].keys()) == set(oa.state_dict()["param_groups"][0].keys())
