@@ -62,6 +62,12 @@ int mmnn_conv_rows(const struct RowsParams* p /*HOST*/, int amode, int trans, in
  *                   shared memory, taps = descriptor start addresses); used when the spatial dims are >= 8. */
 int mmnn_conv3_brick(const struct BrickParams* p /*HOST*/, int grad, void* stream);
 int mmnn_sizeof_brick_params(void);
+/* mmnn_stem_brick : the stem Conv3d(C_in -> 64, k 7, s 2, p 3) (/root/reference/models/densenet.py:199) in brick mode on
+ *                   the padded space-to-depth image (4x4x4 taps over 16 channels, weights resident in shared memory),
+ *                   fused per-channel statistics of the stored output for norm0.  StemBrickParams: csrc/stem.cuh. */
+struct StemBrickParams;
+int mmnn_stem_brick(const struct StemBrickParams* p /*HOST*/, void* stream);
+int mmnn_sizeof_stem_brick_params(void);
 int mmnn_conv_wgrad(const struct WgradParams* p /*HOST*/, int kind, int split, void* stream);
 int mmnn_pack_weights(const struct PackDesc* descs /*HOST*/, int n, void* dev_descs, void* stream);
 int mmnn_sizeof_rows_params(void);

@@ -48,6 +48,12 @@ class BrickParams(C.Structure):
                 ("bnE", BnSrc)]
 
 
+class StemBrickParams(C.Structure):
+    _fields_ = [("B", C.c_int), ("D0", C.c_int), ("H0", C.c_int), ("W0", C.c_int), ("Sz", C.c_int), ("Sy", C.c_int),
+                ("Sx", C.c_int), ("xs2d", C.c_void_p), ("w_packed", C.c_void_p), ("out", C.c_void_p),
+                ("out_pitch", C.c_longlong), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p)]
+
+
 class WgradParams(C.Structure):
     _fields_ = [("M", C.c_int), ("CB", C.c_int), ("NB", C.c_int), ("na_total", C.c_int), ("nb_total", C.c_int),
                 ("Dz", C.c_int), ("Dy", C.c_int), ("Dx", C.c_int), ("Sz", C.c_int), ("Sy", C.c_int), ("Sx", C.c_int),
@@ -105,6 +111,9 @@ def _declare(l):
     l.mmnn_conv3_brick.argtypes = [C.POINTER(BrickParams), C.c_int, C.c_void_p]
     l.mmnn_conv3_brick.restype = C.c_int
     assert l.mmnn_sizeof_brick_params() == C.sizeof(BrickParams), (l.mmnn_sizeof_brick_params(), C.sizeof(BrickParams))
+    l.mmnn_stem_brick.argtypes = [C.POINTER(StemBrickParams), C.c_void_p]
+    l.mmnn_stem_brick.restype = C.c_int
+    assert l.mmnn_sizeof_stem_brick_params() == C.sizeof(StemBrickParams), (l.mmnn_sizeof_stem_brick_params(), C.sizeof(StemBrickParams))
     l.mmnn_conv_wgrad.argtypes = [C.POINTER(WgradParams), C.c_int, C.c_int, C.c_void_p]
     l.mmnn_conv_wgrad.restype = C.c_int
     assert l.mmnn_sizeof_wgrad_params() == C.sizeof(WgradParams), (l.mmnn_sizeof_wgrad_params(), C.sizeof(WgradParams))

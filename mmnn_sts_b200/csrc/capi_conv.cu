@@ -4,6 +4,7 @@
 #include "engine.cuh"
 #include "pack.cuh"
 #include "prof.h"
+#include "stem.cuh"
 
 using namespace mmnn;
 
@@ -90,6 +91,19 @@ int launch_brick(const BrickParams& p, int grad, cudaStream_t stream) {
   return launch_brick_t<T_NONE, EP_MASK_STATS, true>(p, stream);
 }
 
+// Stem convolution in brick mode (stem.cuh): persistent, one CTA per SM
+int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
+  if (p.Sz != p.D0 + 3 || p.Sy != p.H0 + 3 || p.Sx != p.W0 + 3) return -2;
+  cudaError_t e = cudaFuncSetAttribute(stem_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  const long long ntiles = (long long)p.B * p.D0 * ((p.H0 + SB_TY - 1) / SB_TY) * ((p.W0 + SB_TX - 1) / SB_TX);
+  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return -2;
+  const int grid = ntiles < 148 ? (int)ntiles : 148;
+  stem_brick_kernel<<<grid, SB_THREADS, SB_SMEM, stream>>>(p);
+  MMNN_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream) {
   uint32_t offs[4];
@@ -162,6 +176,8 @@ int mmnn_profile_collect(float* ms, int* counts) {
 
 int mmnn_conv3_brick(const BrickParams* p, int grad, void* stream) { return launch_brick(*p, grad, (cudaStream_t)stream); }
 int mmnn_sizeof_brick_params() { return (int)sizeof(BrickParams); }
+int mmnn_stem_brick(const StemBrickParams* p, void* stream) { return launch_stem_brick(*p, (cudaStream_t)stream); }
+int mmnn_sizeof_stem_brick_params() { return (int)sizeof(StemBrickParams); }
 
 int mmnn_conv_wgrad(const WgradParams* p, int kind, int split, void* stream) {
   return launch_wgrad(*p, kind, split, (cudaStream_t)stream);

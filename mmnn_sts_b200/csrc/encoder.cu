@@ -21,8 +21,10 @@
 #include "engine.cuh"
 #include "pack.cuh"
 #include "prof.h"
+#include "stem.cuh"
 
 namespace mmnn {
+int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream);
 int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream);
 int launch_brick(const BrickParams& p, int grad, cudaStream_t stream);
@@ -377,14 +379,12 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     { ProfScope ps_(PC_S2D, st);
       s2d_pack_kernel<<<ew_grid(cells), EW_THREADS, 0, st>>>(image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
     LAUNCH_RET();
-    RowsParams p = {};
-    p.M = (int)g.M0; p.NT = 64; p.Ncols = 64; p.Cin = 64; p.kbw = 64; p.ntaps = 16; p.tap_sign = 1;
-    p.Dz = g.D0; p.Dy = g.H0; p.Dx = g.W0; p.Sz = g.Sz; p.Sy = g.Sy; p.Sx = g.Sx;
-    p.a_src = xs2d; p.a_pitch = 16;
-    p.b_packed = packed + pl->pk_stem;
+    StemBrickParams p = {};
+    p.B = B; p.D0 = g.D0; p.H0 = g.H0; p.W0 = g.W0; p.Sz = g.Sz; p.Sy = g.Sy; p.Sx = g.Sx;
+    p.xs2d = xs2d; p.w_packed = packed + pl->pk_stem;
     p.out = (bf16*)(ws + g.stem_out); p.out_pitch = 64;
     p.st_sum = fstats + pl->n0.fwd_off; p.st_sq = fstats + FC + pl->n0.fwd_off;
-    { ProfScope ps_(PC_STEM_FPROP, st); RET_IF(launch_rows(p, A_STEM, T_NONE, EP_STORE_STATS, 0, st)); }
+    { ProfScope ps_(PC_STEM_FPROP, st); RET_IF(launch_stem_brick(p, st)); }
     PoolParams q = {};
     q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
     q.src = (const bf16*)(ws + g.stem_out);

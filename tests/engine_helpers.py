@@ -90,3 +90,15 @@ def brick(B, dims, CH, NT, a_src, a_pitch, b_packed, out, out_pitch, grad=0, tap
     p.e_pitch = e_pitch
     p.bnE = bnE if bnE is not None else L.BnSrc()
     L.check(L.lib().mmnn_conv3_brick(C.byref(p), grad, stream_ptr()), "conv3_brick")
+
+
+def stem_brick(B, dims, xs2d, w_packed, out, out_pitch, st_sum=None, st_sq=None):
+    p = L.StemBrickParams()
+    p.B = B
+    p.D0, p.H0, p.W0 = dims
+    p.Sz, p.Sy, p.Sx = dims[0] + 3, dims[1] + 3, dims[2] + 3
+    p.xs2d, p.w_packed = xs2d.data_ptr(), w_packed.data_ptr()
+    p.out, p.out_pitch = out.data_ptr(), out_pitch
+    p.st_sum = st_sum.data_ptr() if st_sum is not None else None
+    p.st_sq = st_sq.data_ptr() if st_sq is not None else None
+    L.check(L.lib().mmnn_stem_brick(C.byref(p), stream_ptr()), "stem_brick")

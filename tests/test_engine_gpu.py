@@ -160,6 +160,35 @@ def test_stem_conv7_s2():
         assert torch.allclose(st[0], out.double().sum(0), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 20, 16), (3, 16, 64, 32), (5, 40, 36, 24)])
+def test_stem_brick_conv7_s2(shape):
+    """Brick-mode stem (stem.cuh) against F.conv3d on the same rounded operands: partial tiles in y and x, more tiles
+    than SMs (persistent loop, 3-deep brick ring, TMEM double buffering), register-accumulated statistics."""
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(14)
+    for cin in (1, 2):
+        B, X, Y, Z = shape
+        img = torch.rand(B, cin, X, Y, Z, device="cuda")
+        w = torch.randn(64, cin, 7, 7, 7, device="cuda") * 0.05
+        Dz, Dy, Dx = (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1
+        Sz, Sy, Sx = Dz + 3, Dy + 3, Dx + 3
+        pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
+        pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
+        s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(_actdt())
+        M = B * Dz * Dy * Dx
+        bp = H.pack(w, 64, 64, 64, 64, 16, 0, 0, 0, mode=L.PACK_STEM, cin_real=cin)
+        out = torch.zeros(M, 64, dtype=_actdt(), device="cuda")
+        st = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
+        H.stem_brick(B, (Dz, Dy, Dx), s2d, bp, out, 64, st_sum=st[0], st_sq=st[1])
+        torch.cuda.synchronize()
+        ref = F.conv3d(_act(img), _act(w), stride=2, padding=3).permute(0, 2, 3, 4, 1).reshape(M, 64)
+        _close(out, ref, rtol=1 / 64, atol=5e-2)
+        assert (out.float() - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (out.float() - ref).abs().max()
+        assert torch.allclose(st[0], out.double().sum(0), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(st[1], (out.double() ** 2).sum(0), rtol=1e-5, atol=1e-3)
+
+
 def test_wgrad_conv1x1():
     from tests import engine_helpers as H
     torch.manual_seed(5)
