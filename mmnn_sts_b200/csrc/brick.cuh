@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   constexpr int BR_MMA_WARP = NPW, BR_LOAD_WARP = NPW + 1, BR_EPI_WARP0 = NPW + 2;
   static_assert(BR_EPI_WARP0 + NEW == BR_THREADS / 32, "warp roles must fill the CTA");
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, offs);
   const uint32_t sbase = smem_u32(smem);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
+  pdl_wait();   // nothing above touches global memory
   if (TRANS == T_BNRELU) {
     for (int c = tid; c < p.CH; c += BR_THREADS) {
       float mean, rstd;

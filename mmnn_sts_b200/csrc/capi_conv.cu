@@ -2,6 +2,7 @@
 // encoder orchestrator in encoder.cu).  Plain pointers and sizes only; see include/mmnn_b200.h.
 #include "brick.cuh"
 #include "engine.cuh"
+#include "launch.h"
 #include "pack.cuh"
 #include "prof.h"
 #include "stem.cuh"
@@ -35,7 +36,7 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((p.M + TILE_ROWS - 1) / TILE_ROWS, (p.Ncols + p.NT - 1) / p.NT);
-  kern<<<grid, ENGINE_THREADS, smem, stream>>>(p);
+  launch_pdl(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }
@@ -71,7 +72,7 @@ int launch_brick_t(const BrickParams& p, cudaStream_t stream) {
   if (e != cudaSuccess) return (int)e;
   const int ntiles = p.B * p.Dz * ((p.Dy + BR_TY - 1) / BR_TY) * ((p.Dx + BR_TX - 1) / BR_TX);
   const int grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
-  kern<<<grid, BR_THREADS, smem, stream>>>(p);
+  launch_pdl(kern, dim3(grid), dim3(BR_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }
@@ -99,7 +100,7 @@ int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
   const long long ntiles = (long long)p.B * p.D0 * ((p.H0 + SB_TY - 1) / SB_TY) * ((p.W0 + SB_TX - 1) / SB_TX);
   if (ntiles <= 0 || ntiles > 0x7fffffffLL) return -2;
   const int grid = ntiles < 148 ? (int)ntiles : 148;
-  stem_brick_kernel<<<grid, SB_THREADS, SB_SMEM, stream>>>(p);
+  launch_pdl(stem_brick_kernel, dim3(grid), dim3(SB_THREADS), (size_t)SB_SMEM, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }
@@ -122,7 +123,7 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
     if (split < 1) split = 1;
   }
   if (split > ntiles) split = ntiles;
-  kern<<<dim3(split, gy, gz), ENGINE_THREADS, smem, stream>>>(p);
+  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

@@ -80,6 +80,15 @@ MMNN_DEVINL bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel launched through launch_pdl() (launch.h) calls pdl_trigger() first (the next kernel in the stream may
+// then be scheduled as soon as all CTAs of this one are resident) and pdl_wait() in ALL threads before its first
+// global-memory access (returns when the preceding kernel has completed and its writes are visible), so the launch
+// latency and the prologue (barrier init, TMEM allocation, index tables) overlap the previous kernel's tail.
+// Without the launch attribute (the default, see launch.h) both are no-ops.
+MMNN_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+MMNN_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 MMNN_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -85,6 +85,7 @@ struct PoolParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const __grid_constant__ PoolParams p) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[128];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -159,6 +160,7 @@ struct PoolBwdParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(const __grid_constant__ PoolBwdParams p) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[256];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -237,6 +239,7 @@ struct AvgPoolParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [2][C]
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -274,6 +277,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const
 // PASS == 1: accumulate sum v, sum v*xhat with v = relu'(bn(x)) * dpooled[parent]/8.   PASS == 2: dx = k (v - c1 - xhat c2)
 template <int PASS>
 static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [6][C]: s, t, mean, rstd, (pass2) k*c1', k*c2'
   __shared__ float red[PASS == 1 ? EW_THREADS * 16 : 1];
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
@@ -353,6 +357,7 @@ struct BnApplyParams {
 
 template <int OUT>
 static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_constant__ BnApplyParams p) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [3][C]: a (on v), b (on x), d (const):  out = a*v + b*x + d
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -415,6 +420,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
 static __global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* __restrict__ src, long long src_pitch,
                                                                    bf16* __restrict__ dst, long long M, int C,
                                                                    const float* __restrict__ colscale, int vps) {
+  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   const int cpr = C / 8;
   const long long total = M * cpr;
   for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {

@@ -20,6 +20,7 @@
 #include "eltwise.cuh"
 #include "engine.cuh"
 #include "pack.cuh"
+#include "launch.h"
 #include "prof.h"
 #include "stem.cuh"
 
@@ -393,7 +394,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     q.argmax = ws + g.argmax;
     q.st_sum = fstats + pl->blocks[0].fwd_off; q.st_sq = fstats + FC + pl->blocks[0].fwd_off;
     int blocks = (int)std::min<long long>((g.M[0] + 31) / 32, NUM_SMS * 8);
-    { ProfScope ps_(PC_MAXPOOL, st); bnrelu_maxpool_kernel<<<blocks, EW_THREADS, 0, st>>>(q); }
+    { ProfScope ps_(PC_MAXPOOL, st); launch_pdl(bnrelu_maxpool_kernel, dim3(blocks), dim3(EW_THREADS), 0, st, q); }
     LAUNCH_RET();
   }
 
@@ -449,7 +450,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       a.bn = make_bn(bi.tn, params, buffers, fstats, FC, M, batch);
       a.pooled = (bf16*)(ws + g.pooled[b]);
       { ProfScope ps_(PC_TRANS_POOL, st);
-        bnrelu_avgpool_kernel<<<ew_grid(g.M[b + 1] * (bi.ctot / 8)), EW_THREADS, 2 * bi.ctot * sizeof(float), st>>>(a); }
+        launch_pdl(bnrelu_avgpool_kernel, dim3(ew_grid(g.M[b + 1] * (bi.ctot / 8))), dim3(EW_THREADS), 2 * bi.ctot * sizeof(float), st, a); }
       LAUNCH_RET();
       RowsParams p = {};
       p.M = (int)g.M[b + 1]; p.NT = 128; p.Ncols = bi.ctot / 2; p.Cin = bi.ctot; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
@@ -548,9 +549,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     const int grid = ew_grid(M * (C / 8));
     const size_t sm = 3 * C * sizeof(float);
     ProfScope ps_(PC_BN_APPLY, st);
-    if (out_mode == BA_OUT_BF16) bn_bwd_apply_kernel<BA_OUT_BF16><<<grid, EW_THREADS, sm, st>>>(a);
-    else if (out_mode == BA_OUT_F32_ADD) bn_bwd_apply_kernel<BA_OUT_F32_ADD><<<grid, EW_THREADS, sm, st>>>(a);
-    else bn_bwd_apply_kernel<BA_OUT_F32_STORE><<<grid, EW_THREADS, sm, st>>>(a);
+    if (out_mode == BA_OUT_BF16) launch_pdl(bn_bwd_apply_kernel<BA_OUT_BF16>, dim3(grid), dim3(EW_THREADS), sm, st, a);
+    else if (out_mode == BA_OUT_F32_ADD) launch_pdl(bn_bwd_apply_kernel<BA_OUT_F32_ADD>, dim3(grid), dim3(EW_THREADS), sm, st, a);
+    else launch_pdl(bn_bwd_apply_kernel<BA_OUT_F32_STORE>, dim3(grid), dim3(EW_THREADS), sm, st, a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
   };
@@ -592,7 +593,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       // emitted it while it had the final values in registers (fused slice extraction).
       if (l == (int)bi.layers.size() - 1) {
         ProfScope ps_(PC_EXTRACT, st);
-        extract_slice_kernel<<<ew_grid(M * 4), EW_THREADS, 0, st>>>(
+        launch_pdl(extract_slice_kernel, dim3(ew_grid(M * 4)), dim3(EW_THREADS), 0, st, 
             dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps);
         LAUNCH_RET();
       }
@@ -692,7 +693,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       const bf16* pooled = (const bf16*)(ws + g.pooled[b - 1]);
       if (trans_done) CUDA_RET(cudaStreamWaitEvent(st, trans_done, 0));   // previous transition's wgrad still reads gout
       { ProfScope ps_(PC_EXTRACT, st);
-        extract_slice_kernel<<<ew_grid(M * (bi.c0 / 8)), EW_THREADS, 0, st>>>(dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps); }
+        launch_pdl(extract_slice_kernel, dim3(ew_grid(M * (bi.c0 / 8))), dim3(EW_THREADS), 0, st, dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps); }
       LAUNCH_RET();
       {
         WgradParams w = {};
@@ -733,8 +734,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       const int rows_per_block = EW_THREADS / (pv.ctot / 8);
       int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
       { ProfScope ps_(PC_AVGPOOL_BWD, st, 2);
-        avgpool_bnrelu_bwd_kernel<1><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a);
-        avgpool_bnrelu_bwd_kernel<2><<<blocks, EW_THREADS, 6 * pv.ctot * sizeof(float), st>>>(a); }
+        launch_pdl(avgpool_bnrelu_bwd_kernel<1>, dim3(blocks), dim3(EW_THREADS), 6 * pv.ctot * sizeof(float), st, a);
+        launch_pdl(avgpool_bnrelu_bwd_kernel<2>, dim3(blocks), dim3(EW_THREADS), 6 * pv.ctot * sizeof(float), st, a); }
       LAUNCH_RET();
     } else {
       // pool0 + relu0 + norm0 + conv0
@@ -747,7 +748,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       q.dr = (bf16*)(ws + g.dr);
       q.g_sum = gsum(pl->n0); q.g_dot = gdot(pl->n0);
       int blocks = (int)std::min<long long>((g.M0 + 31) / 32, NUM_SMS * 8);
-      { ProfScope ps_(PC_MAXPOOL_BWD, st); maxpool_bnrelu_bwd_kernel<<<blocks, EW_THREADS, 0, st>>>(q); }
+      { ProfScope ps_(PC_MAXPOOL_BWD, st); launch_pdl(maxpool_bnrelu_bwd_kernel, dim3(blocks), dim3(EW_THREADS), 0, st, q); }
       LAUNCH_RET();
       RET_IF(bn_apply(BA_OUT_BF16, g.M0, 64, q.dr, nullptr, 64, q.x, 64, q.bn, gsum(pl->n0), gdot(pl->n0), q.dr, 64));
       WgradParams w = {};

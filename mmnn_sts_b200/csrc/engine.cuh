@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   uint32_t offs[6];
   rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
   const uint32_t sbase = smem_u32(smem);
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
+  pdl_wait();   // nothing above touches global memory
   if (TRANS == T_BNRELU) {
     for (int c = tid; c < p.Cin; c += ENGINE_THREADS) {
       float mean, rstd;
@@ -664,6 +666,7 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   uint32_t offs[4];
   const int NP = p.NP < 1 ? 1 : p.NP;
   wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs);
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
+  pdl_wait();   // nothing above touches global memory
   if (ATRANS == T_BNRELU) {
     for (int c = tid; c < 128; c += ENGINE_THREADS) {
       const int ch = ztile * 128 + c;

@@ -41,6 +41,7 @@ struct StemBrickParams {
 static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const __grid_constant__ StemBrickParams p) {
   constexpr bool F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   const uint32_t sbase = smem_u32(smem);
   // barriers (8 B each): brick_full[3] 0..2 | brick_empty[3] 3..5 | w_full 6 | acc_full[2] 7,8 | acc_empty[2] 9,10
   auto BAR = [&](int i) { return sbase + 8u * i; };
@@ -59,16 +60,19 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
       mbar_init(BAR(6), 1);
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(7 + i), 1); mbar_init(BAR(9 + i), SB_NET); }
       fence_mbar_init();
-      mbar_arrive_expect_tx(BAR(6), SB_WBYTES);
-      for (int i = 0; i < 16; ++i) bulk_g2s(wsm + i * 8192, p.w_packed + (size_t)i * 4096, 8192, BAR(6));
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
   }
+  pdl_wait();   // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp == SB_MMA_WARP && lane == 0) {
+    mbar_arrive_expect_tx(BAR(6), SB_WBYTES);
+    for (int i = 0; i < 16; ++i) bulk_g2s(wsm + i * 8192, p.w_packed + (size_t)i * 4096, 8192, BAR(6));
+  }
 
   auto tile_coords = [&](int t, int& n, int& z, int& y0, int& x0) {
     const int tx = t % tiles_x; t /= tiles_x;
