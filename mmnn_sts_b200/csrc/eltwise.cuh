@@ -102,29 +102,36 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long M1 = (long long)p.B * p.D1 * p.H1 * p.W1;
   for (long long m = (long long)blockIdx.x * (EW_THREADS / 8) + (threadIdx.x >> 3); m < M1; m += (long long)gridDim.x * (EW_THREADS / 8)) {
-    long long t = m;
-    const int x = (int)(t % p.W1); t /= p.W1;
-    const int y = (int)(t % p.H1); t /= p.H1;
-    const int z = (int)(t % p.D1);
-    const int b = (int)(t / p.D1);
+    unsigned t = (unsigned)m;                       // M1 < 2^31 (checked by the host): 32-bit index arithmetic
+    const int x = (int)(t % (unsigned)p.W1); t /= (unsigned)p.W1;
+    const int y = (int)(t % (unsigned)p.H1); t /= (unsigned)p.H1;
+    const int z = (int)(t % (unsigned)p.D1);
+    const int b = (int)(t / (unsigned)p.D1);
     float best[8];
     int code[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; code[e] = 0; }
+    // one z-plane of the window at a time: its 9 loads are issued together (predicated), then compared in the
+    // (dz, dy, dx) scan order so that the first maximum wins like torch
+#pragma unroll
     for (int dz = 0; dz < 3; ++dz) {
       const int iz = 2 * z + dz - 1;
-      if (iz < 0 || iz >= p.D0) continue;
-      for (int dy = 0; dy < 3; ++dy) {
-        const int iy = 2 * y + dy - 1;
-        if (iy < 0 || iy >= p.H0) continue;
+      const bool zok = (unsigned)iz < (unsigned)p.D0;
+      uint4 v[9];
+      bool ok[9];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int ix = 2 * x + dx - 1;
-          if (ix < 0 || ix >= p.W0) continue;
-          const uint4 v = ldg16(p.src + ((((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix) * 64 + chunk * 8);
+      for (int k = 0; k < 9; ++k) {
+        const int iy = 2 * y + k / 3 - 1, ix = 2 * x + k % 3 - 1;
+        ok[k] = zok && (unsigned)iy < (unsigned)p.H0 && (unsigned)ix < (unsigned)p.W0;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (ok[k]) v[k] = ldg16(p.src + ((((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix) * 64 + chunk * 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (ok[k]) {
           float f[8];
-          unpack8<ACT>(v, f);
-          const int cd = (dz * 3 + dy) * 3 + dx;
+          unpack8<ACT>(v[k], f);
+          const int cd = dz * 9 + k;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float a = fmaxf(fmaf(f[e], sc[e], sh[e]), 0.f);
@@ -174,11 +181,12 @@ static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(c
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long M0 = (long long)p.B * p.D0 * p.H0 * p.W0;
   for (long long m = (long long)blockIdx.x * (EW_THREADS / 8) + (threadIdx.x >> 3); m < M0; m += (long long)gridDim.x * (EW_THREADS / 8)) {
-    long long t = m;
-    const int ix = (int)(t % p.W0); t /= p.W0;
-    const int iy = (int)(t % p.H0); t /= p.H0;
-    const int iz = (int)(t % p.D0);
-    const int b = (int)(t / p.D0);
+    unsigned t = (unsigned)m;                       // M0 < 2^31 (checked by the host)
+    const int ix = (int)(t % (unsigned)p.W0); t /= (unsigned)p.W0;
+    const int iy = (int)(t % (unsigned)p.H0); t /= (unsigned)p.H0;
+    const int iz = (int)(t % (unsigned)p.D0);
+    const int b = (int)(t / (unsigned)p.D0);
+    const uint4 xraw = ldg16(p.x + m * 64 + chunk * 8);   // issued before the window loop
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // windows o with 2o-1 <= i <= 2o+1
     for (int oz = iz >> 1; oz <= (iz + 1) >> 1; ++oz) {
@@ -205,7 +213,7 @@ static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(c
       }
     }
     float f[8], r[8];
-    unpack8<ACT>(ldg16(p.x + m * 64 + chunk * 8), f);
+    unpack8<ACT>(xraw, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = chunk * 8 + e;
@@ -299,11 +307,11 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long m = (long long)blockIdx.x * rows_per_block + threadIdx.x / cpr; m < M && threadIdx.x < rows_per_block * cpr;
        m += (long long)gridDim.x * rows_per_block) {
-    long long t = m;
-    const int x = (int)(t % p.W); t /= p.W;
-    const int y = (int)(t % p.H); t /= p.H;
-    const int z = (int)(t % p.D);
-    const int b = (int)(t / p.D);
+    unsigned t = (unsigned)m;                       // M < 2^31 (checked by the host)
+    const int x = (int)(t % (unsigned)p.W); t /= (unsigned)p.W;
+    const int y = (int)(t % (unsigned)p.H); t /= (unsigned)p.H;
+    const int z = (int)(t % (unsigned)p.D);
+    const int b = (int)(t / (unsigned)p.D);
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if ((z >> 1) < Do && (y >> 1) < Ho && (x >> 1) < Wo) {
       const long long mo = (((long long)b * Do + (z >> 1)) * Ho + (y >> 1)) * Wo + (x >> 1);
@@ -372,18 +380,22 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
   __syncthreads();
   const int cpr = p.C / 8;
   const long long total = p.M * cpr;
-  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
-    const int chunk = (int)(idx % cpr);
-    const long long m = idx / cpr;
+  // (row, chunk) of a cell are carried incrementally: one 64-bit division per thread instead of one per 16-byte cell
+  // (the division made this pass issue-bound: 4.0 TB/s at 28 % issue utilisation with long-scoreboard stalls, ncu r01f)
+  const long long stride = (long long)gridDim.x * EW_THREADS;
+  const long long sm_ = stride / cpr;
+  const int sc_ = (int)(stride - sm_ * cpr);
+  long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+  long long m = idx / cpr;
+  int chunk = (int)(idx - m * cpr);
+  auto cell = [&](long long m, int chunk, const uint4& vraw, const float4& va, const float4& vb, const uint4& xraw) {
     float v[8], f[8], o[8];
     if (p.v != nullptr) {
-      unpack8<GRD>(ldg16(p.v + m * p.v_pitch + chunk * 8), v);
+      unpack8<GRD>(vraw, v);
     } else {
-      const float4 a = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8);
-      const float4 b = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8 + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[0] = va.x; v[1] = va.y; v[2] = va.z; v[3] = va.w; v[4] = vb.x; v[5] = vb.y; v[6] = vb.z; v[7] = vb.w;
     }
-    unpack8<ACT>(ldg16(p.x + m * p.x_pitch + chunk * 8), f);
+    unpack8<ACT>(xraw, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = chunk * 8 + e;
@@ -412,6 +424,32 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
         d[1] = make_float4(o[4], o[5], o[6], o[7]);
       }
     }
+  };
+  auto load = [&](long long m, int chunk, uint4& vraw, float4& va, float4& vb, uint4& xraw) {
+    if (p.v != nullptr) {
+      vraw = ldg16(p.v + m * p.v_pitch + chunk * 8);
+    } else {
+      va = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8);
+      vb = *reinterpret_cast<const float4*>(p.v32 + m * p.v_pitch + chunk * 8 + 4);
+    }
+    xraw = ldg16(p.x + m * p.x_pitch + chunk * 8);
+  };
+  // two cells per iteration: both cells' loads are issued before either is consumed
+  while (idx < total) {
+    long long m1 = m + sm_;
+    int chunk1 = chunk + sc_;
+    if (chunk1 >= cpr) { chunk1 -= cpr; ++m1; }
+    const bool two = idx + stride < total;
+    uint4 vr0 = make_uint4(0, 0, 0, 0), xr0, vr1 = make_uint4(0, 0, 0, 0), xr1 = make_uint4(0, 0, 0, 0);
+    float4 a0 = make_float4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+    load(m, chunk, vr0, a0, b0, xr0);
+    if (two) load(m1, chunk1, vr1, a1, b1, xr1);
+    cell(m, chunk, vr0, a0, b0, xr0);
+    if (two) cell(m1, chunk1, vr1, a1, b1, xr1);
+    idx += 2 * stride;
+    m = m1 + sm_;
+    chunk = chunk1 + sc_;
+    if (chunk >= cpr) { chunk -= cpr; ++m; }
   }
 }
 

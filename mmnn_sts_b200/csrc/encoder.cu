@@ -131,6 +131,7 @@ bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
   g.D0 = (X - 1) / 2 + 1; g.H0 = (Y - 1) / 2 + 1; g.W0 = (Z - 1) / 2 + 1;
   g.Sz = g.D0 + 3; g.Sy = g.H0 + 3; g.Sx = g.W0 + 3;
   g.M0 = (long long)B * g.D0 * g.H0 * g.W0;
+  if (g.M0 <= 0 || g.M0 * 128 > 0x7fffffffLL) return false;   // kernels index voxel rows (x chunk counts) in 32 bits
   int d = (g.D0 - 1) / 2 + 1, h = (g.H0 - 1) / 2 + 1, w = (g.W0 - 1) / 2 + 1;
   const int nb = (int)pl.blocks.size();
   for (int b = 0; b < nb; ++b) {

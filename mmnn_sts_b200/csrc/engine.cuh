@@ -928,6 +928,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
               tc_mma_bf16(td, desc_advance(ad, k16 * 256), desc_advance(bd0, k16 * 256), idesc, 1u);
           }
+        } else if (p.NB == 9 && p.CB == 32) {
+          // the 9 shifted gradient tiles are 36 consecutive chunk planes = ONE MN-major operand of N = 288 columns
+          // (column = tap*32 + co, the accumulator layout the epilogue expects): two N = 144 MMAs per K step instead of
+          // nine N = 32 ones, so the A tile is read from shared memory 2x instead of 9x per step
+          const uint32_t idesc2 = make_idesc(128, 144, 1, 1, false);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t td = tmem_base + h * 144;
+            const uint64_t bd = desc_advance(bd0, h * 18 * PLANE_BYTES);
+            tc_mma_bf16(td, ad0, bd, idesc2, acc0);
+#pragma unroll
+            for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
+              tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd, k16 * 256), idesc2, 1u);
+          }
         } else
         for (int j = 0; j < p.NB; ++j) {
           const uint32_t td = tmem_base + j * p.CB;
