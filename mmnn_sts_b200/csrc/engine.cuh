@@ -209,13 +209,31 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
   pdl_wait();   // nothing above touches global memory
+  H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // fp16 operands: packed per-pair table in place of the fp32 one (same size)
   if (TRANS == T_BNRELU) {
-    for (int c = tid; c < p.Cin; c += ENGINE_THREADS) {
-      float mean, rstd;
-      bn_mean_rstd(p.bnA, c, mean, rstd);
-      const float s = p.bnA.gamma[c] * rstd;
-      coefA[c] = s;
-      coefA[p.Cin + c] = p.bnA.beta[c] - mean * s;
+    if (OP_F16) {
+      for (int j = tid; j < p.Cin / 2; j += ENGINE_THREADS) {
+        float m0, r0, m1, r1;
+        bn_mean_rstd(p.bnA, 2 * j, m0, r0);
+        bn_mean_rstd(p.bnA, 2 * j + 1, m1, r1);
+        const float s0 = p.bnA.gamma[2 * j] * r0, s1 = p.bnA.gamma[2 * j + 1] * r1;
+        const float t0 = p.bnA.beta[2 * j] - m0 * s0, t1 = p.bnA.beta[2 * j + 1] - m1 * s1;
+        H2Coef c;
+        c.s_hi = __floats2half2_rn(s0, s1);
+        c.t_hi = __floats2half2_rn(t0, t1);
+        const float2 sh = __half22float2(c.s_hi), th = __half22float2(c.t_hi);
+        c.s_lo = __floats2half2_rn(s0 - sh.x, s1 - sh.y);
+        c.t_lo = __floats2half2_rn(t0 - th.x, t1 - th.y);
+        coefH[j] = c;
+      }
+    } else {
+      for (int c = tid; c < p.Cin; c += ENGINE_THREADS) {
+        float mean, rstd;
+        bn_mean_rstd(p.bnA, c, mean, rstd);
+        const float s = p.bnA.gamma[c] * rstd;
+        coefA[c] = s;
+        coefA[p.Cin + c] = p.bnA.beta[c] - mean * s;
+      }
     }
   }
   if (EPI == EP_MASK_STATS) {
@@ -329,16 +347,25 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
       const int ch0 = gq.cb * p.kbw + chunk * 8;
       float sc[8], sh[8];
+      H2Coef hc[4];
       if (TRANS == T_BNRELU) {
+        if (OP_F16) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
+          for (int i = 0; i < 4; ++i) hc[i] = coefH[ch0 / 2 + i];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
+        }
       }
 #pragma unroll
       for (int ps = 0; ps < MAX_PASSES; ++ps) {
         if (ps < npass) {
           const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
           uint4 v = regs[ps];
-          if (TRANS == T_BNRELU && ((okm >> ps) & 1u)) apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+          if (TRANS == T_BNRELU && ((okm >> ps) & 1u)) {
+            if (OP_F16) apply_bnrelu8_h2(v, hc);     // 12 packed HFMA2 per cell instead of 28 scalar instructions
+            else apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+          }
           sts16(sA + chunk * PLANE_BYTES + r * 16, v);
         }
       }

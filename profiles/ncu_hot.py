@@ -2,8 +2,12 @@
 import csv, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 lines = out.splitlines()
-start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-r = list(csv.DictReader(lines[start:]))
+# a report with several launches repeats the header: keep the first launch's table only (or the one named by argv[3])
+starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+start = starts[which]
+end = next((i for i, l in enumerate(lines[start + 1:], start + 1) if l.startswith('"Kernel Name"')), len(lines))
+r = list(csv.DictReader(lines[start:end]))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 tot = sum(int(x["# Samples"] or 0) for x in r)
 print("total samples", tot, "instructions", len(r))
