@@ -3,7 +3,8 @@
 // The gather engine (engine.cuh) rebuilds the A operand once per tap: 27 loads + 27 BN/ReLU transforms per input
 // element -- it is instruction-issue bound (ncu: 71 % issue slots busy, 4.6 % tensor pipe; profiles/r01_*).
 // Here a persistent CTA stages the input HALO BRICK of one output tile (1 x 16 x 8 voxels -> 3 x 18 x 10 voxel slots)
-// in shared memory ONCE (one load + one transform per element, 4.2x the tile instead of 27x) in the chunk-plane layout
+// in shared memory ONCE (one load + one transform per element, 4.2x the tile instead of 27x), 32 channels (4 chunk
+// planes) per brick buffer, in the chunk-plane layout
 //      brick[chunk][slot]  (16-byte cells, slot = (z'*18 + y')*10 + x')
 // and every tap is just a different START ADDRESS of the same SWIZZLE_NONE K-major descriptor:
 //      start = plane0 + ((dz*18 + dy)*10 + dx)*16,  SBO (next 8-row group = next y) = 10*16 B,  LBO = plane stride.
@@ -19,10 +20,17 @@ namespace mmnn {
 
 constexpr int BR_TY = 16, BR_TX = 8, BR_HY = BR_TY + 2, BR_HX = BR_TX + 2;
 constexpr int BR_SLOTS = 3 * BR_HY * BR_HX;            // 540
+#ifdef MMNN_BRICK_TEST_ALIGNED   // timing experiment only (wrong results): every A core matrix 128-byte aligned
+constexpr int BR_PLANE = 8704;
+#else
 constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple of 16 -> conflict-free chunk planes
+#endif
 constexpr int BR_THREADS = 448;
-constexpr int BR_BSTAGES = 6;
-constexpr int BR_BTAPS = 3;     // taps per weight-ring stage (one dx row): 9 waits per brick buffer instead of 27
+// Weight ring: forward (2 KB per tap and 32-channel buffer) 4 stages of 9 taps (one dz plane), data gradient (8 KB per
+// tap) 6 stages of 3 taps (one dx row).  The MMA warp pays ~280 cycles of wait / fence / commit per ring stage
+// (measured: 36 stages per tile instead of 18 cost +5 k cycles per tile), so forward stages carry as many taps as fit.
+__host__ __device__ constexpr int brick_btaps(bool grad) { return grad ? 3 : 9; }
+__host__ __device__ constexpr int brick_bstages(bool grad) { return grad ? 6 : 4; }
 
 struct BrickParams {
   int B, Dz, Dy, Dx;
@@ -43,17 +51,19 @@ struct BrickParams {
   BnSrc bnE;
 };
 
+constexpr int BR_PH = 4;         // chunk planes (of 8 channels) per brick buffer
+__host__ __device__ inline int brick_nbuf(int CH) { return CH >= 64 ? 4 : 2; }   // fprop: 4 quarter-bricks in flight; dgrad: 2
 __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* offs /*[6]*/) {
-  const int PH = CH >= 64 ? 8 : CH / 8;
+  const int PH = BR_PH;
   uint32_t o = 0;
   offs[0] = o; o += 256;                       // barriers + tmem ptr
   offs[1] = o; o += 2u * CH * 4 + 8u * CH;    // coefA (fp32 scale, shift) + packed half2 hi/lo table (16 B per channel pair)
   offs[2] = o; o += 4u * NT * 4;               // coefE
   offs[3] = o; o += 8u * NT * 4;               // red
   o = (o + 127u) & ~127u;
-  offs[4] = o; o += 2u * PH * BR_PLANE;        // two brick buffers
+  offs[4] = o; o += (uint32_t)brick_nbuf(CH) * PH * BR_PLANE;   // brick buffer ring
   o = (o + 127u) & ~127u;
-  offs[5] = o; o += BR_BSTAGES * BR_BTAPS * (uint32_t)PH * NT * 16;
+  offs[5] = o; o += (uint32_t)(brick_bstages(CH < 64) * brick_btaps(CH < 64)) * PH * NT * 16;
   return o;
 }
 
@@ -72,17 +82,25 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, offs);
   const uint32_t sbase = smem_u32(smem);
-  // barrier map (8 B each): brick_full[2] 0,1 | brick_empty[2] 2,3 | b_full[6] 4..9 | b_empty[6] 10..15 | acc_full[2] 16,17 | acc_empty[2] 18,19
+  // barrier map (8 B each): brick_full[4] 0..3 | brick_empty[4] 4..7 | b_full[6] 8..13 | b_empty[6] 14..19 | acc_full[2] 20,21 | acc_empty[2] 22,23
+  constexpr int BR_BTAPS = brick_btaps(GRAD), BR_BSTAGES = brick_bstages(GRAD);
+  // Independent accumulators: tcgen05.mma instructions that accumulate into the SAME TMEM tile execute as a dependent
+  // chain (~95 cycles each, measured on the N = 32 forward and the N = 64 stem), far above the 16-cycle tensor floor of
+  // an N = 32 MMA.  The forward therefore rotates over NACC accumulators, which the epilogue sums.
+  constexpr int NACC = GRAD ? 1 : 4;
+  constexpr int NBUF = GRAD ? 2 : 4;   // brick buffers (GRAD launches have CH = 32, forward ones CH = 128: checked by the host)
+  constexpr int LAG = GRAD ? 1 : 2;    // producer look-ahead: buffers whose copies are in flight while an older one is finished
+  constexpr int BF = 0, BE = 4, WF = 8, WE = 8 + BR_BSTAGES, AF = 8 + 2 * BR_BSTAGES, AE = AF + 2;
   const uint32_t bars = sbase + offs[0];
   auto BAR = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * (8 + 2 * BR_BSTAGES));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * (AE + 2));
   float* coefA = reinterpret_cast<float*>(smem + offs[1]);
   float* coefE = reinterpret_cast<float*>(smem + offs[2]);
   float* red = reinterpret_cast<float*>(smem + offs[3]);
-  const int PH = p.CH >= 64 ? 8 : p.CH / 8;      // planes per brick buffer
-  const int NH = p.CH >= 64 ? p.CH / 64 : 1;     // brick buffers ("halves") per tile
+  constexpr int PH = BR_PH;                       // planes per brick buffer
+  const int NH = p.CH / (8 * PH);                // brick buffers per tile: 4 (fprop) or 1 (dgrad)
   const uint32_t brick0 = sbase + offs[4];
-  const uint32_t brick_bytes = (uint32_t)PH * BR_PLANE;
+  constexpr uint32_t brick_bytes = (uint32_t)PH * BR_PLANE;
   const uint32_t bst0 = sbase + offs[5];
   const uint32_t b_bytes = (uint32_t)PH * p.NT * 16;              // one tap
   const uint32_t bs_bytes = BR_BTAPS * b_bytes;                  // one ring stage
@@ -93,13 +111,13 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int rot = (int)(blockIdx.x % (27 / BR_BTAPS));   // per-CTA rotation of the tap-group order
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * NACC * p.NT) tmem_cols <<= 1;
 
   if (warp == BR_MMA_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), NPT); mbar_init(BAR(2 + i), 1); }
-      for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(4 + BR_BSTAGES + i), 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(BAR(4 + 2 * BR_BSTAGES + i), 1); mbar_init(BAR(6 + 2 * BR_BSTAGES + i), NET); }
+      for (int i = 0; i < NBUF; ++i) { mbar_init(BAR(BF + i), NPT); mbar_init(BAR(BE + i), 1); }
+      for (int i = 0; i < BR_BSTAGES; ++i) { mbar_init(BAR(WF + i), 1); mbar_init(BAR(WE + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(AF + i), 1); mbar_init(BAR(AE + i), NET); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -141,83 +159,90 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   };
 
   if (warp < NPW) {
-    // ================= producers: one load + one transform per brick cell
-    const int cells = BR_SLOTS * PH;
-    // A thread owns the same brick cells for every tile: cell c = tid + u*256 -> chunk = c % PH (constant per thread),
-    // slot = c / PH.  The slot's halo coordinates are decoded ONCE (packed z|y|x) instead of per tile.
-    constexpr int MAXU = (BR_SLOTS * (GRAD ? 4 : 8) + NPT - 1) / NPT;   // 17 (dgrad launches always have PH = 4)
-    const int chunk = (PH == 8) ? (tid & 7) : (tid & 3);
+    // ================= producers: one load + one transform per brick cell.  Software-pipelined over the buffer ring:
+    // the asynchronous copies of buffer seq (and seq-1 in forward) are in flight while buffer seq-LAG is transformed
+    // in place and handed to the MMA warp, so the L2 / HBM round trip is never exposed (before: issue, wait,
+    // transform, hand over -- one exposed round trip per buffer; the MMA warp spun ~150x per brick_full wait, ncu).
+    constexpr int cells = BR_SLOTS * PH;
+    // A thread owns the same brick cells for every buffer: cell c = tid + u*NPT -> chunk = c % 4 (constant per thread),
+    // slot = c / 4.  The slot's halo coordinates are decoded ONCE (packed z|y|x) instead of per tile.
+    constexpr int MAXU = (cells + NPT - 1) / NPT;   // 9 (forward) / 17 (dgrad)
+    const int chunk = tid & 3;
     int pk[MAXU];
 #pragma unroll
     for (int u = 0; u < MAXU; ++u) {
       const int c = tid + u * NPT;
-      const int slot = (PH == 8) ? (c >> 3) : (c >> 2);
+      const int slot = c >> 2;
       const int xx = slot % BR_HX, r2 = slot / BR_HX;
       pk[u] = (c < cells) ? (((r2 / BR_HY) << 16) | ((r2 % BR_HY) << 8) | xx) : -1;
     }
-    for (int it = 0; it < my_tiles; ++it) {
-      int n, z, y0, x0;
-      tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
-      const long long nbase = (long long)n * p.Dz;
-      for (int h = 0; h < NH; ++h) {
-        const int seq = it * NH + h;
-        const int q = seq & 1;
-        const uint32_t par = (uint32_t)(seq >> 1) & 1u;
-        mbar_wait(BAR(2 + q), par ^ 1u, 21);
+    const int total = my_tiles * NH;
+    uint32_t m_prev1 = 0, m_prev2 = 0;     // validity masks of the buffers issued 1 and 2 iterations ago
+    int it = 0, h = 0;                      // (tile, buffer-of-tile) of the buffer being ISSUED
+    int n = 0, z = 0, y0 = 0, x0 = 0;
+    for (int seq = 0; seq < total + LAG; ++seq) {
+      uint32_t okmask = 0;
+      if (seq < total) {
+        if (h == 0) tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+        const int q = seq % NBUF;
+        mbar_wait(BAR(BE + q), ((uint32_t)(seq / NBUF) & 1u) ^ 1u, 21);
         const uint32_t dst = brick0 + q * brick_bytes + chunk * BR_PLANE;
-        const int ch0 = h * 64 + chunk * 8;
-        const bf16* src = p.a_src + ch0;
-        // every cell of this buffer goes out as one asynchronous 16-byte copy (zero-fill outside the volume): all loads
-        // of a thread are in flight together; the BN/ReLU transform then runs in place on the thread's own cells.
-        uint32_t okmask = 0;
+        const bf16* src = p.a_src + h * 32 + chunk * 8;
+        const long long nbase = (long long)n * p.Dz;
 #pragma unroll
         for (int u = 0; u < MAXU; ++u) {
           if (pk[u] >= 0) {
             const int sz = z + (pk[u] >> 16) - 1, sy = y0 + ((pk[u] >> 8) & 0xff) - 1, sx = x0 + (pk[u] & 0xff) - 1;
             const bool ok = (unsigned)sz < (unsigned)p.Dz && (unsigned)sy < (unsigned)p.Dy && (unsigned)sx < (unsigned)p.Dx;
             const long long m = ok ? ((nbase + sz) * p.Dy + sy) * p.Dx + sx : 0;
-            const int slot = ((PH == 8) ? (tid >> 3) : (tid >> 2)) + u * (NPT / ((PH == 8) ? 8 : 4));
-            cp_async16(dst + slot * 16, src + m * p.a_pitch, ok ? 16u : 0u);
+            const int slot = (tid >> 2) + u * (NPT / 4);
+            cp_async16(dst + slot * 16, src + m * p.a_pitch, ok ? 16u : 0u);   // zero-fill outside the volume
             okmask |= (uint32_t)ok << u;
           }
         }
-        cp_async_commit();
+        if (++h == NH) { h = 0; ++it; }
+      }
+      cp_async_commit();                    // (an empty group past the end keeps the group count uniform)
+      if (seq >= LAG) {
+        const int j = seq - LAG;            // buffer to finish: its copies are complete once at most LAG groups are pending
+        cp_async_wait<LAG>();
+        const int qj = j % NBUF;
         if (TRANS == T_BNRELU) {
+          const uint32_t okj = (LAG == 1) ? m_prev1 : m_prev2;
+          const uint32_t dstj = brick0 + qj * brick_bytes + chunk * BR_PLANE;
+          const int ch0 = (j % NH) * 32 + chunk * 8;
           if (OP_F16) {
             H2Coef hc[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) hc[i] = coefH[ch0 / 2 + i];
-            cp_async_wait<0>();
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
-              if ((okmask >> u) & 1u) {
-                const int slot = (tid >> 3) + u * (NPT / 8);
-                uint4 v = lds16(dst + slot * 16);
+              if ((okj >> u) & 1u) {
+                const int slot = (tid >> 2) + u * (NPT / 4);
+                uint4 v = lds16(dstj + slot * 16);
                 apply_bnrelu8_h2(v, hc);
-                sts16(dst + slot * 16, v);
+                sts16(dstj + slot * 16, v);
               }
             }
           } else {
             float sc[8], sh[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.CH + ch0 + e]; }
-            cp_async_wait<0>();
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
-              if ((okmask >> u) & 1u) {
-                const int slot = (tid >> 3) + u * (NPT / 8);
-                uint4 v = lds16(dst + slot * 16);
+              if ((okj >> u) & 1u) {
+                const int slot = (tid >> 2) + u * (NPT / 4);
+                uint4 v = lds16(dstj + slot * 16);
                 apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
-                sts16(dst + slot * 16, v);
+                sts16(dstj + slot * 16, v);
               }
             }
           }
-        } else {
-          cp_async_wait<0>();
         }
         fence_proxy_async_smem();
-        mbar_arrive(BAR(q));
+        mbar_arrive(BAR(BF + qj));
       }
+      m_prev2 = m_prev1; m_prev1 = okmask;
     }
   } else if (warp == BR_LOAD_WARP) {
     // ================= weight loader: ring of BR_BSTAGES stages of BR_BTAPS tap images each
@@ -228,14 +253,14 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
             const int s = j % BR_BSTAGES;
             const uint32_t par = (uint32_t)(j / BR_BSTAGES) & 1u;
-            mbar_wait(BAR(4 + BR_BSTAGES + s), par ^ 1u, 22);
-            mbar_arrive_expect_tx(BAR(4 + s), bs_bytes);
+            mbar_wait(BAR(WE + s), par ^ 1u, 22);
+            mbar_arrive_expect_tx(BAR(WF + s), bs_bytes);
             // every CTA walks the 9 tap groups in a different rotation: otherwise all 148 SMs request the same 12-24 KB of
             // weights at the same moment and the few L2 slices holding those lines serialise them
             const int tgr = (tg + rot) % (27 / BR_BTAPS);
             for (int u = 0; u < BR_BTAPS; ++u)
               bulk_g2s(bst0 + s * bs_bytes + u * b_bytes,
-                       p.b_packed + (size_t)((tgr * BR_BTAPS + u) * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(4 + s));
+                       p.b_packed + (size_t)((tgr * BR_BTAPS + u) * NH + h) * (size_t)(PH * p.NT * 8), b_bytes, BAR(WF + s));
           }
     }
   } else if (warp == BR_MMA_WARP) {
@@ -245,43 +270,49 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
       const uint32_t apar = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(BAR(6 + 2 * BR_BSTAGES + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
+      mbar_wait(BAR(AE + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
       tc_fence_after();
       for (int h = 0; h < NH; ++h) {
         const int seq = it * NH + h;
-        const int q = seq & 1;
-        mbar_wait(BAR(q), (uint32_t)(seq >> 1) & 1u, 24);
+        const int q = seq % NBUF;
+        mbar_wait(BAR(BF + q), (uint32_t)(seq / NBUF) & 1u, 24);
         tc_fence_after();
         const uint64_t ad_base = make_smem_desc(brick0 + q * brick_bytes, BR_PLANE, BR_HX * 16);
-        const uint32_t td = tmem_base + abuf * p.NT;
+        const uint32_t td0 = tmem_base + abuf * NACC * p.NT;
         for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
           const int s = j % BR_BSTAGES;
-          mbar_wait(BAR(4 + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
+          mbar_wait(BAR(WF + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
           tc_fence_after();
           if (elect_one()) {
-            // taps tg*3 + u, u = 0..2: (t9, t3) fixed, t1 = u.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
+            // taps tgr*BR_BTAPS + v.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
             const int tgr = (tg + rot) % (27 / BR_BTAPS);
-            const int t9 = tgr / 3, t3 = tgr - t9 * 3;
-            const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1;
             uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
 #pragma unroll
-            for (int u = 0; u < BR_BTAPS; ++u) {
-              const int ox = (u - 1) * p.tap_sign + 1;
+            for (int v = 0; v < BR_BTAPS; ++v) {
+              const int t9 = BR_BTAPS == 9 ? tgr : tgr / 3;
+              const int t3 = BR_BTAPS == 9 ? v / 3 : tgr - (tgr / 3) * 3;
+              const int t1 = BR_BTAPS == 9 ? v % 3 : v;
+              const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
+#ifdef MMNN_BRICK_TEST_ALIGNED
+              const uint64_t ad = desc_advance(ad_base, (uint32_t)(oz + oy + ox) * 0u);
+#else
               const uint64_t ad = desc_advance(ad_base, (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u);
-              tc_mma_bf16(td, ad, bd, idesc, (h > 0 || tg > 0 || u > 0) ? 1u : 0u);
-#pragma unroll
-              for (int k16 = 1; k16 < 4; ++k16)
-                if (k16 < PH / 2)
-                  tc_mma_bf16(td, desc_advance(ad, k16 * 2 * BR_PLANE), desc_advance(bd, k16 * 2 * p.NT * 16), idesc, 1u);
+#endif
+              // consecutive MMAs go to different accumulators: (2v, 2v+1) mod NACC
+              const uint32_t tdA = td0 + ((2 * v) % NACC) * p.NT, tdB = td0 + ((2 * v + 1) % NACC) * p.NT;
+              const bool first = (h == 0 && tg == 0 && 2 * v < NACC);          // first MMA into this accumulator for this tile
+              tc_mma_bf16(tdA, ad, bd, idesc, first ? 0u : 1u);
+              tc_mma_bf16(tdB, desc_advance(ad, 2 * BR_PLANE), desc_advance(bd, 2 * p.NT * 16), idesc,
+                          (first && NACC > 1) ? 0u : 1u);   // K 16..31
               bd = desc_advance(bd, b_bytes);
             }
-            tc_commit(BAR(4 + BR_BSTAGES + s));
+            tc_commit(BAR(WE + s));
           }
           __syncwarp();
         }
         if (elect_one()) {
-          tc_commit(BAR(2 + q));
-          if (h == NH - 1) tc_commit(BAR(4 + 2 * BR_BSTAGES + abuf));
+          tc_commit(BAR(BE + q));
+          if (h == NH - 1) tc_commit(BAR(AF + abuf));
         }
         __syncwarp();
       }
@@ -312,14 +343,20 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           for (int i = 0; i < 4; ++i)
             xpre[k][i] = (row_ok && (cc0 + k) * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + (cc0 + k) * 32 + i * 8) : make_uint4(0, 0, 0, 0);
       }
-      mbar_wait(BAR(4 + 2 * BR_BSTAGES + abuf), (uint32_t)(it >> 1) & 1u, 26);
+      mbar_wait(BAR(AF + abuf), (uint32_t)(it >> 1) & 1u, 26);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < CCW; ++k) {
         const int cc = cc0 + k;
         if (cc * 32 >= p.NT) break;
         float v[32], qv[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * p.NT + cc * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * NACC * p.NT + cc * 32), v);
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) {     // sum the rotating accumulators (forward only)
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((abuf * NACC + a) * p.NT + cc * 32), qv);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] += qv[jj];
+        }
         if (EPI == EP_MASK_STATS) {
           uint4 xv[4];
 #pragma unroll
@@ -365,7 +402,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(6 + 2 * BR_BSTAGES + abuf));
+      mbar_arrive(BAR(AE + abuf));
     }
     if (EPI != EP_STORE) {
 #pragma unroll
