@@ -13,6 +13,12 @@
 // dgrad (32 input channels, 128 output columns): the producer is light and the mask + statistics epilogue is the
 // critical path (ncu r01f: MMA warp waits on acc_empty, 4 epilogue warps 87 % busy at 16 % issue rate), so the roles
 // are 0-3 producers, 4 MMA, 5 loader, 6-13 epilogue: two warps per TMEM lane quarter, each taking half the columns.
+//
+// Tile pairs (template TP = 2, experiment switch MMNN_BRICK_TP=2): a CTA keeps the bricks of TWO tiles in shared memory
+// and issues the MMAs of both against each weight stage, halving the weight re-fetch from L2 (221 KB per tile; ncu
+// r01c: 925 MB L2->SM per layer at 5.5 TB/s, half of it weights).  Measured: no gain (dgrad) / slower (forward), so
+// it is off by default -- what bounds the N = 32 forward is the 4 KB A-operand read per MMA from shared memory
+// (6 912 + 1 728 of the ~11 k shared-memory wavefronts per tile; the shared pipe saturates near 70 %).
 #pragma once
 #include "engine.cuh"
 
@@ -29,8 +35,9 @@ constexpr int BR_THREADS = 448;
 // Weight ring: forward (2 KB per tap and 32-channel buffer) 4 stages of 9 taps (one dz plane), data gradient (8 KB per
 // tap) 6 stages of 3 taps (one dx row).  The MMA warp pays ~280 cycles of wait / fence / commit per ring stage
 // (measured: 36 stages per tile instead of 18 cost +5 k cycles per tile), so forward stages carry as many taps as fit.
+// With tile pairs (TP = 2, below) the data gradient keeps 4 brick buffers, so its ring shrinks to 3 stages.
 __host__ __device__ constexpr int brick_btaps(bool grad) { return grad ? 3 : 9; }
-__host__ __device__ constexpr int brick_bstages(bool grad) { return grad ? 6 : 4; }
+__host__ __device__ constexpr int brick_bstages(bool grad, int tp) { return grad ? (tp == 2 ? 3 : 6) : 4; }
 
 struct BrickParams {
   int B, Dz, Dy, Dx;
@@ -52,8 +59,8 @@ struct BrickParams {
 };
 
 constexpr int BR_PH = 4;         // chunk planes (of 8 channels) per brick buffer
-__host__ __device__ inline int brick_nbuf(int CH) { return CH >= 64 ? 4 : 2; }   // fprop: 4 quarter-bricks in flight; dgrad: 2
-__host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* offs /*[6]*/) {
+__host__ __device__ inline int brick_nbuf(int CH, int tp) { return (CH >= 64 || tp == 2) ? 4 : 2; }
+__host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, int tp, uint32_t* offs /*[6]*/) {
   const int PH = BR_PH;
   uint32_t o = 0;
   offs[0] = o; o += 256;                       // barriers + tmem ptr
@@ -61,13 +68,13 @@ __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, uint32_t* 
   offs[2] = o; o += 4u * NT * 4;               // coefE
   offs[3] = o; o += 8u * NT * 4;               // red
   o = (o + 127u) & ~127u;
-  offs[4] = o; o += (uint32_t)brick_nbuf(CH) * PH * BR_PLANE;   // brick buffer ring
+  offs[4] = o; o += (uint32_t)brick_nbuf(CH, tp) * PH * BR_PLANE;   // brick buffer ring
   o = (o + 127u) & ~127u;
-  offs[5] = o; o += (uint32_t)(brick_bstages(CH < 64) * brick_btaps(CH < 64)) * PH * NT * 16;
+  offs[5] = o; o += (uint32_t)(brick_bstages(CH < 64, tp) * brick_btaps(CH < 64)) * PH * NT * 16;
   return o;
 }
 
-template <int TRANS, int EPI, bool GRAD>
+template <int TRANS, int EPI, bool GRAD, int TP>
 __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid_constant__ BrickParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;
   constexpr bool E_F16 = kActF16;
@@ -80,16 +87,12 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   uint32_t offs[6];
-  brick_smem_layout(p.CH, p.NT, offs);
+  brick_smem_layout(p.CH, p.NT, TP, offs);
   const uint32_t sbase = smem_u32(smem);
-  // barrier map (8 B each): brick_full[4] 0..3 | brick_empty[4] 4..7 | b_full[6] 8..13 | b_empty[6] 14..19 | acc_full[2] 20,21 | acc_empty[2] 22,23
-  constexpr int BR_BTAPS = brick_btaps(GRAD), BR_BSTAGES = brick_bstages(GRAD);
-  // Independent accumulators: tcgen05.mma instructions that accumulate into the SAME TMEM tile execute as a dependent
-  // chain (~95 cycles each, measured on the N = 32 forward and the N = 64 stem), far above the 16-cycle tensor floor of
-  // an N = 32 MMA.  The forward therefore rotates over NACC accumulators, which the epilogue sums.
-  constexpr int NACC = GRAD ? 1 : 4;
-  constexpr int NBUF = GRAD ? 2 : 4;   // brick buffers (GRAD launches have CH = 32, forward ones CH = 128: checked by the host)
-  constexpr int LAG = GRAD ? 1 : 2;    // producer look-ahead: buffers whose copies are in flight while an older one is finished
+  constexpr int BR_BTAPS = brick_btaps(GRAD), BR_BSTAGES = brick_bstages(GRAD, TP);
+  constexpr int NBUF = (!GRAD || TP == 2) ? 4 : 2;   // brick buffers (GRAD launches have CH = 32, forward ones CH = 128: checked by the host)
+  constexpr int LAG = NBUF == 4 ? 2 : 1;             // producer look-ahead: buffers whose copies are in flight while an older one is finished
+  // barrier map (8 B each): brick_full[4] | brick_empty[4] | b_full[BSTAGES] | b_empty[BSTAGES] | acc_full[2] | acc_empty[2]
   constexpr int BF = 0, BE = 4, WF = 8, WE = 8 + BR_BSTAGES, AF = 8 + 2 * BR_BSTAGES, AE = AF + 2;
   const uint32_t bars = sbase + offs[0];
   auto BAR = [&](int i) { return bars + 8u * i; };
@@ -108,10 +111,12 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_y = (p.Dy + BR_TY - 1) / BR_TY, tiles_x = (p.Dx + BR_TX - 1) / BR_TX;
   const int ntiles = p.B * p.Dz * tiles_y * tiles_x;
-  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // the unit of work is a GROUP of TP consecutive tiles (the last group may hold an invalid tile: zero-filled, not stored)
+  const int ngroups = (ntiles + TP - 1) / TP;
+  const int my_groups = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int rot = (int)(blockIdx.x % (27 / BR_BTAPS));   // per-CTA rotation of the tap-group order
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * NACC * p.NT) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * TP * p.NT) tmem_cols <<= 1;   // TP accumulators per group, double-buffered
 
   if (warp == BR_MMA_WARP) {
     if (lane == 0) {
@@ -151,18 +156,23 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // tile index -> coordinates; returns false for the padding tile of the last group
   auto tile_coords = [&](int t, int& n, int& z, int& y0, int& x0) {
+    const bool valid = t < ntiles;
+    if (!valid) t = 0;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y; t /= tiles_y;
     z = t % p.Dz; n = t / p.Dz;
     y0 = ty * BR_TY; x0 = tx * BR_TX;
+    return valid;
   };
+  // Brick buffers are filled and consumed in the order (group, channel quarter h, tile-of-group t):
+  //   seq = ((group_iteration * NH) + h) * TP + t,   ring slot = seq % NBUF.
 
   if (warp < NPW) {
     // ================= producers: one load + one transform per brick cell.  Software-pipelined over the buffer ring:
-    // the asynchronous copies of buffer seq (and seq-1 in forward) are in flight while buffer seq-LAG is transformed
-    // in place and handed to the MMA warp, so the L2 / HBM round trip is never exposed (before: issue, wait,
-    // transform, hand over -- one exposed round trip per buffer; the MMA warp spun ~150x per brick_full wait, ncu).
+    // the asynchronous copies of buffer seq (and seq-1) are in flight while buffer seq-LAG is transformed in place and
+    // handed to the MMA warp, so the L2 / HBM round trip is not exposed.
     constexpr int cells = BR_SLOTS * PH;
     // A thread owns the same brick cells for every buffer: cell c = tid + u*NPT -> chunk = c % 4 (constant per thread),
     // slot = c / 4.  The slot's halo coordinates are decoded ONCE (packed z|y|x) instead of per tile.
@@ -176,14 +186,16 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
       const int xx = slot % BR_HX, r2 = slot / BR_HX;
       pk[u] = (c < cells) ? (((r2 / BR_HY) << 16) | ((r2 % BR_HY) << 8) | xx) : -1;
     }
-    const int total = my_tiles * NH;
+    const int total = my_groups * NH * TP;
     uint32_t m_prev1 = 0, m_prev2 = 0;     // validity masks of the buffers issued 1 and 2 iterations ago
-    int it = 0, h = 0;                      // (tile, buffer-of-tile) of the buffer being ISSUED
-    int n = 0, z = 0, y0 = 0, x0 = 0;
+    int it = 0, h = 0, t = 0;               // (group, quarter, tile-of-group) of the buffer being ISSUED
+    int hq1 = 0, hq2 = 0;                   // quarter index of the buffers issued 1 and 2 iterations ago
     for (int seq = 0; seq < total + LAG; ++seq) {
       uint32_t okmask = 0;
+      const int h_cur = h;
       if (seq < total) {
-        if (h == 0) tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+        int n, z, y0, x0;
+        const bool tvalid = tile_coords(((int)blockIdx.x + it * (int)gridDim.x) * TP + t, n, z, y0, x0);
         const int q = seq % NBUF;
         mbar_wait(BAR(BE + q), ((uint32_t)(seq / NBUF) & 1u) ^ 1u, 21);
         const uint32_t dst = brick0 + q * brick_bytes + chunk * BR_PLANE;
@@ -193,14 +205,14 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         for (int u = 0; u < MAXU; ++u) {
           if (pk[u] >= 0) {
             const int sz = z + (pk[u] >> 16) - 1, sy = y0 + ((pk[u] >> 8) & 0xff) - 1, sx = x0 + (pk[u] & 0xff) - 1;
-            const bool ok = (unsigned)sz < (unsigned)p.Dz && (unsigned)sy < (unsigned)p.Dy && (unsigned)sx < (unsigned)p.Dx;
+            const bool ok = tvalid && (unsigned)sz < (unsigned)p.Dz && (unsigned)sy < (unsigned)p.Dy && (unsigned)sx < (unsigned)p.Dx;
             const long long m = ok ? ((nbase + sz) * p.Dy + sy) * p.Dx + sx : 0;
             const int slot = (tid >> 2) + u * (NPT / 4);
             cp_async16(dst + slot * 16, src + m * p.a_pitch, ok ? 16u : 0u);   // zero-fill outside the volume
             okmask |= (uint32_t)ok << u;
           }
         }
-        if (++h == NH) { h = 0; ++it; }
+        if (++t == TP) { t = 0; if (++h == NH) { h = 0; ++it; } }
       }
       cp_async_commit();                    // (an empty group past the end keeps the group count uniform)
       if (seq >= LAG) {
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         if (TRANS == T_BNRELU) {
           const uint32_t okj = (LAG == 1) ? m_prev1 : m_prev2;
           const uint32_t dstj = brick0 + qj * brick_bytes + chunk * BR_PLANE;
-          const int ch0 = (j % NH) * 32 + chunk * 8;
+          const int ch0 = ((LAG == 1) ? hq1 : hq2) * 32 + chunk * 8;
           if (OP_F16) {
             H2Coef hc[4];
 #pragma unroll
@@ -243,20 +255,21 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
         mbar_arrive(BAR(BF + qj));
       }
       m_prev2 = m_prev1; m_prev1 = okmask;
+      hq2 = hq1; hq1 = h_cur;
     }
   } else if (warp == BR_LOAD_WARP) {
-    // ================= weight loader: ring of BR_BSTAGES stages of BR_BTAPS tap images each
+    // ================= weight loader: ring of BR_BSTAGES stages of BR_BTAPS tap images each (one pass per group)
     if (lane == 0) {
       int j = 0;
-      for (int it = 0; it < my_tiles; ++it)
+      for (int it = 0; it < my_groups; ++it)
         for (int h = 0; h < NH; ++h)
           for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
             const int s = j % BR_BSTAGES;
             const uint32_t par = (uint32_t)(j / BR_BSTAGES) & 1u;
             mbar_wait(BAR(WE + s), par ^ 1u, 22);
             mbar_arrive_expect_tx(BAR(WF + s), bs_bytes);
-            // every CTA walks the 9 tap groups in a different rotation: otherwise all 148 SMs request the same 12-24 KB of
-            // weights at the same moment and the few L2 slices holding those lines serialise them
+            // every CTA walks the tap groups in a different rotation: otherwise all 148 SMs request the same weights
+            // at the same moment and the few L2 slices holding those lines serialise them
             const int tgr = (tg + rot) % (27 / BR_BTAPS);
             for (int u = 0; u < BR_BTAPS; ++u)
               bulk_g2s(bst0 + s * bs_bytes + u * b_bytes,
@@ -267,18 +280,16 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     // ================= MMA issuer
     const uint32_t idesc = make_idesc(TILE_ROWS, p.NT, 0, 0, OP_F16);
     int j = 0;
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0; it < my_groups; ++it) {
       const int abuf = it & 1;
       const uint32_t apar = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(BAR(AE + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator
+      mbar_wait(BAR(AE + abuf), apar ^ 1u, 23);   // epilogue has drained this accumulator set
       tc_fence_after();
       for (int h = 0; h < NH; ++h) {
-        const int seq = it * NH + h;
-        const int q = seq % NBUF;
-        mbar_wait(BAR(BF + q), (uint32_t)(seq / NBUF) & 1u, 24);
+        const int seq0 = (it * NH + h) * TP;      // buffers seq0 .. seq0+TP-1 hold quarter h of the group's tiles
+#pragma unroll
+        for (int t = 0; t < TP; ++t) mbar_wait(BAR(BF + (seq0 + t) % NBUF), (uint32_t)((seq0 + t) / NBUF) & 1u, 24);
         tc_fence_after();
-        const uint64_t ad_base = make_smem_desc(brick0 + q * brick_bytes, BR_PLANE, BR_HX * 16);
-        const uint32_t td0 = tmem_base + abuf * NACC * p.NT;
         for (int tg = 0; tg < 27 / BR_BTAPS; ++tg, ++j) {
           const int s = j % BR_BSTAGES;
           mbar_wait(BAR(WF + s), (uint32_t)(j / BR_BSTAGES) & 1u, 25);
@@ -286,32 +297,30 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
           if (elect_one()) {
             // taps tgr*BR_BTAPS + v.  Window start slot = (d+1) per axis, d = (t-1)*tap_sign.
             const int tgr = (tg + rot) % (27 / BR_BTAPS);
-            uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
 #pragma unroll
-            for (int v = 0; v < BR_BTAPS; ++v) {
-              const int t9 = BR_BTAPS == 9 ? tgr : tgr / 3;
-              const int t3 = BR_BTAPS == 9 ? v / 3 : tgr - (tgr / 3) * 3;
-              const int t1 = BR_BTAPS == 9 ? v % 3 : v;
-              const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
-#ifdef MMNN_BRICK_TEST_ALIGNED
-              const uint64_t ad = desc_advance(ad_base, (uint32_t)(oz + oy + ox) * 0u);
-#else
-              const uint64_t ad = desc_advance(ad_base, (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u);
-#endif
-              // consecutive MMAs go to different accumulators: (2v, 2v+1) mod NACC
-              const uint32_t tdA = td0 + ((2 * v) % NACC) * p.NT, tdB = td0 + ((2 * v + 1) % NACC) * p.NT;
-              const bool first = (h == 0 && tg == 0 && 2 * v < NACC);          // first MMA into this accumulator for this tile
-              tc_mma_bf16(tdA, ad, bd, idesc, first ? 0u : 1u);
-              tc_mma_bf16(tdB, desc_advance(ad, 2 * BR_PLANE), desc_advance(bd, 2 * p.NT * 16), idesc,
-                          (first && NACC > 1) ? 0u : 1u);   // K 16..31
-              bd = desc_advance(bd, b_bytes);
+            for (int t = 0; t < TP; ++t) {
+              const uint64_t ad_base = make_smem_desc(brick0 + ((seq0 + t) % NBUF) * brick_bytes, BR_PLANE, BR_HX * 16);
+              const uint32_t td = tmem_base + (abuf * TP + t) * p.NT;
+              uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
+#pragma unroll
+              for (int v = 0; v < BR_BTAPS; ++v) {
+                const int t9 = BR_BTAPS == 9 ? tgr : tgr / 3;
+                const int t3 = BR_BTAPS == 9 ? v / 3 : tgr - (tgr / 3) * 3;
+                const int t1 = BR_BTAPS == 9 ? v % 3 : v;
+                const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
+                const uint64_t ad = desc_advance(ad_base, (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u);
+                tc_mma_bf16(td, ad, bd, idesc, (h > 0 || tg > 0 || v > 0) ? 1u : 0u);
+                tc_mma_bf16(td, desc_advance(ad, 2 * BR_PLANE), desc_advance(bd, 2 * p.NT * 16), idesc, 1u);   // K 16..31
+                bd = desc_advance(bd, b_bytes);
+              }
             }
             tc_commit(BAR(WE + s));
           }
           __syncwarp();
         }
         if (elect_one()) {
-          tc_commit(BAR(BE + q));
+#pragma unroll
+          for (int t = 0; t < TP; ++t) tc_commit(BAR(BE + (seq0 + t) % NBUF));
           if (h == NH - 1) tc_commit(BAR(AF + abuf));
         }
         __syncwarp();
@@ -329,76 +338,75 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     float acc1[CCW], acc2[CCW];   // per-lane column partials
 #pragma unroll
     for (int k = 0; k < CCW; ++k) { acc1[k] = 0.f; acc2[k] = 0.f; }
-    for (int it = 0; it < my_tiles; ++it) {
-      int n, z, y0, x0;
-      tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
+    for (int it = 0; it < my_groups; ++it) {
       const int abuf = it & 1;
-      const bool row_ok = (y0 + ry < p.Dy) && (x0 + rx < p.Dx);
-      const long long m = (((long long)n * p.Dz + z) * p.Dy + (y0 + ry)) * p.Dx + (x0 + rx);
-      uint4 xpre[CCW][4];   // gating activations of this row: fetched before the accumulator is ready
-      if (EPI == EP_MASK_STATS) {
 #pragma unroll
-        for (int k = 0; k < CCW; ++k)
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            xpre[k][i] = (row_ok && (cc0 + k) * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + (cc0 + k) * 32 + i * 8) : make_uint4(0, 0, 0, 0);
-      }
-      mbar_wait(BAR(AF + abuf), (uint32_t)(it >> 1) & 1u, 26);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < CCW; ++k) {
-        const int cc = cc0 + k;
-        if (cc * 32 >= p.NT) break;
-        float v[32], qv[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * NACC * p.NT + cc * 32), v);
-#pragma unroll
-        for (int a = 1; a < NACC; ++a) {     // sum the rotating accumulators (forward only)
-          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((abuf * NACC + a) * p.NT + cc * 32), qv);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] += qv[jj];
-        }
+      for (int t = 0; t < TP; ++t) {
+        int n, z, y0, x0;
+        const bool tvalid = tile_coords(((int)blockIdx.x + it * (int)gridDim.x) * TP + t, n, z, y0, x0);
+        const bool row_ok = tvalid && (y0 + ry < p.Dy) && (x0 + rx < p.Dx);
+        const long long m = (((long long)n * p.Dz + z) * p.Dy + (y0 + ry)) * p.Dx + (x0 + rx);
+        uint4 xpre[CCW][4];   // gating activations of this row: fetched before the accumulator is ready
         if (EPI == EP_MASK_STATS) {
-          uint4 xv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xv[i] = xpre[k][i];
-          const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+          for (int k = 0; k < CCW; ++k)
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            float xlo, xhi;
-            unpack2<E_F16>(xw[jj >> 1], xlo, xhi);
-            const float x = (jj & 1) ? xhi : xlo;
-            const int c = cc * 32 + jj;
-            const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
-            const float g = (row_ok && act) ? round16<OP_F16>(v[jj]) : 0.f;
-            v[jj] = g;
-            qv[jj] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
-          }
-        } else {
-          if (p.colscale != nullptr) {
-            const float* cs = p.colscale + (size_t)n * p.NT + cc * 32;
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] *= __ldg(cs + jj);
-          }
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float g = row_ok ? round16<OP_F16>(v[jj]) : 0.f;
-            v[jj] = g;
-            qv[jj] = g * g;
-          }
+            for (int i = 0; i < 4; ++i)
+              xpre[k][i] = (row_ok && (cc0 + k) * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + (cc0 + k) * 32 + i * 8) : make_uint4(0, 0, 0, 0);
         }
-        if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + cc * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
-            o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
-            op[i] = o;
-          }
+        if (t == 0) {
+          mbar_wait(BAR(AF + abuf), (uint32_t)(it >> 1) & 1u, 26);
+          tc_fence_after();
         }
-        if (EPI != EP_STORE) {
-          acc1[k] += warp_transpose_sum32(v, lane);
-          acc2[k] += warp_transpose_sum32(qv, lane);
+#pragma unroll
+        for (int k = 0; k < CCW; ++k) {
+          const int cc = cc0 + k;
+          if (cc * 32 >= p.NT) break;
+          float v[32], qv[32];
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((abuf * TP + t) * p.NT + cc * 32), v);
+          if (EPI == EP_MASK_STATS) {
+            uint4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = xpre[k][i];
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              float xlo, xhi;
+              unpack2<E_F16>(xw[jj >> 1], xlo, xhi);
+              const float x = (jj & 1) ? xhi : xlo;
+              const int c = cc * 32 + jj;
+              const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
+              const float g = (row_ok && act) ? round16<OP_F16>(v[jj]) : 0.f;
+              v[jj] = g;
+              qv[jj] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
+            }
+          } else {
+            if (p.colscale != nullptr) {
+              const float* cs = p.colscale + (size_t)n * p.NT + cc * 32;
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] *= __ldg(cs + jj);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const float g = row_ok ? round16<OP_F16>(v[jj]) : 0.f;
+              v[jj] = g;
+              qv[jj] = g * g;
+            }
+          }
+          if (row_ok) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + cc * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
+              o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
+              op[i] = o;
+            }
+          }
+          if (EPI != EP_STORE) {
+            acc1[k] += warp_transpose_sum32(v, lane);
+            acc2[k] += warp_transpose_sum32(qv, lane);
+          }
         }
       }
       tc_fence_before();

@@ -63,18 +63,30 @@ int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cu
   return -3;
 }
 
-template <int TRANS, int EPI, bool GRAD>
-int launch_brick_t(const BrickParams& p, cudaStream_t stream) {
+template <int TRANS, int EPI, bool GRAD, int TP>
+int launch_brick_tp(const BrickParams& p, int ntiles, cudaStream_t stream) {
   uint32_t offs[6];
-  const uint32_t smem = brick_smem_layout(p.CH, p.NT, offs);
-  auto kern = conv3_brick_kernel<TRANS, EPI, GRAD>;
+  const uint32_t smem = brick_smem_layout(p.CH, p.NT, TP, offs);
+  auto kern = conv3_brick_kernel<TRANS, EPI, GRAD, TP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int ntiles = p.B * p.Dz * ((p.Dy + BR_TY - 1) / BR_TY) * ((p.Dx + BR_TX - 1) / BR_TX);
-  const int grid = ntiles < 148 ? ntiles : 148;   // persistent: one CTA per SM
+  const int ngroups = (ntiles + TP - 1) / TP;
+  const int grid = ngroups < 148 ? ngroups : 148;   // persistent: one CTA per SM
   launch_pdl(kern, dim3(grid), dim3(BR_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
+}
+
+// Tile pairs (two tiles per weight pass, brick.cuh) halve the weight re-fetch from L2.  Measured on B200 at block-1 size
+// (round 1): data gradient 110 us either way, forward 151 -> 222 us (the 4-buffer ring then looks only one channel
+// quarter ahead) -- the weight traffic is not what bounds these kernels, so pairs are OFF unless MMNN_BRICK_TP=2 asks
+// for them (kept for experiments; covered by the parity tests under that setting).
+template <int TRANS, int EPI, bool GRAD>
+int launch_brick_t(const BrickParams& p, cudaStream_t stream) {
+  const int ntiles = p.B * p.Dz * ((p.Dy + BR_TY - 1) / BR_TY) * ((p.Dx + BR_TX - 1) / BR_TX);
+  static const int forced = [] { const char* e = getenv("MMNN_BRICK_TP"); return e ? atoi(e) : 0; }();
+  const bool pair = forced == 2;
+  return pair ? launch_brick_tp<TRANS, EPI, GRAD, 2>(p, ntiles, stream) : launch_brick_tp<TRANS, EPI, GRAD, 1>(p, ntiles, stream);
 }
 
 // 3x3x3 convolution in brick mode: grad == 0 forward (BN+ReLU prologue, store + statistics), grad == 1 data gradient
