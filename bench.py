@@ -369,6 +369,43 @@ def run_inference(args):
                       "cindex_std": [float(v) for v in std], "workload": wl["name"], "note": "inputs generated on the device per batch (random volumes)"}), flush=True)
 
 
+def run_preprocess(args):
+    """SURVEY.md section 8f rank 1 (extra mode, prints its own JSON line): Normalize -> ScaleIntensity -> Resize of raw
+    2-channel volumes to the bench workload's input shape on the GPU, next to the oracle on the host cores."""
+    import numpy as np
+    from mmnn_sts_b200 import _lib as L
+    from mmnn_sts_b200.data.transforms import ValTransformsGPU, IMAGE_DATA_MEAN, IMAGE_DATA_STDDEV
+    from oracle import preprocess as op
+    dev = torch.device("cuda", 0)
+    wl = WORKLOADS[args.workload]
+    B, C = wl["batch"], wl["cin"]
+    rawdims = tuple(int(v * 1.5) for v in wl["spatial"])          # raw scans are larger than the network input
+    g = torch.Generator(device=dev).manual_seed(5)
+    raws = [torch.rand((B, C) + rawdims, device=dev, generator=g) * 2000.0 for _ in range(2)]    # 2 x 0.85 GB > L2
+    tf = ValTransformsGPU(IMAGE_DATA_MEAN, IMAGE_DATA_STDDEV, wl["spatial"])
+    for i in range(3):
+        tf(raws[i % 2])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for i in range(args.steps):
+        out = tf(raws[i % 2])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    raw_bytes = raws[0].numel() * 4
+    alg = 2 * raw_bytes + out.numel() * 4
+    peaks = load_peaks()
+    one = raws[0][0].cpu().numpy()
+    t0 = time.perf_counter(); ref = op.val_transforms(one, IMAGE_DATA_MEAN, IMAGE_DATA_STDDEV, wl["spatial"]); cpu_s = time.perf_counter() - t0
+    err = float(np.abs(tf(raws[0])[0].cpu().numpy() - ref).max())
+    print(json.dumps({"mode": "preprocess", "metric": "volumes/sec", "value": round(B / (ms / 1e3), 1), "ms_per_batch": round(ms, 3),
+                      "batch": B, "raw_shape": [C] + list(rawdims), "out_shape": [C] + list(wl["spatial"]),
+                      "roofline": {"bound": "hbm", "achieved": round(alg / (ms / 1e3) / 1e9, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                   "frac": round(alg / (ms / 1e3) / 1e9 / peaks["hbm"], 4), "algorithmic_bytes": alg},
+                      "cpu_baseline": {"value": round(1.0 / cpu_s, 2), "unit": "volumes/s", "kind": "port", "cores": os.cpu_count(),
+                                       "sample": "1 volume, numpy/torch oracle"},
+                      "max_abs_err_vs_oracle": err}), flush=True)
+
+
 def cpu_reference_arm(wl, steps, warmup, sample_batch):
     """The reference's algorithm for one training step on the host cores: fp32 torch CPU forward of the oracle
     restatement (bit-exact to the unchanged reference files, tests/golden), GradientBlender/Cox loss as the reference
@@ -422,7 +459,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "inference"])
+    ap.add_argument("--mode", default="train", choices=["train", "inference", "preprocess"])
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as one CUDA graph (static shapes)")
     ap.add_argument("--patients", type=int, default=10000)
     ap.add_argument("--resamples", type=int, default=1000)
@@ -431,6 +468,8 @@ if __name__ == "__main__":
         a.warmup = 3
     if a.mode == "inference":
         run_inference(a)
+    elif a.mode == "preprocess":
+        run_preprocess(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

@@ -112,6 +112,15 @@ int mmnn_sgd_step(void* const* p /*HOST*/, const void* const* g /*HOST*/, void* 
 int mmnn_sgd_chunk_elems(void);
 int mmnn_sgd_max_tensors(void);
 
+/* ------------------------------------------------------------------------------------------------ input pipeline
+ * mmnn_preprocess_volumes : the deterministic image transforms of the reference's val_transforms / train_transforms
+ *                     (/root/reference/main.py:64-92): Normalize(mean, std) (/root/reference/utils/utils.py:346-355)
+ *                     -> monai ScaleIntensity() -> monai Resize(spatial_size) ("area" = adaptive average pooling),
+ *                     per patient over the whole multi-channel volume.  src fp32 [B][C][X][Y][Z], dst fp32
+ *                     [B][C][ox][oy][oz], scratch 2*B uint32. */
+int mmnn_preprocess_volumes(const float* src, float* dst, void* scratch, int B, int C, int X, int Y, int Z, int ox, int oy,
+                            int oz, float mean, float std, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ instrumentation */
 void mmnn_profile_enable(int on);
 long long mmnn_launch_count(void);

@@ -150,6 +150,8 @@ def _declare(l):
     l.mmnn_sgd_step.restype = I
     l.mmnn_sgd_chunk_elems.restype = I
     l.mmnn_sgd_max_tensors.restype = I
+    l.mmnn_preprocess_volumes.argtypes = [VP, VP, VP, I, I, I, I, I, I, I, I, C.c_float, C.c_float, VP]
+    l.mmnn_preprocess_volumes.restype = I
     l.mmnn_profile_enable.argtypes = [I]
     l.mmnn_profile_enable.restype = None
     l.mmnn_launch_count.restype = LL
@@ -179,7 +181,7 @@ def packed_elems(N, NT, Cin, kbw, ntaps):
 
 PROF_CLASSES = ["pack", "s2d", "stem_fprop", "maxpool", "conv1_fprop", "conv2_fprop", "trans_pool", "trans_fprop", "norm5",
                 "bn_running", "norm5_bwd", "extract", "conv2_wgrad", "conv2_dgrad", "bn_apply", "conv1_wgrad", "conv1_dgrad",
-                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd"]
+                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd", "preprocess"]
 
 
 def profile_collect():

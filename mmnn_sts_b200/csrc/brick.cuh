@@ -354,6 +354,16 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
             for (int i = 0; i < 4; ++i)
               xpre[k][i] = (row_ok && (cc0 + k) * 32 < p.NT) ? ldg16(p.e_src + m * p.e_pitch + (cc0 + k) * 32 + i * 8) : make_uint4(0, 0, 0, 0);
         }
+        if (EPI == EP_MASK_STATS && TP == 1 && it + 1 < my_groups) {
+          // the gating activations come from HBM (written a whole forward pass ago): pull the NEXT tile's rows into L2
+          // now, so that its loads at the top of the next iteration are L2 hits instead of an exposed HBM round trip
+          int n2, z2, y2, x2;
+          tile_coords((int)blockIdx.x + (it + 1) * (int)gridDim.x, n2, z2, y2, x2);
+          if ((y2 + ry < p.Dy) && (x2 + rx < p.Dx)) {
+            const long long m2 = (((long long)n2 * p.Dz + z2) * p.Dy + (y2 + ry)) * p.Dx + (x2 + rx);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.e_src + m2 * p.e_pitch + cc0 * 32));
+          }
+        }
         if (t == 0) {
           mbar_wait(BAR(AF + abuf), (uint32_t)(it >> 1) & 1u, 26);
           tc_fence_after();
