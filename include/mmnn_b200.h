@@ -99,6 +99,12 @@ struct CindexArgs;
 int mmnn_cindex_bootstrap(const struct CindexArgs* args /*HOST*/, void* stream);
 int mmnn_sizeof_cindex_args(void);
 
+/* mmnn_bce_logits   : nn.BCEWithLogitsLoss(pos_weight) of the classification path (/root/reference/main.py:148-153):
+ *                     elementwise loss and dloss/dlogit for all stacked heads in one launch (targets [N][C] reused by
+ *                     every head), plus the per-class tp / fp / fn counters of main.py:226-229 (sigmoid > threshold). */
+int mmnn_bce_logits(const float* x, const float* y, const float* pos_weight, long long n, int C, long long y_elems, float* loss,
+                    float* grad, float threshold, long long count_elems, int* counts, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ optimiser
  * mmnn_sgd_step     : torch.optim.SGD(momentum, nesterov, weight_decay, dampening 0) as the reference builds it
  *                     (/root/reference/main.py:410-414) and steps it (:479-481), for ALL parameter tensors in one

@@ -150,6 +150,8 @@ def _declare(l):
     l.mmnn_sgd_step.restype = I
     l.mmnn_sgd_chunk_elems.restype = I
     l.mmnn_sgd_max_tensors.restype = I
+    l.mmnn_bce_logits.argtypes = [VP, VP, VP, LL, I, LL, VP, VP, C.c_float, LL, VP, VP]
+    l.mmnn_bce_logits.restype = I
     l.mmnn_preprocess_volumes.argtypes = [VP, VP, VP, I, I, I, I, I, I, I, I, C.c_float, C.c_float, VP]
     l.mmnn_preprocess_volumes.restype = I
     l.mmnn_profile_enable.argtypes = [I]

@@ -504,6 +504,32 @@ __global__ void __launch_bounds__(32) cindex_bootstrap_kernel(const __grid_const
 }  // namespace mmnn_heads
 using namespace mmnn_heads;
 
+// ------------------------------------------------------------------------------------------------- BCE with logits
+// nn.BCEWithLogitsLoss(pos_weight) as the reference's classification path builds it (/root/reference/main.py:148-153):
+//   l = (1 - y) x + (1 + (pw - 1) y) * (log1p(exp(-|x|)) + max(-x, 0))          (torch's stable form), elementwise,
+//   dl/dx = (1 - y) - (1 + (pw - 1) y) * (1 - sigmoid(x)),
+// for all stacked heads in one launch; plus the F1 counters of main.py:226-229 (sigmoid(x) > thr vs. label) per class
+// for the first `count_rows` rows (the multimodal head).  x, y: [rows][C] (y broadcast over heads by the caller's view).
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ pw,
+                                                         long long n, int C, long long y_rows_elems, float* __restrict__ loss, float* __restrict__ grad,
+                                                         float thr, long long count_elems, int* __restrict__ counts /*[3][C] tp fp fn or null*/) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const float xv = x[i], yv = y[i % y_rows_elems];
+    const float w = 1.f + ((pw != nullptr ? pw[c] : 1.f) - 1.f) * yv;
+    const float sp = log1pf(expf(-fabsf(xv))) + fmaxf(-xv, 0.f);
+    loss[i] = (1.f - yv) * xv + w * sp;
+    const float sig = 1.f / (1.f + expf(-xv));
+    grad[i] = (1.f - yv) - w * (1.f - sig);
+    if (counts != nullptr && i < count_elems) {
+      const bool pred = sig > thr, pos = yv == 1.f, neg = yv == 0.f;
+      if (pred && pos) atomicAdd(counts + c, 1);
+      if (pred && neg) atomicAdd(counts + C + c, 1);
+      if (!pred && pos) atomicAdd(counts + 2 * C + c, 1);
+    }
+  }
+}
+
 extern "C" {
 
 int mmnn_gap_linear_fwd(const float* y, int B, int V, int C, const float* W, const float* bias, const float* mask, int F,
@@ -567,5 +593,20 @@ int mmnn_cindex_bootstrap(const CindexArgs* a, void* stream) {
   return 0;
 }
 int mmnn_sizeof_cindex_args() { return (int)sizeof(CindexArgs); }
+
+// x [n] logits of all stacked heads ([H][N][C] flattened), y [y_elems] targets ([N][C], reused by every head),
+// pos_weight [C] or NULL; loss / grad [n] elementwise; counts int32 [3][C] (tp, fp, fn; caller-zeroed) over the first
+// count_elems elements, or NULL.
+int mmnn_bce_logits(const float* x, const float* y, const float* pos_weight, long long n, int C, long long y_elems, float* loss,
+                    float* grad, float threshold, long long count_elems, int* counts, void* stream) {
+  if (n <= 0) return 0;
+  if (C <= 0 || y_elems <= 0 || y_elems % C != 0) return -2;
+  mmnn::ProfScope ps_(mmnn::PC_HEADS, (cudaStream_t)stream, 1);
+  long long blocks = (n + 255) / 256;
+  bce_logits_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(x, y, pos_weight, n, C, y_elems, loss,
+                                                                                                 grad, threshold, count_elems, counts);
+  LAUNCH_RET();
+  return 0;
+}
 
 }  // extern "C"

@@ -1,5 +1,5 @@
 """GradientBlender with the reference's constructor, method names and update rule
-(/root/reference/losses/GradientBlender.py:9-256; survival branch :48-103,181-205).  Differences from the reference,
+(/root/reference/losses/GradientBlender.py:9-256; survival branch :48-103,181-205, classification branch :105-179).  Differences from the reference,
 all on purpose: the per-head / per-class Cox losses of one step are ONE kernel launch instead of six, and the weights
 live on the predictions' device so a step has no device->host synchronisation (quirk Q5)."""
 import numpy as np
@@ -53,16 +53,56 @@ class GradientBlender:
         self.lvn, self.ltn = val_loss, train_loss
         self.history.append(self.weights.detach().cpu().numpy())
 
-    # ---- dispatch (classification branch: SURVEY.md section 8f rank 3, not built)
+    # ---- classification (/root/reference/losses/GradientBlender.py:105-179,207-226)
+    def computeLossClassification(self, preds, targets, reduceToHeads=False, no_reduce=False):
+        """preds [k+1, N, C] stacked head logits, targets [N, C]; loss_function has reduction='none'.  The reference stacks
+        the targets k+1 times (:166-168); the fused loss reuses one copy per head instead."""
+        loss = self.loss_function(preds, targets)
+        if self.weights is None:
+            self.weights = self.normalize(torch.ones(preds.shape[0]))
+            self.history.append(self.weights.detach().cpu().numpy())
+        if no_reduce:
+            return loss
+        loss = self.reduceToHeads(loss)
+        if reduceToHeads:
+            return loss
+        if self.weights.device != loss.device or self.weights.dtype != loss.dtype:
+            self.weights = self.weights.to(device=loss.device, dtype=loss.dtype)
+        return self.reduce(self.weights * loss)
+
+    def updateWeightsClass(self, train_preds, train_targs, val_preds, val_targs):
+        train_loss = self.computeLossClassification(train_preds, train_targs, reduceToHeads=True).detach()
+        val_loss = self.computeLossClassification(val_preds, val_targs, reduceToHeads=True).detach()
+        if self.lvn is None or self.ltn is None:
+            self.weights = self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device))
+        else:
+            o_n = self.lvn - self.ltn
+            o_npn = val_loss - train_loss
+            delta_g = val_loss - self.lvn            # sign as in the reference's classification branch (:128)
+            delta_o = o_npn - o_n
+            self.weights = self.normalize(delta_g / torch.pow(delta_o, 2))
+        self.lvn, self.ltn = val_loss, train_loss
+
+    def reduceToHeads(self, loss):
+        if self.reduction.startswith("sum"):
+            return torch.sum(loss, dim=(1, 2))
+        if self.reduction.startswith("mean"):
+            return torch.mean(loss, dim=(1, 2))
+        if self.reduction.startswith("none"):
+            return loss
+        raise ValueError("Unable to reduce loss, unrecognized reduction: {}".format(self.reduction))
+
+    # ---- dispatch
     def updateWeights(self, *args, **kwargs):
-        if not self.survival:
-            raise NotImplementedError("classification blending is outside the hot path (SURVEY.md section 8f)")
-        self.updateWeightsSurv(*args, **kwargs)
+        if self.survival:
+            self.updateWeightsSurv(*args, **kwargs)
+        else:
+            self.updateWeightsClass(*args, **kwargs)
 
     def computeLoss(self, *args, **kwargs):
-        if not self.survival:
-            raise NotImplementedError("classification blending is outside the hot path (SURVEY.md section 8f)")
-        return self.computeLossSurv(*args, **kwargs)
+        if self.survival:
+            return self.computeLossSurv(*args, **kwargs)
+        return self.computeLossClassification(*args, **kwargs)
 
     def reduce(self, loss):
         if self.reduction.startswith("sum"):

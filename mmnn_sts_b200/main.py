@@ -26,6 +26,23 @@ NUM_BOOTSTRAP_ITERATIONS = 50   # /root/reference/main.py:61
 SUPER_BATCH_SIZE = 64           # /root/reference/main.py:62
 
 
+CLASSIFICATION_THRESHOLD = 0.5   # /root/reference/main.py (threshold applied to sigmoid outputs, :226)
+
+
+def getF1Score(tps, fps, fns):
+    """/root/reference/main.py:98-104: per-class F1 = tp / (tp + 0.5 (fn + fp)) as Python floats."""
+    f1s = []
+    for idx in range(len(tps)):
+        f1 = tps[idx] / (tps[idx] + 0.5 * (fns[idx] + fps[idx]))
+        f1s.append(f1.item())
+    return f1s
+
+
+def classification_pos_weights(class_freqs):
+    """/root/reference/main.py:148: pos_weight = (1 - f) / f."""
+    return (torch.ones_like(class_freqs) - class_freqs) / class_freqs
+
+
 def _cindex_from_counts(correct, tied, pairs):
     if pairs == 0:
         raise ZeroDivisionError("No admissable pairs in the dataset.")

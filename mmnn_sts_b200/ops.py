@@ -171,6 +171,39 @@ def cox_ph_segments(log_h, sort_key, weight):
     return CoxSegments.apply(log_h, sort_key, weight)
 
 
+# ------------------------------------------------------------------------------------------------ BCE with logits
+class BCEWithLogitsElementwise(torch.autograd.Function):
+    """Elementwise nn.BCEWithLogitsLoss(pos_weight, reduction='none') of logits [..., N, C] against targets [N, C]
+    (the same targets for every leading "head" index) in one launch; saves dloss/dlogit for backward."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, pos_weight, threshold, counts):
+        _require_cuda(logits, "BCEWithLogitsLoss")
+        x = logits.contiguous().float()
+        y = targets.contiguous().float()
+        Cc = x.shape[-1]
+        if y.numel() == 0 or x.numel() % y.numel() != 0 or y.shape[-1] != Cc:
+            raise ValueError(f"targets {tuple(targets.shape)} do not tile logits {tuple(logits.shape)}")
+        pw = pos_weight.contiguous().float() if pos_weight is not None else None
+        loss = torch.empty_like(x)
+        grad = torch.empty_like(x)
+        nc = y.numel() if counts is not None else 0
+        with torch.cuda.device(x.device):
+            L.check(L.lib().mmnn_bce_logits(_p(x), _p(y), _p(pw), x.numel(), Cc, y.numel(), _p(loss), _p(grad), float(threshold), nc,
+                                            _p(counts), _stream()), "mmnn_bce_logits")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None, None
+
+
+def bce_with_logits(logits, targets, pos_weight=None, threshold=0.5, counts=None):
+    return BCEWithLogitsElementwise.apply(logits, targets, pos_weight, threshold, counts)
+
+
 # ------------------------------------------------------------------------------------------------ concordance index
 def concordance_counts(event_times, predicted_scores, event_observed, resample_indices=None):
     """lifelines.utils.concordance_index pair counts (oracle/cindex.py) on the GPU, exact in integers.
