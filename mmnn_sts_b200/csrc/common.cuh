@@ -192,6 +192,11 @@ MMNN_DEVINL void sts16(uint32_t addr, uint4 v) {
 MMNN_DEVINL void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+// .ca variant: the line is also kept in L1 -- for operands whose rows are re-read within the tile (the 9 shifted
+// gradient tiles of the 3x3x3 weight gradient share most of their rows)
+MMNN_DEVINL void cp_async16_ca(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 MMNN_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 MMNN_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
