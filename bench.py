@@ -46,16 +46,29 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append((time.time(), l)) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
         return self
+
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs a few hundred ms to start: do not begin the timed region before it delivers."""
+        t = time.time()
+        while self.proc is not None and not self.lines and time.time() - t < timeout:
+            time.sleep(0.02)
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -66,8 +79,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        """Median SM clock and the union of throttle reasons over the samples taken between mark_start and mark_end (the
+        device-resident and end-to-end timed regions, both under the same load)."""
         sm, mx, reasons = [], 0, set()
-        for l in self.lines:
+        for ts, l in self.lines:
+            if self.t0 is not None and (ts < self.t0 or (self.t1 is not None and ts > self.t1 + 0.05)):
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -255,13 +272,19 @@ def run_ours(args):
         step = lambda *b: graphed(*b)
     launches0 = L.lib().mmnn_launch_count()
     with ClockSampler(device.index or 0) as cs:
+        cs.wait_first_sample()
+        timed(2, e2e=True)                       # settle the e2e pipeline (staging buffers, events) before anything is timed
+        launches0 = L.lib().mmnn_launch_count()
+        cs.mark_start()
         ms = timed(args.steps, e2e=False)
-    launches = (L.lib().mmnn_launch_count() - launches0) // max(1, args.steps)
+        launches = (L.lib().mmnn_launch_count() - launches0) // max(1, args.steps)
+        ms_e2e = timed(args.steps, e2e=True)
+        if ms + ms_e2e < 400.0:                  # short runs: keep the same load going until a few 50 ms samples exist
+            timed(int((400.0 - ms - ms_e2e) / max(ms / args.steps, 0.1)) + 1, e2e=False)   # (ms is the max over ranks: same count everywhere)
+        cs.mark_end()
     if args.graph and world == 1:                # a replayed graph launches the captured kernels without passing the counter
         l0 = L.lib().mmnn_launch_count(); eager_step(*dev_batches[0]); launches = L.lib().mmnn_launch_count() - l0
     clocks = cs.summary()
-    timed(2, e2e=True)                           # settle the e2e pipeline (staging buffers, events) before timing it
-    ms_e2e = timed(args.steps, e2e=True)
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); h0.record()
     for _ in range(3):
