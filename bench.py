@@ -204,6 +204,7 @@ def run_ours(args):
     def step(im, cl, ev, du):
         out = model({"image": im, "clinical": cl})
         loss, _ = blender.computeLoss(out, ev, du)
+        sync.arm()                               # step every batch: the trunk's gradient groups are all-reduced during backward
         loss.backward()
         sync()
         opt.step()

@@ -43,6 +43,16 @@ int mmnn_encoder_backward(void* plan, int B, int X, int Y, int Z, const void* co
                           void* const* buffers /*HOST*/, void* const* grads /*HOST*/, const float* dropmask, void* workspace,
                           const float* grad_out, void* stream);
 
+/* Gradient groups for data-parallel overlap (all-reduce overlapped with backward).  Backward
+ * finalises the gradients block by block, last block first; group k = dense block (nblocks-1-k) with the transition
+ * after it (+ norm5 for k = 0), group nblocks = the stem.  Each group is a contiguous element range [lo, hi) of a
+ * buffer that holds all gradients back to back in parameter order (what mmnn_sts_b200.models.densenet passes as
+ * `grads`); mmnn_encoder_wait_grad_group makes `stream` wait (cudaStreamWaitEvent) until group k of the most recent
+ * mmnn_encoder_backward is final, so its NCCL all-reduce can run while earlier blocks are still in backward. */
+int mmnn_encoder_num_grad_groups(void* plan);
+int mmnn_encoder_grad_group_range(void* plan, int k, long long* lo /*HOST*/, long long* hi /*HOST*/);
+int mmnn_encoder_wait_grad_group(void* plan, int k, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ trunk (fine-grained)
  * The tcgen05 tile engine behind the trunk, exposed for per-kernel parity tests.
  * mmnn_conv_rows  : implicit-GEMM forward / data-gradient of nn.Conv3d 1x1x1, 3x3x3 (pad 1), 7x7x7 (stride 2, pad 3)

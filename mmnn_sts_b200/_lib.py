@@ -135,6 +135,12 @@ def _declare(l):
     l.mmnn_encoder_forward.restype = I
     l.mmnn_encoder_backward.argtypes = [VP, I, I, I, I, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), VP, VP, VP, VP]
     l.mmnn_encoder_backward.restype = I
+    l.mmnn_encoder_num_grad_groups.argtypes = [VP]
+    l.mmnn_encoder_num_grad_groups.restype = I
+    l.mmnn_encoder_grad_group_range.argtypes = [VP, I, C.POINTER(LL), C.POINTER(LL)]
+    l.mmnn_encoder_grad_group_range.restype = I
+    l.mmnn_encoder_wait_grad_group.argtypes = [VP, I, VP]
+    l.mmnn_encoder_wait_grad_group.restype = I
     l.mmnn_encoder_debug_offsets.argtypes = [VP, I, I, I, I, C.POINTER(LL), C.POINTER(LL)]
     l.mmnn_encoder_debug_offsets.restype = I
     l.mmnn_mlp_heads.argtypes = [C.POINTER(MlpArgs), I, VP]

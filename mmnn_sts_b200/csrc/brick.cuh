@@ -31,7 +31,8 @@ constexpr int BR_PLANE = 8704;
 #else
 constexpr int BR_PLANE = BR_SLOTS * 16 + 16;           // 8656 B: odd multiple of 16 -> conflict-free chunk planes
 #endif
-constexpr int BR_THREADS = 448;
+constexpr int BR_THREADS = 448;          // forward: 14 warps
+__host__ __device__ constexpr int brick_threads(bool grad) { return 448; }   // (16 epilogue + 2 producer warps for dgrad, 640 threads, was tried: 105 -> 149 us)
 // Weight ring: forward (2 KB per tap and 32-channel buffer) 4 stages of 9 taps (one dz plane), data gradient (8 KB per
 // tap) 6 stages of 3 taps (one dx row).  The MMA warp pays ~280 cycles of wait / fence / commit per ring stage
 // (measured: 36 stages per tile instead of 18 cost +5 k cycles per tile), so forward stages carry as many taps as fit.
@@ -75,15 +76,16 @@ __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, int tp, ui
 }
 
 template <int TRANS, int EPI, bool GRAD, int TP>
-__global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid_constant__ BrickParams p) {
+__global__ void __launch_bounds__(brick_threads(GRAD), 1) conv3_brick_kernel(const __grid_constant__ BrickParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;
   constexpr bool E_F16 = kActF16;
+  constexpr int NTHREADS = brick_threads(GRAD);
   constexpr int NPW = GRAD ? 4 : 8;                    // producer warps
   constexpr int NPT = NPW * 32;                        // producer threads
-  constexpr int NEW = GRAD ? 8 : 4;                    // epilogue warps
+  constexpr int NEW = GRAD ? 8 : 4;                    // epilogue warps (dgrad: two per TMEM lane quarter, two 32-column chunks each)
   constexpr int NET = NEW * 32;
   constexpr int BR_MMA_WARP = NPW, BR_LOAD_WARP = NPW + 1, BR_EPI_WARP0 = NPW + 2;
-  static_assert(BR_EPI_WARP0 + NEW == BR_THREADS / 32, "warp roles must fill the CTA");
+  static_assert(BR_EPI_WARP0 + NEW == NTHREADS / 32, "warp roles must fill the CTA");
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   uint32_t offs[6];
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   }
   pdl_wait();   // nothing above touches global memory
   if (TRANS == T_BNRELU) {
-    for (int c = tid; c < p.CH; c += BR_THREADS) {
+    for (int c = tid; c < p.CH; c += NTHREADS) {
       float mean, rstd;
       bn_mean_rstd(p.bnA, c, mean, rstd);
       const float s = p.bnA.gamma[c] * rstd;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
     }
   }
   if (EPI == EP_MASK_STATS) {
-    for (int c = tid; c < p.NT; c += BR_THREADS) {
+    for (int c = tid; c < p.NT; c += NTHREADS) {
       float mean, rstd;
       bn_mean_rstd(p.bnE, c, mean, rstd);
       const float s = p.bnE.gamma[c] * rstd;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA + 2 * p.CH);
   if (TRANS == T_BNRELU && OP_F16) {
     __syncthreads();
-    fill_h2coef(coefH, coefA, coefA + p.CH, p.CH, tid, BR_THREADS);
+    fill_h2coef(coefH, coefA, coefA + p.CH, p.CH, tid, NTHREADS);
   }
   tc_fence_before();
   __syncthreads();
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(BR_THREADS, 1) conv3_brick_kernel(const __grid
   } else if (warp >= BR_EPI_WARP0) {
     // ================= epilogue (TMEM lane quarter = warp % 4; with 8 warps, warp e and e+4 share a quarter and split
     // the 32-column chunks: CCW chunks per warp starting at cc0)
-    constexpr int CCW = GRAD ? 2 : 4;
+    constexpr int CCW = 16 / NEW;      // 32-column chunks per warp: 4 (forward, only one in use), 2 (dgrad)
     const int qd = warp & 3;
     const int etid = (warp - BR_EPI_WARP0) * 32 + lane;
     const int cc0 = ((warp - BR_EPI_WARP0) >> 2) * CCW;

@@ -72,7 +72,7 @@ int launch_brick_tp(const BrickParams& p, int ntiles, cudaStream_t stream) {
   if (e != cudaSuccess) return (int)e;
   const int ngroups = (ntiles + TP - 1) / TP;
   const int grid = ngroups < 148 ? ngroups : 148;   // persistent: one CTA per SM
-  launch_pdl(kern, dim3(grid), dim3(BR_THREADS), smem, stream, p);
+  launch_pdl(kern, dim3(grid), dim3(brick_threads(GRAD)), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

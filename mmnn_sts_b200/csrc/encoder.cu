@@ -82,6 +82,11 @@ struct Plan {
   // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
   // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
   cudaStream_t side = nullptr;
+  // Gradient groups, in the order backward finalises them: group k = dense block nb-1-k with the transition that
+  // follows it (the last block's group also holds norm5), group nb = the stem (conv0, norm0).  Each group is a
+  // contiguous range of the parameter-order gradient buffer; grad_ev[k] is recorded when its last writer has been
+  // enqueued, so a data-parallel reducer can all-reduce it while the earlier blocks are still in backward.
+  std::vector<cudaEvent_t> grad_ev;
   std::vector<cudaEvent_t> events;
   size_t ev_next = 0;
   cudaEvent_t next_event() {
@@ -282,6 +287,34 @@ void* mmnn_encoder_create(int in_channels, const int* block_config, int nblocks,
 }
 
 void mmnn_encoder_destroy(void* h) { delete (Plan*)h; }
+int mmnn_encoder_num_grad_groups(void* h) { return (int)((Plan*)h)->blocks.size() + 1; }
+// element range [lo, hi) of gradient group k in a buffer holding all gradients back to back in parameter order
+int mmnn_encoder_grad_group_range(void* h, int k, long long* lo, long long* hi) {
+  Plan* pl = (Plan*)h;
+  const int nb = (int)pl->blocks.size();
+  if (k < 0 || k > nb) return -2;
+  int p0, p1;
+  if (k == nb) { p0 = 0; p1 = pl->blocks[0].layers[0].n1.param_idx; }
+  else {
+    const BlockInfo& bi = pl->blocks[nb - 1 - k];
+    p0 = bi.layers[0].n1.param_idx;
+    p1 = bi.has_trans ? bi.tconv_idx + 1 : pl->n5.param_idx + 2;
+  }
+  long long off = 0, a = 0, b = 0;
+  for (int i = 0; i < pl->num_params; ++i) {
+    if (i == p0) a = off;
+    off += pl->param_numel[i];
+    if (i == p1 - 1) b = off;
+  }
+  *lo = a; *hi = b;
+  return 0;
+}
+// makes `stream` wait until gradient group k of the most recent mmnn_encoder_backward is final
+int mmnn_encoder_wait_grad_group(void* h, int k, void* stream) {
+  Plan* pl = (Plan*)h;
+  if (k < 0 || k >= (int)pl->grad_ev.size()) return -2;
+  return (int)cudaStreamWaitEvent((cudaStream_t)stream, pl->grad_ev[k], 0);
+}
 int mmnn_encoder_num_params(void* h) { return ((Plan*)h)->num_params; }
 int mmnn_encoder_num_buffers(void* h) { return ((Plan*)h)->num_buffers; }
 int mmnn_encoder_num_layers(void* h) { return ((Plan*)h)->num_layers; }
@@ -557,6 +590,58 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     return e == cudaSuccess ? 0 : (int)e;
   };
 
+  // ---- tails (BN parameter gradients from the statistics arena, conv2 gradient scratch -> reference layout): the
+  // tables are uploaded now, the launches happen per gradient group as soon as the group's last writer is enqueued
+  float* gbase = (float*)grads[0];
+  std::vector<int> bn_lo(nb + 2, 0), tt_lo(nb + 2, 0);      // table ranges per group (group k = block nb-1-k; nb = stem)
+  uint8_t* dtab = ws + g.tables + (1 << 19) + (1 << 17);
+  uint8_t* dtt = dtab + (1 << 18);
+  {
+    // table order: [block nb-1 (+n5)] [block nb-2 + its transition] ... [block 0 + its transition] [stem]
+    std::vector<BnTableEntry> tab;
+    std::vector<TransposeEntry> tt;
+    auto add_bn_entry = [&](const BnInfo& bn) {
+      BnTableEntry e = {};
+      e.g_sum = gsum(bn); e.g_dot = gdot(bn);
+      e.grad_gamma_off = (float*)grads[bn.param_idx] - gbase; e.grad_beta_off = (float*)grads[bn.param_idx + 1] - gbase;
+      e.C = bn.C;
+      tab.push_back(e);
+    };
+    for (int k = 0; k < nb; ++k) {
+      const BlockInfo& bi = pl->blocks[nb - 1 - k];
+      bn_lo[k] = (int)tab.size(); tt_lo[k] = (int)tt.size();
+      for (auto& li : bi.layers) {
+        add_bn_entry(li.n1); add_bn_entry(li.n2);
+        TransposeEntry e;
+        e.src = (const float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
+        e.dst_off = (float*)grads[li.conv2_idx] - gbase;
+        tt.push_back(e);
+      }
+      if (bi.has_trans) add_bn_entry(bi.tn); else add_bn_entry(pl->n5);
+    }
+    bn_lo[nb] = (int)tab.size(); tt_lo[nb] = (int)tt.size();
+    add_bn_entry(pl->n0);
+    bn_lo[nb + 1] = (int)tab.size(); tt_lo[nb + 1] = (int)tt.size();
+    RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
+    RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(TransposeEntry), st));
+  }
+  while ((int)pl->grad_ev.size() < nb + 1) {
+    cudaEvent_t e;
+    CUDA_RET(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->grad_ev.push_back(e);
+  }
+  // launches the tails of group k on stream `ts` (which must already be ordered after the group's writers) and
+  // records the group's gradient-ready event there
+  auto group_tail = [&](int k, cudaStream_t ts) -> int {
+    const int nbn = bn_lo[k + 1] - bn_lo[k], ntt = tt_lo[k + 1] - tt_lo[k];
+    ProfScope ps_(PC_TAILS, ts, (nbn > 0) + (ntt > 0));
+    if (nbn > 0) bn_param_grad_kernel<<<(unsigned)nbn, 128, 0, ts>>>((const BnTableEntry*)dtab + bn_lo[k], gbase);
+    if (ntt > 0) conv2_grad_transpose_kernel<<<dim3(16, (unsigned)ntt), 256, 0, ts>>>((const TransposeEntry*)dtt + tt_lo[k], gbase, GROWTH, BOTT);
+    LAUNCH_RET();
+    CUDA_RET(cudaEventRecord(pl->grad_ev[k], ts));
+    return 0;
+  };
+
   // ---- norm5
   {
     const BlockInfo& bi = pl->blocks[nb - 1];
@@ -685,6 +770,14 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
       }
     }
+    {
+      // every gradient of block b (and of the transition after it, done in the previous iteration) has its last writer
+      // enqueued: statistics on this stream, weight gradients on the side stream.  Finish the group on the side stream.
+      cudaEvent_t m = pl->next_event();
+      CUDA_RET(cudaEventRecord(m, st));
+      CUDA_RET(cudaStreamWaitEvent(sd, m, 0));
+      RET_IF(group_tail(nb - 1 - b, sd));
+    }
     if (b > 0) {
       // transition b-1: buf[b][:, :c0] = avgpool(conv(relu(bn(buf[b-1]))))  ==  conv(pooled[b-1])
       const BlockInfo& pv = pl->blocks[b - 1];
@@ -769,35 +862,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     CUDA_RET(cudaEventRecord(e, sd));
     CUDA_RET(cudaStreamWaitEvent(st, e, 0));
   }
-  // ---- tails: BN parameter gradients and conv2 gradient layout, one launch each
-  {
-    float* gbase = (float*)grads[0];
-    std::vector<BnTableEntry> tab;
-    for (BnInfo* bn : pl->bn_order) {
-      BnTableEntry e = {};
-      e.g_sum = gsum(*bn); e.g_dot = gdot(*bn);
-      e.grad_gamma_off = (float*)grads[bn->param_idx] - gbase; e.grad_beta_off = (float*)grads[bn->param_idx + 1] - gbase;
-      e.C = bn->C;
-      tab.push_back(e);
-    }
-    uint8_t* dtab = ws + g.tables + (1 << 19) + (1 << 17);
-    RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
-    ProfScope ps_(PC_TAILS, st, 2);
-    bn_param_grad_kernel<<<(unsigned)tab.size(), 128, 0, st>>>((const BnTableEntry*)dtab, gbase);
-    LAUNCH_RET();
-    std::vector<TransposeEntry> tt;
-    for (auto& bi : pl->blocks)
-      for (auto& li : bi.layers) {
-        TransposeEntry e;
-        e.src = (const float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
-        e.dst_off = (float*)grads[li.conv2_idx] - gbase;
-        tt.push_back(e);
-      }
-    uint8_t* dtt = dtab + (1 << 18);
-    RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(TransposeEntry), st));
-    conv2_grad_transpose_kernel<<<dim3(16, (unsigned)tt.size()), 256, 0, st>>>((const TransposeEntry*)dtt, gbase, GROWTH, BOTT);
-    LAUNCH_RET();
-  }
+  // ---- tail of the stem group (conv0, norm0), then its event
+  RET_IF(group_tail(nb, st));
   return 0;
 }
 

@@ -32,18 +32,54 @@ def shard_patients(num_patients, rank, world, permutation=None):
 
 
 class GradientAllReducer:
-    """Flat-bucket gradient all-reduce (SUM by default).  Parameters that never receive a gradient (the reference's
-    unused class_layers.out / dense6 / modality heads, SURVEY.md section 7 hard part 9) are skipped.
-    Buckets are launched in reverse parameter order (the order backward produces them) on NCCL's own stream via
-    async_op, so the reduction of the late layers overlaps whatever the caller still has queued."""
+    """Gradient all-reduce (SUM by default).  Parameters that never receive a gradient (the reference's unused
+    class_layers.out / dense6 / modality heads, SURVEY.md section 7 hard part 9) are skipped.
 
-    def __init__(self, params, bucket_bytes=64 << 20, average=False, group=None, model=None):
+    The DenseNet trunk keeps all its gradients in ONE flat buffer and finalises them block by block (last block first).
+    With `overlap=True` (default) the reducer hooks the trunk: right after backward has been ENQUEUED it queues one
+    all-reduce per gradient group on a communication stream that waits for the group's gradient-ready event
+    (`mmnn_encoder_wait_grad_group`), so the reduction of blocks 4, 3, 2 runs while blocks 3, 2, 1 and the stem are still
+    in backward; `__call__` (before `optimizer.step()`) then only waits for those collectives and reduces the few small
+    head / MLP tensors in one extra bucket.  The overlap must be requested per backward with `arm()` -- only a backward
+    that starts from empty gradients and is followed directly by the optimiser step may be reduced early (with gradient
+    accumulation the earlier micro-batches must not be reduced on their own).  MMNN_DP_OVERLAP=0, or never calling
+    `arm()`, falls back to one all-reduce of the flat buffer after backward."""
+
+    def __init__(self, params, bucket_bytes=64 << 20, average=False, group=None, model=None, overlap=True):
         self.params = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.average = average
         self.group = group
         # modules that keep their gradients in one flat buffer (the DenseNet trunk) are reduced in place, without packing
         self.flat_modules = [m for m in model.modules() if hasattr(m, "flat_grad_buffer")] if model is not None else []
+        self._inflight = {}
+        self._comm_stream = None
+        self._armed = False
+        if overlap and os.environ.get("MMNN_DP_OVERLAP", "1") != "0":
+            for m in self.flat_modules:
+                if hasattr(m, "grad_groups"):
+                    m.grad_group_hook = self._on_trunk_backward
+
+    def arm(self):
+        """Call right before the `loss.backward()` whose gradients go straight to `optimizer.step()` (no accumulation)."""
+        self._armed = True
+
+    def _on_trunk_backward(self, backbone, flat):
+        armed, self._armed = self._armed, False
+        if not armed or not dist.is_initialized() or dist.get_world_size(self.group) == 1 or not flat.is_cuda:
+            return
+        if any(p.grad is not None for p in backbone.parameters()):
+            return                                   # accumulating into existing gradients: reduce after backward instead
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=flat.device)
+        comm = self._comm_stream
+        flat.record_stream(comm)
+        works = []
+        for k, (lo, hi) in enumerate(backbone.grad_groups()):
+            backbone.wait_grad_group(k, comm)
+            with torch.cuda.stream(comm):
+                works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._inflight[id(backbone)] = (works, flat)
 
     def __call__(self, *_):
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
@@ -52,7 +88,17 @@ class GradientAllReducer:
         pending_flat, covered = [], set()
         for m in self.flat_modules:
             flat = m.flat_grad_buffer()
-            if flat is not None:
+            started = self._inflight.pop(id(m), None)
+            if flat is not None and started is not None and started[1] is flat:
+                for w in started[0]:                      # per-group collectives queued during backward
+                    pending_flat.append((w, None))
+                if self.average:
+                    pending_flat.append((None, flat))
+                covered.update(id(p) for p in m.parameters())
+            elif flat is not None:
+                if started is not None:
+                    for w in started[0]:
+                        w.wait()
                 pending_flat.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
                 covered.update(id(p) for p in m.parameters())
         grads = [p.grad for p in reversed(self.params) if p.grad is not None and id(p) not in covered]
@@ -69,8 +115,9 @@ class GradientAllReducer:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             pending.append((work, flat, b))
         for work, flat in pending_flat:
-            work.wait()
-            if self.average:
+            if work is not None:
+                work.wait()
+            if self.average and flat is not None:
                 flat.div_(world)
         for work, flat, b in pending:
             work.wait()

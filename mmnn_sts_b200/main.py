@@ -102,6 +102,8 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                 loss, _ = blender.computeLoss(outputs, events, durations)
             else:
                 loss = surv_criterion(CoxPH, outputs, events, durations, device)
+            if grad_sync is not None and super_batch_interval == 1 and hasattr(grad_sync, "arm"):
+                grad_sync.arm()                     # no accumulation: the trunk's gradient groups are all-reduced during backward
             loss.backward()
             losses.append(loss.detach())            # no per-step .item(): one sync per epoch instead of one per step
             if (i + 1) % super_batch_interval == 0 or i == len(train_batches) - 1:
@@ -109,7 +111,7 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                     grad_sync(model)
                 optimizer.step()
                 scheduler.step()
-                optimizer.zero_grad()
+                optimizer.zero_grad(set_to_none=True)
             c_pred.append(outputs.detach()); c_events.append(events); c_durations.append(durations)
         c_pred = torch.cat(c_pred, dim=1 if args.blend else 0)
         c_events, c_durations = torch.cat(c_events), torch.cat(c_durations)

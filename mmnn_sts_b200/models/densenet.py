@@ -93,6 +93,7 @@ class Backbone(nn.Sequential):
         self._plan = None
         self._workspaces = {}
         self.injected_dropmask = None  # tests: [num_layers, B, growth] keep-mask / (1-p)
+        self.grad_group_hook = None    # data parallel: callable(backbone, flat_grad) run right after backward is enqueued
 
     # ---- C-ABI plumbing
     def _get_plan(self):
@@ -181,7 +182,24 @@ class Backbone(nn.Sequential):
                                            ws.tensor.data_ptr(), g.data_ptr(), stream)
         L.check(rc, "mmnn_encoder_backward")
         self._flat_grad = flat
+        if self.grad_group_hook is not None:
+            # everything is only ENQUEUED at this point: the hook can queue per-group all-reduces that start as soon as
+            # the group's gradient-ready event fires, i.e. while the earlier blocks are still in backward
+            self.grad_group_hook(self, flat)
         return grads
+
+    def grad_groups(self):
+        """[(lo, hi)] element ranges of the flat gradient buffer in the order backward finalises them."""
+        plan = self._get_plan()
+        out = []
+        for k in range(L.lib().mmnn_encoder_num_grad_groups(plan)):
+            lo, hi = C.c_longlong(), C.c_longlong()
+            L.check(L.lib().mmnn_encoder_grad_group_range(plan, k, C.byref(lo), C.byref(hi)), "mmnn_encoder_grad_group_range")
+            out.append((lo.value, hi.value))
+        return out
+
+    def wait_grad_group(self, k, stream):
+        L.check(L.lib().mmnn_encoder_wait_grad_group(self._get_plan(), k, stream.cuda_stream), "mmnn_encoder_wait_grad_group")
 
     def flat_grad_buffer(self):
         """The single contiguous fp32 buffer holding every trunk gradient, if the parameters' .grad tensors are still the

@@ -117,7 +117,13 @@ class MLPHeads(torch.autograd.Function):
         params = ctx.saved_tensors[6:]
         dpreds = dpreds.contiguous().float()
         B = x.shape[0]
-        grads = [torch.zeros_like(p) for p in params]
+        # one zero fill for all 30 gradient tensors (views of a flat buffer, 16-byte aligned) instead of 30 fill launches
+        offs, tot = [], 0
+        for p in params:
+            offs.append(tot)
+            tot += (p.numel() + 3) & ~3
+        flat = torch.zeros(tot, dtype=torch.float32, device=x.device)
+        grads = [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
         d_img = torch.empty_like(img_f)
         scratch = torch.empty(2 * B * 32, dtype=torch.float32, device=x.device)
         args = L.MlpArgs()
