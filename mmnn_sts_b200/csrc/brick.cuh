@@ -37,8 +37,9 @@ __host__ __device__ constexpr int brick_threads(bool grad) { return 448; }   // 
 // tap) 6 stages of 3 taps (one dx row).  The MMA warp pays ~280 cycles of wait / fence / commit per ring stage
 // (measured: 36 stages per tile instead of 18 cost +5 k cycles per tile), so forward stages carry as many taps as fit.
 // With tile pairs (TP = 2, below) the data gradient keeps 4 brick buffers, so its ring shrinks to 3 stages.
-__host__ __device__ constexpr int brick_btaps(bool grad) { return grad ? 3 : 9; }
-__host__ __device__ constexpr int brick_bstages(bool grad, int tp) { return grad ? (tp == 2 ? 3 : 6) : 4; }
+// With tile pairs the data gradient uses 9 stages of ONE tap (8 KB): same 72 KB, three times the look-ahead.
+__host__ __device__ constexpr int brick_btaps(bool grad, int tp) { return grad ? (tp == 2 ? 1 : 3) : 9; }
+__host__ __device__ constexpr int brick_bstages(bool grad, int tp) { return grad ? (tp == 2 ? 9 : 6) : 4; }
 
 struct BrickParams {
   int B, Dz, Dy, Dx;
@@ -71,7 +72,7 @@ __host__ __device__ inline uint32_t brick_smem_layout(int CH, int NT, int tp, ui
   o = (o + 127u) & ~127u;
   offs[4] = o; o += (uint32_t)brick_nbuf(CH, tp) * PH * BR_PLANE;   // brick buffer ring
   o = (o + 127u) & ~127u;
-  offs[5] = o; o += (uint32_t)(brick_bstages(CH < 64, tp) * brick_btaps(CH < 64)) * PH * NT * 16;
+  offs[5] = o; o += (uint32_t)(brick_bstages(CH < 64, tp) * brick_btaps(CH < 64, tp)) * PH * NT * 16;
   return o;
 }
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(brick_threads(GRAD), 1) conv3_brick_kernel(con
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, TP, offs);
   const uint32_t sbase = smem_u32(smem);
-  constexpr int BR_BTAPS = brick_btaps(GRAD), BR_BSTAGES = brick_bstages(GRAD, TP);
+  constexpr int BR_BTAPS = brick_btaps(GRAD, TP), BR_BSTAGES = brick_bstages(GRAD, TP);
   constexpr int NBUF = (!GRAD || TP == 2) ? 4 : 2;   // brick buffers (GRAD launches have CH = 32, forward ones CH = 128: checked by the host)
   constexpr int LAG = NBUF == 4 ? 2 : 1;             // producer look-ahead: buffers whose copies are in flight while an older one is finished
   // barrier map (8 B each): brick_full[4] | brick_empty[4] | b_full[BSTAGES] | b_empty[BSTAGES] | acc_full[2] | acc_empty[2]
@@ -306,9 +307,9 @@ __global__ void __launch_bounds__(brick_threads(GRAD), 1) conv3_brick_kernel(con
               uint64_t bd = make_smem_desc(bst0 + s * bs_bytes, p.NT * 16, 128);
 #pragma unroll
               for (int v = 0; v < BR_BTAPS; ++v) {
-                const int t9 = BR_BTAPS == 9 ? tgr : tgr / 3;
-                const int t3 = BR_BTAPS == 9 ? v / 3 : tgr - (tgr / 3) * 3;
-                const int t1 = BR_BTAPS == 9 ? v % 3 : v;
+                const int t9 = BR_BTAPS == 9 ? tgr : (BR_BTAPS == 3 ? tgr / 3 : tgr / 9);
+                const int t3 = BR_BTAPS == 9 ? v / 3 : (BR_BTAPS == 3 ? tgr - (tgr / 3) * 3 : (tgr / 3) % 3);
+                const int t1 = BR_BTAPS == 9 ? v % 3 : (BR_BTAPS == 3 ? v : tgr % 3);
                 const int oz = (t9 - 1) * p.tap_sign + 1, oy = (t3 - 1) * p.tap_sign + 1, ox = (t1 - 1) * p.tap_sign + 1;
                 const uint64_t ad = desc_advance(ad_base, (uint32_t)((oz * BR_HY + oy) * BR_HX + ox) * 16u);
                 tc_mma_bf16(td, ad, bd, idesc, (h > 0 || tg > 0 || v > 0) ? 1u : 0u);
