@@ -99,7 +99,7 @@ class PackDesc(C.Structure):
 A_LINEAR_CONV, A_STEM = 0, 1
 T_NONE, T_BNRELU = 0, 1
 EP_STORE, EP_STORE_STATS, EP_MASK_STATS = 0, 1, 2
-PACK_GENERIC, PACK_STEM = 0, 1
+PACK_GENERIC, PACK_STEM, PACK_STEM_SW32 = 0, 1, 2
 
 
 def _declare(l):

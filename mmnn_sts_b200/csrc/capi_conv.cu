@@ -215,3 +215,60 @@ int mmnn_sizeof_rows_params() { return (int)sizeof(RowsParams); }
 int mmnn_sizeof_pack_desc() { return (int)sizeof(PackDesc); }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05.mma issue-rate microbenchmark (instrumentation; tests/microbench_mma.py): one CTA, one elected thread issues
+// `iters` back-to-back MMAs  D[128 x N] += A[128 x 16] * B[N x 16]  from fixed shared-memory operands and commits; the
+// elapsed SM clock cycles between the first issue and the arrival of the commit are written to out[0].
+// layout 0: SWIZZLE_NONE core matrices (LBO = plane stride, SBO = 128 B), 6: SWIZZLE_32B rows of 32 B (SBO = 256 B).
+namespace mmnn {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int iters, int a_step_bytes, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase, tptr = sbase + 16, sA = sbase + 1024, sB = sA + 64 * 1024;
+  for (int i = threadIdx.x; i < (64 + 16) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + 1024)[i] = 0x3c003c00u;  // fp16 1.0
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    tmem_alloc(tptr, 512);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + 16);
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(128, N, 0, 0, true);
+    const uint64_t ad0 = layout == 0 ? make_smem_desc(sA, 2064, 128) : make_smem_desc_sw(sA, 16, 256, (uint32_t)layout);
+    const uint64_t bd0 = layout == 0 ? make_smem_desc(sB, (uint32_t)N * 16, 128) : make_smem_desc_sw(sB, 16, 256, (uint32_t)layout);
+    long long t0 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i)
+        tc_mma_bf16(tmem_base + (i & 1) * 256, desc_advance(ad0, (uint32_t)((i & 7) * a_step_bytes)), bd0, idesc, i > 1 ? 1u : 0u);
+      tc_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0, 90);
+    const long long t1 = clock64();
+    if (t0 != 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+}  // namespace mmnn
+
+extern "C" int mmnn_mma_rate(int N, int layout, int iters, int a_step_bytes, long long* out_cycles, void* stream) {
+  const int smem = (1 + 64 + 16 + 1) * 1024;
+  cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, layout, iters, a_step_bytes, out_cycles);
+  return (int)cudaGetLastError();
+}
+
+#ifdef MMNN_STEM_TIMING
+extern "C" int mmnn_stem_dbg(long long* out) { return (int)cudaMemcpyFromSymbol(out, mmnn::g_stem_dbg, 8 * sizeof(long long)); }
+#endif

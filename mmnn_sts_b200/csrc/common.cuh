@@ -135,6 +135,10 @@ MMNN_DEVINL uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
 }
+// Same descriptor with a swizzle mode in bits [61,64): 0 none, 1 128B (32B atom base), 2 128B, 4 64B, 6 32B.
+MMNN_DEVINL uint64_t make_smem_desc_sw(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return make_smem_desc(addr, lbo, sbo) | ((uint64_t)(layout & 7u) << 61);
+}
 // Advancing a descriptor's start address by `bytes` (multiple of 16) is an add on the low word: the 14-bit field never
 // carries because shared-memory addresses stay below 256 KB.
 MMNN_DEVINL uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }

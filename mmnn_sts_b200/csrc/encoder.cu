@@ -387,7 +387,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
       d.mode = mode; d.cin_real = pl->cin_real; d.f16 = (fwd && kActF16) ? 1 : 0; d.sn = sn; d.sc = sc; d.st = stt;
       descs.push_back(d);
     };
-    add(params[pl->conv0_idx], pl->pk_stem, 64, 64, 64, 64, 16, PACK_STEM, 0, 0, 0, true);
+    add(params[pl->conv0_idx], pl->pk_stem, 64, 64, 64, 64, 16, SB_SW32 ? PACK_STEM_SW32 : PACK_STEM, 0, 0, 0, true);
     for (auto& bi : pl->blocks) {
       for (auto& li : bi.layers) {
         add(params[li.conv1_idx], li.pk_c1f, BOTT, 128, li.cin, 64, 1, PACK_GENERIC, li.cin, 1, 0, true);

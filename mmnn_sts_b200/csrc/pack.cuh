@@ -5,7 +5,7 @@
 
 namespace mmnn {
 
-enum { PACK_GENERIC = 0, PACK_STEM = 1 };
+enum { PACK_GENERIC = 0, PACK_STEM = 1, PACK_STEM_SW32 = 2 };
 
 struct PackDesc {
   const float* src;
@@ -23,6 +23,34 @@ struct PackDesc {
 
 static __global__ void pack_weights_kernel(const PackDesc* __restrict__ descs) {
   const PackDesc d = descs[blockIdx.y];
+  if (d.mode == PACK_STEM_SW32) {
+    // stem.cuh B operand: dst[tap = (dz*4+dy)*4+dx][n (64)][32 B] = the 16 space-to-depth channels (pz,py,px,ci) of one tap,
+    // K-major rows of 32 bytes written with the 32-byte swizzle (16-byte half h of row n at h ^ bit2(n): the image is
+    // copied to a 256-byte aligned shared-memory address, so address bit 7 of a row is bit 2 of n)
+    const long long cells = 64LL * 64 * 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < cells; idx += (long long)gridDim.x * blockDim.x) {
+      const int hp = (int)(idx & 1), n = (int)((idx >> 1) & 63), tap = (int)(idx >> 7);
+      const int half = hp ^ ((n >> 2) & 1);
+      const int dz = tap >> 4, dy = (tap >> 2) & 3, dx = tap & 3;
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int kz = 2 * dz + half, ky = 2 * dy + ((e >> 2) & 1), kx = 2 * dx + ((e >> 1) & 1), ci = e & 1;
+        float val = 0.f;
+        if (kz < 7 && ky < 7 && kx < 7 && ci < d.cin_real && n < d.N)
+          val = d.src[((((long long)n * d.cin_real + ci) * 7 + kz) * 7 + ky) * 7 + kx];
+        w[e] = val;
+      }
+      uint4 o;
+      if (d.f16) {
+        o.x = pack2<true>(w[0], w[1]); o.y = pack2<true>(w[2], w[3]); o.z = pack2<true>(w[4], w[5]); o.w = pack2<true>(w[6], w[7]);
+      } else {
+        o.x = pack_bf16(w[0], w[1]); o.y = pack_bf16(w[2], w[3]); o.z = pack_bf16(w[4], w[5]); o.w = pack_bf16(w[6], w[7]);
+      }
+      reinterpret_cast<uint4*>(d.dst)[idx] = o;
+    }
+    return;
+  }
   const int planes = d.kbw / 8;
   const int kb_per_tap = (d.Cin + d.kbw - 1) / d.kbw;
   const int KB = d.ntaps * kb_per_tap;

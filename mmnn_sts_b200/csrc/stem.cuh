@@ -18,30 +18,43 @@ namespace mmnn {
 
 constexpr int SB_TY = 16, SB_TX = 8, SB_HZ = 4, SB_HY = SB_TY + 3, SB_HX = SB_TX + 3;
 constexpr int SB_SLOTS = SB_HZ * SB_HY * SB_HX;          // 836
-constexpr int SB_PLANE = SB_SLOTS * 16 + 16;             // 13392 B: odd multiple of 16
-constexpr int SB_BRICK = 2 * SB_PLANE;                   // 16 channels = 2 chunk planes
+#ifndef MMNN_STEM_SW32
+#define MMNN_STEM_SW32 1
+#endif
+// Brick layout.  SW32 (default): one 32-byte row per slot (the 16 channels of a voxel = exactly the K = 16 of one MMA),
+// written with the 32-byte swizzle (16-byte half h of the slot at byte address a goes to h ^ bit7(a)); the A descriptor
+// uses SWIZZLE_32B, 8-row groups = 8 consecutive x slots (256 B atoms), SBO = 11 slots.  Fallback (0): two chunk planes,
+// SWIZZLE_NONE core matrices -- the operand fetch of that layout runs at ~64 B/clk.
+constexpr bool SB_SW32 = MMNN_STEM_SW32 != 0;
+constexpr int SB_PLANE = SB_SLOTS * 16 + 16;             // 13392 B: odd multiple of 16 (plane layout)
+constexpr int SB_BRICK = SB_SW32 ? ((SB_SLOTS * 32 + 255) / 256) * 256 : 2 * SB_PLANE;   // 26880 / 26784 B
 constexpr int SB_STAGES = 3;
 constexpr int SB_NPW = 4, SB_NPT = SB_NPW * 32, SB_MMA_WARP = SB_NPW, SB_EPI_WARP0 = SB_NPW + 1, SB_NEW = 8, SB_NET = SB_NEW * 32;
 constexpr int SB_THREADS = (SB_EPI_WARP0 + SB_NEW) * 32;  // 416
 constexpr int SB_WBYTES = 64 * 2048;                     // 64 taps x [2 planes][64 n][8] 16-bit
-constexpr uint32_t SB_OFF_RED = 256, SB_OFF_W = 256 + 2 * 4 * 64 * 4, SB_OFF_BRICK = SB_OFF_W + SB_WBYTES;
-constexpr uint32_t SB_SMEM = SB_OFF_BRICK + SB_STAGES * SB_BRICK;
+constexpr uint32_t SB_OFF_RED = 256, SB_OFF_W = 256 + 2 * 4 * 64 * 4, SB_OFF_BRICK = SB_OFF_W + SB_WBYTES;   // 133376 = 521 * 256
+constexpr uint32_t SB_SMEM = SB_OFF_BRICK + SB_STAGES * SB_BRICK + 1024;   // + slack to align the dynamic base to 1 KB
 
 struct StemBrickParams {
   int B, D0, H0, W0;       // output dims
   int Sz, Sy, Sx;          // xs2d dims (D0+3, H0+3, W0+3)
   const bf16* xs2d;
-  const bf16* w_packed;    // PACK_STEM image: [tap16 = dz*4+dy][chunk8 = dx*2+half][64 n][8]
+  const bf16* w_packed;    // SW32: PACK_STEM_SW32 image [tap64][64 n][32 B swizzled]; else PACK_STEM [tap16][chunk8][64 n][8]
   bf16* out;               // [B*D0*H0*W0][out_pitch]
   long long out_pitch;
   double* st_sum;          // [64] or nullptr
   double* st_sq;
 };
 
+#ifdef MMNN_STEM_TIMING
+__device__ long long g_stem_dbg[8];
+#endif
 static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const __grid_constant__ StemBrickParams p) {
   constexpr bool F16 = kActF16;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   pdl_trigger();
+  // swizzle patterns are functions of the shared-memory byte address: work from a 1 KB aligned base
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   // barriers (8 B each): brick_full[3] 0..2 | brick_empty[3] 3..5 | w_full 6 | acc_full[2] 7,8 | acc_empty[2] 9,10
   auto BAR = [&](int i) { return sbase + 8u * i; };
@@ -52,9 +65,9 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
   const int tiles_y = (p.H0 + SB_TY - 1) / SB_TY, tiles_x = (p.W0 + SB_TX - 1) / SB_TX;
   const int ntiles = p.B * p.D0 * tiles_y * tiles_x;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  // MMAs into one accumulator form a dependent chain (~95 cycles each, measured): rotate over 4 accumulators per tile
-  // (summed by the epilogue); 2 tiles x 4 x 64 columns = all 512 TMEM columns
-  constexpr int NACC = 4;
+  // (rotating over NACC > 1 accumulators per tile, summed by the epilogue, was measured: no gain -- back-to-back MMAs
+  // into one accumulator already run at the operand-fetch rate, tests/microbench_mma.py)
+  constexpr int NACC = 1;
   constexpr uint32_t TMEM_COLS = 2 * NACC * 64;
 
   if (warp == SB_MMA_WARP) {
@@ -103,7 +116,7 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
       tile_coords((int)blockIdx.x + it * (int)gridDim.x, n, z, y0, x0);
       const int s = it % SB_STAGES;
       mbar_wait(BAR(3 + s), ((uint32_t)(it / SB_STAGES) & 1u) ^ 1u, 41);
-      const uint32_t dst = brick0 + s * SB_BRICK + plane * SB_PLANE;
+      const uint32_t dst = brick0 + s * SB_BRICK + (SB_SW32 ? 0 : plane * SB_PLANE);
       const long long nbase = (long long)n * p.Sz + z;
 #pragma unroll
       for (int u = 0; u < MAXU; ++u) {
@@ -112,7 +125,8 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
           const bool ok = sy < p.Sy && sx < p.Sx;
           const long long cell = ok ? ((nbase + sz) * p.Sy + sy) * p.Sx + sx : 0;
           const int slot = (tid >> 1) + u * (SB_NPT / 2);
-          cp_async16(dst + slot * 16, src0 + cell * 16, ok ? 16u : 0u);
+          const uint32_t off = SB_SW32 ? (uint32_t)slot * 32u + (uint32_t)((plane ^ ((slot >> 2) & 1)) << 4) : (uint32_t)slot * 16u;
+          cp_async16(dst + off, src0 + cell * 16, ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -130,15 +144,28 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
   } else if (warp == SB_MMA_WARP) {
     // ================= MMA issuer: 64 taps per tile, weights resident
     const uint32_t idesc = make_idesc(TILE_ROWS, 64, 0, 0, F16);
-    const uint64_t bd_base = make_smem_desc(wsm, 1024, 128);
+    const uint64_t bd_base = SB_SW32 ? make_smem_desc_sw(wsm, 16, 256, 6) : make_smem_desc(wsm, 1024, 128);
     if (my_tiles > 0) mbar_wait(BAR(6), 0u, 42);
+#ifdef MMNN_STEM_TIMING
+    long long w_acc = 0, w_brick = 0, t_all0 = clock64();
+#endif
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1, s = it % SB_STAGES;
+#ifdef MMNN_STEM_TIMING
+      long long c0 = clock64();
+#endif
       mbar_wait(BAR(9 + abuf), ((uint32_t)(it >> 1) & 1u) ^ 1u, 43);   // epilogue has drained this accumulator
+#ifdef MMNN_STEM_TIMING
+      long long c1 = clock64();
+#endif
       mbar_wait(BAR(s), (uint32_t)(it / SB_STAGES) & 1u, 44);
+#ifdef MMNN_STEM_TIMING
+      long long c2 = clock64(); w_acc += c1 - c0; w_brick += c2 - c1;
+#endif
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t ad_base = make_smem_desc(brick0 + s * SB_BRICK, SB_PLANE, SB_HX * 16);
+        const uint64_t ad_base = SB_SW32 ? make_smem_desc_sw(brick0 + s * SB_BRICK, 16, SB_HX * 32, 6)
+                                         : make_smem_desc(brick0 + s * SB_BRICK, SB_PLANE, SB_HX * 16);
         const uint32_t td = tmem_base + abuf * NACC * 64;
 #pragma unroll
         for (int dz = 0; dz < 4; ++dz)
@@ -146,13 +173,17 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
           for (int dy = 0; dy < 4; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 4; ++dx)
-              tc_mma_bf16(td + (dx % NACC) * 64, desc_advance(ad_base, (uint32_t)((dz * SB_HY + dy) * SB_HX + dx) * 16u),
-                          desc_advance(bd_base, (uint32_t)((dz * 4 + dy) * 8 + dx * 2) * 1024u), idesc, (dz | dy) ? 1u : 0u);
+              tc_mma_bf16(td + (dx % NACC) * 64, desc_advance(ad_base, (uint32_t)((dz * SB_HY + dy) * SB_HX + dx) * (SB_SW32 ? 32u : 16u)),
+                          desc_advance(bd_base, SB_SW32 ? (uint32_t)((dz * 4 + dy) * 4 + dx) * 2048u : (uint32_t)((dz * 4 + dy) * 8 + dx * 2) * 1024u),
+                          idesc, ((dz | dy) != 0 || dx >= NACC) ? 1u : 0u);
         tc_commit(BAR(3 + s));
         tc_commit(BAR(7 + abuf));
       }
       __syncwarp();
     }
+#ifdef MMNN_STEM_TIMING
+    if (blockIdx.x == 0 && lane == 0) { g_stem_dbg[0] = w_acc; g_stem_dbg[1] = w_brick; g_stem_dbg[2] = clock64() - t_all0; g_stem_dbg[3] = my_tiles; }
+#endif
   } else {
     // ================= epilogue: warp e and e+4 share TMEM lane quarter (warp & 3); chunk cc = e >> 2
     const int e = warp - SB_EPI_WARP0;

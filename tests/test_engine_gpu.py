@@ -177,7 +177,7 @@ def test_stem_brick_conv7_s2(shape):
         pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
         s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(_actdt())
         M = B * Dz * Dy * Dx
-        bp = H.pack(w, 64, 64, 64, 64, 16, 0, 0, 0, mode=L.PACK_STEM, cin_real=cin)
+        bp = H.pack(w, 64, 64, 64, 64, 16, 0, 0, 0, mode=L.PACK_STEM_SW32, cin_real=cin)   # the brick kernel's swizzled weight image
         out = torch.zeros(M, 64, dtype=_actdt(), device="cuda")
         st = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
         H.stem_brick(B, (Dz, Dy, Dx), s2d, bp, out, 64, st_sum=st[0], st_sq=st[1])
