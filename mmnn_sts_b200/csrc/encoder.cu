@@ -81,6 +81,7 @@ struct Plan {
   size_t pinned_bytes[4] = {0, 0, 0, 0};
   // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
   // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
+  bool fwd_training = true;   // mode of the most recent forward: backward must differentiate the SAME BatchNorm (batch or running statistics)
   cudaStream_t side = nullptr;
   // Gradient groups, in the order backward finalises them: group k = dense block nb-1-k with the transition that
   // follows it (the last block's group also holds norm5), group nb = the stem (conv0, norm0).  Each group is a
@@ -372,6 +373,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
   double* fstats = (double*)(ws + g.fstats);
   const int FC = pl->fwd_channels;
   const bool batch = training != 0;
+  pl->fwd_training = batch;
   bf16* packed = (bf16*)(ws + g.packed);
   const int nb = (int)pl->blocks.size();
 
@@ -552,6 +554,10 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   const double* fstats = (const double*)(ws + g.fstats);
   double* bstats = (double*)(ws + g.bstats);
   const int FC = pl->fwd_channels, BC = pl->bwd_channels;
+  // Eval-mode backward (GradCAM, frozen-BN fine-tuning): BatchNorm is the fixed affine map of its running statistics, so the
+  // masks use those and the batch-statistic terms of the BN gradient vanish (inv_count = 0 -> c1 = c2 = 0); the statistics
+  // the epilogues still accumulate are then exactly d(gamma) = sum dy*xhat and d(beta) = sum dy.
+  const bool batch = pl->fwd_training;
   bf16* packed = (bf16*)(ws + g.packed);
   const int nb = (int)pl->blocks.size();
   auto gsum = [&](const BnInfo& bn) { return bstats + bn.bwd_off; };
@@ -579,7 +585,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     BnApplyParams a = {};
     a.slice_out = slice_out; a.slice_c0 = slice_c0; a.slice_scale = slice_scale; a.vps = vps_;
     a.M = M; a.C = C; a.v = v; a.v32 = v32; a.v_pitch = v_pitch; a.x = x; a.x_pitch = x_pitch; a.bn = bn;
-    a.g_sum = gs; a.g_dot = gd; a.inv_count = 1.0f / (float)M; a.out = outp; a.out_pitch = out_pitch;
+    a.g_sum = gs; a.g_dot = gd; a.inv_count = batch ? 1.0f / (float)M : 0.f; a.out = outp; a.out_pitch = out_pitch;
     const int grid = ew_grid(M * (C / 8));
     const size_t sm = 3 * C * sizeof(float);
     ProfScope ps_(PC_BN_APPLY, st);
@@ -647,7 +653,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     const BlockInfo& bi = pl->blocks[nb - 1];
     const long long M = g.M[nb - 1];
     const int C = bi.ctot;
-    BnSrc bn = make_bn(pl->n5, params, buffers, fstats, FC, M, true);
+    BnSrc bn = make_bn(pl->n5, params, buffers, fstats, FC, M, batch);
     const bf16* x = (const bf16*)(ws + g.buf[nb - 1]);
     const int rows_per_block = EW_THREADS / (C / 8);
     int blocks = (int)std::min<long long>((M + rows_per_block - 1) / rows_per_block, NUM_SMS * 4);
@@ -672,8 +678,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       if (side_done[parity][0]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity][0], 0));
       if (side_done[parity][1]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity][1], 0));
       bf16* bott = (bf16*)(ws + g.bott[b]) + (size_t)l * M * BOTT;
-      const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, true);
-      const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, true);
+      const BnSrc bn1 = make_bn(li.n1, params, buffers, fstats, FC, M, batch);
+      const BnSrc bn2 = make_bn(li.n2, params, buffers, fstats, FC, M, batch);
       // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf): for the top
       // layer of a block it is extracted here; for every other layer the previous iteration's BN-backward pass already
       // emitted it while it had the final values in registers (fused slice extraction).
@@ -820,11 +826,11 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       AvgPoolParams a = {};
       a.B = B; a.D = g.D[b - 1]; a.H = g.H[b - 1]; a.W = g.W[b - 1]; a.C = pv.ctot;
       a.x = (const bf16*)(ws + g.buf[b - 1]); a.x_pitch = pv.ctot;
-      a.bn = make_bn(pv.tn, params, buffers, fstats, FC, Mp, true);
+      a.bn = make_bn(pv.tn, params, buffers, fstats, FC, Mp, batch);
       a.dpooled = dpooled;
       a.dx = (float*)(ws + g.dbuf[b - 1]); a.dx_pitch = pv.ctot;
       a.g_sum = gsum(pv.tn); a.g_dot = gdot(pv.tn); a.g_sum_in = gsum(pv.tn); a.g_dot_in = gdot(pv.tn);
-      a.inv_count = 1.0f / (float)Mp;
+      a.inv_count = batch ? 1.0f / (float)Mp : 0.f;
       const int rows_per_block = EW_THREADS / (pv.ctot / 8);
       int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
       { ProfScope ps_(PC_AVGPOOL_BWD, st, 2);
@@ -836,7 +842,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       PoolBwdParams q = {};
       q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
       q.x = (const bf16*)(ws + g.stem_out);
-      q.bn = make_bn(pl->n0, params, buffers, fstats, FC, g.M0, true);
+      q.bn = make_bn(pl->n0, params, buffers, fstats, FC, g.M0, batch);
       q.dpool = dbuf; q.dpool_pitch = bi.ctot;
       q.argmax = ws + g.argmax;
       q.dr = (bf16*)(ws + g.dr);

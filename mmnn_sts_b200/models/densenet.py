@@ -48,7 +48,7 @@ class _Workspace:
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bb, x, *params):
-        out, ws, mask = bb._run_forward(x, params)
+        out, ws, mask = bb._run_forward(x, params, track=True)   # (autograd is disabled inside Function.forward: say it explicitly)
         ctx.bb, ctx.ws, ctx.mask, ctx.shape = bb, ws, mask, tuple(x.shape)
         ctx.params = params
         return out
@@ -57,7 +57,8 @@ class _BackboneFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         bb = ctx.bb
         grads = bb._run_backward(ctx.shape, ctx.params, ctx.ws, ctx.mask, grad_out)
-        ctx.ws.busy = False
+        if bb.training:
+            ctx.ws.busy = False            # (an eval-mode graph may be differentiated again: one GradCAM pass per class)
         return (None, None) + tuple(grads)
 
 
@@ -125,6 +126,12 @@ class Backbone(nn.Sequential):
         for w in pool:
             if not w.busy:
                 return w
+        if len(pool) >= 2:
+            # forwards under autograd whose backward never ran (each pins ~2 GB at configs[1]): recycle the oldest
+            # instead of growing without bound; differentiating that stale graph afterwards is an error of the caller
+            w = pool.pop(0)
+            pool.append(w)
+            return w
         w = _Workspace(nbytes, device)
         pool.append(w)
         return w
@@ -133,7 +140,7 @@ class Backbone(nn.Sequential):
     def _ptr_array(tensors):
         return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
-    def _run_forward(self, x, params):
+    def _run_forward(self, x, params, track=False):
         if not x.is_cuda:
             raise L.MMNNLibraryError("mmnn_sts_b200 has no CPU path: move the model and inputs to a CUDA device")
         plan = self._get_plan()
@@ -162,7 +169,16 @@ class Backbone(nn.Sequential):
                                           mask.data_ptr() if mask is not None else None, ws.tensor.data_ptr(),
                                           out.data_ptr(), int(self.training), stream)
         L.check(rc, "mmnn_encoder_forward")
-        ws.busy = self.training and torch.is_grad_enabled()
+        ws.busy = bool(track)                  # a backward pass will read this workspace
+        if ws.busy:
+            self._last_ws, self._last_xshape, self._last_out_dims = ws, (B, cin, X, Y, Z), (dims[0], dims[1], dims[2])
+        if ws.busy and not self.training:
+            # eval-mode forward under autograd (GradCAM, frozen-BN fine-tuning): keep the workspace for its backward, but
+            # only the most recent one -- an eval forward that is never differentiated must not pin 2 GB per call
+            prev = getattr(self, "_eval_ws", None)
+            if prev is not None and prev is not ws:
+                prev.busy = False
+            self._eval_ws = ws
         return out.permute(0, 4, 1, 2, 3), ws, mask
 
     def _run_backward(self, xshape, params, ws, mask, grad_out):
@@ -201,6 +217,21 @@ class Backbone(nn.Sequential):
     def wait_grad_group(self, k, stream):
         L.check(L.lib().mmnn_encoder_wait_grad_group(self._get_plan(), k, stream.cuda_stream), "mmnn_encoder_wait_grad_group")
 
+    def block_buffer_views(self, ws, xshape, block):
+        """(activations [M, Ctot] in the storage dtype, gradient accumulator [M, Ctot] fp32) of dense block `block` inside
+        workspace `ws`, plus the block's spatial dims: what GradCAM reads for the last convolution's output channels."""
+        B, cin, X, Y, Z = xshape
+        nb = len(self._cfg[1])
+        offs = (C.c_longlong * (3 + 3 * nb + 2))()
+        dims = (C.c_longlong * (4 + 4 * nb + 1))()
+        L.check(L.lib().mmnn_encoder_debug_offsets(self._get_plan(), B, X, Y, Z, offs, dims), "mmnn_encoder_debug_offsets")
+        M, ctot = int(dims[4 + 4 * block]), int(dims[4 + 4 * block + 1])
+        adt = torch.float16 if L.lib().mmnn_act_is_fp16() else torch.bfloat16
+        base = ws.tensor
+        act = base[int(offs[3 + block]):int(offs[3 + block]) + M * ctot * 2].view(adt).view(M, ctot)
+        grad = base[int(offs[3 + 2 * nb + block]):int(offs[3 + 2 * nb + block]) + M * ctot * 4].view(torch.float32).view(M, ctot)
+        return act, grad
+
     def flat_grad_buffer(self):
         """The single contiguous fp32 buffer holding every trunk gradient, if the parameters' .grad tensors are still the
         views handed to autograd by the last backward (autograd adopts them on the first accumulation and adds in place
@@ -219,8 +250,7 @@ class Backbone(nn.Sequential):
         params = tuple(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _BackboneFn.apply(self, x, *params)
-        out, ws, _ = self._run_forward(x, params)
-        ws.busy = False
+        out, ws, _ = self._run_forward(x, params, track=False)
         return out
 
 

@@ -42,4 +42,6 @@ class MultiModalModel(nn.Module):
         return self.image_model.model.backbone
 
     def add_gradcam(self, output_dir):
-        raise NotImplementedError("GradCAM is outside the hot path (SURVEY.md section 8f, rank 4)")
+        """/root/reference/models/multimodal.py:86-90."""
+        from ..utils.utils import MultiModalGradCAM
+        return MultiModalGradCAM(self)

@@ -1,6 +1,7 @@
 """Hot-path helpers with the reference's names and argument meaning (/root/reference/utils/utils.py:20-29,238-251)."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 def criterion(loss_func, preds, labels, device):
@@ -60,3 +61,58 @@ def loadWeights(model, path, device):
         else:
             raise e1
     return model
+
+
+class MultiModalGradCAM(nn.Module):
+    """GradCAM of the reference (/root/reference/utils/utils.py:253-344) on the fused trunk.
+
+    The reference hooks the LAST nn.Conv3d of `model.gradcam_layer` (= denseblock4.denselayer16.layers.conv2) for its
+    output and the gradient of that output.  Here the trunk is one fused call, so both are read from its workspace: the
+    conv's output is the last 32 channels of the final dense block's buffer, its gradient the same channels of that
+    block's fp32 gradient accumulator after a backward pass (mmnn_encoder_debug_offsets).  Everything else follows the
+    reference line by line -- including that the activations are scaled IN PLACE class after class (:306-307), so the
+    map of class c carries the pooled gradients of classes 0..c -- and that only batch size 1 is accepted (:330).
+    The model must be in eval mode (the reference calls it from inference_survival) on a CUDA device."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.input_shape = None
+
+    def forward(self, x):
+        outputs = self.model(x)
+        self.input_shape = x['image'].shape
+        att_maps = self.attentionMaps(outputs)
+        return outputs, att_maps
+
+    def _last_conv_views(self):
+        bb = self.model.gradcam_layer
+        ws, xshape = getattr(bb, "_last_ws", None), getattr(bb, "_last_xshape", None)
+        if ws is None:
+            raise RuntimeError("GradCAM needs a forward pass with autograd enabled (do not wrap it in torch.no_grad())")
+        nb = len(bb._cfg[1])
+        act, grad = bb.block_buffer_views(ws, xshape, nb - 1)
+        d, h, w = bb._last_out_dims
+        B, growth = xshape[0], bb._cfg[3]
+
+        def to_ncdhw(t):
+            return t[:, t.shape[1] - growth:].float().reshape(B, d, h, w, growth).permute(0, 4, 1, 2, 3).contiguous()
+        return act, grad, to_ncdhw
+
+    def attentionMaps(self, outputs):
+        act, grad, to_ncdhw = self._last_conv_views()
+        activations = to_ncdhw(act)
+        att_maps = []
+        for cls in range(outputs.shape[1]):
+            outputs[0, cls].backward(retain_graph=True)
+            grads = to_ncdhw(grad)
+            pooled_grads = torch.mean(grads, dim=[0, 2, 3, 4])
+            activations *= pooled_grads[None, :, None, None, None]
+            heatmap = torch.mean(activations, dim=1).squeeze()
+            heatmap = heatmap - torch.min(heatmap)
+            heatmap = heatmap / torch.max(heatmap)
+            att_map = heatmap.squeeze()
+            assert att_map.ndim == 3, 'Batch dimension found in attention map - Must use batch size 1 when computing attention maps'
+            att_map = F.interpolate(att_map[None, None, ...], self.input_shape[2:], mode='trilinear').squeeze()
+            att_maps.append(att_map)
+        return att_maps
