@@ -119,6 +119,8 @@ int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
 
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream) {
+  static const bool piped_on = [] { const char* e = getenv("MMNN_WGRAD_PIPED"); return e != nullptr && e[0] == '1'; }();
+  if (piped_on && p.NB == 9) p.NP = -1;   // experiment switch: cp.async-pipelined producer for the 3x3x3 weight gradient (engine.cuh)
   uint32_t offs[4];
   if (p.stages <= 0) {
     p.stages = 1;

@@ -779,9 +779,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     // the loads of tile it+1 (A into registers, B asynchronously) are issued BEFORE tile it is transformed, stored
     // and handed to the MMA warp.  Before, every tile exposed one full L2 / HBM round trip (ncu r01f: 10 % of all
     // samples on the first use of the A loads, 288 threads at 31 % issue utilisation).
-    // (measured, configs[1]: 3x3x3 weight gradients 2.37 -> 2.32 ms with L1-cached copies -- 2.63 ms when the copies
-    // bypass L1, the 9 shifted tiles share their rows; the 1x1x1 ones got 3 % slower, so they keep the register path)
-    const bool piped = AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4;
+    // MEASURED SLOWER than the register-staged path below in a same-box A/B at configs[1] (3x3x3 weight gradients 2.56 vs
+    // 2.37 ms, step 15.17 vs 14.94 ms; 2.63 ms when the copies bypass L1 -- the 9 shifted tiles share their rows), so it
+    // is OFF unless MMNN_WGRAD_PIPED=1 (kept as a parity-tested experiment).
+    const bool piped = AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4 && p.NP == -1;   // NP == -1: opt-in experiment switch (MMNN_WGRAD_PIPED=1)
     if (piped) {
       auto issue = [&](int it, uint4 (&aregs)[2 * MAX_PASSES], uint32_t& aok) {
         const int s = it % S;
