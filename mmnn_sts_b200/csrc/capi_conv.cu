@@ -5,6 +5,7 @@
 #include "launch.h"
 #include "pack.cuh"
 #include "prof.h"
+#include "rows_persist.cuh"
 #include "stem.cuh"
 
 using namespace mmnn;
@@ -41,9 +42,37 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   return 0;
 }
 
+// Persistent warp-specialised 1x1x1 kernel (rows_persist.cuh): one CTA per SM, all tiles of a CTA share one N tile
+template <int TRANS, int EPI, bool GRAD>
+int launch_rows_persist(RowsParams p, cudaStream_t stream) {
+  uint32_t offs[5];
+  p.stages = 1;
+  for (int s = 1; s <= 6; ++s)
+    if (rowsp_smem_layout(p.Cin, p.NT, p.kbw, s, offs) <= 200 * 1024) p.stages = s;
+  const uint32_t smem = rowsp_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  auto kern = conv1_persist_kernel<TRANS, EPI, GRAD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int tiles_m = (p.M + TILE_ROWS - 1) / TILE_ROWS, ntn = (p.Ncols + p.NT - 1) / p.NT;
+  int per_n = 148 / ntn;
+  if (per_n > tiles_m) per_n = tiles_m;
+  if (per_n < 1) return -2;
+  launch_pdl(kern, dim3(per_n * ntn), dim3(RP_THREADS), smem, stream, p);
+  MMNN_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int AMODE, int TRANS, int EPI, bool GRAD>
 int launch_rows_t(const RowsParams& p, cudaStream_t stream) {
   const long long tiles = (long long)((p.M + TILE_ROWS - 1) / TILE_ROWS) * ((p.Ncols + p.NT - 1) / p.NT);
+  // big 1x1x1 layers (at least two tiles per SM) CAN run on the persistent kernel (MMNN_ROWS_PERSIST=1, parity-tested).
+  // Same-box A/B at configs[1] (round 1): forward 1.71 vs 1.75 ms, data gradient 2.10 vs 1.92 ms, step 14.97 vs 14.93 ms --
+  // no gain: both kernels are bound by the instruction count of the epilogue (~0.6 warp instructions per output
+  // element: TMEM load, rounding, mask, two warp transposes per 32-column chunk for the statistics), not by the
+  // per-CTA fixed costs the persistent form removes.  Off by default.
+  static const bool persist = [] { const char* e = getenv("MMNN_ROWS_PERSIST"); return e != nullptr && e[0] == '1'; }();
+  if (AMODE == A_LINEAR_CONV && persist && p.ntaps == 1 && p.NT <= 256 && (p.Ncols + p.NT - 1) / p.NT <= 148 && tiles >= 2 * 148)
+    return launch_rows_persist<TRANS, EPI, GRAD>(p, stream);
   if (tiles <= 148) return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 2>(p, stream);   // latency-bound small grids
   return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 1>(p, stream);
 }

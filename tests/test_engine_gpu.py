@@ -69,6 +69,56 @@ def test_linear_bnrelu_stats_ntiles_strided():
     assert torch.allclose(st[1], (o ** 2).sum(0), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M", [40000 + 77, 3 * 148 * 128])
+def test_persistent_1x1_fprop_and_dgrad(M):
+    """1x1x1 GEMMs at >= 2 tiles per SM: the one-tile-per-CTA kernel by default, the persistent warp-specialised kernel
+    (rows_persist.cuh) under MMNN_ROWS_PERSIST=1 (both are run by the round's GPU logs): forward with
+    BN+ReLU prologue + statistics over 2 N tiles, and the data gradient with ReLU mask + BN-backward statistics; several
+    tiles per CTA (TMEM double buffering, stage ring wrap-around), ragged last tile."""
+    from mmnn_sts_b200 import _lib as L
+    from tests import engine_helpers as H
+    torch.manual_seed(21)
+    Ctot, Cin, N = 256, 160, 224
+    buf = torch.randn(M, Ctot, device="cuda").to(_actdt())
+    x = buf[:, :Cin].float()
+    w = torch.randn(N, Cin, device="cuda") * 0.1
+    gamma = torch.rand(Cin, device="cuda") + 0.5
+    beta = torch.randn(Cin, device="cuda") * 0.3
+    s1 = x.double().sum(0); s2 = (x.double() ** 2).sum(0)
+    bp = H.pack(w, N, 128, Cin, 64, 1, Cin, 1, 0)
+    out = torch.zeros(M, N, dtype=_actdt(), device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    H.rows(M, 128, N, Cin, 64, 1, (1, 1, M), buf, Ctot, bp, out, N, trans=L.T_BNRELU, epi=L.EP_STORE_STATS,
+           bnA=H.bnsrc(s1, s2, gamma, beta, count=M), st_sum=st[0], st_sq=st[1])
+    torch.cuda.synchronize()
+    a = _act(F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.0, 1e-5)))
+    ref = a @ _act(w).t()
+    _close(out, ref, rtol=1 / 64, atol=5e-2)
+    o = out.double()
+    assert torch.allclose(st[0], o.sum(0), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(st[1], (o ** 2).sum(0), rtol=1e-5, atol=1e-2)
+    # data gradient of conv1: dX[m][ci] = sum_co g[m][co] W[co][ci], gated by relu(bn1(x)) > 0, + BN1-backward statistics
+    Co = 128
+    g = (torch.randn(M, Co, device="cuda") * 0.1).to(torch.bfloat16)
+    w1 = torch.randn(Co, Cin, device="cuda") * 0.1                       # conv1.weight [co][ci]
+    bpd = H.pack(w1, Cin, 128, Co, 64, 1, 1, Cin, 0, fwd=False)           # operand rows n = ci, channels = co
+    dr = torch.zeros(M, Cin, dtype=torch.bfloat16, device="cuda")
+    std = torch.zeros(2, Cin, dtype=torch.float64, device="cuda")
+    H.rows(M, 128, Cin, Co, 64, 1, (1, 1, M), g, Co, bpd, dr, Cin, epi=L.EP_MASK_STATS, grad=1, st_sum=std[0], st_sq=std[1],
+           e_src=buf, e_pitch=Ctot, bnE=H.bnsrc(s1, s2, gamma, beta, count=M))
+    torch.cuda.synchronize()
+    mean = x.mean(0); rstd = (x.var(0, unbiased=False) + 1e-5).rsqrt()
+    xhat = (x - mean) * rstd
+    pre = xhat * gamma + beta
+    refd = (g.float() @ _bf(w1)) * (pre > 0)
+    band = pre.abs() < 1e-3
+    d = ((dr.float() - refd).abs() - (refd.abs() / 64 + 5e-2)).masked_fill(band, -1)
+    assert float(d.max()) <= 0
+    od = dr.double()
+    assert torch.allclose(std[0], od.sum(0), rtol=1e-4, atol=5e-2)
+    assert torch.allclose(std[1], (od * xhat.double()).sum(0), rtol=2e-3, atol=0.5)
+
+
 def test_conv3x3x3_fprop_bnrelu_dropout_slice():
     from mmnn_sts_b200 import _lib as L
     from tests import engine_helpers as H
