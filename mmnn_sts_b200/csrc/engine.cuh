@@ -471,8 +471,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
         }
       }
       if (EPI != EP_STORE) {
+#ifdef MMNN_TEST_NO_STATS   // timing experiment only
+        const float s1 = v[0] + v[31], s2 = q[0] + q[31];
+#else
         const float s1 = warp_transpose_sum32(v, lane);
         const float s2 = warp_transpose_sum32(q, lane);
+#endif
         red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = s1;
         red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = s2;
       }
