@@ -33,6 +33,8 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   uint32_t offs[6];
   if (p.stages <= 0) p.stages = choose_stages(p, 100 * 1024);
   const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  static const bool tc_stats_on = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '1'; }();
+  if (tc_stats_on) p.stages |= 0x100;    // experiment switch: column statistics on the tensor core (engine.cuh)
   auto kern = conv_rows_kernel<AMODE, TRANS, EPI, GRAD, PF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

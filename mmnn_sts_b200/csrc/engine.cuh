@@ -155,7 +155,11 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
   o = (o + 127u) & ~127u;
   offs[5] = o;
   const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
-  return o + stages * stage;
+  const uint32_t ring = stages * stage;
+  // the operand ring is reused by the epilogue to stage the rounded output tile (16 chunk planes) + 512 B of ones for the
+  // tensor-core column statistics (NT == 128 launches)
+  const uint32_t tcstats = 16u * PLANE_BYTES + 512u;
+  return o + (ring > tcstats ? ring : tcstats);
 }
 
 // GRAD == false: forward GEMM  -- A = activations (act format), weights packed in act format, output act format.
@@ -170,11 +174,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   uint32_t offs[6];
-  rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages & 0xff, offs);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
   const uint32_t bar_accum = bar_full + 8 * 12;
+  const uint32_t bar_staged = bar_full + 8 * 14, bar_stats = bar_full + 8 * 15;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 13);
   int4* rowinfo = reinterpret_cast<int4*>(smem + offs[1]);
   float* coefA = reinterpret_cast<float*>(smem + offs[2]);
@@ -188,12 +193,22 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  const int S = p.stages;
+  const int S = p.stages & 0xff;
   const int kb_per_tap = (p.Cin + p.kbw - 1) / p.kbw;
   const int KB = p.ntaps * kb_per_tap;
   const int vps = p.Dz * p.Dy * p.Dx;
+  // Column statistics on the tensor core (NT == 128): the epilogue stages the ROUNDED output tile in the (by then free)
+  // operand ring as an MN-major operand G[row][col]; the MMA warp computes  sum_rows G = G^T x ones  (N = 16, TMEM columns
+  // NT..NT+15) and, for the forward statistics, sum_rows G^2 = diag(G^T x G) (into the drained accumulator columns) --
+  // exact products, fp32 accumulation -- instead of one / two 32x32 warp transposes per column chunk, which are 40 % of
+  // the epilogue's instructions.  Parity-tested, but in a same-box A/B at configs[1] it is NEUTRAL (step 14.92 vs 14.90 ms:
+  // forward -0.6 %, data gradient +2.4 %): in a one-tile-per-CTA kernel the extra stage -> MMA -> commit -> TMEM-load round
+  // trip at the end of the CTA costs what the transposes did.  OFF unless MMNN_TC_STATS=1; the place for it is a
+  // persistent kernel where that round trip overlaps the next tile.
+  const bool tcs = (EPI != EP_STORE) && p.NT == 128 && (p.stages & 0x100) != 0;   // bit 8 of `stages`: opt-in switch (MMNN_TC_STATS=1)
+  const uint32_t sG = stage0, sOnes = stage0 + 16u * PLANE_BYTES;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.NT + (tcs ? 32 : 0)) tmem_cols <<= 1;
 
   // ---------------- prologue
   if (warp == MMA_WARP) {
@@ -203,6 +218,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
+      mbar_init(bar_staged, NUM_PRODUCER_THREADS);
+      mbar_init(bar_stats, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -460,25 +477,51 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           q[j] = g * g;
         }
       }
-      if (row_ok) {
+      {
         uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + col0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
           o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
           o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
-          op[i] = o;
+          if (row_ok) op[i] = o;
+          if (tcs) sts16(sG + (uint32_t)(cc * 4 + i) * PLANE_BYTES + (uint32_t)r * 16u, o);   // rows beyond M stage zeros
         }
       }
       if (EPI != EP_STORE) {
-#ifdef MMNN_TEST_NO_STATS   // timing experiment only
-        const float s1 = v[0] + v[31], s2 = q[0] + q[31];
-#else
-        const float s1 = warp_transpose_sum32(v, lane);
-        const float s2 = warp_transpose_sum32(q, lane);
-#endif
-        red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = s1;
-        red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = s2;
+        if (!tcs) {
+          const float s1 = warp_transpose_sum32(v, lane);
+          red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = s1;
+        }
+        if (!tcs || EPI == EP_MASK_STATS) {
+          const float s2 = warp_transpose_sum32(q, lane);
+          red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = s2;
+        }
+      }
+    }
+    if (tcs) {
+      if (warp == 0) {   // 512 B of 1.0 in the operand format
+        const uint32_t one = OP_F16 ? 0x3c003c00u : 0x3f803f80u;
+        sts16(sOnes + lane * 16, make_uint4(one, one, one, one));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_staged);
+      mbar_wait(bar_stats, 0, 4);
+      tc_fence_after();
+      if (warp < 4) {    // one warp per TMEM lane quarter: lane = output column qd*32 + lane
+        float d[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)p.NT, d);
+        const int c = qd * 32 + lane;
+        red[(0 * 4 + 0) * p.NT + c] = d[0];
+        red[(0 * 4 + 1) * p.NT + c] = 0.f; red[(0 * 4 + 2) * p.NT + c] = 0.f; red[(0 * 4 + 3) * p.NT + c] = 0.f;
+        if (EPI == EP_STORE_STATS) {
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(qd * 32), d);   // the 32x32 block holding the diagonal
+          float x = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x = (lane == j) ? d[j] : x;
+          red[(1 * 4 + 0) * p.NT + c] = x;
+          red[(1 * 4 + 1) * p.NT + c] = 0.f; red[(1 * 4 + 2) * p.NT + c] = 0.f; red[(1 * 4 + 3) * p.NT + c] = 0.f;
+        }
       }
     }
     if (EPI != EP_STORE) {
@@ -516,6 +559,26 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           if (k16 < cpl / 2) tc_mma_bf16(tmem_base, desc_advance(ad0, k16 * a_step), desc_advance(bd0, k16 * b_step), idesc, 1u);
         tc_commit(bar_empty + 8 * s);
         if (kb == KB - 1) tc_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+    if (tcs) {
+      mbar_wait(bar_staged, 0, 5);     // the rounded tile is staged (generic-proxy stores fenced by their writers)
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t gd = make_smem_desc(sG, 128, PLANE_BYTES);          // MN-major: 8-column chunks PLANE_BYTES apart, 8-row groups 128 B apart
+        const uint64_t od = make_smem_desc(sOnes, 128, 128);
+        const uint32_t id_sum = make_idesc(TILE_ROWS, 16, 1, 1, OP_F16);
+#pragma unroll
+        for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16)
+          tc_mma_bf16(tmem_base + p.NT, desc_advance(gd, k16 * 256), od, id_sum, k16 > 0 ? 1u : 0u);
+        if (EPI == EP_STORE_STATS) {
+          const uint32_t id_sq = make_idesc(TILE_ROWS, 128, 1, 1, OP_F16);
+#pragma unroll
+          for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16)
+            tc_mma_bf16(tmem_base, desc_advance(gd, k16 * 256), desc_advance(gd, k16 * 256), id_sq, k16 > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_stats);
       }
       __syncwarp();
     }
