@@ -47,11 +47,14 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
 // Persistent warp-specialised 1x1x1 kernel (rows_persist.cuh): one CTA per SM, all tiles of a CTA share one N tile
 template <int TRANS, int EPI, bool GRAD>
 int launch_rows_persist(RowsParams p, cudaStream_t stream) {
-  uint32_t offs[5];
-  p.stages = 1;
+  uint32_t offs[6];
+  static const bool tc_stats_off = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '0'; }();
+  const bool tcs = EPI != EP_STORE && p.NT == 128 && !tc_stats_off;   // persistent kernel: tensor-core statistics by default
+  int stages = 1;
   for (int s = 1; s <= 6; ++s)
-    if (rowsp_smem_layout(p.Cin, p.NT, p.kbw, s, offs) <= 200 * 1024) p.stages = s;
-  const uint32_t smem = rowsp_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+    if (rowsp_smem_layout(p.Cin, p.NT, p.kbw, s, tcs, offs) <= 220 * 1024) stages = s;
+  const uint32_t smem = rowsp_smem_layout(p.Cin, p.NT, p.kbw, stages, tcs, offs);
+  p.stages = stages | (tcs ? 0x100 : 0);
   auto kern = conv1_persist_kernel<TRANS, EPI, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -67,12 +70,12 @@ int launch_rows_persist(RowsParams p, cudaStream_t stream) {
 template <int AMODE, int TRANS, int EPI, bool GRAD>
 int launch_rows_t(const RowsParams& p, cudaStream_t stream) {
   const long long tiles = (long long)((p.M + TILE_ROWS - 1) / TILE_ROWS) * ((p.Ncols + p.NT - 1) / p.NT);
-  // big 1x1x1 layers (at least two tiles per SM) CAN run on the persistent kernel (MMNN_ROWS_PERSIST=1, parity-tested).
-  // Same-box A/B at configs[1] (round 1): forward 1.71 vs 1.75 ms, data gradient 2.10 vs 1.92 ms, step 14.97 vs 14.93 ms --
-  // no gain: both kernels are bound by the instruction count of the epilogue (~0.6 warp instructions per output
-  // element: TMEM load, rounding, mask, two warp transposes per 32-column chunk for the statistics), not by the
-  // per-CTA fixed costs the persistent form removes.  Off by default.
-  static const bool persist = [] { const char* e = getenv("MMNN_ROWS_PERSIST"); return e != nullptr && e[0] == '1'; }();
+  // Big 1x1x1 layers (at least two tiles per SM): the persistent kernel (rows_persist.cuh) with tensor-core column statistics
+  // accumulated in TMEM.  Same-box A/B at configs[1] (round 1): forward 1.68 vs 1.76 ms -> ON for the forward; data
+  // gradient 2.04 vs 1.86 ms (its ReLU-mask + second-statistic epilogue has 8 warps per SM there instead of 16) -> OFF.
+  // MMNN_ROWS_PERSIST=0 / 1 forces the one-tile-per-CTA / the persistent kernel for both (parity tests run both).
+  static const int persist_env = [] { const char* e = getenv("MMNN_ROWS_PERSIST"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
+  const bool persist = persist_env == 1 || (persist_env == -1 && !GRAD && EPI == EP_STORE_STATS);
   if (AMODE == A_LINEAR_CONV && persist && p.ntaps == 1 && p.NT <= 256 && (p.Ncols + p.NT - 1) / p.NT <= 148 && tiles >= 2 * 148)
     return launch_rows_persist<TRANS, EPI, GRAD>(p, stream);
   if (tiles <= 148) return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 2>(p, stream);   // latency-bound small grids

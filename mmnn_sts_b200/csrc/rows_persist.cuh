@@ -16,16 +16,22 @@ namespace mmnn {
 constexpr int RP_NPW = 8, RP_NPT = RP_NPW * 32, RP_MMA_WARP = RP_NPW, RP_EPI_WARP0 = RP_NPW + 1, RP_NEW = 8, RP_NET = RP_NEW * 32;
 constexpr int RP_THREADS = (RP_EPI_WARP0 + RP_NEW) * 32;   // 544
 
-__host__ __device__ inline uint32_t rowsp_smem_layout(int Cin, int NT, int kbw, int stages, uint32_t* offs /*[5]*/) {
+// offs[5]: two staging buffers of the rounded output tile (16 chunk planes each) + 512 B of ones for the tensor-core
+// column statistics (NT == 128 launches with statistics; size 0 otherwise)
+__host__ __device__ inline uint32_t rowsp_smem_layout(int Cin, int NT, int kbw, int stages, bool tcs, uint32_t* offs /*[6]*/) {
   uint32_t o = 0;
-  offs[0] = o; o += 256;                 // barriers: full[6] empty[6] acc_full[2] acc_empty[2] + tmem ptr
+  offs[0] = o; o += 256;                 // barriers: full[6] empty[6] acc_full[2] acc_empty[2] staged[2] gfree[2] stats_final + tmem ptr
   offs[1] = o; o += 2u * Cin * 4;        // coefA: fp32 scale / shift or packed half2 table (same size)
   offs[2] = o; o += 4u * NT * 4;         // coefE: scale, shift, mean, rstd
   offs[3] = o; o += 8u * NT * 4;         // red[2][4][NT]
   o = (o + 127u) & ~127u;
   offs[4] = o;
   const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
-  return o + stages * stage;
+  o += stages * stage;
+  o = (o + 127u) & ~127u;
+  offs[5] = o;
+  if (tcs) o += 2u * 16u * PLANE_BYTES + 512u;
+  return o;
 }
 
 template <int TRANS, int EPI, bool GRAD>
@@ -34,12 +40,19 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
-  uint32_t offs[5];
-  rowsp_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  // Column statistics on the tensor core (see conv_rows_kernel): here the staged tile of tile t is consumed by the MMA
+  // warp AFTER it has issued the main MMAs of tile t+1, and the statistics accumulate in TMEM across all tiles of the
+  // CTA -- no transposes and no per-tile read-out for sum / sum of squares (forward) and sum (data gradient).
+  const bool tcs = (EPI != EP_STORE) && p.NT == 128 && (p.stages & 0x100) != 0;
+  const int S = p.stages & 0xff;
+  uint32_t offs[6];
+  rowsp_smem_layout(p.Cin, p.NT, p.kbw, S, tcs, offs);
   const uint32_t sbase = smem_u32(smem);
-  constexpr int FULL = 0, EMPTY = 6, AF = 12, AE = 14;
+  constexpr int FULL = 0, EMPTY = 6, AF = 12, AE = 14, STAGED = 16, GFREE = 18, SFINAL = 20;
+  const uint32_t sG0 = sbase + offs[5], sOnes = sG0 + 2u * 16u * PLANE_BYTES;
+  constexpr uint32_t D1_COL = 256, D2_COL = 288;   // statistics accumulators in TMEM (main accumulators: 0..255)
   auto BAR = [&](int i) { return sbase + offs[0] + 8u * i; };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 16);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 22);
   float* coefA = reinterpret_cast<float*>(smem + offs[1]);
   H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);
   float* coefE = reinterpret_cast<float*>(smem + offs[2]);
@@ -51,7 +64,6 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   const uint32_t stage0 = sbase + offs[4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.stages;
   const int KB = (p.Cin + p.kbw - 1) / p.kbw;
   const int vps = p.Dz * p.Dy * p.Dx;
   const int tiles_m = (p.M + TILE_ROWS - 1) / TILE_ROWS;
@@ -61,12 +73,14 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   const int m_first = (int)blockIdx.x / ntn, m_step = (int)gridDim.x / ntn;
   const int my_tiles = m_first < tiles_m ? (tiles_m - 1 - m_first) / m_step + 1 : 0;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
+  while ((int)tmem_cols < (tcs ? 512 : 2 * p.NT)) tmem_cols <<= 1;
 
   if (warp == RP_MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(BAR(FULL + s), RP_NPT + 1); mbar_init(BAR(EMPTY + s), 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(AF + i), 1); mbar_init(BAR(AE + i), RP_NET); }
+      for (int i = 0; i < 2; ++i) { mbar_init(BAR(STAGED + i), RP_NET); mbar_init(BAR(GFREE + i), 1); }
+      mbar_init(BAR(SFINAL), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -110,6 +124,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
       }
       coefE[c] = s; coefE[p.NT + c] = t; coefE[2 * p.NT + c] = mean; coefE[3 * p.NT + c] = rstd;
     }
+  }
+  if (tcs && warp == 0) {   // 512 B of 1.0 in the operand format
+    const uint32_t one = OP_F16 ? 0x3c003c00u : 0x3f803f80u;
+    sts16(sOnes + lane * 16, make_uint4(one, one, one, one));
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -204,6 +223,27 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   } else if (warp == RP_MMA_WARP) {
     // ================= MMA issuer
     const uint32_t idesc = make_idesc(TILE_ROWS, p.NT, 0, 0, OP_F16);
+    auto issue_stats = [&](int t) {   // statistics MMAs over the staged tile of tile iteration t
+      const int b = t & 1;
+      mbar_wait(BAR(STAGED + b), (uint32_t)(t >> 1) & 1u, 65);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t gd = make_smem_desc(sG0 + (uint32_t)b * 16u * PLANE_BYTES, 128, PLANE_BYTES);   // MN-major
+        const uint64_t od = make_smem_desc(sOnes, 128, 128);
+        const uint32_t id_sum = make_idesc(TILE_ROWS, 16, 1, 1, OP_F16);
+#pragma unroll
+        for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16)
+          tc_mma_bf16(tmem_base + D1_COL, desc_advance(gd, k16 * 256), od, id_sum, (t > 0 || k16 > 0) ? 1u : 0u);
+        if (EPI == EP_STORE_STATS) {
+          const uint32_t id_sq = make_idesc(TILE_ROWS, 128, 1, 1, OP_F16);
+#pragma unroll
+          for (int k16 = 0; k16 < TILE_ROWS / 16; ++k16)
+            tc_mma_bf16(tmem_base + D2_COL, desc_advance(gd, k16 * 256), desc_advance(gd, k16 * 256), id_sq, (t > 0 || k16 > 0) ? 1u : 0u);
+        }
+        tc_commit(BAR(GFREE + b));
+      }
+      __syncwarp();
+    };
     long long g = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
@@ -230,6 +270,12 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
         }
         __syncwarp();
       }
+      if (tcs && it > 0) issue_stats(it - 1);   // its epilogue ran while this tile's MMAs were being fed
+    }
+    if (tcs && my_tiles > 0) {
+      issue_stats(my_tiles - 1);
+      if (elect_one()) tc_commit(BAR(SFINAL));
+      __syncwarp();
     }
   } else {
     // ================= epilogue: warps e and e+4 share TMEM lane quarter (warp & 3); warp handles chunks cc0, cc0+1 (+4, +5 for NT = 256)
@@ -264,6 +310,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
       }
       mbar_wait(BAR(AF + abuf), (uint32_t)(it >> 1) & 1u, 64);
       tc_fence_after();
+      const uint32_t sG = sG0 + (uint32_t)(it & 1) * 16u * PLANE_BYTES;
+      if (tcs) mbar_wait(BAR(GFREE + (it & 1)), ((uint32_t)(it >> 1) & 1u) ^ 1u, 66);   // statistics MMAs of tile it-2 have read this buffer
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int cc = half + 2 * k;
@@ -307,25 +355,50 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
             q[j] = gq * gq;
           }
         }
-        if (row_ok) {
+        {
           uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + col0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 o;
             o.x = pack2<OP_F16>(v[8 * i + 0], v[8 * i + 1]); o.y = pack2<OP_F16>(v[8 * i + 2], v[8 * i + 3]);
             o.z = pack2<OP_F16>(v[8 * i + 4], v[8 * i + 5]); o.w = pack2<OP_F16>(v[8 * i + 6], v[8 * i + 7]);
-            op[i] = o;
+            if (row_ok) op[i] = o;
+            if (tcs) sts16(sG + (uint32_t)(cc * 4 + i) * PLANE_BYTES + (uint32_t)r * 16u, o);   // rows beyond M stage zeros
           }
         }
         if (EPI != EP_STORE) {
-          acc1[k] += warp_transpose_sum32(v, lane);
-          acc2[k] += warp_transpose_sum32(q, lane);
+          if (!tcs) acc1[k] += warp_transpose_sum32(v, lane);
+          if (!tcs || EPI == EP_MASK_STATS) acc2[k] += warp_transpose_sum32(q, lane);
         }
       }
       tc_fence_before();
       mbar_arrive(BAR(AE + abuf));
+      if (tcs) {
+        fence_proxy_async_smem();
+        mbar_arrive(BAR(STAGED + (it & 1)));
+      }
     }
-    if (EPI != EP_STORE) {
+    if (tcs && my_tiles > 0) {
+      // read the TMEM statistics accumulators once per CTA: lane quarter qd, lane = output column qd*32 + lane
+      mbar_wait(BAR(SFINAL), 0, 67);
+      tc_fence_after();
+      if (e < 4) {
+        float d[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + D1_COL, d);
+        const int c = qd * 32 + lane;
+        const int col = tile_n * p.NT + c;
+        if (col < p.Ncols) atomicAdd(p.st_sum + col, (double)d[0]);
+        if (EPI == EP_STORE_STATS) {
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + D2_COL + (uint32_t)(qd * 32), d);   // block holding the diagonal
+          float x = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x = (lane == j) ? d[j] : x;
+          if (col < p.Ncols) atomicAdd(p.st_sq + col, (double)x);
+        }
+      }
+    }
+    const bool reg1 = EPI != EP_STORE && !tcs, reg2 = EPI != EP_STORE && (!tcs || EPI == EP_MASK_STATS);   // statistics still in registers
+    if (reg1 || reg2) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int cc = half + 2 * k;
@@ -340,8 +413,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
         if (col < p.Ncols) {
           const float a = red[(0 * 4 + 0) * p.NT + c] + red[(0 * 4 + 1) * p.NT + c] + red[(0 * 4 + 2) * p.NT + c] + red[(0 * 4 + 3) * p.NT + c];
           const float b = red[(1 * 4 + 0) * p.NT + c] + red[(1 * 4 + 1) * p.NT + c] + red[(1 * 4 + 2) * p.NT + c] + red[(1 * 4 + 3) * p.NT + c];
-          atomicAdd(p.st_sum + col, (double)a);
-          atomicAdd(p.st_sq + col, (double)b);
+          if (reg1) atomicAdd(p.st_sum + col, (double)a);
+          if (reg2) atomicAdd(p.st_sq + col, (double)b);
         }
       }
     }
