@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "cfg2": dict(name="configs[1]: T1+T2 2x128x128x64 + 20 clinical, blend, batch 16/GPU", cin=2, spatial=(128, 128, 64), batch=16),
     "cfg1": dict(name="configs[0]: T1 1x64x64x32 + 20 clinical, blend, batch 4/GPU (debug size)", cin=1, spatial=(64, 64, 32), batch=4),
+    "cfg4": dict(name="configs[3]: image-only classification, 3-D ResNet (r3d_18) on 1x256x256x64 volumes, batch 8/GPU "
+                      "(1 channel: the reference's stem is Conv3d(1, 64), SURVEY.md section 0)", cin=1, spatial=(256, 256, 64), batch=8),
 }
 BLOCKS = (6, 12, 24, 16)
 
@@ -430,6 +432,147 @@ def run_preprocess(args):
                       "max_abs_err_vs_oracle": err}), flush=True)
 
 
+def resnet_cpu_arm(wl, steps, warmup, sample_batch, num_classes=2):
+    """The reference's r3d_18 classification train step (oracle/resnet.py restatement, pinned to the unchanged reference
+    module by tests/golden/resnet_*.npz) on the host cores: forward, BCE-with-logits 'sum' on the sigmoid output as
+    /root/reference/main.py:208 applies it, backward, SGD step; `sample_batch` volumes per step."""
+    from oracle import resnet as orn
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    sd = orn.make_state_dict(42, num_classes, perturb_bn=False)
+    params = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.SGD([p for p in params.values() if p.requires_grad], 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    image, labels = orn.make_batch(77, sample_batch, wl["spatial"], num_classes)
+    g = torch.Generator().manual_seed(78)
+    masks = [(torch.rand(s, generator=g) >= 0.2).float() for s in orn.stage_shapes(sample_batch, wl["spatial"])]
+    pw = torch.tensor([1.5, 2.0])[:num_classes]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = orn.resnet_forward(params, image, True, 0.2, masks)
+        loss = orn.train_step_loss(out, labels, pw)
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return {"value": round(sample_batch / t, 3), "unit": "volumes/s", "cores": ncores, "kind": "port",
+            "sample": f"{steps} timed step(s) of {sample_batch} volumes of 1x{'x'.join(map(str, wl['spatial']))} (same model/loss/optimizer), {warmup} warm-up",
+            "sec_per_step": round(t, 3)}
+
+
+def run_resnet(args):
+    """SURVEY.md section 8f rank 3 / BASELINE configs[3] (extra mode, prints its own JSON line): image-only classification
+    training step of the 3-D ResNet encoder -- forward, BCEWithLogitsLoss(pos_weight, 'sum') on the sigmoid output (the
+    reference's own call, main.py:208), backward, SGD(nesterov) step -- batch 8 per GPU of 1x256x256x64 volumes."""
+    import torch.distributed as dist
+    from mmnn_sts_b200 import _lib as L
+    from mmnn_sts_b200 import ops
+    from mmnn_sts_b200.models.resnet import algorithmic_cost, r3d_18
+    from mmnn_sts_b200.optim import SGD
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS["cfg4"]
+    B, K = wl["batch"], 2
+    torch.manual_seed(42)
+    m = r3d_18(K).to(dev).train()
+    opt = SGD(m.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    params = [q for q in m.parameters()]
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [(torch.rand((B, 1) + wl["spatial"], generator=g).pin_memory(), (torch.rand((B, K), generator=g) < 0.4).float().pin_memory()) for _ in range(2)]
+    devb = [(a.to(dev), b.to(dev)) for a, b in host]           # two batches alternate: 2 x 134 MB of input, activations >> L2
+    pw = torch.tensor([1.5, 2.0], device=dev)
+    stage = [(torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])) for _ in range(2)]
+
+    def step(im, lab):
+        out = m(im)
+        loss = ops.bce_with_logits(out, lab, pw).sum()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([q.grad.reshape(-1) for q in params])
+            dist.all_reduce(flat)                               # SUM, as the reference accumulates micro-batches
+            off = 0
+            for q in params:
+                q.grad.copy_(flat[off:off + q.numel()].view_as(q.grad)); off += q.numel()
+        opt.step(); opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record()
+        for i in range(n):
+            if e2e:
+                s = stage[i % 2]
+                s[0].copy_(host[i % 2][0], non_blocking=True); s[1].copy_(host[i % 2][1], non_blocking=True)
+                step(s[0], s[1]).item()
+            else:
+                step(*devb[i % 2])
+        e1.record(); barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    with ClockSampler(local) as clk:
+        for i in range(max(3, args.warmup)):
+            step(*devb[i % 2])
+        clk.wait_first_sample()
+        lc0 = L.lib().mmnn_launch_count()
+        clk.mark_start()
+        ms = timed(args.steps, False)
+        launches = (L.lib().mmnn_launch_count() - lc0) // args.steps
+        timed(1, True)
+        ms_e2e = timed(args.steps, True)
+        clk.mark_end()
+        clocks = clk.summary()
+    L.lib().mmnn_profile_enable(1)
+    step(*devb[0])
+    prof = L.profile_collect()
+    L.lib().mmnn_profile_enable(0)
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    cost = algorithmic_cost(m, B, wl["spatial"])
+    kernels = {}
+    for k, (kms, cnt) in prof.items():
+        if cnt and kms > 0:
+            kernels[k] = {"ms_per_step": round(kms, 3), "launches_per_step": cnt}
+            if k in cost:
+                kernels[k]["gbps"] = round(cost[k]["bytes"] / kms / 1e6, 1)
+                kernels[k]["frac_of_hbm_peak"] = round(cost[k]["bytes"] / kms / 1e6 / peaks["hbm"], 4)
+                if cost[k]["flops"]:
+                    kernels[k]["tflops_fp32"] = round(cost[k]["flops"] / kms / 1e9, 2)
+    top = max((k for k in kernels if k in cost), key=lambda k: kernels[k]["ms_per_step"])
+    line = {"mode": "resnet", "metric": "train volumes/sec", "value": round(B * world / (ms / 1e3), 2), "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "dtype_detail": "fp32 CUDA-core FMA on fp16 activations / bf16 gradients (8-16 channel direct convolutions, DESIGN.md 3.4)",
+            "config": {"workload": wl["name"], "global_batch": B * world, "volume": list(wl["spatial"]), "in_channels": 1,
+                       "parallelism": f"dp{world}", "optimizer_step": "every batch",
+                       "l2": "two input batches alternate; every activation tensor of layer1 (135 MB - 1.08 GB) exceeds the 126 MB L2"},
+            "e2e": {"value": round(B * world / (ms_e2e / 1e3), 2), "unit": "volumes/s", "h2d_bytes_per_step": host[0][0].numel() * 4 + host[0][1].numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 3)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": top, "bound": "hbm", "achieved": kernels[top]["gbps"], "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": kernels[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (" + peaks["src"] + ")",
+                         "algorithmic_bytes_per_step": cost[top]["bytes"]},
+            "kernels": kernels}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = resnet_cpu_arm(wl, steps=1, warmup=1, sample_batch=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_reference_arm(wl, steps, warmup, sample_batch):
     """The reference's algorithm for one training step on the host cores: fp32 torch CPU forward of the oracle
     restatement (bit-exact to the unchanged reference files, tests/golden), GradientBlender/Cox loss as the reference
@@ -483,7 +626,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "inference", "preprocess"])
+    ap.add_argument("--mode", default="train", choices=["train", "inference", "preprocess", "resnet"])
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as one CUDA graph (static shapes)")
     ap.add_argument("--patients", type=int, default=10000)
     ap.add_argument("--resamples", type=int, default=1000)
@@ -494,6 +637,8 @@ if __name__ == "__main__":
         run_inference(a)
     elif a.mode == "preprocess":
         run_preprocess(a)
+    elif a.mode == "resnet":
+        run_resnet(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

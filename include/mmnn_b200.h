@@ -137,6 +137,44 @@ int mmnn_sgd_max_tensors(void);
 int mmnn_preprocess_volumes(const float* src, float* dst, void* scratch, int B, int C, int X, int Y, int Z, int ox, int oy,
                             int oz, float mean, float std, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ 3-D ResNet encoder
+ * The image-only classification encoder of BASELINE configs[3] (/root/reference/models/resnet.py) as
+ * direct convolutions on channels-last (NDHWC) bf16 tensors; parameters / statistics fp32 / fp64.  RnConvGeom:
+ * mmnn_sts_b200/csrc/resnet.cu (18 ints: N Di Hi Wi Cin Do Ho Wo Cout kd kh kw sd sh sw pd ph pw).
+ * mmnn_rn_conv        : nn.Conv3d forward (dgrad 0: src = input [fp32 when src_is_f32, C_in = 1: the stem, :10], dst = output,
+ *                       stats = fp64 [2][Cout] sum / sum of squares of the stored output, zero-initialised, or NULL) or its
+ *                       data gradient (dgrad 1: src = output gradient, dst = input gradient, `add` = optional tensor summed in:
+ *                       the identity-residual gradient of BasicBlock.forward :83-95, may alias dst).  w fp32 [Cout][Cin][taps].
+ * mmnn_rn_conv_wgrad  : dw [Cout][Cin][taps] += x (*) dy (fp32 atomics, zero-initialise for a fresh gradient).
+ * mmnn_rn_bn_coeffs   : nn.BatchNorm3d coefficient table coef fp32 [4][C] = scale, shift, mean, rstd from the batch statistics
+ *                       (training: also the running-statistics update, momentum, unbiased variance) or the running ones.
+ * mmnn_rn_bn_act      : y = [relu](raw * scale + shift [+ res (res_mode 1) | + res * scale2 + shift2 (res_mode 2)]), then
+ *                       nn.Dropout(drop_p) (:156-163) from a counter hash of (seed, element) or an injected uint8 keep-mask.
+ * mmnn_rn_act_bwd_reduce / mmnn_rn_bn_bwd_apply : backward of that pass: dz = dy * [y > 0] * post_scale; sums fp64 [3][C] =
+ *                       sum dz, sum dz * xhat(raw), sum dz * xhat(raw2); draw (draw2) = BatchNorm backward; dz optionally
+ *                       stored (identity residual); dgamma / dbeta written (not accumulated).
+ * mmnn_rn_head_fwd/bwd: AdaptiveAvgPool3d(1) -> flatten -> Linear(C -> K) -> sigmoid (:165-170); dW / db accumulate. */
+struct RnConvGeom;
+int mmnn_sizeof_rn_conv_geom(void);
+int mmnn_rn_conv(const struct RnConvGeom* g /*HOST*/, int dgrad, int src_is_f32, const void* src, const float* w, void* dst,
+                 const void* add, double* stats, void* stream);
+int mmnn_rn_conv_wgrad(const struct RnConvGeom* g /*HOST*/, int x_is_f32, const void* x, const void* dy, float* dw, void* stream);
+int mmnn_rn_bn_coeffs(const double* stats, double count, const float* gamma, const float* beta, float* rmean, float* rvar,
+                      long long* nbt, float eps, float momentum, int training, int C, float* coef, void* stream);
+int mmnn_rn_bn_act(const void* raw, const float* coef, int res_mode, const void* res, const float* coef2, void* y,
+                   long long elems, int C, int relu, float drop_p, unsigned long long seed, const unsigned char* mask,
+                   void* stream);
+int mmnn_rn_act_bwd_reduce(const void* dy, const void* y, float post_scale, const void* raw, const float* coef,
+                           const void* raw2, const float* coef2, double* sums, long long elems, int C, void* stream);
+int mmnn_rn_bn_bwd_apply(const void* dy, const void* y, float post_scale, const void* raw, const float* coef, const void* raw2,
+                         const float* coef2, const double* sums, double inv_count, int eval_mode, void* draw, void* draw2,
+                         void* dz, float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, long long elems, int C,
+                         void* stream);
+int mmnn_rn_head_fwd(const void* y, int B, int V, int C, const float* W, const float* bias, int K, float* pooled, float* out,
+                     void* stream);
+int mmnn_rn_head_bwd(const float* dout, const float* out, const float* pooled, const float* W, int B, int V, int C, int K,
+                     void* dy, float* dW, float* db, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ instrumentation */
 void mmnn_profile_enable(int on);
 long long mmnn_launch_count(void);

@@ -96,6 +96,12 @@ class PackDesc(C.Structure):
                 ("sn", C.c_longlong), ("sc", C.c_longlong), ("st", C.c_longlong)]
 
 
+class RnConvGeom(C.Structure):
+    """csrc/resnet.cu RnConvGeom: channels-last conv geometry (input N,Di,Hi,Wi,Cin -> output Do,Ho,Wo,Cout; kernel, stride, pad)."""
+    _fields_ = [(n, C.c_int) for n in ("N", "Di", "Hi", "Wi", "Cin", "Do", "Ho", "Wo", "Cout", "kd", "kh", "kw", "sd", "sh",
+                                       "sw", "pd", "ph", "pw")]
+
+
 A_LINEAR_CONV, A_STEM = 0, 1
 T_NONE, T_BNRELU = 0, 1
 EP_STORE, EP_STORE_STATS, EP_MASK_STATS = 0, 1, 2
@@ -160,6 +166,20 @@ def _declare(l):
     l.mmnn_bce_logits.restype = I
     l.mmnn_preprocess_volumes.argtypes = [VP, VP, VP, I, I, I, I, I, I, I, I, C.c_float, C.c_float, VP]
     l.mmnn_preprocess_volumes.restype = I
+    D, F, ULL, GP = C.c_double, C.c_float, C.c_ulonglong, C.POINTER(RnConvGeom)
+    l.mmnn_sizeof_rn_conv_geom.restype = I
+    assert l.mmnn_sizeof_rn_conv_geom() == C.sizeof(RnConvGeom), (l.mmnn_sizeof_rn_conv_geom(), C.sizeof(RnConvGeom))
+    l.mmnn_rn_conv.argtypes = [GP, I, I, VP, VP, VP, VP, VP, VP]
+    l.mmnn_rn_conv_wgrad.argtypes = [GP, I, VP, VP, VP, VP]
+    l.mmnn_rn_bn_coeffs.argtypes = [VP, D, VP, VP, VP, VP, VP, F, F, I, I, VP, VP]
+    l.mmnn_rn_bn_act.argtypes = [VP, VP, I, VP, VP, VP, LL, I, I, F, ULL, VP, VP]
+    l.mmnn_rn_act_bwd_reduce.argtypes = [VP, VP, F, VP, VP, VP, VP, VP, LL, I, VP]
+    l.mmnn_rn_bn_bwd_apply.argtypes = [VP, VP, F, VP, VP, VP, VP, VP, D, I, VP, VP, VP, VP, VP, VP, VP, LL, I, VP]
+    l.mmnn_rn_head_fwd.argtypes = [VP, I, I, I, VP, VP, I, VP, VP, VP]
+    l.mmnn_rn_head_bwd.argtypes = [VP, VP, VP, VP, I, I, I, I, VP, VP, VP, VP]
+    for nm in ("mmnn_rn_conv", "mmnn_rn_conv_wgrad", "mmnn_rn_bn_coeffs", "mmnn_rn_bn_act", "mmnn_rn_act_bwd_reduce",
+               "mmnn_rn_bn_bwd_apply", "mmnn_rn_head_fwd", "mmnn_rn_head_bwd"):
+        getattr(l, nm).restype = I
     l.mmnn_profile_enable.argtypes = [I]
     l.mmnn_profile_enable.restype = None
     l.mmnn_launch_count.restype = LL
@@ -189,7 +209,8 @@ def packed_elems(N, NT, Cin, kbw, ntaps):
 
 PROF_CLASSES = ["pack", "s2d", "stem_fprop", "maxpool", "conv1_fprop", "conv2_fprop", "trans_pool", "trans_fprop", "norm5",
                 "bn_running", "norm5_bwd", "extract", "conv2_wgrad", "conv2_dgrad", "bn_apply", "conv1_wgrad", "conv1_dgrad",
-                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd", "preprocess"]
+                "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd", "preprocess",
+                "rn_fprop", "rn_dgrad", "rn_wgrad", "rn_eltwise", "rn_head"]
 
 
 def profile_collect():

@@ -10,7 +10,8 @@ namespace mmnn {
 enum ProfClass {
   PC_PACK = 0, PC_S2D, PC_STEM_FPROP, PC_MAXPOOL, PC_CONV1_FPROP, PC_CONV2_FPROP, PC_TRANS_POOL, PC_TRANS_FPROP, PC_NORM5,
   PC_BN_RUNNING, PC_NORM5_BWD, PC_EXTRACT, PC_CONV2_WGRAD, PC_CONV2_DGRAD, PC_BN_APPLY, PC_CONV1_WGRAD, PC_CONV1_DGRAD,
-  PC_TRANS_WGRAD, PC_TRANS_DGRAD, PC_AVGPOOL_BWD, PC_MAXPOOL_BWD, PC_STEM_WGRAD, PC_TAILS, PC_HEADS, PC_SGD, PC_PREPROC, PC_COUNT
+  PC_TRANS_WGRAD, PC_TRANS_DGRAD, PC_AVGPOOL_BWD, PC_MAXPOOL_BWD, PC_STEM_WGRAD, PC_TAILS, PC_HEADS, PC_SGD, PC_PREPROC,
+  PC_RN_FPROP, PC_RN_DGRAD, PC_RN_WGRAD, PC_RN_ELTWISE, PC_RN_HEAD, PC_COUNT
 };
 
 struct ProfRec { int cls; cudaEvent_t a, b; };
