@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -231,8 +232,10 @@ static int dispatch_conv(const RnConvGeom& g, int src_f32, const void* src, cons
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dw[co][ci][tap] += sum_voxels dy[n,o,co] * x[n, o*s - p + tap, ci].  Tile = TW consecutive output voxels of one output row
 // (n, od, oh): the kd x kh input rows the tile touches ((TW-1) sw + kw voxels each, zero-filled outside the volume) and the
-// tile's dy are staged in shared memory, so the inner loop has no bounds checks and only fixed-latency operands.  Work
-// item = (tap, ci, group of 8 co); a thread owns up to MAXI items (8 fp32 accumulators each) across all tiles of its block
+// tile's dy are staged in shared memory, so the inner loop has no bounds checks and only fixed-latency operands.  The
+// input rows of tile t+1 arrive by cp.async (zero-fill form) into the other half of a double buffer and its dy through
+// registers while tile t is being accumulated: one __syncthreads per tile, no exposed global latency.  Work item =
+// (tap, ci, group of 8 co); a thread owns up to MAXI items (8 fp32 accumulators each) across all tiles of its block
 // (grid-stride), and finishes with fp32 atomics.
 constexpr int WG_TW = 32;
 
@@ -242,101 +245,436 @@ __device__ __forceinline__ float wg_ld(const TX* p) {
   else return __half2float(*p);
 }
 
-template <typename TX, int MAXI>
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? BYTES : 0;
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+// ---- 64 -> 8 forward on HMMA (placed here: uses cp_async_zfill)
+// The one convolution of the network with a reduction deep enough for the tensor pipe: layer1.0.conv1, Conv3d(64 -> 8, 3x3x3,
+// stride 1, pad 1) over the 1.08 GB stem activation (234 GFLOP per batch of 8 at configs[3], 12.5 ms on the FMA pipe).
+// N = 8 output channels is far below a tcgen05 tile (a 128 x 8 UMMA would be bound by re-reading A from shared memory,
+// DESIGN.md 3.1), but it is exactly the n8 of the warp-level mma.sync.m16n8k16: M = 16 voxels along W, K = 16 of the 64
+// input channels, 27 taps x 4 k-chunks per m-tile.  Tile = 2 output rows x 32 voxels of one (n, od): the 3 x 4 halo rows
+// (34 voxels each, zero-filled outside the volume) arrive by cp.async into shared memory with a 144-byte voxel stride
+// (conflict-free ldmatrix), the B fragments of all 108 (tap, k-chunk) pairs are packed once per block; 8 warps = 4 m-tiles
+// x 2 halves of the tap range, summed through shared memory; fp16 store + the BatchNorm statistics of the stored values.
+constexpr int MF_R = 2, MF_XW = 34, MF_VS = 72, MF_HR = MF_R + 2, MF_ROWS = 3 * MF_HR;
+constexpr int MF_XS_BYTES = MF_ROWS * MF_XW * MF_VS * 2;            // 58 752
+constexpr int MF_WB_BYTES = 27 * 4 * 32 * 8;                        // 27 648
+constexpr int MF_SMEM = MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16 + 64;
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnConvGeom g, const __half* __restrict__ x,
+                                                                      const float* __restrict__ w, __half* __restrict__ y,
+                                                                      double* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* xs = reinterpret_cast<__half*>(smem_raw);
+  uint2* wb = reinterpret_cast<uint2*>(smem_raw + MF_XS_BYTES);
+  float4* red = reinterpret_cast<float4*>(smem_raw + MF_XS_BYTES + MF_WB_BYTES);
+  float* sstat = reinterpret_cast<float*>(smem_raw + MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 108 * 32; i += THREADS) {
+    const int l = i & 31, t = i >> 5, tap = t >> 2, kc = t & 3;
+    const int n = l >> 2, k0 = kc * 16 + (l & 3) * 2;
+    const float* pw = w + ((long long)n * 64 + k0) * 27 + tap;      // w[n][ci][tap], ci stride 27
+    wb[i] = make_uint2(pack_h2(pw[0], pw[27]), pack_h2(pw[8 * 27], pw[9 * 27]));
+  }
+  if (tid < 16) sstat[tid] = 0.f;
+  float ssum0 = 0.f, ssum1 = 0.f, ssq0 = 0.f, ssq1 = 0.f;
+  const int tiles_w = (g.Wo + 31) / 32, tiles_h = (g.Ho + MF_R - 1) / MF_R;
+  const int ntiles = g.N * g.Do * tiles_h * tiles_w;
+  const int mt = warp & 3, half_ = warp >> 2, rr = mt >> 1, wbase = (mt & 1) * 16;
+  const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, koff = (lane >> 4) * 8;
+  const int tap_lo = half_ ? 14 : 0, tap_hi = half_ ? 27 : 14;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int oh0 = th * MF_R, ow0 = tw * 32;
+    __syncthreads();                                        // everyone is done with xs / red of the previous tile
+    for (int i = tid; i < MF_ROWS * MF_XW * 8; i += THREADS) {
+      const int c = i & 7, vp = i >> 3;
+      const int p = vp % MF_XW, r = vp / MF_XW;
+      const int a = r / MF_HR, hb = r % MF_HR;
+      const int zd = od - 1 + a, zh = oh0 - 1 + hb, zw = ow0 - 1 + p;
+      const bool ok = (unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi;
+      const __half* src = ok ? x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * 64 + c * 8 : x;
+      cp_async_zfill<16>(xs + (r * MF_XW + p) * MF_VS + c * 8, src, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    for (int tap = tap_lo; tap < tap_hi; ++tap) {
+      const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+      const __half* arow = xs + (((a * MF_HR + rr + b) * MF_XW + wbase + c + row_l) * MF_VS + koff);
+      const uint32_t abase = (uint32_t)__cvta_generic_to_shared(arow);
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(abase + kc * 32));
+        const uint2 bf = wb[(tap * 4 + kc) * 32 + lane];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+      }
+    }
+    if (half_ == 1) red[mt * 32 + lane] = make_float4(c0, c1, c2, c3);
+    __syncthreads();
+    if (half_ == 0) {
+      const float4 o = red[mt * 32 + lane];
+      c0 += o.x; c1 += o.y; c2 += o.z; c3 += o.w;
+      const int oh = oh0 + rr, gq = lane >> 2, co = (lane & 3) * 2;
+      if (oh < g.Ho) {
+        const long long rowbase = (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo;
+        const int owa = ow0 + wbase + gq, owb = owa + 8;
+        if (owa < g.Wo) {
+          const __half2 h = __floats2half2_rn(c0, c1);
+          *reinterpret_cast<__half2*>(y + (rowbase + owa) * 8 + co) = h;
+          const float2 f = __half22float2(h);
+          ssum0 += f.x; ssum1 += f.y; ssq0 = fmaf(f.x, f.x, ssq0); ssq1 = fmaf(f.y, f.y, ssq1);
+        }
+        if (owb < g.Wo) {
+          const __half2 h = __floats2half2_rn(c2, c3);
+          *reinterpret_cast<__half2*>(y + (rowbase + owb) * 8 + co) = h;
+          const float2 f = __half22float2(h);
+          ssum0 += f.x; ssum1 += f.y; ssq0 = fmaf(f.x, f.x, ssq0); ssq1 = fmaf(f.y, f.y, ssq1);
+        }
+      }
+    }
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      ssum0 += __shfl_xor_sync(0xffffffffu, ssum0, off); ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, off);
+      ssq0 += __shfl_xor_sync(0xffffffffu, ssq0, off); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, off);
+    }
+    if (lane < 4) {
+      atomicAdd(&sstat[lane * 2], ssum0); atomicAdd(&sstat[lane * 2 + 1], ssum1);
+      atomicAdd(&sstat[8 + lane * 2], ssq0); atomicAdd(&sstat[8 + lane * 2 + 1], ssq1);
+    }
+    __syncthreads();
+    if (tid < 16) atomicAdd(&stats[tid], (double)sstat[tid]);
+  }
+}
+
+// ---- 8-channel source, 3x3x3 stride 1 pad 1, on HMMA with TAP PAIRS as the k16: the forward of the 8 -> 8 convolutions
+// (fp16), their data gradient (bf16) and the data gradient 8 -> 64 of layer1.0.conv1 (NT = 8 n-tiles).  One voxel of the
+// source is 8 channels = one 16-byte ldmatrix row, so the four 8x8 matrices of an ldmatrix.x4 can come from two different
+// taps (lanes 16-31 point into the second tap's window): k = (tap pair, 8 channels), 14 pairs cover the 27 taps (the 28th
+// has zero weights).  NT = 1: tile = 4 rows x 32 voxels, one m-tile per warp, direct 128-byte-per-instruction stores;
+// NT = 8: tile = 2 rows x 32, warps = 4 m-tiles x 2 halves of the 64 output channels, stores staged through shared memory
+// so every voxel's 64 bytes leave as full sectors.
+template <int NT, bool DGRAD>
+__global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnConvGeom g, const uint16_t* __restrict__ src,
+                                                                     const float* __restrict__ w, uint16_t* __restrict__ dst,
+                                                                     const uint16_t* __restrict__ add, double* __restrict__ stats) {
+  constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2, NH = (NT == 1) ? 1 : 4, OC = 8 * NT;
+  constexpr int XS_BYTES = 3 * HR * MF_XW * 16, WB_BYTES = 14 * NT * 32 * 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);
+  uint2* wb = reinterpret_cast<uint2*>(smem_raw + XS_BYTES);
+  uint16_t* stg = reinterpret_cast<uint16_t*>(smem_raw + XS_BYTES + WB_BYTES);      // NT == 8: [8 warps][16][40]
+  float* sstat = reinterpret_cast<float*>(smem_raw + XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wCin = g.Cin;                                   // weight tensor is [Cout][Cin][27]
+  for (int i = tid; i < 14 * NT * 32; i += THREADS) {
+    const int l = i & 31, j = (i >> 5) % NT, pair = (i >> 5) / NT;
+    const int n = 8 * j + (l >> 2), k = (l & 3) * 2;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tap = 2 * pair + (q >> 1), kk = k + (q & 1);
+      const int co = DGRAD ? kk : n, ci = DGRAD ? n : kk;
+      v[q] = (tap < 27) ? w[((long long)co * wCin + ci) * 27 + tap] : 0.f;
+    }
+    wb[i] = DGRAD ? make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3])) : make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+  }
+  if (tid < 16) sstat[tid] = 0.f;
+  float ssum0 = 0.f, ssum1 = 0.f, ssq0 = 0.f, ssq1 = 0.f;
+  const int tiles_w = (g.Wo + 31) / 32, tiles_h = (g.Ho + R - 1) / R;
+  const int ntiles = g.N * g.Do * tiles_h * tiles_w;
+  const int mt = (NT == 1) ? warp : (warp & 3), nh = (NT == 1) ? 0 : (warp >> 2);
+  const int rr = mt >> 1, wbase = (mt & 1) * 16;
+  const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, second = lane >> 4;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int oh0 = th * R, ow0 = tw * 32;
+    __syncthreads();
+    for (int i = tid; i < 3 * HR * MF_XW; i += THREADS) {
+      const int p = i % MF_XW, r = i / MF_XW;
+      const int a = r / HR, hb = r % HR;
+      const int zd = od - 1 + a, zh = oh0 - 1 + hb, zw = ow0 - 1 + p;
+      const bool ok = (unsigned)zd < (unsigned)g.Do && (unsigned)zh < (unsigned)g.Ho && (unsigned)zw < (unsigned)g.Wo;
+      const uint16_t* sp = ok ? src + ((((long long)n * g.Do + zd) * g.Ho + zh) * g.Wo + zw) * 8 : src;
+      cp_async_zfill<16>(xs + i * 8, sp, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    float acc[NH][4];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll 2
+    for (int pair = 0; pair < 14; ++pair) {
+      int tap = 2 * pair + second;
+      if (tap > 26) tap = 26;                               // zero weights: any finite window will do
+      int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+      if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
+      const uint32_t aaddr = (uint32_t)__cvta_generic_to_shared(xs + ((a * HR + rr + b) * MF_XW + wbase + c + row_l) * 8);
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(aaddr));
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        const uint2 bf = wb[(pair * NT + nh * NH + j) * 32 + lane];
+        if (DGRAD)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+        else
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+      }
+    }
+    const int oh = oh0 + rr;
+    const long long rowbase = (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo;
+    if (NT == 1) {
+      const int gq = lane >> 2, co = (lane & 3) * 2;
+      if (oh < g.Ho) {
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int ow = ow0 + wbase + gq + hsel * 8;
+          if (ow < g.Wo) {
+            float v0 = acc[0][hsel * 2], v1 = acc[0][hsel * 2 + 1];
+            const long long o = (rowbase + ow) * 8 + co;
+            if (add != nullptr) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(add + o);
+              if (DGRAD) { v0 += bf_lo(u); v1 += bf_hi(u); }
+              else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u)); v0 += f.x; v1 += f.y; }
+            }
+            if (DGRAD) {
+              *reinterpret_cast<uint32_t*>(dst + o) = pack2(v0, v1);
+            } else {
+              const __half2 h = __floats2half2_rn(v0, v1);
+              *reinterpret_cast<__half2*>(dst + o) = h;
+              const float2 f = __half22float2(h);
+              ssum0 += f.x; ssum1 += f.y; ssq0 = fmaf(f.x, f.x, ssq0); ssq1 = fmaf(f.y, f.y, ssq1);
+            }
+          }
+        }
+      }
+    } else {
+      uint16_t* st_ = stg + warp * (16 * 40);
+      const int gq = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        *reinterpret_cast<uint32_t*>(st_ + gq * 40 + 8 * j + t2) = DGRAD ? pack2(acc[j][0], acc[j][1]) : pack_h2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<uint32_t*>(st_ + (gq + 8) * 40 + 8 * j + t2) = DGRAD ? pack2(acc[j][2], acc[j][3]) : pack_h2(acc[j][2], acc[j][3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = (lane >> 2) + it * 8, chunk = lane & 3;
+        const int ow = ow0 + wbase + row;
+        if (oh < g.Ho && ow < g.Wo)
+          *reinterpret_cast<uint4*>(dst + (rowbase + ow) * OC + nh * 32 + chunk * 8) = *reinterpret_cast<const uint4*>(st_ + row * 40 + chunk * 8);
+      }
+      __syncwarp();
+    }
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      ssum0 += __shfl_xor_sync(0xffffffffu, ssum0, off); ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, off);
+      ssq0 += __shfl_xor_sync(0xffffffffu, ssq0, off); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, off);
+    }
+    if (lane < 4) {
+      atomicAdd(&sstat[lane * 2], ssum0); atomicAdd(&sstat[lane * 2 + 1], ssum1);
+      atomicAdd(&sstat[8 + lane * 2], ssq0); atomicAdd(&sstat[8 + lane * 2 + 1], ssq1);
+    }
+    __syncthreads();
+    if (tid < 16) atomicAdd(&stats[tid], (double)sstat[tid]);
+  }
+}
+
+template <int NT, bool DGRAD>
+static int launch_conv3_k8_mma(const RnConvGeom& g, const void* src, const float* w, void* dst, const void* add, double* stats,
+                               cudaStream_t st) {
+  constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2;
+  constexpr int SMEM = 3 * HR * MF_XW * 16 + 14 * NT * 32 * 8 + 8 * 16 * 40 * 2 + 64;
+  auto kern = rn_conv3_k8_mma_kernel<NT, DGRAD>;
+  static bool attr = false;
+  if (!attr && SMEM > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 31) / 32);
+  if (ntiles > 0x7fffffffLL) return -6;
+  const int blocks = (int)(ntiles < 148 * 4 ? ntiles : 148 * 4);
+  kern<<<blocks, THREADS, SMEM, st>>>(g, (const uint16_t*)src, w, (uint16_t*)dst, (const uint16_t*)add, stats);
+  return (int)cudaGetLastError();
+}
+
+static bool rn_mma_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMNN_RN_MMA"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+static int launch_conv3_mma_fwd(const RnConvGeom& g, const void* x, const float* w, void* y, double* stats, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    const cudaError_t e = cudaFuncSetAttribute(rn_conv3_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const long long ntiles = (long long)g.N * g.Do * ((g.Ho + MF_R - 1) / MF_R) * ((g.Wo + 31) / 32);
+  if (ntiles > 0x7fffffffLL) return -6;
+  const int blocks = (int)(ntiles < 296 ? ntiles : 296);
+  rn_conv3_mma_fwd_kernel<<<blocks, THREADS, MF_SMEM, st>>>(g, (const __half*)x, w, (__half*)y, stats);
+  return (int)cudaGetLastError();
+}
+
+struct WgTile { int n, od, oh, ow0; };
+__device__ __forceinline__ WgTile wg_decode(long long tile, int tiles_w, const RnConvGeom& g) {
+  WgTile t;
+  t.ow0 = (int)(tile % tiles_w) * WG_TW;
+  long long r = tile / tiles_w;
+  t.oh = (int)(r % g.Ho);
+  r /= g.Ho;
+  t.od = (int)(r % g.Do);
+  t.n = (int)(r / g.Do);
+  return t;
+}
+
+template <typename TX, int CIN, int MAXI>
 __global__ void __launch_bounds__(THREADS, (MAXI > 2 ? 2 : 3)) rn_wgrad_kernel(const RnConvGeom g, const TX* __restrict__ x,
                                                                               const uint16_t* __restrict__ dy,
                                                                               float* __restrict__ dw, int tiles_w,
                                                                               long long ntiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int taps = g.kd * g.kh * g.kw;
-  const int items = taps * g.Cin * (g.Cout / 8);
+  const int items = taps * CIN * (g.Cout / 8);
   const int tid = threadIdx.x;
   const int XW = (WG_TW - 1) * g.sw + g.kw;               // staged voxels per input row
-  const int rowlen = XW * g.Cin;                          // elements per staged input row
-  float* dy_s = reinterpret_cast<float*>(smem_raw);       // [WG_TW][Cout] fp32
-  TX* x_s = reinterpret_cast<TX*>(smem_raw + (size_t)WG_TW * g.Cout * sizeof(float));   // [kd*kh][XW][Cin]
-  int xo[MAXI], icog[MAXI];
+  const int rowlen = XW * CIN;                            // elements per staged input row
+  const int nrows = g.kd * g.kh;
+  const int xbuf = nrows * rowlen;                        // elements per x buffer (a multiple of 8 when CIN >= 8)
+  const int xbuf_al = (xbuf + 7) & ~7;
+  float* dy_s = reinterpret_cast<float*>(smem_raw);       // [2][WG_TW][Cout] fp32
+  TX* x_s = reinterpret_cast<TX*>(smem_raw + (size_t)2 * WG_TW * g.Cout * sizeof(float));   // [2][kd*kh][XW][CIN]
+  int xo[MAXI], icog[MAXI], dyo[MAXI];
   float acc[MAXI][8];
 #pragma unroll
   for (int j = 0; j < MAXI; ++j) {
     const int it = tid + j * THREADS;
-    const int ci = it % g.Cin, rest = it / g.Cin;
+    const int ci = it % CIN, rest = it / CIN;
     const int tap = rest % taps;
     icog[j] = (it < items) ? rest / taps : -1;
     const int a = tap / (g.kh * g.kw), b = (tap / g.kw) % g.kh, c = tap % g.kw;
-    xo[j] = ((a * g.kh + b) * XW + c) * g.Cin + ci;
+    xo[j] = (it < items) ? ((a * g.kh + b) * XW + c) * CIN + ci : 0;      // idle items read element 0 (branch-free inner loop)
+    dyo[j] = (it < items) ? (rest / taps) * 8 : 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
   }
   const bool one = (g.Cout == 8);
-  const int step = g.sw * g.Cin;
-  constexpr int VEC = 16 / (int)sizeof(TX);               // elements per 16-byte copy
-  const bool vec_ok = (g.Cin % VEC) == 0;
+  const int step = g.sw * CIN;
+  constexpr int VEC = (CIN * (int)sizeof(TX) >= 16) ? 16 / (int)sizeof(TX) : 1;     // elements per cp.async
+  constexpr int CPB = VEC * (int)sizeof(TX);                                          // 16 or 4 bytes
+  static_assert(CPB == 16 || CPB == 4, "cp.async size");
+  const int dyvecs = WG_TW * g.Cout / 8;                  // <= 64: one uint4 of dy per thread
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tw = (int)(tile % tiles_w);
-    long long t = tile / tiles_w;
-    const int oh = (int)(t % g.Ho);
-    t /= g.Ho;
-    const int od = (int)(t % g.Do);
-    const int n = (int)(t / g.Do);
-    const int ow0 = tw * WG_TW;
-    __syncthreads();                                      // previous tile fully consumed
-    // ---- stage dy (bf16 -> fp32; voxels past the row end are zero)
-    for (int i = tid; i < WG_TW * g.Cout / 8; i += THREADS) {
-      const int v = i / (g.Cout / 8), c8 = i % (g.Cout / 8);
-      float d[8];
-      if (ow0 + v < g.Wo) {
-        const long long o = ((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow0 + v) * g.Cout + c8 * 8;
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), d);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] = 0.f;
+  auto stage_x = [&](const WgTile& t, int buf) {
+    TX* xs = x_s + (size_t)buf * xbuf_al;
+    const int iw0 = t.ow0 * g.sw - g.pw;
+    const int per_row = rowlen / VEC;
+    for (int a = 0; a < g.kd; ++a) {
+      const int zd = t.od * g.sd - g.pd + a;
+      for (int b = 0; b < g.kh; ++b) {
+        const int zh = t.oh * g.sh - g.ph + b;
+        const bool row_ok = (unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi;
+        const long long rowbase = (((long long)t.n * g.Di + zd) * g.Hi + zh) * g.Wi;
+        TX* xr = xs + (a * g.kh + b) * rowlen;
+        for (int j = tid; j < per_row; j += THREADS) {
+          const int e = j * VEC;
+          const int zw = iw0 + e / CIN;
+          const bool ok = row_ok && (unsigned)zw < (unsigned)g.Wi;
+          const TX* src = ok ? x + (rowbase + zw) * CIN + e % CIN : x;
+          cp_async_zfill<CPB>(xr + e, src, ok);
+        }
       }
-      float4* dst = reinterpret_cast<float4*>(dy_s + v * g.Cout + c8 * 8);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  auto load_dy = [&](const WgTile& t) -> uint4 {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < dyvecs) {
+      const int v = tid / (g.Cout / 8), c8 = tid % (g.Cout / 8);
+      if (t.ow0 + v < g.Wo)
+        q = __ldg(reinterpret_cast<const uint4*>(dy + ((((long long)t.n * g.Do + t.od) * g.Ho + t.oh) * g.Wo + t.ow0 + v) * g.Cout + c8 * 8));
+    }
+    return q;
+  };
+  auto store_dy = [&](const uint4 q, int buf) {
+    if (tid < dyvecs) {
+      float d[8];
+      unpack8(q, d);
+      float4* dst = reinterpret_cast<float4*>(dy_s + (size_t)buf * WG_TW * g.Cout + tid * 8);
       dst[0] = make_float4(d[0], d[1], d[2], d[3]);
       dst[1] = make_float4(d[4], d[5], d[6], d[7]);
     }
-    // ---- stage the kd x kh input rows
-    const int iw0 = ow0 * g.sw - g.pw;
-    const int nrows = g.kd * g.kh;
-    if (vec_ok) {
-      const int per_row = rowlen / VEC;
-      for (int i = tid; i < nrows * per_row; i += THREADS) {
-        const int r = i / per_row, e = (i % per_row) * VEC;
-        const int zd = od * g.sd - g.pd + r / g.kh, zh = oh * g.sh - g.ph + r % g.kh;
-        const int zw = iw0 + e / g.Cin;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if ((unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi)
-          q = __ldg(reinterpret_cast<const uint4*>(x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * g.Cin + e % g.Cin));
-        *reinterpret_cast<uint4*>(x_s + (long long)r * rowlen + e) = q;
-      }
-    } else {
-      for (int i = tid; i < nrows * rowlen; i += THREADS) {
-        const int r = i / rowlen, e = i % rowlen;
-        const int zd = od * g.sd - g.pd + r / g.kh, zh = oh * g.sh - g.ph + r % g.kh;
-        const int zw = iw0 + e / g.Cin;
-        TX q = TX(0);
-        if ((unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi)
-          q = x[((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * g.Cin + e % g.Cin];
-        x_s[(long long)r * rowlen + e] = q;
-      }
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) {
+    const WgTile t0 = wg_decode(tile, tiles_w, g);
+    stage_x(t0, 0);
+    store_dy(load_dy(t0), 0);
+  }
+  int buf = 0;
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();                                      // tile `buf` staged; everyone is done with buffer buf^1
+    const long long nxt = tile + gridDim.x;
+    uint4 dq = make_uint4(0u, 0u, 0u, 0u);
+    if (nxt < ntiles) {
+      const WgTile tn = wg_decode(nxt, tiles_w, g);
+      stage_x(tn, buf ^ 1);
+      dq = load_dy(tn);
     }
-    __syncthreads();
-    // ---- accumulate
+    const TX* xs = x_s + (size_t)buf * xbuf_al;
+    const float* ds = dy_s + (size_t)buf * WG_TW * g.Cout;
 #pragma unroll 4
     for (int v = 0; v < WG_TW; ++v) {
       float d[8];
       if (one) {
-        const float4 d0 = *reinterpret_cast<const float4*>(dy_s + v * 8), d1 = *reinterpret_cast<const float4*>(dy_s + v * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(ds + v * 8), d1 = *reinterpret_cast<const float4*>(ds + v * 8 + 4);
         d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
       }
 #pragma unroll
       for (int j = 0; j < MAXI; ++j) {
-        if (icog[j] < 0) continue;
-        const float xv = wg_ld(x_s + xo[j] + v * step);
+        const float xv = wg_ld(xs + xo[j] + v * step);
         if (!one) {
-          const float* pd = dy_s + v * g.Cout + icog[j] * 8;
+          const float* pd = ds + v * g.Cout + dyo[j];
           const float4 d0 = *reinterpret_cast<const float4*>(pd), d1 = *reinterpret_cast<const float4*>(pd + 4);
           d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
         }
@@ -344,25 +682,28 @@ __global__ void __launch_bounds__(THREADS, (MAXI > 2 ? 2 : 3)) rn_wgrad_kernel(c
         for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(xv, d[k], acc[j][k]);
       }
     }
+    if (nxt < ntiles) store_dy(dq, buf ^ 1);
   }
 #pragma unroll
   for (int j = 0; j < MAXI; ++j) {
     if (icog[j] < 0) continue;
     const int it = tid + j * THREADS;
-    const int ci = it % g.Cin, tap = (it / g.Cin) % taps;
+    const int ci = it % CIN, tap = (it / CIN) % taps;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      atomicAdd(&dw[((long long)(icog[j] * 8 + k) * g.Cin + ci) * taps + tap], acc[j][k]);
+      atomicAdd(&dw[((long long)(icog[j] * 8 + k) * CIN + ci) * taps + tap], acc[j][k]);
   }
 }
 
-template <typename TX, int MAXI>
+template <typename TX, int CIN, int MAXI>
 static int launch_wgrad(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
   const int tiles_w = (g.Wo + WG_TW - 1) / WG_TW;
   const long long ntiles = (long long)g.N * g.Do * g.Ho * tiles_w;
   const int XW = (WG_TW - 1) * g.sw + g.kw;
-  const size_t smem = (size_t)WG_TW * g.Cout * sizeof(float) + (size_t)g.kd * g.kh * XW * g.Cin * sizeof(TX);
-  auto kern = rn_wgrad_kernel<TX, MAXI>;
+  const size_t xbuf_al = ((size_t)g.kd * g.kh * XW * CIN + 7) & ~(size_t)7;
+  const size_t smem = (size_t)2 * WG_TW * g.Cout * sizeof(float) + 2 * xbuf_al * sizeof(TX);
+  if (WG_TW * g.Cout / 8 > THREADS) return -5;
+  auto kern = rn_wgrad_kernel<TX, CIN, MAXI>;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -374,6 +715,15 @@ static int launch_wgrad(const RnConvGeom& g, const void* x, const void* dy, floa
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, THREADS, smem, st>>>(g, (const TX*)x, (const uint16_t*)dy, dw, tiles_w, ntiles);
   return (int)cudaGetLastError();
+}
+
+template <int CIN>
+static int dispatch_wgrad_h(const RnConvGeom& g, int per, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  if (per <= 1) return launch_wgrad<__half, CIN, 1>(g, x, dy, dw, st);
+  if (per <= 2) return launch_wgrad<__half, CIN, 2>(g, x, dy, dw, st);
+  if (per <= 4) return launch_wgrad<__half, CIN, 4>(g, x, dy, dw, st);
+  if (per <= 7) return launch_wgrad<__half, CIN, 7>(g, x, dy, dw, st);
+  return -4;
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm coefficients
@@ -618,6 +968,14 @@ int mmnn_rn_conv(const RnConvGeom* g, int dgrad, int src_is_f32, const void* src
                  double* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps(dgrad ? PC_RN_DGRAD : PC_RN_FPROP, st);
+  if (!dgrad && !src_is_f32 && add == nullptr && g->Cin == 64 && g->Cout == 8 && g->kd == 3 && g->kh == 3 && g->kw == 3 &&
+      g->sd == 1 && g->sh == 1 && g->sw == 1 && g->pd == 1 && g->ph == 1 && g->pw == 1 && rn_mma_enabled())
+    return launch_conv3_mma_fwd(*g, src, w, dst, stats, st);
+  const bool k333 = g->kd == 3 && g->kh == 3 && g->kw == 3 && g->sd == 1 && g->sh == 1 && g->sw == 1 && g->pd == 1 && g->ph == 1 &&
+                    g->pw == 1 && !src_is_f32 && rn_mma_enabled();
+  if (k333 && !dgrad && g->Cin == 8 && g->Cout == 8) return launch_conv3_k8_mma<1, false>(*g, src, w, dst, add, stats, st);
+  if (k333 && dgrad && g->Cout == 8 && g->Cin == 8) return launch_conv3_k8_mma<1, true>(*g, src, w, dst, add, nullptr, st);
+  if (k333 && dgrad && g->Cout == 8 && g->Cin == 64 && add == nullptr) return launch_conv3_k8_mma<8, true>(*g, src, w, dst, nullptr, nullptr, st);
   if (dgrad) return dispatch_conv<true>(*g, src_is_f32, src, w, dst, add, stats, st);
   return dispatch_conv<false>(*g, src_is_f32, src, w, dst, add, stats, st);
 }
@@ -629,14 +987,14 @@ int mmnn_rn_conv_wgrad(const RnConvGeom* g, int x_is_f32, const void* x, const v
   const int items = g->kd * g->kh * g->kw * g->Cin * (g->Cout / 8);
   const int per = (items + THREADS - 1) / THREADS;
   if (x_is_f32) {
-    if (per <= 2) return launch_wgrad<float, 2>(*g, x, dy, dw, st);
-    if (per <= 4) return launch_wgrad<float, 4>(*g, x, dy, dw, st);
+    if (g->Cin != 1) return -3;
+    if (per <= 2) return launch_wgrad<float, 1, 2>(*g, x, dy, dw, st);
+    if (per <= 4) return launch_wgrad<float, 1, 4>(*g, x, dy, dw, st);
     return -3;
   }
-  if (per <= 1) return launch_wgrad<__half, 1>(*g, x, dy, dw, st);
-  if (per <= 2) return launch_wgrad<__half, 2>(*g, x, dy, dw, st);
-  if (per <= 4) return launch_wgrad<__half, 4>(*g, x, dy, dw, st);
-  if (per <= 7) return launch_wgrad<__half, 7>(*g, x, dy, dw, st);
+  if (g->Cin == 8) return dispatch_wgrad_h<8>(*g, per, x, dy, dw, st);
+  if (g->Cin == 16) return dispatch_wgrad_h<16>(*g, per, x, dy, dw, st);
+  if (g->Cin == 64) return dispatch_wgrad_h<64>(*g, per, x, dy, dw, st);
   return -4;
 }
 
