@@ -550,12 +550,14 @@ def run_resnet(args):
                 kernels[k]["gbps"] = round(cost[k]["bytes"] / kms / 1e6, 1)
                 kernels[k]["frac_of_hbm_peak"] = round(cost[k]["bytes"] / kms / 1e6 / peaks["hbm"], 4)
                 if cost[k]["flops"]:
-                    kernels[k]["tflops_fp32"] = round(cost[k]["flops"] / kms / 1e9, 2)
+                    kernels[k]["tflops"] = round(cost[k]["flops"] / kms / 1e9, 2)
     top = max((k for k in kernels if k in cost), key=lambda k: kernels[k]["ms_per_step"])
     line = {"mode": "resnet", "metric": "train volumes/sec", "value": round(B * world / (ms / 1e3), 2), "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "dtype_detail": "fp32 CUDA-core FMA on fp16 activations / bf16 gradients (8-16 channel direct convolutions, DESIGN.md 3.4)",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "dtype_detail": "fp16 activations / bf16 gradients, fp32 accumulate: mma.sync m16n8k16 for the 8/16/64-channel 3x3x3 and 1x1x1 convolutions "
+                            "(forward 64->8 and 8->8, data gradient 8->64 and 8->8, every weight gradient), fp32 FMA for the stem and the strided / 16-channel "
+                            "forward and data-gradient launches (DESIGN.md 3.4)",
             "config": {"workload": wl["name"], "global_batch": B * world, "volume": list(wl["spatial"]), "in_channels": 1,
                        "parallelism": f"dp{world}", "optimizer_step": "every batch",
                        "l2": "two input batches alternate; every activation tensor of layer1 (135 MB - 1.08 GB) exceeds the 126 MB L2"},

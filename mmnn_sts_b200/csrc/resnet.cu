@@ -534,6 +534,154 @@ static int launch_conv3_k8_mma(const RnConvGeom& g, const void* src, const float
   return (int)cudaGetLastError();
 }
 
+// ---- weight gradient on HMMA: dw^T[ci][co] (per tap) = sum_v x[v + tap][ci] * dy[v][co] with the VOXELS as the k16.  Both
+// operands are stored voxel-major (channels contiguous), which is the transposed form of what mma.sync wants, so both
+// fragments come from ldmatrix.trans: A = 16 ci x 16 voxels from the staged input rows (for C_in = 8 the two halves of the
+// m16 are two different taps), B = 16 voxels x 8 co from the staged dy.  dy is bf16, so the fp16 input rows are converted
+// to bf16 while they are staged (the weight gradient averages over ~10^6 voxels; 8 mantissa bits of x are plenty).
+// A warp owns up to MAXU (tap, ci-chunk) units x NTN co-tiles of accumulators across all tiles of its block; fp32 atomics
+// at the end.  Any kernel size / stride / padding (each lane supplies its own ldmatrix row address).
+template <int CIN, int NTN, int MAXU>
+__global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma_kernel(const RnConvGeom g, const __half* __restrict__ x,
+                                                                  const uint16_t* __restrict__ dy, float* __restrict__ dw, int R) {
+  constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);   // voxel stride in shared memory (conflict-free ldmatrix)
+  constexpr int COUT = 8 * NTN, CH8 = CIN / 8, C16 = (CIN >= 16) ? CIN / 16 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int taps = g.kd * g.kh * g.kw;
+  const int HRs = (R - 1) * g.sh + g.kh, XW = 31 * g.sw + g.kw, nrows = g.kd * HRs;
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);
+  uint16_t* dys = xs + (size_t)nrows * XW * VS;               // [R][32][COUT]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, vl = (lane & 7) + (q >> 1) * 8;
+  const int nunits = (CIN >= 16) ? taps * C16 : (taps + 1) / 2;
+  int ubase[MAXU];
+  float acc[MAXU][NTN][4];
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int u = warp + 8 * i;
+    const int uu = (u < nunits) ? u : 0;
+    int tap, choff;
+    if (CIN >= 16) { tap = uu / C16; choff = (uu % C16) * 16 + (q & 1) * 8; }
+    else { tap = 2 * uu + (q & 1); if (tap >= taps) tap = 2 * uu; choff = 0; }
+    const int a = tap / (g.kh * g.kw), b = (tap / g.kw) % g.kh, c = tap % g.kw;
+    ubase[i] = ((a * HRs + b) * XW + c + vl * g.sw) * VS + choff;
+#pragma unroll
+    for (int j = 0; j < NTN; ++j) { acc[i][j][0] = 0.f; acc[i][j][1] = 0.f; acc[i][j][2] = 0.f; acc[i][j][3] = 0.f; }
+  }
+  const int tiles_w = (g.Wo + 31) / 32, tiles_h = (g.Ho + R - 1) / R;
+  const int ntiles = g.N * g.Do * tiles_h * tiles_w;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs), dys_addr = (uint32_t)__cvta_generic_to_shared(dys);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int oh0 = th * R, ow0 = tw * 32;
+    __syncthreads();
+    for (int i = tid; i < nrows * XW * CH8; i += THREADS) {
+      const int ch = i % CH8, vp = i / CH8;
+      const int p = vp % XW, r = vp / XW;
+      const int a = r / HRs, hb = r % HRs;
+      const int zd = od * g.sd - g.pd + a, zh = oh0 * g.sh - g.ph + hb, zw = ow0 * g.sw - g.pw + p;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if ((unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi) {
+        float f[8];
+        unpack8h(__ldg(reinterpret_cast<const uint4*>(x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * CIN + ch * 8)), f);
+        o = pack8(f);
+      }
+      *reinterpret_cast<uint4*>(xs + (size_t)vp * VS + ch * 8) = o;
+    }
+    for (int i = tid; i < R * 32 * NTN; i += THREADS) {
+      const int c8 = i % NTN, v = (i / NTN) % 32, rr = i / NTN / 32;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (oh0 + rr < g.Ho && ow0 + v < g.Wo)
+        o = __ldg(reinterpret_cast<const uint4*>(dy + ((((long long)n * g.Do + od) * g.Ho + oh0 + rr) * g.Wo + ow0 + v) * COUT + c8 * 8));
+      *reinterpret_cast<uint4*>(dys + (size_t)i * 8) = o;
+    }
+    __syncthreads();
+    for (int kc = 0; kc < R * 2; ++kc) {
+      const int rr = kc >> 1, wh = kc & 1;
+      const int koff = (rr * g.sh * XW + wh * 16 * g.sw) * VS;
+      uint32_t b0[NTN], b1[NTN];
+#pragma unroll
+      for (int j = 0; j < NTN; ++j) {
+        const uint32_t baddr = dys_addr + (uint32_t)(((rr * 32 + wh * 16 + (lane & 15)) * COUT + j * 8) * 2);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(b0[j]), "=r"(b1[j]) : "r"(baddr));
+      }
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(xs_addr + (uint32_t)((ubase[i] + koff) * 2)));
+#pragma unroll
+        for (int j = 0; j < NTN; ++j)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0[j]), "r"(b1[j]));
+      }
+    }
+  }
+  const int gq = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int u = warp + 8 * i;
+    if (u >= nunits) continue;
+#pragma unroll
+    for (int hsel = 0; hsel < 2; ++hsel) {                  // accumulator rows g (hsel 0) and g + 8 (hsel 1)
+      int tap, ci;
+      if (CIN >= 16) { tap = u / C16; ci = (u % C16) * 16 + gq + hsel * 8; }
+      else { tap = 2 * u + hsel; ci = gq; }
+      if (tap >= taps) continue;
+#pragma unroll
+      for (int j = 0; j < NTN; ++j) {
+        const int co = j * 8 + t2;
+        atomicAdd(&dw[((long long)co * CIN + ci) * taps + tap], acc[i][j][hsel * 2]);
+        atomicAdd(&dw[((long long)(co + 1) * CIN + ci) * taps + tap], acc[i][j][hsel * 2 + 1]);
+      }
+    }
+  }
+}
+
+template <int CIN, int NTN, int MAXU>
+static int launch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);
+  const int XW = 31 * g.sw + g.kw;
+  int R = 4;
+  size_t smem = 0;
+  for (;; R >>= 1) {
+    const int HRs = (R - 1) * g.sh + g.kh;
+    smem = ((size_t)g.kd * HRs * XW * VS + (size_t)R * 32 * 8 * NTN) * 2;
+    if (smem <= 60 * 1024 || R == 1) break;
+  }
+  if (smem > 200 * 1024) return -7;
+  auto kern = rn_wgrad_mma_kernel<CIN, NTN, MAXU>;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 31) / 32);
+  if (ntiles > 0x7fffffffLL) return -6;
+  const int blocks = (int)(ntiles < 148 * 3 ? ntiles : 148 * 3);
+  kern<<<blocks, THREADS, smem, st>>>(g, (const __half*)x, (const uint16_t*)dy, dw, R);
+  return (int)cudaGetLastError();
+}
+
+template <int CIN, int NTN>
+static int dispatch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  const int taps = g.kd * g.kh * g.kw;
+  const int nunits = (CIN >= 16) ? taps * (CIN / 16) : (taps + 1) / 2;
+  const int per = (nunits + 7) / 8;
+  if (per <= 1) return launch_wgrad_mma<CIN, NTN, 1>(g, x, dy, dw, st);
+  if (per <= 2) return launch_wgrad_mma<CIN, NTN, 2>(g, x, dy, dw, st);
+  if (per <= 4) return launch_wgrad_mma<CIN, NTN, 4>(g, x, dy, dw, st);
+  if (per <= 14 && NTN == 1) return launch_wgrad_mma<CIN, NTN, (NTN == 1 ? 14 : 4)>(g, x, dy, dw, st);
+  return -8;
+}
+
 static bool rn_mma_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MMNN_RN_MMA"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
@@ -991,6 +1139,13 @@ int mmnn_rn_conv_wgrad(const RnConvGeom* g, int x_is_f32, const void* x, const v
     if (per <= 2) return launch_wgrad<float, 1, 2>(*g, x, dy, dw, st);
     if (per <= 4) return launch_wgrad<float, 1, 4>(*g, x, dy, dw, st);
     return -3;
+  }
+  if (rn_mma_enabled() && (g->Cout == 8 || g->Cout == 16)) {
+    int rc = -8;
+    if (g->Cin == 8) rc = g->Cout == 8 ? dispatch_wgrad_mma<8, 1>(*g, x, dy, dw, st) : dispatch_wgrad_mma<8, 2>(*g, x, dy, dw, st);
+    else if (g->Cin == 16) rc = g->Cout == 8 ? dispatch_wgrad_mma<16, 1>(*g, x, dy, dw, st) : dispatch_wgrad_mma<16, 2>(*g, x, dy, dw, st);
+    else if (g->Cin == 64 && g->Cout == 8) rc = dispatch_wgrad_mma<64, 1>(*g, x, dy, dw, st);
+    if (rc != -8) return rc;
   }
   if (g->Cin == 8) return dispatch_wgrad_h<8>(*g, per, x, dy, dw, st);
   if (g->Cin == 16) return dispatch_wgrad_h<16>(*g, per, x, dy, dw, st);
