@@ -685,6 +685,187 @@ static int dispatch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy
   return -8;
 }
 
+// ---- the stem, Conv3d(1 -> 64, k (1,7,7), s (1,2,2), p (pd,3,3)) on a single-channel fp32 image, on HMMA through an
+// explicit im2col in shared memory: tile = 32 voxels of one output row; its 7 input rows (69 voxels) are read once
+// (coalesced fp32), converted to 16 bit, expanded to A_s[32 voxels][49 -> 64 taps]; forward: M = 16 voxels, N = 64 channels
+// (8 warps = 2 m-tiles x 4 channel quarters), K = 4 k16 chunks of taps; the 32 x 64 output tile is staged in shared memory
+// so each voxel's 128 bytes leave as one line, statistics from the staged (rounded) values.  Weight gradient: M = 64
+// channels (dy^T by ldmatrix.trans), N = 56 taps (im2col by ldmatrix.trans), K = the tile's 32 voxels; bf16 operands.
+constexpr int ST_XW = 72, ST_AS = 72;
+
+template <bool BF>
+__device__ __forceinline__ uint16_t st_cvt(float v) {
+  if (BF) { const __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<const uint16_t*>(&h); }
+  const __half h = __float2half_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+
+template <bool BF>
+__device__ __forceinline__ void stem_stage(const RnConvGeom& g, const float* __restrict__ x, int n, int od, int oh, int ow0,
+                                           uint16_t* in_s, uint16_t* A_s, int tid) {
+  const int zd = od * g.sd - g.pd;
+  const bool d_ok = (unsigned)zd < (unsigned)g.Di;
+  for (int i = tid; i < 7 * ST_XW; i += THREADS) {
+    const int b = i / ST_XW, p = i % ST_XW;
+    const int zh = oh * 2 - 3 + b, zw = ow0 * 2 - 3 + p;
+    float v = 0.f;
+    if (d_ok && p < 69 && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi)
+      v = __ldg(x + (((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw);
+    in_s[i] = st_cvt<BF>(v);
+  }
+  __syncthreads();
+  for (int i = tid; i < 32 * 64; i += THREADS) {
+    const int v = i >> 6, tap = i & 63;
+    uint16_t val = 0;
+    if (tap < 49) { const int b = tap / 7, c = tap % 7; val = in_s[b * ST_XW + 2 * v + c]; }
+    A_s[v * ST_AS + tap] = val;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 4) rn_stem_mma_fwd_kernel(const RnConvGeom g, const float* __restrict__ x,
+                                                                     const float* __restrict__ w, __half* __restrict__ y,
+                                                                     double* __restrict__ stats) {
+  __shared__ __align__(16) uint16_t in_s[7 * ST_XW];
+  __shared__ __align__(16) uint16_t A_s[32 * ST_AS];
+  __shared__ __align__(16) uint16_t out_s[32 * ST_AS];
+  __shared__ __align__(16) uint2 wb[4 * 8 * 32];
+  __shared__ float sstat[128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 4 * 8 * 32; i += THREADS) {
+    const int l = i & 31, nt = (i >> 5) & 7, kc = i >> 8;
+    const int n = nt * 8 + (l >> 2), k0 = kc * 16 + (l & 3) * 2;
+    const float* pw = w + (long long)n * 49;
+    const float w0 = k0 < 49 ? pw[k0] : 0.f, w1 = k0 + 1 < 49 ? pw[k0 + 1] : 0.f;
+    const float w8 = k0 + 8 < 49 ? pw[k0 + 8] : 0.f, w9 = k0 + 9 < 49 ? pw[k0 + 9] : 0.f;
+    wb[i] = make_uint2(pack_h2(w0, w1), pack_h2(w8, w9));
+  }
+  if (tid < 128) sstat[tid] = 0.f;
+  float ssum = 0.f, ssq = 0.f;
+  const int tiles_w = (g.Wo + 31) / 32;
+  const int ntiles = g.N * g.Do * g.Ho * tiles_w;
+  const int mt = warp & 1, nq = warp >> 1;
+  const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, koff = (lane >> 4) * 8;
+  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(A_s + (mt * 16 + row_l) * ST_AS + koff);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int oh = r_ % g.Ho;
+    r_ /= g.Ho;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int ow0 = tw * 32;
+    stem_stage<false>(g, x, n, od, oh, ow0, in_s, A_s, tid);
+    __syncthreads();
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_addr + kc * 32));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint2 bf = wb[(kc * 8 + nq * 2 + j) * 32 + lane];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                     : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+      }
+    }
+    const int gq = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      *reinterpret_cast<uint32_t*>(out_s + (mt * 16 + gq) * ST_AS + (nq * 2 + j) * 8 + t2) = pack_h2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<uint32_t*>(out_s + (mt * 16 + gq + 8) * ST_AS + (nq * 2 + j) * 8 + t2) = pack_h2(acc[j][2], acc[j][3]);
+    }
+    __syncthreads();
+    {
+      const int v = tid >> 3, chunk = tid & 7;
+      if (ow0 + v < g.Wo)
+        *reinterpret_cast<uint4*>(y + ((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow0 + v) * 64 + chunk * 8) =
+            *reinterpret_cast<const uint4*>(out_s + v * ST_AS + chunk * 8);
+      const int c = tid & 63, vg = tid >> 6;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int vv = vg * 8 + k;
+        if (ow0 + vv < g.Wo) {
+          const float f = __half2float(*reinterpret_cast<const __half*>(out_s + vv * ST_AS + c));
+          ssum += f; ssq = fmaf(f, f, ssq);
+        }
+      }
+    }
+  }
+  if (stats != nullptr) {
+    atomicAdd(&sstat[tid & 63], ssum);
+    atomicAdd(&sstat[64 + (tid & 63)], ssq);
+    __syncthreads();
+    if (tid < 128) atomicAdd(&stats[tid], (double)sstat[tid]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 4) rn_stem_mma_wgrad_kernel(const RnConvGeom g, const float* __restrict__ x,
+                                                                       const uint16_t* __restrict__ dy, float* __restrict__ dw) {
+  __shared__ __align__(16) uint16_t in_s[7 * ST_XW];
+  __shared__ __align__(16) uint16_t A_s[32 * ST_AS];
+  __shared__ __align__(16) uint16_t dy_s[32 * ST_AS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_w = (g.Wo + 31) / 32;
+  const int ntiles = g.N * g.Do * g.Ho * tiles_w;
+  const int mt = warp & 3, nh = warp >> 2;
+  const int q = lane >> 3;
+  const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(dy_s + ((lane & 7) + (q >> 1) * 8) * ST_AS + mt * 16 + (q & 1) * 8);
+  const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(A_s + (lane & 15) * ST_AS + nh * 32);
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int oh = r_ % g.Ho;
+    r_ /= g.Ho;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int ow0 = tw * 32;
+    __syncthreads();                                        // previous tile's fragments are loaded
+    {
+      const int v = tid >> 3, chunk = tid & 7;
+      const bool ok = ow0 + v < g.Wo;
+      const uint16_t* sp = ok ? dy + ((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow0 + v) * 64 + chunk * 8 : dy;
+      cp_async_zfill<16>(dy_s + v * ST_AS + chunk * 8, sp, ok);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    stem_stage<true>(g, x, n, od, oh, ow0, in_s, A_s, tid);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int kc = 0; kc < 2; ++kc) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_addr + kc * 16 * ST_AS * 2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                     : "=r"(b0), "=r"(b1) : "r"(b_addr + (kc * 16 * ST_AS + j * 8) * 2));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                     : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      }
+    }
+  }
+  const int gq = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int tap = (nh * 4 + j) * 8 + t2;
+    const int co = mt * 16 + gq;
+    if (tap < 49) { atomicAdd(&dw[co * 49 + tap], acc[j][0]); atomicAdd(&dw[(co + 8) * 49 + tap], acc[j][2]); }
+    if (tap + 1 < 49) { atomicAdd(&dw[co * 49 + tap + 1], acc[j][1]); atomicAdd(&dw[(co + 8) * 49 + tap + 1], acc[j][3]); }
+  }
+}
+
+static bool rn_is_stem(const RnConvGeom& g) {
+  return g.Cin == 1 && g.Cout == 64 && g.kd == 1 && g.kh == 7 && g.kw == 7 && g.sd == 1 && g.sh == 2 && g.sw == 2 && g.ph == 3 &&
+         g.pw == 3;
+}
+
 static bool rn_mma_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MMNN_RN_MMA"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
@@ -1122,6 +1303,13 @@ int mmnn_rn_conv(const RnConvGeom* g, int dgrad, int src_is_f32, const void* src
   if (!dgrad && !src_is_f32 && add == nullptr && g->Cin == 64 && g->Cout == 8 && g->kd == 3 && g->kh == 3 && g->kw == 3 &&
       g->sd == 1 && g->sh == 1 && g->sw == 1 && g->pd == 1 && g->ph == 1 && g->pw == 1 && rn_mma_enabled())
     return launch_conv3_mma_fwd(*g, src, w, dst, stats, st);
+  if (!dgrad && src_is_f32 && add == nullptr && rn_is_stem(*g) && rn_mma_enabled()) {
+    const long long nt = (long long)g->N * g->Do * g->Ho * ((g->Wo + 31) / 32);
+    if (nt <= 0x7fffffffLL) {
+      rn_stem_mma_fwd_kernel<<<(unsigned)(nt < 148 * 4 ? nt : 148 * 4), THREADS, 0, st>>>(*g, (const float*)src, w, (__half*)dst, stats);
+      return (int)cudaGetLastError();
+    }
+  }
   const bool k333 = g->kd == 3 && g->kh == 3 && g->kw == 3 && g->sd == 1 && g->sh == 1 && g->sw == 1 && g->pd == 1 && g->ph == 1 &&
                     g->pw == 1 && !src_is_f32 && rn_mma_enabled();
   if (k333 && !dgrad && g->Cin == 8 && g->Cout == 8) return launch_conv3_k8_mma<1, false>(*g, src, w, dst, add, stats, st);
@@ -1137,6 +1325,13 @@ int mmnn_rn_conv_wgrad(const RnConvGeom* g, int x_is_f32, const void* x, const v
   if (g->Cout % 8 != 0) return -2;
   const int items = g->kd * g->kh * g->kw * g->Cin * (g->Cout / 8);
   const int per = (items + THREADS - 1) / THREADS;
+  if (x_is_f32 && rn_is_stem(*g) && rn_mma_enabled()) {
+    const long long nt = (long long)g->N * g->Do * g->Ho * ((g->Wo + 31) / 32);
+    if (nt <= 0x7fffffffLL) {
+      rn_stem_mma_wgrad_kernel<<<(unsigned)(nt < 148 * 4 ? nt : 148 * 4), THREADS, 0, st>>>(*g, (const float*)x, (const uint16_t*)dy, dw);
+      return (int)cudaGetLastError();
+    }
+  }
   if (x_is_f32) {
     if (g->Cin != 1) return -3;
     if (per <= 2) return launch_wgrad<float, 1, 2>(*g, x, dy, dw, st);
