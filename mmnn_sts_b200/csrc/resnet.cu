@@ -294,6 +294,14 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
   const int mt = warp & 3, half_ = warp >> 2, rr = mt >> 1, wbase = (mt & 1) * 16;
   const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, koff = (lane >> 4) * 8;
   const int tap_lo = half_ ? 14 : 0, tap_hi = half_ ? 27 : 14;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+  uint32_t toff[14];                                        // this lane's ldmatrix row address (bytes) for each of its taps
+#pragma unroll
+  for (int ti = 0; ti < 14; ++ti) {
+    const int tap = (tap_lo + ti < 27) ? tap_lo + ti : 26;
+    const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+    toff[ti] = (uint32_t)((((a * MF_HR + rr + b) * MF_XW + wbase + c + row_l) * MF_VS + koff) * 2);
+  }
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tw = tile % tiles_w;
@@ -316,10 +324,11 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-    for (int tap = tap_lo; tap < tap_hi; ++tap) {
-      const int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
-      const __half* arow = xs + (((a * MF_HR + rr + b) * MF_XW + wbase + c + row_l) * MF_VS + koff);
-      const uint32_t abase = (uint32_t)__cvta_generic_to_shared(arow);
+#pragma unroll
+    for (int ti = 0; ti < 14; ++ti) {
+      const int tap = tap_lo + ti;
+      if (tap >= tap_hi) break;
+      const uint32_t abase = xs_addr + toff[ti];
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         uint32_t a0, a1, a2, a3;
@@ -408,6 +417,16 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
   const int mt = (NT == 1) ? warp : (warp & 3), nh = (NT == 1) ? 0 : (warp >> 2);
   const int rr = mt >> 1, wbase = (mt & 1) * 16;
   const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, second = lane >> 4;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+  uint32_t poff[14];                                        // this lane's ldmatrix row address (bytes) for every tap pair
+#pragma unroll
+  for (int pair = 0; pair < 14; ++pair) {
+    int tap = 2 * pair + second;
+    if (tap > 26) tap = 26;                                 // zero weights: any finite window will do
+    int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+    if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
+    poff[pair] = (uint32_t)((((a * HR + rr + b) * MF_XW + wbase + c + row_l) * 8) * 2);
+  }
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tw = tile % tiles_w;
@@ -431,13 +450,9 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
     float acc[NH][4];
 #pragma unroll
     for (int j = 0; j < NH; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-#pragma unroll 2
+#pragma unroll
     for (int pair = 0; pair < 14; ++pair) {
-      int tap = 2 * pair + second;
-      if (tap > 26) tap = 26;                               // zero weights: any finite window will do
-      int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
-      if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
-      const uint32_t aaddr = (uint32_t)__cvta_generic_to_shared(xs + ((a * HR + rr + b) * MF_XW + wbase + c + row_l) * 8);
+      const uint32_t aaddr = xs_addr + poff[pair];
       uint32_t a0, a1, a2, a3;
       asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                    : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(aaddr));
