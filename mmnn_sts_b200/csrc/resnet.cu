@@ -596,20 +596,35 @@ __global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma_kernel(const RnConvGe
     const int od = r_ % g.Do, n = r_ / g.Do;
     const int oh0 = th * R, ow0 = tw * 32;
     __syncthreads();
-    // input rows, fp16 -> bf16 on the way; one flat loop so that all of a thread's loads are in flight together (a row-by-row
-    // loop measured 1.5-3x slower), runtime divisors replaced by an exact float reciprocal (operands < 2^16)
-    for (int i = tid; i < nrows * XW * CH8; i += THREADS) {
-      const int ch = i % CH8, vp = i / CH8;
-      const int r = __float2int_rd(((float)vp + 0.5f) * inv_xw), p = vp - r * XW;
-      const int a = __float2int_rd(((float)r + 0.5f) * inv_hrs), hb = r - a * HRs;
-      const int zd = od * g.sd - g.pd + a, zh = oh0 * g.sh - g.ph + hb, zw = ow0 * g.sw - g.pw + p;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if ((unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi) {
-        float f[8];
-        unpack8h(__ldg(reinterpret_cast<const uint4*>(x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * CIN + ch * 8)), f);
-        o = pack8(f);
+    // input rows, fp16 -> bf16 on the way; one flat loop (a row-by-row loop measured 1.5-3x slower), runtime divisors replaced
+    // by an exact float reciprocal (operands < 2^16), loads batched U at a time so their latencies overlap
+    {
+      constexpr int U = 4;                                  // loads of U chunks in flight before the first conversion
+      const int total = nrows * XW * CH8;
+      for (int base = 0; base < total; base += THREADS * U) {
+        uint4 qv[U];
+        int dsto[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * THREADS + tid;
+          const int ch = i % CH8, vp = i / CH8;
+          const int r = __float2int_rd(((float)vp + 0.5f) * inv_xw), p = vp - r * XW;
+          const int a = __float2int_rd(((float)r + 0.5f) * inv_hrs), hb = r - a * HRs;
+          const int zd = od * g.sd - g.pd + a, zh = oh0 * g.sh - g.ph + hb, zw = ow0 * g.sw - g.pw + p;
+          dsto[u] = (i < total) ? vp * VS + ch * 8 : -1;
+          qv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (i < total && (unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi)
+            qv[u] = __ldg(reinterpret_cast<const uint4*>(x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * CIN + ch * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (dsto[u] >= 0) {
+            float f[8];
+            unpack8h(qv[u], f);                             // fp16 zero -> bf16 zero
+            *reinterpret_cast<uint4*>(xs + dsto[u]) = pack8(f);
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(xs + (size_t)vp * VS + ch * 8) = o;
     }
     for (int i = tid; i < R * 32 * NTN; i += THREADS) {
       const int c8 = i % NTN, v = (i / NTN) % 32, rr = i / NTN / 32;
