@@ -703,11 +703,220 @@ static int launch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy, 
   return (int)cudaGetLastError();
 }
 
+// ---- the same weight gradient with fp16 operands: dy (bf16) is rescaled by a power of two S = 2^floor(log2(8192 / max|dy|))
+// while its small tile passes through registers, so the fp16 input rows need NO conversion and arrive by zero-filling
+// cp.async into the other half of a double buffer while the current tile is in the tensor pipe (the bf16 variant above
+// spends its time converting 59 KB per tile through registers, ncu: long-scoreboard 6.5 of 12.5 cycles per issue).
+// max|dy| comes from rn_absmax_kernel (one pass over dy, < 2 % of the weight gradient's own traffic at layer1); fp16
+// keeps 11 significant bits of every dy within 2^-14 of the maximum, more than the 8 of its bf16 storage.
+__global__ void __launch_bounds__(THREADS) rn_absmax_kernel(const uint4* __restrict__ dy, long long n8, unsigned* __restrict__ out) {
+  unsigned m = 0;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < n8; i += (long long)gridDim.x * THREADS) {
+    const uint4 q = __ldg(dy + i);
+    const unsigned w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m = max(m, w4[k] & 0x7fffu); m = max(m, (w4[k] >> 16) & 0x7fffu); }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m << 16);       // bf16 magnitude bits -> fp32 bits
+}
+
+template <int CIN, int NTN, int MAXU>
+__global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma16_kernel(const RnConvGeom g, const __half* __restrict__ x,
+                                                                    const uint16_t* __restrict__ dy, float* __restrict__ dw, int R,
+                                                                    const unsigned* __restrict__ amax_bits) {
+  constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);
+  constexpr int COUT = 8 * NTN, CH8 = CIN / 8, C16 = (CIN >= 16) ? CIN / 16 : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int taps = g.kd * g.kh * g.kw;
+  const int HRs = (R - 1) * g.sh + g.kh, XW = 31 * g.sw + g.kw, nrows = g.kd * HRs;
+  const int xbuf = nrows * XW * VS, dbuf = R * 32 * COUT;          // elements per buffer
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);            // [2][xbuf]
+  uint16_t* dys = xs + 2 * (size_t)xbuf;                           // [2][dbuf]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, vl = (lane & 7) + (q >> 1) * 8;
+  const int nunits = (CIN >= 16) ? taps * C16 : (taps + 1) / 2;
+  const float amax = __uint_as_float(*amax_bits);
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) S = exp2f(floorf(log2f(8192.f / amax)));
+  int ubase[MAXU];
+  float acc[MAXU][NTN][4];
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int u = warp + 8 * i;
+    const int uu = (u < nunits) ? u : 0;
+    int tap, choff;
+    if (CIN >= 16) { tap = uu / C16; choff = (uu % C16) * 16 + (q & 1) * 8; }
+    else { tap = 2 * uu + (q & 1); if (tap >= taps) tap = 2 * uu; choff = 0; }
+    const int a = tap / (g.kh * g.kw), b = (tap / g.kw) % g.kh, c = tap % g.kw;
+    ubase[i] = ((a * HRs + b) * XW + c + vl * g.sw) * VS + choff;
+#pragma unroll
+    for (int j = 0; j < NTN; ++j) { acc[i][j][0] = 0.f; acc[i][j][1] = 0.f; acc[i][j][2] = 0.f; acc[i][j][3] = 0.f; }
+  }
+  const int tiles_w = (g.Wo + 31) / 32, tiles_h = (g.Ho + R - 1) / R;
+  const int ntiles = g.N * g.Do * tiles_h * tiles_w;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs), dys_addr = (uint32_t)__cvta_generic_to_shared(dys);
+  const float inv_xw = 1.0f / (float)XW, inv_hrs = 1.0f / (float)HRs;
+  const int dyvecs = R * 32 * NTN;                                  // <= 256: one uint4 of dy per thread
+
+  auto decode = [&](int tile, int& n, int& od, int& oh0, int& ow0) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    od = r_ % g.Do; n = r_ / g.Do; oh0 = th * R; ow0 = tw * 32;
+  };
+  auto stage_x = [&](int tile, int buf) {
+    int n, od, oh0, ow0;
+    decode(tile, n, od, oh0, ow0);
+    uint16_t* xb = xs + (size_t)buf * xbuf;
+    const int total = nrows * XW * CH8;
+    for (int i = tid; i < total; i += THREADS) {
+      const int ch = i % CH8, vp = i / CH8;
+      const int r = __float2int_rd(((float)vp + 0.5f) * inv_xw), p = vp - r * XW;
+      const int a = __float2int_rd(((float)r + 0.5f) * inv_hrs), hb = r - a * HRs;
+      const int zd = od * g.sd - g.pd + a, zh = oh0 * g.sh - g.ph + hb, zw = ow0 * g.sw - g.pw + p;
+      const bool ok = (unsigned)zd < (unsigned)g.Di && (unsigned)zh < (unsigned)g.Hi && (unsigned)zw < (unsigned)g.Wi;
+      const __half* sp = ok ? x + ((((long long)n * g.Di + zd) * g.Hi + zh) * g.Wi + zw) * CIN + ch * 8 : x;
+      cp_async_zfill<16>(xb + vp * VS + ch * 8, sp, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  auto load_dy = [&](int tile) -> uint4 {
+    int n, od, oh0, ow0;
+    decode(tile, n, od, oh0, ow0);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < dyvecs) {
+      const int c8 = tid % NTN, v = (tid / NTN) % 32, rr = tid / NTN / 32;
+      if (oh0 + rr < g.Ho && ow0 + v < g.Wo)
+        o = __ldg(reinterpret_cast<const uint4*>(dy + ((((long long)n * g.Do + od) * g.Ho + oh0 + rr) * g.Wo + ow0 + v) * COUT + c8 * 8));
+    }
+    return o;
+  };
+  auto store_dy = [&](const uint4 o, int buf) {
+    if (tid < dyvecs) {
+      float f[8];
+      unpack8(o, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= S;
+      *reinterpret_cast<uint4*>(dys + (size_t)buf * dbuf + (size_t)tid * 8) = pack8h(f);
+    }
+  };
+
+  int tile = blockIdx.x, buf = 0;
+  if (tile < ntiles) { stage_x(tile, 0); store_dy(load_dy(tile), 0); }
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();                                        // tile `buf` staged; everyone is done with buffer buf ^ 1
+    const int nxt = tile + gridDim.x;
+    uint4 dq = make_uint4(0u, 0u, 0u, 0u);
+    if (nxt < ntiles) { stage_x(nxt, buf ^ 1); dq = load_dy(nxt); }
+    const uint32_t xa = xs_addr + (uint32_t)(buf * xbuf * 2), da = dys_addr + (uint32_t)(buf * dbuf * 2);
+    for (int kc = 0; kc < R * 2; ++kc) {
+      const int rr = kc >> 1, wh = kc & 1;
+      const int koff = (rr * g.sh * XW + wh * 16 * g.sw) * VS;
+      uint32_t b0[NTN], b1[NTN];
+#pragma unroll
+      for (int j = 0; j < NTN; ++j) {
+        const uint32_t baddr = da + (uint32_t)(((rr * 32 + wh * 16 + (lane & 15)) * COUT + j * 8) * 2);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(b0[j]), "=r"(b1[j]) : "r"(baddr));
+      }
+#pragma unroll
+      for (int i = 0; i < MAXU; ++i) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(xa + (uint32_t)((ubase[i] + koff) * 2)));
+#pragma unroll
+        for (int j = 0; j < NTN; ++j)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0[j]), "r"(b1[j]));
+      }
+    }
+    if (nxt < ntiles) store_dy(dq, buf ^ 1);
+  }
+  const float invS = 1.f / S;
+  const int gq = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int u = warp + 8 * i;
+    if (u >= nunits) continue;
+#pragma unroll
+    for (int hsel = 0; hsel < 2; ++hsel) {
+      int tap, ci;
+      if (CIN >= 16) { tap = u / C16; ci = (u % C16) * 16 + gq + hsel * 8; }
+      else { tap = 2 * u + hsel; ci = gq; }
+      if (tap >= taps) continue;
+#pragma unroll
+      for (int j = 0; j < NTN; ++j) {
+        const int co = j * 8 + t2;
+        atomicAdd(&dw[((long long)co * CIN + ci) * taps + tap], acc[i][j][hsel * 2] * invS);
+        atomicAdd(&dw[((long long)(co + 1) * CIN + ci) * taps + tap], acc[i][j][hsel * 2 + 1] * invS);
+      }
+    }
+  }
+}
+
+__device__ unsigned g_rn_amax_slot[1];
+
+static bool rn_wgrad16_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMNN_RN_WGRAD16"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+template <int CIN, int NTN, int MAXU>
+static int launch_wgrad_mma16(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);
+  const int XW = 31 * g.sw + g.kw;
+  int R = 4;
+  size_t smem = 0;
+  for (;; R >>= 1) {
+    const int HRs = (R - 1) * g.sh + g.kh;
+    smem = 2 * ((size_t)g.kd * HRs * XW * VS + (size_t)R * 32 * 8 * NTN) * 2;
+    if (smem <= 120 * 1024 || R == 1) break;
+  }
+  if (smem > 220 * 1024) return -8;                         // caller falls back to the converting variant
+  auto kern = rn_wgrad_mma16_kernel<CIN, NTN, MAXU>;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  unsigned* slot = nullptr;
+  cudaError_t e = cudaGetSymbolAddress((void**)&slot, g_rn_amax_slot);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(slot, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return (int)e;
+  const long long n8 = (long long)g.N * g.Do * g.Ho * g.Wo * g.Cout / 8;
+  long long ab = (n8 + THREADS - 1) / THREADS;
+  if (ab > 148 * 8) ab = 148 * 8;
+  rn_absmax_kernel<<<(unsigned)ab, THREADS, 0, st>>>((const uint4*)dy, n8, slot);
+  const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 31) / 32);
+  if (ntiles > 0x7fffffffLL) return -6;
+  int bps = (int)((200 * 1024) / (smem + 1024));
+  if (bps > 2) bps = 2;                                     // __launch_bounds__(256, 2)
+  if (bps < 1) bps = 1;
+  const int blocks = (int)(ntiles < 148LL * bps ? ntiles : 148LL * bps);
+  kern<<<blocks, THREADS, smem, st>>>(g, (const __half*)x, (const uint16_t*)dy, dw, R, slot);
+  return (int)cudaGetLastError();
+}
+
 template <int CIN, int NTN>
 static int dispatch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
   const int taps = g.kd * g.kh * g.kw;
   const int nunits = (CIN >= 16) ? taps * (CIN / 16) : (taps + 1) / 2;
   const int per = (nunits + 7) / 8;
+  if (rn_wgrad16_enabled()) {
+    int rc = -8;
+    if (per <= 1) rc = launch_wgrad_mma16<CIN, NTN, 1>(g, x, dy, dw, st);
+    else if (per <= 2) rc = launch_wgrad_mma16<CIN, NTN, 2>(g, x, dy, dw, st);
+    else if (per <= 4) rc = launch_wgrad_mma16<CIN, NTN, 4>(g, x, dy, dw, st);
+    else if (per <= 14 && NTN == 1) rc = launch_wgrad_mma16<CIN, NTN, (NTN == 1 ? 14 : 4)>(g, x, dy, dw, st);
+    if (rc != -8) return rc;
+  }
   if (per <= 1) return launch_wgrad_mma<CIN, NTN, 1>(g, x, dy, dw, st);
   if (per <= 2) return launch_wgrad_mma<CIN, NTN, 2>(g, x, dy, dw, st);
   if (per <= 4) return launch_wgrad_mma<CIN, NTN, 4>(g, x, dy, dw, st);

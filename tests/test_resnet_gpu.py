@@ -73,11 +73,12 @@ def test_conv_kernels_match_torch(cin, cout, k, s, p, dims):
     dw = torch.zeros_like(w_dev)
     assert lib.mmnn_rn_conv_wgrad(C.byref(geom), int(f32), x_dev.data_ptr(), dy_dev.data_ptr(), dw.data_ptr(), st) == 0
     if True:
-        # the HMMA weight gradients read the activations / the image as bf16 (dy is bf16; mma.sync wants one operand type)
+        # mma.sync wants one operand type: the stem's weight gradient reads the image as bf16 (dy is bf16), the others keep the
+        # fp16 activations and rescale dy by a power of two into fp16 (exact) -> one of the two references matches to 1e-4
         xb = xq.bfloat16().float().requires_grad_(False)
         wb_ = w.clone().requires_grad_(True)
         F.conv3d(xb, wb_, None, s, p).backward(dy)
-        assert _rel(dw, wb_.grad) < 1e-4
+        assert min(_rel(dw, wb_.grad), _rel(dw, wa.grad)) < 1e-4
         assert _rel(dw, wa.grad) < 5e-3
     if not f32:
         add = torch.randn((N,) + dims + (cin,), generator=g).bfloat16()
