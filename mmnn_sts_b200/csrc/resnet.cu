@@ -1105,6 +1105,161 @@ static bool rn_is_stem(const RnConvGeom& g) {
          g.pw == 3;
 }
 
+// ---- 16-channel source, 16 outputs, 3x3x3 stride 1 pad 1 (layer2 / layer4): one tap = one k16.  The rows of these stages
+// are 16 (or fewer) voxels wide, so the tile shape adapts: TWm m-tiles along W (1 when Wo <= 16) x 8 / TWm rows.
+template <bool DGRAD>
+__global__ void __launch_bounds__(THREADS, 2) rn_conv3_k16_mma_kernel(const RnConvGeom g, const uint16_t* __restrict__ src,
+                                                                      const float* __restrict__ w, uint16_t* __restrict__ dst,
+                                                                      const uint16_t* __restrict__ add, double* __restrict__ stats,
+                                                                      int TWm) {
+  constexpr int VS = 24;
+  const int R = 8 / TWm, HR = R + 2, XW = 16 * TWm + 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);
+  uint2* wb = reinterpret_cast<uint2*>(smem_raw + (size_t)3 * HR * XW * VS * 2);
+  float* sstat = reinterpret_cast<float*>(wb + 27 * 2 * 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 27 * 2 * 32; i += THREADS) {
+    const int l = i & 31, j = (i >> 5) & 1, tap = i >> 6;
+    const int n = 8 * j + (l >> 2), k = (l & 3) * 2;
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk = k + (q & 1) + (q >> 1) * 8;
+      const int co = DGRAD ? kk : n, ci = DGRAD ? n : kk;
+      v[q] = w[((long long)co * 16 + ci) * 27 + tap];
+    }
+    wb[i] = DGRAD ? make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3])) : make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+  }
+  if (tid < 32) sstat[tid] = 0.f;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tiles_w = (g.Wo + 16 * TWm - 1) / (16 * TWm), tiles_h = (g.Ho + R - 1) / R;
+  const int ntiles = g.N * g.Do * tiles_h * tiles_w;
+  const int rr = warp / TWm, wbase = (warp % TWm) * 16;
+  const int row_l = (lane & 7) + ((lane >> 3) & 1) * 8, koff = (lane >> 4) * 8;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+  uint32_t toff[27];
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+    int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
+    if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
+    toff[tap] = (uint32_t)((((a * HR + rr + b) * XW + wbase + c + row_l) * VS + koff) * 2);
+  }
+  const float inv_xw = 1.0f / (float)XW, inv_hr = 1.0f / (float)HR;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int oh0 = th * R, ow0 = tw * 16 * TWm;
+    __syncthreads();
+    for (int i = tid; i < 3 * HR * XW * 2; i += THREADS) {
+      const int ch = i & 1, vp = i >> 1;
+      const int r = __float2int_rd(((float)vp + 0.5f) * inv_xw), p = vp - r * XW;
+      const int a = __float2int_rd(((float)r + 0.5f) * inv_hr), hb = r - a * HR;
+      const int zd = od - 1 + a, zh = oh0 - 1 + hb, zw = ow0 - 1 + p;
+      const bool ok = (unsigned)zd < (unsigned)g.Do && (unsigned)zh < (unsigned)g.Ho && (unsigned)zw < (unsigned)g.Wo;
+      const uint16_t* sp = ok ? src + ((((long long)n * g.Do + zd) * g.Ho + zh) * g.Wo + zw) * 16 + ch * 8 : src;
+      cp_async_zfill<16>(xs + vp * VS + ch * 8, sp, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(xs_addr + toff[tap]));
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint2 bf = wb[(tap * 2 + j) * 32 + lane];
+        if (DGRAD)
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+        else
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+      }
+    }
+    const int oh = oh0 + rr, gq = lane >> 2, t2 = (lane & 3) * 2;
+    if (oh < g.Ho) {
+      const long long rowbase = (((long long)n * g.Do + od) * g.Ho + oh) * g.Wo;
+#pragma unroll
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        const int ow = ow0 + wbase + gq + hsel * 8;
+        if (ow < g.Wo) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v0 = acc[j][hsel * 2], v1 = acc[j][hsel * 2 + 1];
+            const long long o = (rowbase + ow) * 16 + j * 8 + t2;
+            if (add != nullptr) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(add + o);
+              if (DGRAD) { v0 += bf_lo(u); v1 += bf_hi(u); }
+              else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u)); v0 += f.x; v1 += f.y; }
+            }
+            if (DGRAD) {
+              *reinterpret_cast<uint32_t*>(dst + o) = pack2(v0, v1);
+            } else {
+              const __half2 h = __floats2half2_rn(v0, v1);
+              *reinterpret_cast<__half2*>(dst + o) = h;
+              const float2 f = __half22float2(h);
+              ssum[j * 2] += f.x; ssum[j * 2 + 1] += f.y;
+              ssq[j * 2] = fmaf(f.x, f.x, ssq[j * 2]); ssq[j * 2 + 1] = fmaf(f.y, f.y, ssq[j * 2 + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
+        ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
+      }
+    }
+    if (lane < 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int co = (k >> 1) * 8 + lane * 2 + (k & 1);
+        atomicAdd(&sstat[co], ssum[k]);
+        atomicAdd(&sstat[16 + co], ssq[k]);
+      }
+    }
+    __syncthreads();
+    if (tid < 32) atomicAdd(&stats[tid], (double)sstat[tid]);
+  }
+}
+
+template <bool DGRAD>
+static int launch_conv3_k16_mma(const RnConvGeom& g, const void* src, const float* w, void* dst, const void* add, double* stats,
+                                cudaStream_t st) {
+  const int TWm = g.Wo > 16 ? 2 : 1;
+  const int R = 8 / TWm, HR = R + 2, XW = 16 * TWm + 2;
+  const size_t smem = (size_t)3 * HR * XW * 24 * 2 + 27 * 2 * 32 * 8 + 32 * 4;
+  auto kern = rn_conv3_k16_mma_kernel<DGRAD>;
+  static bool attr = false;
+  if (!attr) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 16 * TWm - 1) / (16 * TWm));
+  if (ntiles > 0x7fffffffLL || smem > 64 * 1024) return -6;
+  const int blocks = (int)(ntiles < 148 * 3 ? ntiles : 148 * 3);
+  kern<<<blocks, THREADS, smem, st>>>(g, (const uint16_t*)src, w, (uint16_t*)dst, (const uint16_t*)add, stats, TWm);
+  return (int)cudaGetLastError();
+}
+
 static bool rn_mma_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MMNN_RN_MMA"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
@@ -1553,6 +1708,10 @@ int mmnn_rn_conv(const RnConvGeom* g, int dgrad, int src_is_f32, const void* src
                     g->pw == 1 && !src_is_f32 && rn_mma_enabled();
   if (k333 && !dgrad && g->Cin == 8 && g->Cout == 8) return launch_conv3_k8_mma<1, false>(*g, src, w, dst, add, stats, st);
   if (k333 && dgrad && g->Cout == 8 && g->Cin == 8) return launch_conv3_k8_mma<1, true>(*g, src, w, dst, add, nullptr, st);
+  if (k333 && g->Cin == 16 && g->Cout == 16) {
+    if (dgrad) return launch_conv3_k16_mma<true>(*g, src, w, dst, add, nullptr, st);
+    if (add == nullptr) return launch_conv3_k16_mma<false>(*g, src, w, dst, nullptr, stats, st);
+  }
   if (k333 && dgrad && g->Cout == 8 && g->Cin == 64 && add == nullptr) return launch_conv3_k8_mma<8, true>(*g, src, w, dst, nullptr, nullptr, st);
   if (dgrad) return dispatch_conv<true>(*g, src_is_f32, src, w, dst, add, stats, st);
   return dispatch_conv<false>(*g, src_is_f32, src, w, dst, add, stats, st);

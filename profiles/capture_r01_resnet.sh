@@ -11,6 +11,8 @@ cap() {  # name regex skip count
   tail -1 gpurun_out/rn_ncu_$1_$TAG.log
 }
 cap mma_fwd 'rn_conv3_mma_fwd_kernel' 0 1
-cap wgrad_mma 'rn_wgrad_mma_kernel<.int.64' 0 1
+cap wgrad_mma 'rn_wgrad_mma16_kernel<.int.64, .int.1, .int.14' 0 1
 cap k8_dgrad 'rn_conv3_k8_mma_kernel<.int.8' 0 1
-cap stem_fwd 'rn_conv_kernel<float' 0 1
+cap stem_fwd 'rn_stem_mma_fwd_kernel' 0 1
+cap stem_wgrad 'rn_stem_mma_wgrad_kernel' 0 1
+cap bn_bwd_apply 'rn_bn_bwd_apply_kernel<.bool.0' 6 1     # the stem's (last launch of the backward)

@@ -33,6 +33,7 @@ GEOMS = [
     (8, 16, (3, 3, 3), (2, 2, 2), (1, 1, 1), (7, 8, 9)),
     (8, 16, (1, 1, 1), (2, 2, 2), (0, 0, 0), (7, 8, 9)),
     (16, 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), (4, 5, 6)),
+    (16, 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), (3, 11, 21)),
     (16, 8, (3, 3, 3), (2, 2, 2), (1, 1, 1), (6, 5, 8)),
     (16, 8, (1, 1, 1), (2, 2, 2), (0, 0, 0), (6, 5, 8)),
 ]
