@@ -158,6 +158,13 @@ struct RnConvGeom;
 int mmnn_sizeof_rn_conv_geom(void);
 int mmnn_rn_conv(const struct RnConvGeom* g /*HOST*/, int dgrad, int src_is_f32, const void* src, const float* w, void* dst,
                  const void* add, double* stats, void* stream);
+/* BasicBlock.conv1 (64 -> 8, 3x3x3 s1 p1) and the block's 1x1x1 stride-1 down-sample convolution (resnet.py:172-179) on the same
+ * input: forward of both in one launch (the 1.08 GB stem activation is read once), and dx = dgrad(conv1) + dgrad(down-sample)
+ * in one launch.  Return -9 when the geometry is not that pair: the caller then issues the separate mmnn_rn_conv calls. */
+int mmnn_rn_conv_fwd_ds(const struct RnConvGeom* g /*HOST*/, const void* x, const float* w, const float* w_ds, void* y, void* y_ds,
+                        double* stats, double* stats_ds, void* stream);
+int mmnn_rn_conv_dgrad_ds(const struct RnConvGeom* g /*HOST*/, const void* dy, const float* w, const void* dy_ds, const float* w_ds,
+                          void* dx, void* stream);
 int mmnn_rn_conv_wgrad(const struct RnConvGeom* g /*HOST*/, int x_is_f32, const void* x, const void* dy, float* dw, void* stream);
 int mmnn_rn_bn_coeffs(const double* stats, double count, const float* gamma, const float* beta, float* rmean, float* rvar,
                       long long* nbt, float eps, float momentum, int training, int C, float* coef, void* stream);

@@ -171,6 +171,10 @@ def _declare(l):
     assert l.mmnn_sizeof_rn_conv_geom() == C.sizeof(RnConvGeom), (l.mmnn_sizeof_rn_conv_geom(), C.sizeof(RnConvGeom))
     l.mmnn_rn_conv.argtypes = [GP, I, I, VP, VP, VP, VP, VP, VP]
     l.mmnn_rn_conv_wgrad.argtypes = [GP, I, VP, VP, VP, VP]
+    l.mmnn_rn_conv_fwd_ds.argtypes = [GP, VP, VP, VP, VP, VP, VP, VP, VP]
+    l.mmnn_rn_conv_dgrad_ds.argtypes = [GP, VP, VP, VP, VP, VP, VP]
+    l.mmnn_rn_conv_fwd_ds.restype = I
+    l.mmnn_rn_conv_dgrad_ds.restype = I
     l.mmnn_rn_bn_coeffs.argtypes = [VP, D, VP, VP, VP, VP, VP, F, F, I, I, VP, VP]
     l.mmnn_rn_bn_act.argtypes = [VP, VP, I, VP, VP, VP, LL, I, I, F, ULL, VP, VP]
     l.mmnn_rn_act_bwd_reduce.argtypes = [VP, VP, F, VP, VP, VP, VP, VP, LL, I, VP]

@@ -265,7 +265,7 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
 constexpr int MF_R = 2, MF_XW = 34, MF_VS = 72, MF_HR = MF_R + 2, MF_ROWS = 3 * MF_HR;
 constexpr int MF_XS_BYTES = MF_ROWS * MF_XW * MF_VS * 2;            // 58 752
 constexpr int MF_WB_BYTES = 27 * 4 * 32 * 8;                        // 27 648
-constexpr int MF_SMEM = MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16 + 64;
+constexpr int MF_SMEM = MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16 + 64 + 4 * 32 * 8 + 64;
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -274,13 +274,27 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnConvGeom g, const __half* __restrict__ x,
                                                                       const float* __restrict__ w, __half* __restrict__ y,
-                                                                      double* __restrict__ stats) {
+                                                                      double* __restrict__ stats, const float* __restrict__ w_ds,
+                                                                      __half* __restrict__ y_ds, double* __restrict__ stats_ds) {
+  // w_ds / y_ds / stats_ds: the block's 1x1x1 stride-1 down-sample convolution (64 -> 8) reads the same input tile: it is the
+  // centre tap with its own weights and accumulator (4 more MMAs per m-tile), so the 1.08 GB input is read once for both
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* xs = reinterpret_cast<__half*>(smem_raw);
   uint2* wb = reinterpret_cast<uint2*>(smem_raw + MF_XS_BYTES);
   float4* red = reinterpret_cast<float4*>(smem_raw + MF_XS_BYTES + MF_WB_BYTES);
   float* sstat = reinterpret_cast<float*>(smem_raw + MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16);
+  uint2* wbd = reinterpret_cast<uint2*>(smem_raw + MF_XS_BYTES + MF_WB_BYTES + 4 * 32 * 16 + 64);   // [4 k-chunks][32]
+  float* sstat2 = reinterpret_cast<float*>(wbd + 4 * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool ds = w_ds != nullptr;
+  if (ds && tid < 128) {
+    const int l = tid & 31, kc = tid >> 5;
+    const int n = l >> 2, k0 = kc * 16 + (l & 3) * 2;
+    const float* pw = w_ds + (long long)n * 64 + k0;          // w_ds[n][ci]
+    wbd[tid] = make_uint2(pack_h2(pw[0], pw[1]), pack_h2(pw[8], pw[9]));
+  }
+  if (tid < 16) sstat2[tid] = 0.f;
+  float dsum0 = 0.f, dsum1 = 0.f, dsq0 = 0.f, dsq1 = 0.f;
   for (int i = tid; i < 108 * 32; i += THREADS) {
     const int l = i & 31, t = i >> 5, tap = t >> 2, kc = t & 3;
     const int n = l >> 2, k0 = kc * 16 + (l & 3) * 2;
@@ -324,11 +338,13 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
     asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
     for (int ti = 0; ti < 14; ++ti) {
       const int tap = tap_lo + ti;
       if (tap >= tap_hi) break;
       const uint32_t abase = xs_addr + toff[ti];
+      const bool centre = ds && tap == 13;
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         uint32_t a0, a1, a2, a3;
@@ -337,6 +353,11 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
         const uint2 bf = wb[(tap * 4 + kc) * 32 + lane];
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                      : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+        if (centre) {                                       // warp-uniform (tap 13 belongs to the first half of the tap range)
+          const uint2 bd = wbd[kc * 32 + lane];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bd.x), "r"(bd.y));
+        }
       }
     }
     if (half_ == 1) red[mt * 32 + lane] = make_float4(c0, c1, c2, c3);
@@ -360,8 +381,35 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
           const float2 f = __half22float2(h);
           ssum0 += f.x; ssum1 += f.y; ssq0 = fmaf(f.x, f.x, ssq0); ssq1 = fmaf(f.y, f.y, ssq1);
         }
+        if (ds) {
+          if (owa < g.Wo) {
+            const __half2 h = __floats2half2_rn(d0, d1);
+            *reinterpret_cast<__half2*>(y_ds + (rowbase + owa) * 8 + co) = h;
+            const float2 f = __half22float2(h);
+            dsum0 += f.x; dsum1 += f.y; dsq0 = fmaf(f.x, f.x, dsq0); dsq1 = fmaf(f.y, f.y, dsq1);
+          }
+          if (owb < g.Wo) {
+            const __half2 h = __floats2half2_rn(d2, d3);
+            *reinterpret_cast<__half2*>(y_ds + (rowbase + owb) * 8 + co) = h;
+            const float2 f = __half22float2(h);
+            dsum0 += f.x; dsum1 += f.y; dsq0 = fmaf(f.x, f.x, dsq0); dsq1 = fmaf(f.y, f.y, dsq1);
+          }
+        }
       }
     }
+  }
+  if (ds && stats_ds != nullptr) {
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, off); dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, off);
+      dsq0 += __shfl_xor_sync(0xffffffffu, dsq0, off); dsq1 += __shfl_xor_sync(0xffffffffu, dsq1, off);
+    }
+    if (lane < 4) {
+      atomicAdd(&sstat2[lane * 2], dsum0); atomicAdd(&sstat2[lane * 2 + 1], dsum1);
+      atomicAdd(&sstat2[8 + lane * 2], dsq0); atomicAdd(&sstat2[8 + lane * 2 + 1], dsq1);
+    }
+    __syncthreads();
+    if (tid < 16) atomicAdd(&stats_ds[tid], (double)sstat2[tid]);
   }
   if (stats != nullptr) {
 #pragma unroll
@@ -388,7 +436,11 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
 template <int NT, bool DGRAD>
 __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnConvGeom g, const uint16_t* __restrict__ src,
                                                                      const float* __restrict__ w, uint16_t* __restrict__ dst,
-                                                                     const uint16_t* __restrict__ add, double* __restrict__ stats) {
+                                                                     const uint16_t* __restrict__ add, double* __restrict__ stats,
+                                                                     const uint16_t* __restrict__ src2, const float* __restrict__ w2) {
+  // src2 / w2 (DGRAD only): the output gradient and [8][OC] weight of the block's 1x1x1 stride-1 down-sample convolution; its
+  // data gradient is one more "tap" (the 28th, at the centre) of the same gather, so dx = dgrad(conv1) + dgrad(downsample)
+  // leaves in ONE pass instead of a second kernel that re-reads and re-writes dx (1.08 GB at layer1)
   constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2, NH = (NT == 1) ? 1 : 4, OC = 8 * NT;
   constexpr int XS_BYTES = 3 * HR * MF_XW * 16, WB_BYTES = 14 * NT * 32 * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -396,6 +448,7 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
   uint2* wb = reinterpret_cast<uint2*>(smem_raw + XS_BYTES);
   uint16_t* stg = reinterpret_cast<uint16_t*>(smem_raw + XS_BYTES + WB_BYTES);      // NT == 8: [8 warps][16][40]
   float* sstat = reinterpret_cast<float*>(smem_raw + XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2);
+  uint16_t* xs2 = reinterpret_cast<uint16_t*>(smem_raw + XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2 + 64);   // [R][32][8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wCin = g.Cin;                                   // weight tensor is [Cout][Cin][27]
   for (int i = tid; i < 14 * NT * 32; i += THREADS) {
@@ -406,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
     for (int q = 0; q < 4; ++q) {
       const int tap = 2 * pair + (q >> 1), kk = k + (q & 1);
       const int co = DGRAD ? kk : n, ci = DGRAD ? n : kk;
-      v[q] = (tap < 27) ? w[((long long)co * wCin + ci) * 27 + tap] : 0.f;
+      v[q] = (tap < 27) ? w[((long long)co * wCin + ci) * 27 + tap] : ((DGRAD && w2 != nullptr) ? w2[(long long)co * wCin + ci] : 0.f);
     }
     wb[i] = DGRAD ? make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3])) : make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
   }
@@ -426,6 +479,8 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
     int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
     if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
     poff[pair] = (uint32_t)((((a * HR + rr + b) * MF_XW + wbase + c + row_l) * 8) * 2);
+    if (DGRAD && src2 != nullptr && 2 * pair + second == 27)
+      poff[pair] = (uint32_t)((xs2 - xs) * 2 + ((rr * 32 + wbase + row_l) * 8) * 2);
   }
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -443,6 +498,12 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
       const bool ok = (unsigned)zd < (unsigned)g.Do && (unsigned)zh < (unsigned)g.Ho && (unsigned)zw < (unsigned)g.Wo;
       const uint16_t* sp = ok ? src + ((((long long)n * g.Do + zd) * g.Ho + zh) * g.Wo + zw) * 8 : src;
       cp_async_zfill<16>(xs + i * 8, sp, ok);
+    }
+    if (DGRAD && src2 != nullptr && tid < R * 32) {
+      const int oh = oh0 + tid / 32, ow = ow0 + (tid & 31);
+      const bool ok = oh < g.Ho && ow < g.Wo;
+      const uint16_t* sp = ok ? src2 + ((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 8 : src2;
+      cp_async_zfill<16>(xs2 + tid * 8, sp, ok);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_all;\n" ::: "memory");
@@ -532,9 +593,9 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
 
 template <int NT, bool DGRAD>
 static int launch_conv3_k8_mma(const RnConvGeom& g, const void* src, const float* w, void* dst, const void* add, double* stats,
-                               cudaStream_t st) {
+                               cudaStream_t st, const void* src2 = nullptr, const float* w2 = nullptr) {
   constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2;
-  constexpr int SMEM = 3 * HR * MF_XW * 16 + 14 * NT * 32 * 8 + 8 * 16 * 40 * 2 + 64;
+  constexpr int SMEM = 3 * HR * MF_XW * 16 + 14 * NT * 32 * 8 + 8 * 16 * 40 * 2 + 64 + R * 32 * 16;
   auto kern = rn_conv3_k8_mma_kernel<NT, DGRAD>;
   static bool attr = false;
   if (!attr && SMEM > 48 * 1024) {
@@ -545,7 +606,8 @@ static int launch_conv3_k8_mma(const RnConvGeom& g, const void* src, const float
   const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 31) / 32);
   if (ntiles > 0x7fffffffLL) return -6;
   const int blocks = (int)(ntiles < 148 * 4 ? ntiles : 148 * 4);
-  kern<<<blocks, THREADS, SMEM, st>>>(g, (const uint16_t*)src, w, (uint16_t*)dst, (const uint16_t*)add, stats);
+  kern<<<blocks, THREADS, SMEM, st>>>(g, (const uint16_t*)src, w, (uint16_t*)dst, (const uint16_t*)add, stats,
+                                      (const uint16_t*)src2, w2);
   return (int)cudaGetLastError();
 }
 
@@ -1266,7 +1328,8 @@ static bool rn_mma_enabled() {
   return v != 0;
 }
 
-static int launch_conv3_mma_fwd(const RnConvGeom& g, const void* x, const float* w, void* y, double* stats, cudaStream_t st) {
+static int launch_conv3_mma_fwd(const RnConvGeom& g, const void* x, const float* w, void* y, double* stats, cudaStream_t st,
+                                const float* w_ds = nullptr, void* y_ds = nullptr, double* stats_ds = nullptr) {
   static bool attr = false;
   if (!attr) {
     const cudaError_t e = cudaFuncSetAttribute(rn_conv3_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM);
@@ -1276,7 +1339,7 @@ static int launch_conv3_mma_fwd(const RnConvGeom& g, const void* x, const float*
   const long long ntiles = (long long)g.N * g.Do * ((g.Ho + MF_R - 1) / MF_R) * ((g.Wo + 31) / 32);
   if (ntiles > 0x7fffffffLL) return -6;
   const int blocks = (int)(ntiles < 296 ? ntiles : 296);
-  rn_conv3_mma_fwd_kernel<<<blocks, THREADS, MF_SMEM, st>>>(g, (const __half*)x, w, (__half*)y, stats);
+  rn_conv3_mma_fwd_kernel<<<blocks, THREADS, MF_SMEM, st>>>(g, (const __half*)x, w, (__half*)y, stats, w_ds, (__half*)y_ds, stats_ds);
   return (int)cudaGetLastError();
 }
 
@@ -1715,6 +1778,30 @@ int mmnn_rn_conv(const RnConvGeom* g, int dgrad, int src_is_f32, const void* src
   if (k333 && dgrad && g->Cout == 8 && g->Cin == 64 && add == nullptr) return launch_conv3_k8_mma<8, true>(*g, src, w, dst, nullptr, nullptr, st);
   if (dgrad) return dispatch_conv<true>(*g, src_is_f32, src, w, dst, add, stats, st);
   return dispatch_conv<false>(*g, src_is_f32, src, w, dst, add, stats, st);
+}
+
+static bool rn_is_l1_block(const RnConvGeom& g) {
+  return g.Cin == 64 && g.Cout == 8 && g.kd == 3 && g.kh == 3 && g.kw == 3 && g.sd == 1 && g.sh == 1 && g.sw == 1 && g.pd == 1 &&
+         g.ph == 1 && g.pw == 1;
+}
+
+// BasicBlock.conv1 (64 -> 8, 3x3x3) and the block's 1x1x1 stride-1 down-sample convolution on the same input in ONE launch;
+// returns -9 when the geometry is not that pair (the caller then issues two mmnn_rn_conv calls).
+int mmnn_rn_conv_fwd_ds(const RnConvGeom* g, const void* x, const float* w, const float* w_ds, void* y, void* y_ds, double* stats,
+                        double* stats_ds, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!rn_is_l1_block(*g) || !rn_mma_enabled()) return -9;
+  ProfScope ps(PC_RN_FPROP, st);
+  return launch_conv3_mma_fwd(*g, x, w, y, stats, st, w_ds, y_ds, stats_ds);
+}
+
+// dx = dgrad(conv1; dy) + dgrad(down-sample; dy_ds) of the same pair in ONE launch (-9: not that pair).
+int mmnn_rn_conv_dgrad_ds(const RnConvGeom* g, const void* dy, const float* w, const void* dy_ds, const float* w_ds, void* dx,
+                          void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!rn_is_l1_block(*g) || !rn_mma_enabled()) return -9;
+  ProfScope ps(PC_RN_DGRAD, st);
+  return launch_conv3_k8_mma<8, true>(*g, dy, w, dx, nullptr, nullptr, st, dy_ds, w_ds);
 }
 
 int mmnn_rn_conv_wgrad(const RnConvGeom* g, int x_is_f32, const void* x, const void* dy, float* dw, void* stream) {

@@ -69,26 +69,46 @@ class _Unit:
     __slots__ = ("conv", "bn", "x", "x_f32", "g", "raw", "coef", "count")
 
 
-def _conv_bn_forward(conv, bn, x, x_f32, N, dims, training, momentum_default=0.1):
-    lib = L.lib()
+def _new_unit(conv, bn, x, x_f32, N, dims):
     u = _Unit()
     u.conv, u.bn, u.x, u.x_f32 = conv, bn, x, x_f32
     u.g = _geom(conv, N, dims)
     g = u.g
-    dev = x.device
-    Cout = g.Cout
-    u.raw = torch.empty((N, g.Do, g.Ho, g.Wo, Cout), dtype=torch.float16, device=dev)
-    stats = torch.zeros((2 * Cout,), dtype=torch.float64, device=dev)
-    w = conv.weight.detach()
-    L.check(lib.mmnn_rn_conv(C.byref(g), 0, 1 if x_f32 else 0, _p(x), _p(w), _p(u.raw), None, _p(stats), _stream()),
-            "mmnn_rn_conv (forward)")
+    u.raw = torch.empty((N, g.Do, g.Ho, g.Wo, g.Cout), dtype=torch.float16, device=x.device)
     u.count = float(N * g.Do * g.Ho * g.Wo)
+    return u, torch.zeros((2 * g.Cout,), dtype=torch.float64, device=x.device)
+
+
+def _bn_table(u, stats, training, momentum_default=0.1):
+    bn, Cout, dev = u.bn, u.g.Cout, u.raw.device
     u.coef = torch.empty((4, Cout), dtype=torch.float32, device=dev)
     mom = bn.momentum if bn.momentum is not None else momentum_default
-    L.check(lib.mmnn_rn_bn_coeffs(_p(stats), u.count, _p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean),
-                                  _p(bn.running_var), _p(bn.num_batches_tracked), bn.eps, mom, 1 if training else 0, Cout,
-                                  _p(u.coef), _stream()), "mmnn_rn_bn_coeffs")
+    L.check(L.lib().mmnn_rn_bn_coeffs(_p(stats), u.count, _p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean),
+                                      _p(bn.running_var), _p(bn.num_batches_tracked), bn.eps, mom, 1 if training else 0, Cout,
+                                      _p(u.coef), _stream()), "mmnn_rn_bn_coeffs")
     return u
+
+
+def _conv_bn_forward_pair(blk, x, N, dims, training):
+    """conv1 and the 1x1x1 down-sample convolution of a block in one launch when the C ABI has the fused kernel for the
+    geometry (layer1.0: 64 -> 8), else None."""
+    if blk.downsample is None or tuple(blk.downsample[0].stride) != (1, 1, 1):
+        return None
+    u1, st1 = _new_unit(blk.conv1[0], blk.conv1[1], x, False, N, dims)
+    ud, std = _new_unit(blk.downsample[0], blk.downsample[1], x, False, N, dims)
+    rc = L.lib().mmnn_rn_conv_fwd_ds(C.byref(u1.g), _p(x), _p(u1.conv.weight.detach()), _p(ud.conv.weight.detach()), _p(u1.raw),
+                                     _p(ud.raw), _p(st1), _p(std), _stream())
+    if rc == -9:
+        return None
+    L.check(rc, "mmnn_rn_conv_fwd_ds")
+    return _bn_table(u1, st1, training), _bn_table(ud, std, training)
+
+
+def _conv_bn_forward(conv, bn, x, x_f32, N, dims, training):
+    u, stats = _new_unit(conv, bn, x, x_f32, N, dims)
+    L.check(L.lib().mmnn_rn_conv(C.byref(u.g), 0, 1 if x_f32 else 0, _p(x), _p(conv.weight.detach()), _p(u.raw), None, _p(stats),
+                                 _stream()), "mmnn_rn_conv (forward)")
+    return _bn_table(u, stats, training)
 
 
 def _bn_act(u, res_mode, res, coef2, relu, drop_p, seed, mask):
@@ -120,7 +140,8 @@ class _ResnetFn(torch.autograd.Function):
             for li, layer in enumerate((model.layer1, model.layer2, model.layer3, model.layer4)):
                 for bi, blk in enumerate(layer):
                     last = bi == len(layer) - 1
-                    u1 = _conv_bn_forward(blk.conv1[0], blk.conv1[1], a, False, N, dims, training)
+                    pair = _conv_bn_forward_pair(blk, a, N, dims, training)
+                    u1 = pair[0] if pair else _conv_bn_forward(blk.conv1[0], blk.conv1[1], a, False, N, dims, training)
                     a1 = _bn_act(u1, 0, None, None, True, 0.0, 0, None)
                     d1 = (u1.g.Do, u1.g.Ho, u1.g.Wo)
                     u2 = _conv_bn_forward(blk.conv2[0], blk.conv2[1], a1, False, N, d1, training)
@@ -131,7 +152,7 @@ class _ResnetFn(torch.autograd.Function):
                     seed = model._next_seed() if drop > 0 else 0
                     ud = None
                     if blk.downsample is not None:
-                        ud = _conv_bn_forward(blk.downsample[0], blk.downsample[1], a, False, N, dims, training)
+                        ud = pair[1] if pair else _conv_bn_forward(blk.downsample[0], blk.downsample[1], a, False, N, dims, training)
                         y = _bn_act(u2, 2, ud.raw, ud.coef, True, drop, seed, mask)
                     else:
                         y = _bn_act(u2, 1, a, None, True, drop, seed, mask)
@@ -216,10 +237,19 @@ class _ResnetFn(torch.autograd.Function):
                     da1 = F._dgrad(u2, draw2, None)
                     draw1, _, _ = F._bn_backward(u1, da1, a1, 1.0, None, False, grads, training)
                     F._wgrad(u1, draw1, grads)
-                    dx = F._dgrad(u1, draw1, dz)               # + identity-residual gradient when there is no down-sample
                     if ud is not None:
                         F._wgrad(ud, drawd, grads)
-                        dx = F._dgrad(ud, drawd, dx, out=dx)   # accumulate the down-sample branch in place
+                        g1 = u1.g
+                        dx = torch.empty((g1.N, g1.Di, g1.Hi, g1.Wi, g1.Cin), dtype=torch.bfloat16, device=draw1.device)
+                        rc = lib.mmnn_rn_conv_dgrad_ds(C.byref(g1), _p(draw1), _p(u1.conv.weight.detach()), _p(drawd),
+                                                       _p(ud.conv.weight.detach()), _p(dx), _stream())
+                        if rc == -9:                           # no fused kernel for this pair: two launches, second in place
+                            dx = F._dgrad(u1, draw1, None, out=dx)
+                            dx = F._dgrad(ud, drawd, dx, out=dx)
+                        else:
+                            L.check(rc, "mmnn_rn_conv_dgrad_ds")
+                    else:
+                        dx = F._dgrad(u1, draw1, dz)           # + identity-residual gradient
                     dy = dx
                 else:
                     _, u0, a0 = entry

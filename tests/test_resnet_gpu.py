@@ -94,6 +94,51 @@ def test_conv_kernels_match_torch(cin, cout, k, s, p, dims):
     torch.cuda.synchronize()
 
 
+def test_fused_downsample_pair_matches_separate_calls():
+    """mmnn_rn_conv_fwd_ds / mmnn_rn_conv_dgrad_ds (layer1.0: conv1 64 -> 8 3x3x3 + 1x1x1 down-sample on the same input) against
+    the two separate mmnn_rn_conv calls and against torch."""
+    from mmnn_sts_b200 import _lib as L
+    lib = L.lib()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    N, dims = 2, (5, 7, 37)
+    x = torch.randn((N, 64) + dims, generator=g).half().float()
+    w1 = torch.randn((8, 64, 3, 3, 3), generator=g) * 0.1
+    wd = torch.randn((8, 64, 1, 1, 1), generator=g) * 0.3
+    geom = L.RnConvGeom(N, *dims, 64, *dims, 8, 3, 3, 3, 1, 1, 1, 1, 1, 1)
+    x_dev = x.permute(0, 2, 3, 4, 1).contiguous().to(dev).half()
+    y1 = torch.empty((N,) + dims + (8,), dtype=torch.float16, device=dev)
+    yd = torch.empty_like(y1)
+    s1 = torch.zeros(16, dtype=torch.float64, device=dev)
+    sd_ = torch.zeros(16, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    w1d, wdd = w1.to(dev), wd.to(dev)
+    assert lib.mmnn_rn_conv_fwd_ds(C.byref(geom), x_dev.data_ptr(), w1d.data_ptr(), wdd.data_ptr(), y1.data_ptr(), yd.data_ptr(),
+                                   s1.data_ptr(), sd_.data_ptr(), st) == 0
+    r1 = F.conv3d(x, w1, None, 1, 1).permute(0, 2, 3, 4, 1)
+    rd = F.conv3d(x, wd, None, 1, 0).permute(0, 2, 3, 4, 1)
+    assert (y1.float().cpu() - r1).abs().max() <= 2e-3 * r1.abs().max()
+    assert (yd.float().cpu() - rd).abs().max() <= 2e-3 * rd.abs().max()
+    torch.testing.assert_close(sd_[:8], yd.double().sum(dim=(0, 1, 2, 3)), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(sd_[8:], (yd.double() ** 2).sum(dim=(0, 1, 2, 3)), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(s1[:8], y1.double().sum(dim=(0, 1, 2, 3)), rtol=1e-5, atol=1e-4)
+    # data gradient of the pair
+    dy1 = torch.randn((N, 8) + dims, generator=g).bfloat16().float()
+    dyd = torch.randn((N, 8) + dims, generator=g).bfloat16().float()
+    xa = x.clone().requires_grad_(True)
+    (F.conv3d(xa, w1.bfloat16().float(), None, 1, 1) * dy1).sum().backward()
+    (F.conv3d(xa, wd.bfloat16().float(), None, 1, 0) * dyd).sum().backward()
+    dx = torch.empty((N,) + dims + (64,), dtype=torch.bfloat16, device=dev)
+    to_cl = lambda t: t.permute(0, 2, 3, 4, 1).contiguous().to(dev).bfloat16()
+    assert lib.mmnn_rn_conv_dgrad_ds(C.byref(geom), to_cl(dy1).data_ptr(), w1d.data_ptr(), to_cl(dyd).data_ptr(), wdd.data_ptr(),
+                                     dx.data_ptr(), st) == 0
+    ref = xa.grad.permute(0, 2, 3, 4, 1)
+    assert (dx.float().cpu() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    bad = L.RnConvGeom(N, *dims, 64, *dims, 8, 3, 3, 3, 1, 1, 1, 0, 1, 1)
+    assert lib.mmnn_rn_conv_dgrad_ds(C.byref(bad), None, None, None, None, None, st) == -9      # not that pair: caller falls back
+    torch.cuda.synchronize()
+
+
 def _model(dev, sd):
     from mmnn_sts_b200.models.resnet import r3d_18
     m = r3d_18(NUM_CLASSES)
