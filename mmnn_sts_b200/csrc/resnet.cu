@@ -784,10 +784,11 @@ __global__ void __launch_bounds__(THREADS) rn_absmax_kernel(const uint4* __restr
   if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(out, m << 16);       // bf16 magnitude bits -> fp32 bits
 }
 
-template <int CIN, int NTN, int MAXU>
-__global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma16_kernel(const RnConvGeom g, const __half* __restrict__ x,
+template <int CIN, int NTN, int MAXU, int NW>
+__global__ void __launch_bounds__(NW * 32, (NW > 8 ? 1 : 2)) rn_wgrad_mma16_kernel(const RnConvGeom g, const __half* __restrict__ x,
                                                                     const uint16_t* __restrict__ dy, float* __restrict__ dw, int R,
                                                                     const unsigned* __restrict__ amax_bits) {
+  // NW warps per block: 16 for the 14-units-per-warp shape (64 -> 8: 7 units per warp, one 512-thread block per SM)
   constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);
   constexpr int COUT = 8 * NTN, CH8 = CIN / 8, C16 = (CIN >= 16) ? CIN / 16 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -806,7 +807,7 @@ __global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma16_kernel(const RnConv
   float acc[MAXU][NTN][4];
 #pragma unroll
   for (int i = 0; i < MAXU; ++i) {
-    const int u = warp + 8 * i;
+    const int u = warp + NW * i;
     const int uu = (u < nunits) ? u : 0;
     int tap, choff;
     if (CIN >= 16) { tap = uu / C16; choff = (uu % C16) * 16 + (q & 1) * 8; }
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma16_kernel(const RnConv
     decode(tile, n, od, oh0, ow0);
     uint16_t* xb = xs + (size_t)buf * xbuf;
     const int total = nrows * XW * CH8;
-    for (int i = tid; i < total; i += THREADS) {
+    for (int i = tid; i < total; i += NW * 32) {
       const int ch = i % CH8, vp = i / CH8;
       const int r = __float2int_rd(((float)vp + 0.5f) * inv_xw), p = vp - r * XW;
       const int a = __float2int_rd(((float)r + 0.5f) * inv_hrs), hb = r - a * HRs;
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(THREADS, 2) rn_wgrad_mma16_kernel(const RnConv
   const int gq = lane >> 2, t2 = (lane & 3) * 2;
 #pragma unroll
   for (int i = 0; i < MAXU; ++i) {
-    const int u = warp + 8 * i;
+    const int u = warp + NW * i;
     if (u >= nunits) continue;
 #pragma unroll
     for (int hsel = 0; hsel < 2; ++hsel) {
@@ -928,7 +929,7 @@ static bool rn_wgrad16_enabled() {
   return v != 0;
 }
 
-template <int CIN, int NTN, int MAXU>
+template <int CIN, int NTN, int MAXU, int NW = 8>
 static int launch_wgrad_mma16(const RnConvGeom& g, const void* x, const void* dy, float* dw, cudaStream_t st) {
   constexpr int VS = (CIN == 64) ? 72 : ((CIN == 16) ? 24 : 8);
   const int XW = 31 * g.sw + g.kw;
@@ -940,7 +941,7 @@ static int launch_wgrad_mma16(const RnConvGeom& g, const void* x, const void* dy
     if (smem <= 120 * 1024 || R == 1) break;
   }
   if (smem > 220 * 1024) return -8;                         // caller falls back to the converting variant
-  auto kern = rn_wgrad_mma16_kernel<CIN, NTN, MAXU>;
+  auto kern = rn_wgrad_mma16_kernel<CIN, NTN, MAXU, NW>;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -960,9 +961,9 @@ static int launch_wgrad_mma16(const RnConvGeom& g, const void* x, const void* dy
   if (ntiles > 0x7fffffffLL) return -6;
   int bps = (int)((200 * 1024) / (smem + 1024));
   if (bps > 2) bps = 2;                                     // __launch_bounds__(256, 2)
-  if (bps < 1) bps = 1;
+  if (bps < 1 || NW > 8) bps = 1;
   const int blocks = (int)(ntiles < 148LL * bps ? ntiles : 148LL * bps);
-  kern<<<blocks, THREADS, smem, st>>>(g, (const __half*)x, (const uint16_t*)dy, dw, R, slot);
+  kern<<<blocks, NW * 32, smem, st>>>(g, (const __half*)x, (const uint16_t*)dy, dw, R, slot);
   return (int)cudaGetLastError();
 }
 
@@ -976,7 +977,7 @@ static int dispatch_wgrad_mma(const RnConvGeom& g, const void* x, const void* dy
     if (per <= 1) rc = launch_wgrad_mma16<CIN, NTN, 1>(g, x, dy, dw, st);
     else if (per <= 2) rc = launch_wgrad_mma16<CIN, NTN, 2>(g, x, dy, dw, st);
     else if (per <= 4) rc = launch_wgrad_mma16<CIN, NTN, 4>(g, x, dy, dw, st);
-    else if (per <= 14 && NTN == 1) rc = launch_wgrad_mma16<CIN, NTN, (NTN == 1 ? 14 : 4)>(g, x, dy, dw, st);
+    else if (per <= 14 && NTN == 1) rc = launch_wgrad_mma16<CIN, NTN, (NTN == 1 ? 7 : 4), 16>(g, x, dy, dw, st);
     if (rc != -8) return rc;
   }
   if (per <= 1) return launch_wgrad_mma<CIN, NTN, 1>(g, x, dy, dw, st);
