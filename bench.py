@@ -506,14 +506,35 @@ def run_resnet(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def fetch(i):
+        """H2D copy of batch i from pinned memory into staging set i % 2 on the copy stream (overlaps the previous step)."""
+        k = i % 2
+        copy_stream.wait_event(done[k])                         # the step that last read this staging set has finished
+        with torch.cuda.stream(copy_stream):
+            stage[k][0].copy_(host[k][0], non_blocking=True); stage[k][1].copy_(host[k][1], non_blocking=True)
+            ready[k].record(copy_stream)
+
     def timed(n, e2e):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream()
+        for k in range(2):
+            done[k].record(main)
         barrier(); e0.record()
+        if e2e:
+            fetch(0)
         for i in range(n):
             if e2e:
-                s = stage[i % 2]
-                s[0].copy_(host[i % 2][0], non_blocking=True); s[1].copy_(host[i % 2][1], non_blocking=True)
-                step(s[0], s[1]).item()
+                k = i % 2
+                if i + 1 < n:
+                    fetch(i + 1)
+                main.wait_event(ready[k])
+                loss = step(stage[k][0], stage[k][1])
+                done[k].record(main)
+                loss.item()
             else:
                 step(*devb[i % 2])
         e1.record(); barrier()
