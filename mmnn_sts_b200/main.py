@@ -4,6 +4,8 @@
   getCIndices          /root/reference/main.py:106-123   (lifelines concordance_index per class)
   train_survival       /root/reference/main.py:385-601   (SGD nesterov + OneCycleLR, gradient accumulation to 64 samples,
                                                           GradientBlender, per-epoch C-index, validation, weight update)
+  train_classification /root/reference/main.py:125-327   (BCE-with-logits 'sum' loss with pos_weight, SGD nesterov + OneCycleLR stepped
+                                                          every batch, tp / fp / fn -> per-class F1, validation, best-F1 state)
   inference_survival   /root/reference/main.py:750-887   (forward + bootstrap C-index; idiomatic form: every patient is
                                                           forwarded ONCE, resamples are index multisets)
 Data arrives as an iterable of batches `({'image': ..., 'clinical': ...}, events, durations)` -- what the reference's
@@ -141,6 +143,85 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                 blender.updateWeights(c_pred, c_events, c_durations, y_pred, y_events, y_durations)
         if log is not None:
             log(f"epoch {epoch + 1}: train loss {hist.train_loss[-1]:.4f} train C {hist.train_c[-1]}")
+    return hist
+
+
+def train_classification(model, train_batches, val_batches, args, device, grad_sync=None, log=None):
+    """Loop body of /root/reference/main.py:125-327 over iterables of collated batches `(inputs, labels)` -- `inputs` is the image
+    tensor [B, C, D, H, W] (image-only models such as r3d_18, `args.multimodal` False) or the {'image', 'clinical'} dict.
+    args: lr, momentum, weight_decay, epochs, batch_size, blend, blend_update_interval, class_freqs, num_train, multimodal.
+    As in the reference the loss is `BCEWithLogitsLoss(pos_weight=(1 - f) / f)` applied to whatever the model returns (:208 --
+    for r3d_18 that is already a sigmoid score, the reference's own quirk), reduction 'sum' for training and 'none' for
+    validation, the optimiser steps EVERY batch (:210) and the F1 counters threshold `sigmoid(outputs)` (:216-229)."""
+    from .losses.losses import BCEWithLogitsLoss
+    from .utils.utils import criterion
+    model = model.to(device)
+    n_train = args.num_train
+    steps_per_epoch = n_train // args.batch_size if n_train % args.batch_size == 0 else 1 + n_train // args.batch_size
+    pos_weights = classification_pos_weights(torch.as_tensor(args.class_freqs, dtype=torch.float32)).to(device)
+    train_loss_function = BCEWithLogitsLoss(pos_weight=pos_weights, reduction="sum").to(device)
+    loss_function = BCEWithLogitsLoss(pos_weight=pos_weights, reduction="none").to(device)
+    optimizer = SGD(model.parameters(), args.lr, momentum=args.momentum, nesterov=True, weight_decay=args.weight_decay)
+    scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=args.lr, steps_per_epoch=steps_per_epoch, epochs=args.epochs)
+    blender = GradientBlender(loss_function, device=device) if args.blend else None
+    hist = SimpleNamespace(train_loss=[], val_loss=[], train_f1=[], val_f1=[], best_metric=-1.0, best_epoch=-1, best_f1s=None,
+                           best_state=None, blender=blender)
+
+    def to_dev(batch):
+        inputs, labels = batch
+        inputs = {k: v.to(device, non_blocking=True) for k, v in inputs.items()} if isinstance(inputs, dict) else inputs.to(device, non_blocking=True)
+        return inputs, labels.to(device, non_blocking=True)
+
+    def counts(preds01, labels):
+        return torch.stack([((preds01 == 1) & (labels == 1)).sum(0), ((preds01 == 1) & (labels == 0)).sum(0),
+                            ((preds01 == 0) & (labels == 1)).sum(0)])
+
+    for epoch in range(args.epochs):
+        model.train()
+        losses, cnt, tr_preds, tr_gt = [], 0, [], []
+        for batch in list(train_batches):
+            inputs, labels = to_dev(batch)
+            optimizer.zero_grad(set_to_none=True)
+            outputs = model(inputs)
+            loss = blender.computeLoss(outputs, labels) if args.blend else criterion(train_loss_function, outputs, labels, device)
+            loss.backward()
+            if grad_sync is not None:
+                grad_sync(model)
+            optimizer.step()
+            scheduler.step()
+            losses.append(loss.detach())                       # no per-step .item(): one host sync per epoch
+            probs = torch.sigmoid(outputs.detach())
+            if args.blend:
+                tr_preds.append(probs); tr_gt.append(labels)
+                probs = probs[0]
+            cnt = cnt + counts((probs > CLASSIFICATION_THRESHOLD).long(), labels.long())
+        hist.train_f1.append(float(np.mean(getF1Score(cnt[0].cpu(), cnt[1].cpu(), cnt[2].cpu()))))
+        hist.train_loss.append(float(torch.stack(losses).sum()) / n_train)
+        if val_batches is not None:
+            model.eval()
+            with torch.no_grad():
+                vcnt, vloss, nval, va_preds, va_gt = 0, 0.0, 0, [], []
+                for batch in val_batches:
+                    inputs, labels = to_dev(batch)
+                    preds = model(inputs)
+                    loss = blender.computeLoss(preds, labels, no_reduce=True) if args.blend else criterion(loss_function, preds, labels, device)
+                    vloss += float(loss.sum())
+                    p01 = (torch.sigmoid(preds) > CLASSIFICATION_THRESHOLD).long()
+                    if args.blend:
+                        va_preds.append(p01.float()); va_gt.append(labels)
+                        p01 = p01[0]
+                    vcnt = vcnt + counts(p01, labels.long())
+                    nval += labels.shape[0]
+                f1s = np.array(getF1Score(vcnt[0].cpu(), vcnt[1].cpu(), vcnt[2].cpu()))
+                hist.val_f1.append(float(np.mean(f1s)))
+                hist.val_loss.append(vloss / max(1, nval))
+                if hist.val_f1[-1] > hist.best_metric:
+                    hist.best_metric, hist.best_f1s, hist.best_epoch = hist.val_f1[-1], f1s, epoch + 1
+                    hist.best_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            if args.blend and (epoch + 1) % args.blend_update_interval == 0:
+                blender.updateWeights(torch.cat(tr_preds, dim=1), torch.cat(tr_gt), torch.cat(va_preds, dim=1), torch.cat(va_gt))
+        if log is not None:
+            log(f"epoch {epoch + 1}: train loss {hist.train_loss[-1]:.4f} train F1 {hist.train_f1[-1]:.4f}")
     return hist
 
 

@@ -247,3 +247,25 @@ def test_hashed_dropout_statistics():
     y2 = torch.empty_like(raw)
     assert L.lib().mmnn_rn_bn_act(raw.data_ptr(), coef.data_ptr(), 0, None, None, y2.data_ptr(), raw.numel(), Cc, 1, 0.2, 54321, None, st) == 0
     assert 0.6 < ((y > 0) == (y2 > 0)).float().mean().item() < 0.76      # independent masks agree on 0.68 of the elements
+
+
+def test_train_classification_driver_with_resnet():
+    """mmnn_sts_b200.main.train_classification (mirror of /root/reference/main.py:125-327) around r3d_18: image-only, no blend,
+    optimiser step every batch, F1 from the thresholded sigmoid of the outputs; the parameters move, the loss stays finite."""
+    from types import SimpleNamespace
+    from mmnn_sts_b200.main import train_classification
+    from mmnn_sts_b200.models.resnet import r3d_18
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    m = r3d_18(3)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    mk = lambda n: [(torch.rand((4, 1, 8, 32, 32), generator=g), (torch.rand((4, 3), generator=g) < 0.4).float()) for _ in range(n)]
+    args = SimpleNamespace(lr=1e-2, momentum=0.9, weight_decay=1e-4, epochs=2, batch_size=4, blend=False, blend_update_interval=5,
+                           class_freqs=[0.3, 0.4, 0.5], num_train=12, multimodal=False)
+    hist = train_classification(m, mk(3), mk(2), args, dev)
+    assert len(hist.train_loss) == 2 and all(np.isfinite(hist.train_loss)) and all(np.isfinite(hist.val_loss))
+    assert len(hist.val_f1) == 2 and 0.0 <= hist.best_metric <= 1.0 and hist.best_state is not None
+    after = m.state_dict()
+    assert any(not torch.equal(before[k].to(dev), after[k]) for k in before if k.endswith("0.weight"))
+    assert int(after["stem.1.num_batches_tracked"]) == 6
