@@ -444,11 +444,12 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
   constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2, NH = (NT == 1) ? 1 : 4, OC = 8 * NT;
   constexpr int XS_BYTES = 3 * HR * MF_XW * 16, WB_BYTES = 14 * NT * 32 * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);
-  uint2* wb = reinterpret_cast<uint2*>(smem_raw + XS_BYTES);
-  uint16_t* stg = reinterpret_cast<uint16_t*>(smem_raw + XS_BYTES + WB_BYTES);      // NT == 8: [8 warps][16][40]
-  float* sstat = reinterpret_cast<float*>(smem_raw + XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2);
-  uint16_t* xs2 = reinterpret_cast<uint16_t*>(smem_raw + XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2 + 64);   // [R][32][8]
+  constexpr int XS2_BYTES = R * 32 * 16;
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem_raw);                               // [2][3 HR][34][8]: double buffer
+  uint2* wb = reinterpret_cast<uint2*>(smem_raw + 2 * XS_BYTES);
+  uint16_t* stg = reinterpret_cast<uint16_t*>(smem_raw + 2 * XS_BYTES + WB_BYTES);  // NT == 8: [8 warps][16][40]
+  float* sstat = reinterpret_cast<float*>(smem_raw + 2 * XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2);
+  uint16_t* xs2 = reinterpret_cast<uint16_t*>(smem_raw + 2 * XS_BYTES + WB_BYTES + 8 * 16 * 40 * 2 + 64);   // [2][R][32][8]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wCin = g.Cin;                                   // weight tensor is [Cout][Cin][27]
   for (int i = tid; i < 14 * NT * 32; i += THREADS) {
@@ -479,41 +480,56 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
     int a = tap / 9, b = (tap / 3) % 3, c = tap % 3;
     if (DGRAD) { a = 2 - a; b = 2 - b; c = 2 - c; }
     poff[pair] = (uint32_t)((((a * HR + rr + b) * MF_XW + wbase + c + row_l) * 8) * 2);
-    if (DGRAD && src2 != nullptr && 2 * pair + second == 27)
-      poff[pair] = (uint32_t)((xs2 - xs) * 2 + ((rr * 32 + wbase + row_l) * 8) * 2);
   }
+  const bool special = DGRAD && src2 != nullptr && second == 1;       // pair 13, lanes 16-31: the down-sample "tap" in xs2
+  const uint32_t xs2_addr = (uint32_t)__cvta_generic_to_shared(xs2);
+  const uint32_t poff2 = (uint32_t)(((rr * 32 + wbase + row_l) * 8) * 2);
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto stage = [&](int tile, int buf) {
     const int tw = tile % tiles_w;
     int r_ = tile / tiles_w;
     const int th = r_ % tiles_h;
     r_ /= tiles_h;
     const int od = r_ % g.Do, n = r_ / g.Do;
     const int oh0 = th * R, ow0 = tw * 32;
-    __syncthreads();
+    uint16_t* xb = xs + (size_t)buf * (XS_BYTES / 2);
     for (int i = tid; i < 3 * HR * MF_XW; i += THREADS) {
       const int p = i % MF_XW, r = i / MF_XW;
       const int a = r / HR, hb = r % HR;
       const int zd = od - 1 + a, zh = oh0 - 1 + hb, zw = ow0 - 1 + p;
       const bool ok = (unsigned)zd < (unsigned)g.Do && (unsigned)zh < (unsigned)g.Ho && (unsigned)zw < (unsigned)g.Wo;
       const uint16_t* sp = ok ? src + ((((long long)n * g.Do + zd) * g.Ho + zh) * g.Wo + zw) * 8 : src;
-      cp_async_zfill<16>(xs + i * 8, sp, ok);
+      cp_async_zfill<16>(xb + i * 8, sp, ok);
     }
     if (DGRAD && src2 != nullptr && tid < R * 32) {
       const int oh = oh0 + tid / 32, ow = ow0 + (tid & 31);
       const bool ok = oh < g.Ho && ow < g.Wo;
       const uint16_t* sp = ok ? src2 + ((((long long)n * g.Do + od) * g.Ho + oh) * g.Wo + ow) * 8 : src2;
-      cp_async_zfill<16>(xs2 + tid * 8, sp, ok);
+      cp_async_zfill<16>(xs2 + (size_t)buf * (XS2_BYTES / 2) + tid * 8, sp, ok);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int tw = tile % tiles_w;
+    int r_ = tile / tiles_w;
+    const int th = r_ % tiles_h;
+    r_ /= tiles_h;
+    const int od = r_ % g.Do, n = r_ / g.Do;
+    const int oh0 = th * R, ow0 = tw * 32;
     asm volatile("cp.async.wait_all;\n" ::: "memory");
-    __syncthreads();
+    __syncthreads();                                        // tile `buf` has landed; everyone is done reading buffer buf ^ 1
+    if (tile + (int)gridDim.x < ntiles) stage(tile + gridDim.x, buf ^ 1);   // next tile streams in behind the MMAs
+    const uint32_t xbase = xs_addr + (uint32_t)(buf * XS_BYTES);
+    const uint32_t x2base = xs2_addr + (uint32_t)(buf * XS2_BYTES) + poff2;
     float acc[NH][4];
 #pragma unroll
     for (int j = 0; j < NH; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
 #pragma unroll
     for (int pair = 0; pair < 14; ++pair) {
-      const uint32_t aaddr = xs_addr + poff[pair];
+      const uint32_t aaddr = (pair == 13 && special) ? x2base : xbase + poff[pair];
       uint32_t a0, a1, a2, a3;
       asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                    : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(aaddr));
@@ -595,7 +611,7 @@ template <int NT, bool DGRAD>
 static int launch_conv3_k8_mma(const RnConvGeom& g, const void* src, const float* w, void* dst, const void* add, double* stats,
                                cudaStream_t st, const void* src2 = nullptr, const float* w2 = nullptr) {
   constexpr int R = (NT == 1) ? 4 : 2, HR = R + 2;
-  constexpr int SMEM = 3 * HR * MF_XW * 16 + 14 * NT * 32 * 8 + 8 * 16 * 40 * 2 + 64 + R * 32 * 16;
+  constexpr int SMEM = 2 * 3 * HR * MF_XW * 16 + 14 * NT * 32 * 8 + 8 * 16 * 40 * 2 + 64 + 2 * R * 32 * 16;
   auto kern = rn_conv3_k8_mma_kernel<NT, DGRAD>;
   static bool attr = false;
   if (!attr && SMEM > 48 * 1024) {
