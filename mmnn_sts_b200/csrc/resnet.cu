@@ -1641,11 +1641,27 @@ __global__ void __launch_bounds__(THREADS) rn_act_bwd_reduce_kernel(const uint4*
       if (TWO) s2[k] = fmaf(dz, (x2[k] - mean2[k]) * rstd2[k], s2[k]);
     }
   }
+  // lanes l and l ^ off own the same 8 channels when 8 * off is a multiple of C: reduce those in registers first, so that
+  // only C / 8 lanes per warp touch shared memory (ncu: the 6 144 same-address shared atomics of the first version showed
+  // as short-scoreboard 11 / barrier 3.8 stall cycles per issue)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sm[c0 + k], s0[k]);
-    atomicAdd(&sm[C + c0 + k], s1[k]);
-    if (TWO) atomicAdd(&sm[2 * C + c0 + k], s2[k]);
+  for (int off = 16; off > 0; off >>= 1) {
+    if ((off * 8) % C == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], off);
+        s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], off);
+        if (TWO) s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], off);
+      }
+    }
+  }
+  if ((threadIdx.x & 31) < C / 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm[c0 + k], s0[k]);
+      atomicAdd(&sm[C + c0 + k], s1[k]);
+      if (TWO) atomicAdd(&sm[2 * C + c0 + k], s2[k]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < (TWO ? 3 : 2) * C; i += THREADS) atomicAdd(&sums[i], (double)sm[i]);
