@@ -105,18 +105,20 @@ __global__ void __launch_bounds__(THREADS) rn_conv_kernel(const RnConvGeom g, co
     float acc[CT];
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[c] = 0.f;
-    for (int a = 0; a < g.kd; ++a) {
+    // data gradient: only the taps congruent to (o + p) modulo the stride reach an integer source coordinate, so the tap loops
+    // start there and step by the stride (a stride-2 3x3x3 gather visits ~3.4 taps instead of testing 27)
+    for (int a = DGRAD ? (od + g.pd) % g.sd : 0; a < g.kd; a += DGRAD ? g.sd : 1) {
       int zd;
       if (!DGRAD) { zd = od * g.sd - g.pd + a; if ((unsigned)zd >= (unsigned)ID) continue; }
-      else { const int q = od + g.pd - a; if (q < 0) continue; zd = q / g.sd; if (zd * g.sd != q || zd >= ID) continue; }
-      for (int b = 0; b < g.kh; ++b) {
+      else { const int q = od + g.pd - a; if (q < 0) continue; zd = q / g.sd; if (zd >= ID) continue; }
+      for (int b = DGRAD ? (oh + g.ph) % g.sh : 0; b < g.kh; b += DGRAD ? g.sh : 1) {
         int zh;
         if (!DGRAD) { zh = oh * g.sh - g.ph + b; if ((unsigned)zh >= (unsigned)IH) continue; }
-        else { const int q = oh + g.ph - b; if (q < 0) continue; zh = q / g.sh; if (zh * g.sh != q || zh >= IH) continue; }
-        for (int c = 0; c < g.kw; ++c) {
+        else { const int q = oh + g.ph - b; if (q < 0) continue; zh = q / g.sh; if (zh >= IH) continue; }
+        for (int c = DGRAD ? (ow + g.pw) % g.sw : 0; c < g.kw; c += DGRAD ? g.sw : 1) {
           int zw;
           if (!DGRAD) { zw = ow * g.sw - g.pw + c; if ((unsigned)zw >= (unsigned)IW) continue; }
-          else { const int q = ow + g.pw - c; if (q < 0) continue; zw = q / g.sw; if (zw * g.sw != q || zw >= IW) continue; }
+          else { const int q = ow + g.pw - c; if (q < 0) continue; zw = q / g.sw; if (zw >= IW) continue; }
           const TIN* px = src + ((((long long)n * ID + zd) * IH + zh) * IW + zw) * KC;
           const float* pw = ws + ((a * g.kh + b) * g.kw + c) * (KC * CT);
           if constexpr (std::is_same<TIN, float>::value) {
