@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(THREADS) rn_absmax_kernel(const uint4* __restr
 }
 
 template <int CIN, int NTN, int MAXU, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW > 8 ? 1 : 2)) rn_wgrad_mma16_kernel(const RnConvGeom g, const __half* __restrict__ x,
+__global__ void __launch_bounds__(NW * 32, (NW > 8 ? 1 : (MAXU * NTN <= 4 ? 4 : 2))) rn_wgrad_mma16_kernel(const RnConvGeom g, const __half* __restrict__ x,
                                                                     const uint16_t* __restrict__ dy, float* __restrict__ dw, int R,
                                                                     const unsigned* __restrict__ amax_bits) {
   // NW warps per block: 16 for the 14-units-per-warp shape (64 -> 8: 7 units per warp, one 512-thread block per SM)
@@ -978,7 +978,8 @@ static int launch_wgrad_mma16(const RnConvGeom& g, const void* x, const void* dy
   const long long ntiles = (long long)g.N * g.Do * ((g.Ho + R - 1) / R) * ((g.Wo + 31) / 32);
   if (ntiles > 0x7fffffffLL) return -6;
   int bps = (int)((200 * 1024) / (smem + 1024));
-  if (bps > 2) bps = 2;                                     // __launch_bounds__(256, 2)
+  const int bmax = (MAXU * NTN <= 4) ? 4 : 2;               // matches __launch_bounds__
+  if (bps > bmax) bps = bmax;
   if (bps < 1 || NW > 8) bps = 1;
   const int blocks = (int)(ntiles < 148LL * bps ? ntiles : 148LL * bps);
   kern<<<blocks, NW * 32, smem, st>>>(g, (const __half*)x, (const uint16_t*)dy, dw, R, slot);
