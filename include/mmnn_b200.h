@@ -145,7 +145,9 @@ int mmnn_preprocess_volumes(const float* src, float* dst, void* scratch, int B, 
  *                       stats = fp64 [2][Cout] sum / sum of squares of the stored output, zero-initialised, or NULL) or its
  *                       data gradient (dgrad 1: src = output gradient, dst = input gradient, `add` = optional tensor summed in:
  *                       the identity-residual gradient of BasicBlock.forward :83-95, may alias dst).  w fp32 [Cout][Cin][taps].
- * mmnn_rn_conv_wgrad  : dw [Cout][Cin][taps] += x (*) dy (fp32 atomics, zero-initialise for a fresh gradient).
+ * mmnn_rn_conv_wgrad  : dw [Cout][Cin][taps] += x (*) dy (fp32 atomics, zero-initialise for a fresh gradient).  The fp16 tensor-core
+ *                       variant first reduces max|dy| into ONE device-global scratch word (no allocation, no host sync): calls
+ *                       on different streams of one device must not overlap (MMNN_RN_WGRAD16=0 selects the variant without it).
  * mmnn_rn_bn_coeffs   : nn.BatchNorm3d coefficient table coef fp32 [4][C] = scale, shift, mean, rstd from the batch statistics
  *                       (training: also the running-statistics update, momentum, unbiased variance) or the running ones.
  * mmnn_rn_bn_act      : y = [relu](raw * scale + shift [+ res (res_mode 1) | + res * scale2 + shift2 (res_mode 2)]), then
