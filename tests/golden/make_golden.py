@@ -63,7 +63,16 @@ def inject_masks(mm, masks):
     cm.features.drop5 = _MaskedDropout(masks["mlp"][5][:, None])
 
 
-def run_case(ns, name, *, seed_w, seed_x, batch, in_channels, spatial, blend, training, dropout, tie_free=True):
+GSUB_MAX = 2048   # per-tensor gradient subsample kept for EVERY parameter (cfg2-scale cases): strided, deterministic
+
+
+def gsub_index(numel):
+    """Indices of the per-tensor gradient subsample: every ceil(numel / GSUB_MAX)-th element."""
+    stride = max(1, -(-numel // GSUB_MAX))
+    return np.arange(0, numel, stride)
+
+
+def run_case(ns, name, *, seed_w, seed_x, batch, in_channels, spatial, blend, training, dropout, tie_free=True, gsub=False):
     sd = synth.make_state_dict(seed_w, in_channels=in_channels)
     mm = build_reference(ns, in_channels, blend, 0.2 if dropout else 0.0, sd)
     image, clinical, events, durations = synth.make_batch(seed_x, batch, in_channels, spatial, tie_free=tie_free)
@@ -95,6 +104,11 @@ def run_case(ns, name, *, seed_w, seed_x, batch, in_channels, spatial, blend, tr
             norms.append(float("nan") if p.grad is None else float(p.grad.double().norm()))
             if k in KEEP_FULL and p.grad is not None:
                 res["grad:" + k] = p.grad.numpy()
+        if gsub:
+            # a strided subsample of EVERY parameter gradient, concatenated in named_parameters() order (tensors the
+            # reference leaves without a gradient contribute nothing): per-tensor cosine / rel-L2 checks at configs[1] scale
+            res["gsub"] = np.concatenate([p.grad.flatten().numpy()[gsub_index(p.numel())] for _, p in mm.named_parameters()
+                                          if p.grad is not None]).astype(np.float32)
         res["grad_norms"] = np.array(norms)
         res["param_names"] = np.array(names)
         new_sd = mm.state_dict()
@@ -154,6 +168,11 @@ def kats(ns):
 
 if __name__ == "__main__":
     ns = shim.load_reference()
+    if "--cfg2" in sys.argv:
+        # BASELINE configs[1] itself: B 16, 2x128x128x64, --blend, dropout 0.2 (injected masks). ~1 min and ~15 GB on 8 cores.
+        run_case(ns, "cfg2_train", seed_w=42, seed_x=11, batch=16, in_channels=2, spatial=(128, 128, 64), blend=True, training=True, dropout=True, gsub=True)
+        run_case(ns, "cfg2_eval", seed_w=42, seed_x=12, batch=4, in_channels=2, spatial=(128, 128, 64), blend=True, training=False, dropout=False)
+        sys.exit(0)
     kats(ns)
     # every case keeps >= 12 samples per BatchNorm channel in the last dense block: with fewer (e.g. 32^3 inputs, one
     # voxel per sample in block 4) batch statistics over 2-4 values make outputs and gradients ill-conditioned in ANY
