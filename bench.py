@@ -197,7 +197,8 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     L.lib()
     model = build_model(wl, device)
-    opt = SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4)   # one-launch torch.optim.SGD subclass
+    opt = SGD(model.parameters(), 5e-4, momentum=0.9, nesterov=True, weight_decay=1e-4,
+              capturable=bool(getattr(args, 'graph', False)))   # one-launch torch.optim.SGD subclass
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion)
     sync = D.GradientAllReducer(model.parameters(), model=model)
     dev_batches = make_batches(wl, 2, device=device, seed=1234 + 100 * rank)

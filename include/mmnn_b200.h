@@ -38,10 +38,11 @@ int mmnn_encoder_debug_offsets(void* plan, int B, int X, int Y, int Z, long long
 int mmnn_encoder_forward(void* plan, int B, int X, int Y, int Z, const float* image, const void* const* params /*HOST*/,
                          void* const* buffers /*HOST*/, const float* dropmask, void* workspace, float* out, int training,
                          void* stream);
-/* grad_out fp32 [B*d*h*w][C];  grads: zero-initialised fp32 tensors shaped like the parameters */
+/* grad_out fp32 [B*d*h*w][C];  grads: zero-initialised fp32 tensors shaped like the parameters;  training: the mode of the
+ * forward pass that filled `workspace` (batch-statistic or running-statistic BatchNorm is differentiated accordingly) */
 int mmnn_encoder_backward(void* plan, int B, int X, int Y, int Z, const void* const* params /*HOST*/,
                           void* const* buffers /*HOST*/, void* const* grads /*HOST*/, const float* dropmask, void* workspace,
-                          const float* grad_out, void* stream);
+                          const float* grad_out, int training, void* stream);
 
 /* Gradient groups for data-parallel overlap (all-reduce overlapped with backward).  Backward
  * finalises the gradients block by block, last block first; group k = dense block (nblocks-1-k) with the transition
@@ -125,6 +126,12 @@ int mmnn_bce_logits(const float* x, const float* y, const float* pos_weight, lon
 int mmnn_sgd_step(void* const* p /*HOST*/, const void* const* g /*HOST*/, void* const* m /*HOST*/,
                   const long long* n /*HOST*/, int ntensors, float lr, float momentum, float weight_decay, int nesterov,
                   void* stream);
+/* Same update with {lr, momentum, weight_decay} read from DEVICE memory (float[3]) when the kernel runs: a step captured in a
+ * CUDA graph then follows OneCycleLR (which cycles lr and momentum after every optimiser step, /root/reference/main.py:414,480)
+ * -- the host rewrites the three floats in place between replays. */
+int mmnn_sgd_step_dev(void* const* p /*HOST*/, const void* const* g /*HOST*/, void* const* m /*HOST*/,
+                      const long long* n /*HOST*/, int ntensors, const float* hyper /*DEVICE float[3]*/, int nesterov,
+                      void* stream);
 int mmnn_sgd_chunk_elems(void);
 int mmnn_sgd_max_tensors(void);
 

@@ -139,7 +139,7 @@ def _declare(l):
     l.mmnn_encoder_out_dims.restype = I
     l.mmnn_encoder_forward.argtypes = [VP, I, I, I, I, VP, C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
     l.mmnn_encoder_forward.restype = I
-    l.mmnn_encoder_backward.argtypes = [VP, I, I, I, I, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), VP, VP, VP, VP]
+    l.mmnn_encoder_backward.argtypes = [VP, I, I, I, I, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
     l.mmnn_encoder_backward.restype = I
     l.mmnn_encoder_num_grad_groups.argtypes = [VP]
     l.mmnn_encoder_num_grad_groups.restype = I
@@ -160,6 +160,8 @@ def _declare(l):
         assert getattr(l, nm)() == C.sizeof(st), (nm, getattr(l, nm)(), C.sizeof(st))
     l.mmnn_sgd_step.argtypes = [C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), C.POINTER(LL), I, C.c_float, C.c_float, C.c_float, I, VP]
     l.mmnn_sgd_step.restype = I
+    l.mmnn_sgd_step_dev.argtypes = [C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), C.POINTER(LL), I, VP, I, VP]
+    l.mmnn_sgd_step_dev.restype = I
     l.mmnn_sgd_chunk_elems.restype = I
     l.mmnn_sgd_max_tensors.restype = I
     l.mmnn_bce_logits.argtypes = [VP, VP, VP, LL, I, LL, VP, VP, C.c_float, LL, VP, VP]

@@ -40,7 +40,11 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(compile_one, zip(srcs, objs)))
     if force or _newer(objs, OUT):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # the CUDA runtime is linked DYNAMICALLY: the process already holds libcudart.so.12 (torch loads its own copy before this
+        # library is opened), and a statically linked runtime would embed every runtime entry point's name -- including calls
+        # this code base never makes -- as strings in the shipped binary
+        cmd = [nvcc, "-shared", "--cudart", "shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                                              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -253,7 +253,7 @@ int mmnn_sizeof_pack_desc() { return (int)sizeof(PackDesc); }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------------
-// tcgen05.mma issue-rate microbenchmark (instrumentation; tests/microbench_mma.py): one CTA, one elected thread issues
+// tcgen05.mma issue-rate microbenchmark (instrumentation; profiles/scripts/microbench_mma.py): one CTA, one elected thread issues
 // `iters` back-to-back MMAs  D[128 x N] += A[128 x 16] * B[N x 16]  from fixed shared-memory operands and commits; the
 // elapsed SM clock cycles between the first issue and the arrival of the commit are written to out[0].
 // layout 0: SWIZZLE_NONE core matrices (LBO = plane stride, SBO = 128 B), 6: SWIZZLE_32B rows of 32 B (SBO = 256 B).

@@ -77,11 +77,17 @@ struct Plan {
   // state free of pageable host->device copies (which synchronise the stream and cannot be graph-captured)
   std::vector<uint8_t> cache[4];
   const void* cache_dst[4] = {nullptr, nullptr, nullptr, nullptr};
-  void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t pinned_bytes[4] = {0, 0, 0, 0};
+  // pinned staging of the table uploads: a ring of STAGE_RING buffers per slot, each guarded by an event recorded right
+  // after its copy was enqueued -- two workspaces used alternately (their tables differ) never overwrite the source of a
+  // copy that has not executed yet
+  static constexpr int STAGE_RING = 4;
+  void* pinned[4][STAGE_RING] = {};
+  size_t pinned_bytes[4][STAGE_RING] = {};
+  cudaEvent_t pinned_ev[4][STAGE_RING] = {};
+  bool pinned_used[4][STAGE_RING] = {};
+  int pinned_next[4] = {0, 0, 0, 0};
   // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
   // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
-  bool fwd_training = true;   // mode of the most recent forward: backward must differentiate the SAME BatchNorm (batch or running statistics)
   cudaStream_t side = nullptr;
   // Gradient groups, in the order backward finalises them: group k = dense block nb-1-k with the transition that
   // follows it (the last block's group also holds norm5), group nb = the stem (conv0, norm0).  Each group is a
@@ -105,15 +111,26 @@ int upload_table(Plan* pl, int slot, void* dst, const void* src, size_t bytes, c
   if (pl->cache_dst[slot] == dst && c.size() == bytes && memcmp(c.data(), src, bytes) == 0) return 0;
   // the copy is sourced from a pinned staging buffer owned by the plan: asynchronous, and still valid if the copy was
   // captured into a CUDA graph and is replayed later
-  if (pl->pinned[slot] == nullptr || pl->pinned_bytes[slot] < bytes) {
-    if (pl->pinned[slot] != nullptr) cudaFreeHost(pl->pinned[slot]);
+  const int r = pl->pinned_next[slot];
+  pl->pinned_next[slot] = (r + 1) % Plan::STAGE_RING;
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap_status);
+  const bool capturing = cap_status != cudaStreamCaptureStatusNone;
+  if (pl->pinned_used[slot][r] && !capturing) cudaEventSynchronize(pl->pinned_ev[slot][r]);   // the copy that last read this buffer has run
+  if (pl->pinned[slot][r] == nullptr || pl->pinned_bytes[slot][r] < bytes) {
+    if (pl->pinned[slot][r] != nullptr) cudaFreeHost(pl->pinned[slot][r]);
     const size_t cap = bytes < (1u << 16) ? (1u << 16) : bytes;
-    if (cudaMallocHost(&pl->pinned[slot], cap) != cudaSuccess) return -20;
-    pl->pinned_bytes[slot] = cap;
+    if (cudaMallocHost(&pl->pinned[slot][r], cap) != cudaSuccess) return -20;
+    pl->pinned_bytes[slot][r] = cap;
   }
-  memcpy(pl->pinned[slot], src, bytes);
-  cudaError_t e = cudaMemcpyAsync(dst, pl->pinned[slot], bytes, cudaMemcpyHostToDevice, st);
+  memcpy(pl->pinned[slot][r], src, bytes);
+  cudaError_t e = cudaMemcpyAsync(dst, pl->pinned[slot][r], bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return (int)e;
+  if (!capturing) {
+    if (pl->pinned_ev[slot][r] == nullptr) cudaEventCreateWithFlags(&pl->pinned_ev[slot][r], cudaEventDisableTiming);
+    cudaEventRecord(pl->pinned_ev[slot][r], st);
+    pl->pinned_used[slot][r] = true;
+  }
   c.assign((const uint8_t*)src, (const uint8_t*)src + bytes);
   pl->cache_dst[slot] = dst;
   return 0;
@@ -373,7 +390,6 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
   double* fstats = (double*)(ws + g.fstats);
   const int FC = pl->fwd_channels;
   const bool batch = training != 0;
-  pl->fwd_training = batch;
   bf16* packed = (bf16*)(ws + g.packed);
   const int nb = (int)pl->blocks.size();
 
@@ -545,7 +561,7 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
 // grads   : device pointers (param order) of ZERO-INITIALISED fp32 tensors shaped like the parameters
 int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const* params, void* const* buffers,
                           void* const* grads, const float* dropmask, void* workspace, const float* grad_out,
-                          void* stream_) {
+                          int training, void* stream_) {
   Plan* pl = (Plan*)h;
   cudaStream_t st = (cudaStream_t)stream_;
   Geo g;
@@ -557,7 +573,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   // Eval-mode backward (GradCAM, frozen-BN fine-tuning): BatchNorm is the fixed affine map of its running statistics, so the
   // masks use those and the batch-statistic terms of the BN gradient vanish (inv_count = 0 -> c1 = c2 = 0); the statistics
   // the epilogues still accumulate are then exactly d(gamma) = sum dy*xhat and d(beta) = sum dy.
-  const bool batch = pl->fwd_training;
+  const bool batch = training != 0;   // mode of the forward pass that filled this workspace (passed per call)
   bf16* packed = (bf16*)(ws + g.packed);
   const int nb = (int)pl->blocks.size();
   auto gsum = [&](const BnInfo& bn) { return bstats + bn.bwd_off; };

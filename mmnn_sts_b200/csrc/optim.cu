@@ -25,8 +25,13 @@ __device__ __forceinline__ void sgd_one(float& p, float g, float& m, float lr, f
   p = fmaf(-lr, s, p);
 }
 
+// hyper != nullptr: lr / momentum / weight decay are read from DEVICE memory ({lr, mu, wd}) at run time, so a step captured
+// in a CUDA graph follows a schedule (OneCycleLR cycles lr AND momentum every optimiser step, /root/reference/main.py:414)
+// that the host updates in place between replays; otherwise the launch-time scalars are used.
 __global__ void __launch_bounds__(SGD_THREADS) sgd_step_kernel(const __grid_constant__ SgdTable tab, int ntensors,
-                                                               float lr, float mu, float wd, int nesterov) {
+                                                               float lr, float mu, float wd, int nesterov,
+                                                               const float* __restrict__ hyper) {
+  if (hyper != nullptr) { lr = hyper[0]; mu = hyper[1]; wd = hyper[2]; }
   // the tensor owning this block's chunk: last entry with first_chunk <= blockIdx.x
   int lo_t = 0, hi_t = ntensors - 1;
   while (lo_t < hi_t) {
@@ -69,8 +74,8 @@ extern "C" {
 int mmnn_sgd_chunk_elems() { return mmnn::SGD_CHUNK; }
 int mmnn_sgd_max_tensors() { return mmnn::SGD_MAX_TENSORS; }
 // p / g / m: HOST arrays of device pointers (parameter, gradient, momentum buffer), n: HOST array of element counts
-int mmnn_sgd_step(void* const* p, const void* const* g, void* const* m, const long long* n, int ntensors, float lr,
-                  float momentum, float weight_decay, int nesterov, void* stream) {
+static int sgd_step_impl(void* const* p, const void* const* g, void* const* m, const long long* n, int ntensors, float lr,
+                         float momentum, float weight_decay, int nesterov, const float* hyper, void* stream) {
   using namespace mmnn;
   for (int base = 0; base < ntensors; base += SGD_MAX_TENSORS) {
     const int cnt = ntensors - base < SGD_MAX_TENSORS ? ntensors - base : SGD_MAX_TENSORS;
@@ -83,10 +88,20 @@ int mmnn_sgd_step(void* const* p, const void* const* g, void* const* m, const lo
       chunks += (int)((n[base + i] + SGD_CHUNK - 1) / SGD_CHUNK);
     }
     ProfScope ps(PC_SGD, (cudaStream_t)stream);
-    sgd_step_kernel<<<chunks, SGD_THREADS, 0, (cudaStream_t)stream>>>(tab, cnt, lr, momentum, weight_decay, nesterov);
+    sgd_step_kernel<<<chunks, SGD_THREADS, 0, (cudaStream_t)stream>>>(tab, cnt, lr, momentum, weight_decay, nesterov, hyper);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   return 0;
+}
+int mmnn_sgd_step(void* const* p, const void* const* g, void* const* m, const long long* n, int ntensors, float lr,
+                  float momentum, float weight_decay, int nesterov, void* stream) {
+  return sgd_step_impl(p, g, m, n, ntensors, lr, momentum, weight_decay, nesterov, nullptr, stream);
+}
+// hyper: DEVICE float[3] = {lr, momentum, weight_decay}, read by the kernel when it RUNS (CUDA-graph replays included)
+int mmnn_sgd_step_dev(void* const* p, const void* const* g, void* const* m, const long long* n, int ntensors,
+                      const float* hyper, int nesterov, void* stream) {
+  if (hyper == nullptr) return -2;
+  return sgd_step_impl(p, g, m, n, ntensors, 0.f, 0.f, 0.f, nesterov, hyper, stream);
 }
 }

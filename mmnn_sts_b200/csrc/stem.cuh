@@ -66,7 +66,7 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
   const int ntiles = p.B * p.D0 * tiles_y * tiles_x;
   const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // (rotating over NACC > 1 accumulators per tile, summed by the epilogue, was measured: no gain -- back-to-back MMAs
-  // into one accumulator already run at the operand-fetch rate, tests/microbench_mma.py)
+  // into one accumulator already run at the operand-fetch rate, profiles/scripts/microbench_mma.py)
   constexpr int NACC = 1;
   constexpr uint32_t TMEM_COLS = 2 * NACC * 64;
 

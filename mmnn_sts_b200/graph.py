@@ -9,9 +9,21 @@ import torch
 
 class GraphedTrainStep:
     """step_fn(image, clinical, events, durations) -> loss tensor; must do backward + optimizer.step + zero_grad itself.
-    Inputs are copied into static buffers before each replay; the returned loss is a static tensor."""
+    Inputs are copied into static buffers before each replay; the returned loss is a static tensor.
 
-    def __init__(self, step_fn, example_batch, warmup=3):
+    What a replay re-reads and what it does not: kernel ARGUMENTS (scalars, pointers) are frozen at capture time, device
+    MEMORY is read afresh.  Hence
+      * `optimizer` (optional): must be `mmnn_sts_b200.optim.SGD(capturable=True)`, whose lr / momentum / weight decay live in
+        device memory; `__call__` refreshes them from `param_groups` before every replay, so a scheduler stepped between
+        replays (OneCycleLR after each optimiser step, /root/reference/main.py:414,480) takes effect.  A torch optimizer or a
+        non-capturable SGD is refused here rather than replayed with stale hyper-parameters;
+      * `GradientBlender.updateWeights` updates its device weight tensor in place, so captured steps see the new weights."""
+
+    def __init__(self, step_fn, example_batch, warmup=3, optimizer=None):
+        if optimizer is not None and not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedTrainStep needs an optimizer whose hyper-parameters live in device memory "
+                             "(mmnn_sts_b200.optim.SGD(..., capturable=True)); scalar lr / momentum would be frozen at capture time")
+        self.optimizer = optimizer
         self.static = [t.clone() for t in example_batch]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -27,5 +39,7 @@ class GraphedTrainStep:
     def __call__(self, image, clinical, events, durations):
         for dst, src in zip(self.static, (image, clinical, events, durations)):
             dst.copy_(src, non_blocking=True)
+        if self.optimizer is not None:
+            self.optimizer.refresh_hyper()
         self.graph.replay()
         return self.loss

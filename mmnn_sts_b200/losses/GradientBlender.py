@@ -19,6 +19,17 @@ class GradientBlender:
         self.surv_criterion = surv_criterion
         self.history = []
 
+    def _set_weights(self, new):
+        """New blending weights.  Once the weights live on the device they are updated IN PLACE: a training step captured
+        in a CUDA graph (mmnn_sts_b200.graph) keeps reading this tensor's storage, so rebinding it would freeze the
+        replayed step at the weights of capture time."""
+        new = new.detach()
+        w = self.weights
+        if w is not None and w.is_cuda and w.shape == new.shape:
+            w.copy_(new.to(device=w.device, dtype=w.dtype))
+        else:
+            self.weights = new
+
     # ---- survival
     def _head_losses(self, preds, events, durations):
         from .losses import CoxPH, _coxph_columns
@@ -43,13 +54,13 @@ class GradientBlender:
         train_loss = self.computeLossSurv(train_preds, train_events, train_durations, reduceToHeads=True).detach()
         val_loss = self.computeLossSurv(val_preds, val_events, val_durations, reduceToHeads=True).detach()
         if self.lvn is None or self.ltn is None:
-            self.weights = self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device))
+            self._set_weights(self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device)))
         else:
             o_n = self.lvn - self.ltn
             o_npn = val_loss - train_loss
             delta_g = self.lvn - val_loss
             delta_o = o_npn - o_n
-            self.weights = self.normalize(delta_g / torch.pow(delta_o, 2))
+            self._set_weights(self.normalize(delta_g / torch.pow(delta_o, 2)))
         self.lvn, self.ltn = val_loss, train_loss
         self.history.append(self.weights.detach().cpu().numpy())
 
@@ -74,13 +85,13 @@ class GradientBlender:
         train_loss = self.computeLossClassification(train_preds, train_targs, reduceToHeads=True).detach()
         val_loss = self.computeLossClassification(val_preds, val_targs, reduceToHeads=True).detach()
         if self.lvn is None or self.ltn is None:
-            self.weights = self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device))
+            self._set_weights(self.normalize(torch.ones(train_preds.shape[0], device=train_loss.device)))
         else:
             o_n = self.lvn - self.ltn
             o_npn = val_loss - train_loss
             delta_g = val_loss - self.lvn            # sign as in the reference's classification branch (:128)
             delta_o = o_npn - o_n
-            self.weights = self.normalize(delta_g / torch.pow(delta_o, 2))
+            self._set_weights(self.normalize(delta_g / torch.pow(delta_o, 2)))
         self.lvn, self.ltn = val_loss, train_loss
 
     def reduceToHeads(self, loss):

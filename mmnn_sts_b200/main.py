@@ -76,6 +76,20 @@ def bootstrap_cindices(preds, events, durations, resample_indices, num_classes=N
     return c, c[ok].mean(axis=0), c[ok].std(axis=0), counts
 
 
+def _with_last_flag(iterable):
+    """(item, is_last) pairs of one pass over `iterable` without materialising it: a DataLoader with shuffle=True is
+    re-iterated (and reshuffled) every epoch, and an epoch of 3-D volumes is never held in host memory at once."""
+    it = iter(iterable)
+    try:
+        prev = next(it)
+    except StopIteration:
+        return
+    for cur in it:
+        yield prev, False
+        prev = cur
+    yield prev, True
+
+
 def _to_device(batch, device):
     inputs, events, durations = batch
     inputs = {k: v.to(device, non_blocking=True) for k, v in inputs.items()}
@@ -95,9 +109,8 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
     hist = SimpleNamespace(train_loss=[], val_loss=[], train_c=[], val_c=[], best_loss=math.inf, best_state=None, blender=blender)
     for epoch in range(args.epochs):
         model.train()
-        train_batches = list(train_batches)
         losses, c_pred, c_events, c_durations = [], [], [], []
-        for i, batch in enumerate(train_batches):
+        for i, (batch, is_last) in enumerate(_with_last_flag(train_batches)):
             inputs, events, durations = _to_device(batch, device)
             outputs = model(inputs)
             if args.blend:
@@ -108,13 +121,15 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                 grad_sync.arm()                     # no accumulation: the trunk's gradient groups are all-reduced during backward
             loss.backward()
             losses.append(loss.detach())            # no per-step .item(): one sync per epoch instead of one per step
-            if (i + 1) % super_batch_interval == 0 or i == len(train_batches) - 1:
+            if (i + 1) % super_batch_interval == 0 or is_last:
                 if grad_sync is not None:
                     grad_sync(model)
                 optimizer.step()
                 scheduler.step()
                 optimizer.zero_grad(set_to_none=True)
             c_pred.append(outputs.detach()); c_events.append(events); c_durations.append(durations)
+        if not c_pred:
+            raise ValueError("train_batches yielded no batch in epoch %d: pass a re-iterable (list, DataLoader), not a one-shot generator" % (epoch + 1))
         c_pred = torch.cat(c_pred, dim=1 if args.blend else 0)
         c_events, c_durations = torch.cat(c_events), torch.cat(c_durations)
         hist.train_c.append(getCIndices(c_pred[0] if args.blend else c_pred, c_events, c_durations))
@@ -132,6 +147,8 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                         loss = sel = surv_criterion(CoxPH, preds, events, durations, device)
                     vloss += float(loss)
                     y_pred.append(preds); y_events.append(events); y_durations.append(durations)
+                if not y_pred:
+                    raise ValueError("val_batches yielded no batch in epoch %d: pass a re-iterable (list, DataLoader), not a one-shot generator" % (epoch + 1))
                 y_pred = torch.cat(y_pred, dim=1 if args.blend else 0)
                 y_events, y_durations = torch.cat(y_events), torch.cat(y_durations)
                 hist.val_c.append(getCIndices(y_pred[0] if args.blend else y_pred, y_events, y_durations))
@@ -179,7 +196,7 @@ def train_classification(model, train_batches, val_batches, args, device, grad_s
     for epoch in range(args.epochs):
         model.train()
         losses, cnt, tr_preds, tr_gt = [], 0, [], []
-        for batch in list(train_batches):
+        for batch in train_batches:
             inputs, labels = to_dev(batch)
             optimizer.zero_grad(set_to_none=True)
             outputs = model(inputs)

@@ -37,12 +37,16 @@ def _dense_layer(in_channels, growth_rate, bn_size, dropout_prob):
     return layer
 
 
+MAX_LIVE_WORKSPACES = 4     # forward passes under autograd that may be outstanding per input shape (each pins ~2 GB at configs[1])
+
+
 class _Workspace:
-    __slots__ = ("tensor", "busy")
+    __slots__ = ("tensor", "busy", "gen")
 
     def __init__(self, nbytes, device):
         self.tensor = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.busy = False
+        self.gen = 0            # bumped every time the workspace is handed to a forward pass
 
 
 class _BackboneFn(torch.autograd.Function):
@@ -50,14 +54,20 @@ class _BackboneFn(torch.autograd.Function):
     def forward(ctx, bb, x, *params):
         out, ws, mask = bb._run_forward(x, params, track=True)   # (autograd is disabled inside Function.forward: say it explicitly)
         ctx.bb, ctx.ws, ctx.mask, ctx.shape = bb, ws, mask, tuple(x.shape)
+        ctx.gen, ctx.training = ws.gen, bb.training
         ctx.params = params
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         bb = ctx.bb
-        grads = bb._run_backward(ctx.shape, ctx.params, ctx.ws, ctx.mask, grad_out)
-        if bb.training:
+        if ctx.ws.gen != ctx.gen:
+            raise RuntimeError(
+                "mmnn_sts_b200: the activations of this forward pass are gone -- its workspace was handed to a later forward "
+                f"because more than {MAX_LIVE_WORKSPACES} forward passes under autograd were outstanding for this input shape. "
+                "Run backward (or drop the graph under torch.no_grad()) before starting that many new forwards.")
+        grads = bb._run_backward(ctx.shape, ctx.params, ctx.ws, ctx.mask, grad_out, ctx.training)
+        if ctx.training:
             ctx.ws.busy = False            # (an eval-mode graph may be differentiated again: one GradCAM pass per class)
         return (None, None) + tuple(grads)
 
@@ -125,12 +135,15 @@ class Backbone(nn.Sequential):
         pool = self._workspaces.setdefault(key, [])
         for w in pool:
             if not w.busy:
+                w.gen += 1
                 return w
-        if len(pool) >= 2:
-            # forwards under autograd whose backward never ran (each pins ~2 GB at configs[1]): recycle the oldest
-            # instead of growing without bound; differentiating that stale graph afterwards is an error of the caller
+        if len(pool) >= MAX_LIVE_WORKSPACES:
+            # forwards under autograd whose backward never ran: reuse the oldest instead of growing without bound.  Its
+            # generation changes, so differentiating that stale graph later RAISES (see _BackboneFn.backward) instead of
+            # reading another forward's activations.
             w = pool.pop(0)
             pool.append(w)
+            w.gen += 1
             return w
         w = _Workspace(nbytes, device)
         pool.append(w)
@@ -181,7 +194,7 @@ class Backbone(nn.Sequential):
             self._eval_ws = ws
         return out.permute(0, 4, 1, 2, 3), ws, mask
 
-    def _run_backward(self, xshape, params, ws, mask, grad_out):
+    def _run_backward(self, xshape, params, ws, mask, grad_out, training=True):
         B, cin, X, Y, Z = xshape
         lib = L.lib()
         g = grad_out.permute(0, 2, 3, 4, 1).contiguous().float()
@@ -195,7 +208,7 @@ class Backbone(nn.Sequential):
             stream = torch.cuda.current_stream().cuda_stream
             rc = lib.mmnn_encoder_backward(self._plan, B, X, Y, Z, self._ptr_array(params), self._ptr_array(bufs),
                                            self._ptr_array(grads), mask.data_ptr() if mask is not None else None,
-                                           ws.tensor.data_ptr(), g.data_ptr(), stream)
+                                           ws.tensor.data_ptr(), g.data_ptr(), int(bool(training)), stream)
         L.check(rc, "mmnn_encoder_backward")
         self._flat_grad = flat
         if self.grad_group_hook is not None:

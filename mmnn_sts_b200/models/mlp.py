@@ -50,6 +50,16 @@ class MLP(nn.Module):
         return torch.bernoulli(torch.full((6, batch), keep, device=device)) / keep
 
     def forward(self, x):
-        raise NotImplementedError(
-            "mmnn_sts_b200 implements the multimodal path: use MultiModalModel (the reference's clinical-only "
-            "model is outside SURVEY.md section 8)")
+        """Clinical-only model of the reference (/root/reference/models/mlp.py:57-63): output_head(features(backbone(x))).
+        Runs the same fused kernel as the multimodal path: `output_head.dense6` takes the clinical head's slot, the image
+        features are zeros and the two other heads are unused zero weights (their outputs are discarded)."""
+        from ..ops import MLPHeads
+        params, buffers = self.kernel_params()
+        C_, F_ = self.out_channels, self.feature_channels
+
+        def zeros(*shape):
+            return torch.zeros(*shape, dtype=torch.float32, device=x.device)
+        heads = [zeros(C_, 2 * F_), zeros(C_), zeros(C_, F_), zeros(C_), self.output_head.dense6.weight, self.output_head.dense6.bias]
+        mask = self.sample_masks(x.shape[0], x.device)
+        preds = MLPHeads.apply(x, zeros(x.shape[0], F_), mask, (self.training, True, C_), buffers, *params, *heads)
+        return preds[2]

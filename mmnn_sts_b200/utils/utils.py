@@ -33,17 +33,19 @@ class BackpropagatableFeatureExtractor(nn.Module):
 
 
 def remap_bhb_checkpoint(checkpoint):
-    """Key remapping the reference applies to the BHB-10K yAware-contrastive DenseNet121 checkpoint so that it loads into
-    the MONAI-style `backbone` (/root/reference/utils/utils.py:373-382): strip `module.`, and insert `layers` after the
-    dense-layer name of every `features.dense*` key.  `checkpoint` is the loaded file (a dict with a 'model' entry)."""
-    new_checkpoint = {}
-    for key in checkpoint['model'].keys():
-        new_key = key.replace('module.', '')
-        heirarchy = new_key.split('.')
-        if heirarchy[0] == 'features' and heirarchy[1].startswith('dense'):
-            heirarchy.insert(3, 'layers')
-        new_checkpoint['.'.join(heirarchy)] = checkpoint['model'][key]
-    return new_checkpoint
+    """State-dict keys of the BHB-10K yAware-contrastive DenseNet121 checkpoint renamed to this package's (= the
+    reference's MONAI-style) layout.  Same mapping as /root/reference/utils/utils.py:373-382: the DataParallel prefix
+    `module.` goes away, and the dense layers of that checkpoint (`features.denseblockB.denselayerL.<leaf>`) gain the
+    `layers` container level (`features.denseblockB.denselayerL.layers.<leaf>`).  `checkpoint` is the loaded file, a
+    dict whose 'model' entry is the state_dict."""
+    def rename(key):
+        parts = key.replace('module.', '').split('.')
+        in_dense_block = len(parts) > 1 and parts[0] == 'features' and parts[1].startswith('dense')
+        if in_dense_block:
+            parts = parts[:3] + ['layers'] + parts[3:]
+        return '.'.join(parts)
+
+    return {rename(key): tensor for key, tensor in checkpoint['model'].items()}
 
 
 def loadWeights(model, path, device):
@@ -100,19 +102,21 @@ class MultiModalGradCAM(nn.Module):
         return act, grad, to_ncdhw
 
     def attentionMaps(self, outputs):
+        """One trilinearly up-sampled, [0, 1]-normalised map per output class (/root/reference/utils/utils.py:293-344).
+        Reference behaviours kept on purpose: the activation tensor is re-weighted cumulatively (class c sees the pooled
+        gradients of classes 0..c multiplied together) and a batch of more than one volume is rejected."""
         act, grad, to_ncdhw = self._last_conv_views()
-        activations = to_ncdhw(act)
-        att_maps = []
-        for cls in range(outputs.shape[1]):
-            outputs[0, cls].backward(retain_graph=True)
-            grads = to_ncdhw(grad)
-            pooled_grads = torch.mean(grads, dim=[0, 2, 3, 4])
-            activations *= pooled_grads[None, :, None, None, None]
-            heatmap = torch.mean(activations, dim=1).squeeze()
-            heatmap = heatmap - torch.min(heatmap)
-            heatmap = heatmap / torch.max(heatmap)
-            att_map = heatmap.squeeze()
-            assert att_map.ndim == 3, 'Batch dimension found in attention map - Must use batch size 1 when computing attention maps'
-            att_map = F.interpolate(att_map[None, None, ...], self.input_shape[2:], mode='trilinear').squeeze()
-            att_maps.append(att_map)
-        return att_maps
+        weighted = to_ncdhw(act)                                     # [1, growth, d, h, w], re-weighted in place below
+        volume_shape = tuple(self.input_shape[2:])
+        maps = []
+        for class_index in range(outputs.shape[1]):
+            outputs[0, class_index].backward(retain_graph=True)      # fills the block's gradient accumulator
+            channel_weight = to_ncdhw(grad).mean(dim=(0, 2, 3, 4))    # GradCAM alpha: gradient pooled over voxels
+            weighted.mul_(channel_weight.view(1, -1, 1, 1, 1))
+            cam = weighted.mean(dim=1).squeeze()
+            cam = cam - cam.min()
+            cam = cam / cam.max()
+            if cam.ndim != 3:
+                raise AssertionError('attention maps are computed one volume at a time: call with batch size 1')
+            maps.append(F.interpolate(cam[None, None], volume_shape, mode='trilinear').squeeze())
+        return maps

@@ -94,3 +94,23 @@ def test_bench_reference_arm_runs_on_cpu():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+@pytest.mark.parametrize("cin", [1, 2])
+def test_seeded_initialisation_is_bit_identical_to_the_reference(cin):
+    """under torch.manual_seed(42) every one of the 779 state_dict tensors of this package's
+    MultiModalModel equals, bit for bit, the tensor the UNCHANGED reference constructs (same module construction order, same
+    initialisation law: /root/reference/models/densenet.py:258-265).  Digests: tests/golden/make_init_golden.py."""
+    import hashlib
+    import json
+    import torch
+    from mmnn_sts_b200.models.densenet import DenseNet121
+    from mmnn_sts_b200.models.multimodal import MultiModalModel
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "init_seed42.json")))[str(cin)]
+    torch.manual_seed(42)
+    m = MultiModalModel(DenseNet121(spatial_dims=3, in_channels=cin, out_channels=2, feature_channels=12, dropout_prob=0.2),
+                        ["x"] * 20, 2, 12, blend=True)
+    got = {k: hashlib.sha1(v.detach().cpu().contiguous().numpy().tobytes()).hexdigest() for k, v in m.state_dict().items()}
+    assert list(got) == list(want)
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, bad[:5]

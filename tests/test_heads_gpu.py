@@ -207,3 +207,108 @@ def test_fused_sgd_matches_torch_sgd():
         if "momentum_buffer" in oa.state[a]:
             torch.testing.assert_close(ob.state[b]["momentum_buffer"], oa.state[a]["momentum_buffer"], rtol=2e-6, atol=2e-6)
     assert set(ob.state_dict()["param_groups"][0].keys()) == set(oa.state_dict()["param_groups"][0].keys())
+
+
+@pytest.mark.gpu
+def test_fused_sgd_survives_state_dict_round_trip_and_moved_tensors():
+    """step -> optimizer.load_state_dict(optimizer.state_dict()) (replaces every momentum tensor) -> `p.data = ...` (moves a
+    parameter without changing id(p)) -> step: the cached pointer tables must follow (they are keyed on the addresses)."""
+    from mmnn_sts_b200.optim import SGD
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(9)
+    shapes = [(64, 32), (7,), (4097,)]
+    pa = [torch.randn(s, device=dev, generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.SGD(pa, 1e-1, momentum=0.9, nesterov=True, weight_decay=1e-3)
+    ob = SGD(pb, 1e-1, momentum=0.9, nesterov=True, weight_decay=1e-3)
+
+    def one_step():
+        for a, b in zip(pa, pb):
+            a.grad = torch.randn(a.shape, device=dev, generator=g); b.grad = a.grad.clone()
+        oa.step(); ob.step()
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-6)
+
+    one_step()
+    import copy
+    oa.load_state_dict(copy.deepcopy(oa.state_dict())); ob.load_state_dict(copy.deepcopy(ob.state_dict()))
+    one_step()
+    for b in pb:
+        b.data = b.data.clone()            # new storage, same Parameter object
+    one_step()
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(ob.state[b]["momentum_buffer"], oa.state[a]["momentum_buffer"], rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_captured_sgd_follows_the_scheduler_and_scalar_capture_is_refused():
+    """A CUDA-graph replay of SGD(capturable=True).step() reads lr / momentum / weight decay from device memory: with OneCycleLR
+    stepped between replays it matches the eager torch optimiser; a non-capturable SGD refuses to be captured."""
+    from mmnn_sts_b200.optim import SGD
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    pa = [torch.randn(s, device=dev, generator=g).requires_grad_(True) for s in [(33, 5), (1000,)]]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    grads = [torch.zeros_like(p) for p in pb]
+    for b, gr in zip(pb, grads):
+        b.grad = gr
+    oa = torch.optim.SGD(pa, 5e-2, momentum=0.9, nesterov=True, weight_decay=1e-2)
+    ob = SGD(pb, 5e-2, momentum=0.9, nesterov=True, weight_decay=1e-2, capturable=True)
+    sa = torch.optim.lr_scheduler.OneCycleLR(oa, max_lr=5e-2, total_steps=8)
+    sb = torch.optim.lr_scheduler.OneCycleLR(ob, max_lr=5e-2, total_steps=8)
+    fresh = [torch.randn(p.shape, device=dev, generator=g) for p in pa]
+    for a, b, gr, f in zip(pa, pb, grads, fresh):
+        a.grad = f.clone(); gr.copy_(f)
+    oa.step(); ob.step(); sa.step(); sb.step()          # eager warm-up step (allocates momentum + device hyper-parameters)
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ob.step()
+    # the capture itself does not execute: parameters still equal
+    for step in range(4):
+        fresh = [torch.randn(p.shape, device=dev, generator=g) for p in pa]
+        for a, gr, f in zip(pa, grads, fresh):
+            a.grad = f.clone(); gr.copy_(f)
+        oa.step(); sa.step()
+        ob.refresh_hyper(); graph.replay(); sb.step()
+        torch.cuda.synchronize()
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(b, a, rtol=3e-6, atol=3e-6)
+    oc = SGD([torch.randn(8, device=dev).requires_grad_(True)], 1e-2, momentum=0.9)
+    oc.param_groups[0]["params"][0].grad = torch.ones(8, device=dev)
+    oc.step()
+    g2 = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="capturable"):
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g2, stream=side):
+                oc.step()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+def test_clinical_only_mlp_forward(training):
+    """MLP.forward of the reference (/root/reference/models/mlp.py:57-63): output_head(features(backbone(x))), forward and
+    gradients against the oracle's restatement of the same layers (dropout masks injected)."""
+    import torch.nn.functional as F
+    from mmnn_sts_b200.models.mlp import MLP
+    from oracle import model as om, synth
+    sd = synth.make_state_dict(42, in_channels=1)
+    pfx = "clinical_model.model."
+    sub = {k[len(pfx):]: v for k, v in sd.items() if k.startswith(pfx)}
+    m = MLP(20, 2, 12).cuda().train(training)
+    m.load_state_dict(sub)
+    _, clinical, _, _ = synth.make_batch(21, 16, 1, (8, 8, 8))
+    masks = synth.make_masks(5, 16)
+    m.injected_masks = torch.stack(masks["mlp"])
+    out = m(clinical.cuda())
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    f = om.mlp_features(p, clinical, training, masks if training else None, pfx)
+    ref = F.linear(f, p[pfx + "output_head.dense6.weight"], p[pfx + "output_head.dense6.bias"])
+    assert out.shape == ref.shape == (16, 2)
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=2e-5, atol=2e-5)
+    if training:
+        gw = torch.randn(16, 2, generator=torch.Generator().manual_seed(3))
+        (out * gw.cuda()).sum().backward(); (ref * gw).sum().backward()
+        for k, q in m.named_parameters():
+            torch.testing.assert_close(q.grad.cpu(), p[pfx + k].grad, rtol=2e-4, atol=2e-5)
