@@ -151,6 +151,31 @@ int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
   return 0;
 }
 
+// Output-tile grid (gy, gz) of a weight-gradient launch and the voxel split (grid x).  Atomic reduction: as many CTAs as fill the
+// GPU.  Slotted (deterministic) reduction: every CTA of the split writes a full partial copy of its output tile, so the split
+// is additionally capped at one CTA per MMNN_WGRAD_MIN_TILES voxel tiles (default 8): the small late-block layers (32 / 4
+// voxel tiles) then write 4 / 1 partial copies instead of 32 / 4 -- their kernels are latency-bound either way.
+void wgrad_grid(const WgradParams& p, int kind, int& gy, int& gz) {
+  gz = (p.na_total + 127) / 128;
+  gy = (p.nb_total + p.CB - 1) / p.CB;
+  if (kind == 1) { gy = 3; gz = 1; }
+  if (kind == 3) { const int np = (p.NP == 1 || p.NP == 2) ? p.NP : 2; gy = 1; gz = 8 / np; }
+}
+int wgrad_split(const WgradParams& p, int kind, bool slotted) {
+  int gy, gz;
+  wgrad_grid(p, kind, gy, gz);
+  const int ntiles = (p.M + TILE_ROWS - 1) / TILE_ROWS;
+  int split = 148 / (gy * gz);
+  if (slotted) {
+    static const int min_tiles = [] { const char* e = getenv("MMNN_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+    const int cap = (ntiles + min_tiles - 1) / min_tiles;
+    if (split > cap) split = cap;
+  }
+  if (split < 1) split = 1;
+  if (split > ntiles) split = ntiles;
+  return split;
+}
+
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream) {
   static const bool piped_on = [] { const char* e = getenv("MMNN_WGRAD_PIPED"); return e != nullptr && e[0] == '1'; }();
@@ -165,12 +190,6 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int ntiles = (p.M + TILE_ROWS - 1) / TILE_ROWS;
-  if (split <= 0) {
-    split = 148 / (gy * gz);
-    if (split < 1) split = 1;
-  }
-  if (split > ntiles) split = ntiles;
   launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
@@ -178,18 +197,23 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
 
 // kind: 0 = conv1x1 (A = BN+ReLU(activation tile), B = raw gradient tile), 1 = conv3x3x3 (A = BN+ReLU(bottleneck),
 // B = 9 shifted raw gradient tiles per CTA), 2 = raw x raw (transition), 3 = stem (A = space-to-depth rows, B = raw)
+// split <= 0: chosen by wgrad_split().  With p.slot_stride > 0 the caller provides `split` slots of slot_stride floats at p.dw.
 int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream) {
   if (p.CB % 32 != 0 || p.CB > 128) return -2;
-  const int gz_lin = (p.na_total + 127) / 128;
-  const int gy_lin = (p.nb_total + p.CB - 1) / p.CB;
+  if (p.slot_stride < 0 || (p.slot_stride & 3) != 0) return -2;
+  int gy, gz;
+  wgrad_grid(p, kind, gy, gz);
+  const int ntiles = (p.M + TILE_ROWS - 1) / TILE_ROWS;
+  if (split <= 0) split = wgrad_split(p, kind, p.slot_stride > 0);
+  if (split > ntiles) split = ntiles;
   switch (kind) {
-    case 0: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
-    case 1: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, 3, 1, stream);
-    case 2: return launch_wgrad_t<WA_LINEAR, T_NONE, T_NONE, WE_STRIDED>(p, split, gy_lin, gz_lin, stream);
+    case 0: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, gy, gz, stream);
+    case 1: return launch_wgrad_t<WA_LINEAR, T_BNRELU, T_NONE, WE_STRIDED>(p, split, gy, gz, stream);
+    case 2: return launch_wgrad_t<WA_LINEAR, T_NONE, T_NONE, WE_STRIDED>(p, split, gy, gz, stream);
     case 3: {
       WgradParams q = p;
       if (q.NP != 1 && q.NP != 2) q.NP = 2;   // two k-block pairs per CTA share one gradient tile
-      return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(q, split, 1, 8 / q.NP, stream);
+      return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(q, split, gy, gz, stream);
     }
   }
   return -3;

@@ -572,19 +572,36 @@ static __global__ void bn_param_grad_kernel(const BnTableEntry* __restrict__ tab
   }
 }
 
-// conv2 weight gradients are accumulated lane-contiguously as [tap][co][ci]; write them out as [co][ci][tap]
-struct TransposeEntry {
+// Ordered reduction of the weight-gradient slots (engine.cuh, WgradParams::slot_stride): dst[i] = sum over s = 0 .. S-1, IN THAT
+// ORDER, of src[s * numel + i] -- the same bits every run, whatever order the CTAs of the voxel split finished in.  The 3x3x3
+// gradients are accumulated lane-contiguously as [tap][co][ci] and written out here as the reference's [co][ci][tap]
+// (taps = 27, coci = co * ci); taps = 0: same layout on both sides.  HBM-bound: S * numel floats read once, numel written.
+struct WReduceEntry {
   const float* src;
   long long dst_off;   // element offset from the gradient base pointer
+  int numel;
+  int S;
+  int taps;
+  int coci;
 };
-static __global__ void conv2_grad_transpose_kernel(const TransposeEntry* __restrict__ tab, float* __restrict__ gbase, int Co,
-                                                   int Ci) {
-  const TransposeEntry e = tab[blockIdx.y];
-  const int total = Co * Ci * 27;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int tap = idx % 27;
-    const int rest = idx / 27;  // co*Ci + ci
-    gbase[e.dst_off + idx] = e.src[(size_t)tap * Co * Ci + rest];
+static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WReduceEntry* __restrict__ tab, float* __restrict__ gbase) {
+  const WReduceEntry e = tab[blockIdx.y];
+  const int nvec = e.numel >> 2;                      // numel is a multiple of 4 for every convolution of the trunk
+  for (int iv = blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += gridDim.x * blockDim.x) {
+    const float4* sp = reinterpret_cast<const float4*>(e.src) + iv;
+    float4 acc = __ldcs(sp);
+    for (int s = 1; s < e.S; ++s) {
+      const float4 v = __ldcs(sp + (size_t)s * nvec);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const int i = iv << 2;
+    if (e.taps == 0) {
+      *reinterpret_cast<float4*>(gbase + e.dst_off + i) = acc;
+    } else {
+      const int tap = i / e.coci, rest = i - tap * e.coci;   // 4 consecutive (co, ci) cells of one tap
+      float* d = gbase + e.dst_off + (long long)rest * e.taps + tap;
+      d[0] = acc.x; d[e.taps] = acc.y; d[2 * e.taps] = acc.z; d[3 * e.taps] = acc.w;
+    }
   }
 }
 

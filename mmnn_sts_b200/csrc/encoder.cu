@@ -28,6 +28,7 @@ namespace mmnn {
 int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream);
 int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cudaStream_t stream);
 int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream);
+int wgrad_split(const WgradParams& p, int kind, bool slotted);
 int launch_brick(const BrickParams& p, int grad, cudaStream_t stream);
 }  // namespace mmnn
 
@@ -89,6 +90,9 @@ struct Plan {
   // Weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them): they run on a second
   // stream, forked / joined with events, so the small late-block launches overlap the data-gradient chain.
   cudaStream_t side = nullptr;
+  // Weight gradients: the voxel split of every weight-gradient GEMM is reduced through slots summed in index order
+  // (deterministic, the default) or, with MMNN_DETERMINISTIC=0, by floating-point atomics (run-dependent last bits).
+  bool det = true;
   // Gradient groups, in the order backward finalises them: group k = dense block nb-1-k with the transition that
   // follows it (the last block's group also holds norm5), group nb = the stem (conv0, norm0).  Each group is a
   // contiguous range of the parameter-order gradient buffer; grad_ev[k] is recorded when its last writer has been
@@ -142,12 +146,22 @@ struct Geo {
   long long M0;
   int D[8], H[8], W[8];
   long long M[8];
-  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, gslice, gout, dpooled, c2scratch, dr, total;
+  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, gslice, gout, dpooled, wslots, dr, total;
+  size_t wslots_bytes;
+  std::vector<size_t> wslot_off;   // per parameter index: element offset of the weight-gradient slots (convolutions only)
+  std::vector<int> wslot_S;        // per parameter index: number of slots == voxel split of that weight-gradient launch
   size_t maxM_;
   size_t buf[8], bott[8], pooled[8], dbuf[8];
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// voxel split of a weight-gradient launch (same rule as launch_wgrad applies: capi_conv.cu)
+int split_for(int kind, long long M, int na_total, int nb_total, int CB, bool slotted) {
+  WgradParams w = {};
+  w.M = (int)M; w.na_total = na_total; w.nb_total = nb_total; w.CB = CB; w.NP = 2;
+  return wgrad_split(w, kind, slotted);
+}
 
 bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
   g.B = B; g.X = X; g.Y = Y; g.Z = Z;
@@ -194,7 +208,29 @@ bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
   g.gslice = take(2 * maxM * GROWTH * 2);
   g.gout = take(maxMoutC2 * 2 + 256);
   g.dpooled = take(maxMoutC * 2 + 256);
-  g.c2scratch = take((size_t)pl.num_layers * 27 * GROWTH * BOTT * 4);
+  {
+    // weight-gradient slots: S partial copies per convolution weight (S = 1 without the ordered reduction, where only the
+    // 3x3x3 gradients go through this scratch -- in [tap][co][ci] order -- and are zeroed + accumulated with atomics)
+    g.wslot_off.assign(pl.num_params, 0);
+    g.wslot_S.assign(pl.num_params, 0);
+    size_t e = 0;
+    auto add = [&](int pidx, int kind, long long M, int na, int nb, int CB) {
+      const int S = pl.det ? split_for(kind, M, na, nb, CB, true) : 1;
+      g.wslot_off[pidx] = e; g.wslot_S[pidx] = S;
+      e += (size_t)S * (size_t)pl.param_numel[pidx];
+    };
+    for (int b = 0; b < nb; ++b) {
+      const BlockInfo& bi = pl.blocks[b];
+      for (auto& li : bi.layers) {
+        if (pl.det) add(li.conv1_idx, 0, g.M[b], li.cin, BOTT, 128);
+        add(li.conv2_idx, 1, g.M[b], BOTT, GROWTH, GROWTH);
+      }
+      if (bi.has_trans && pl.det) add(bi.tconv_idx, 2, g.M[b + 1], bi.ctot, bi.ctot / 2, 128);
+    }
+    if (pl.det) add(pl.conv0_idx, 3, g.M0, 128, 64, 64);
+    g.wslots_bytes = e * sizeof(float);
+    g.wslots = take(g.wslots_bytes + 256);
+  }
   g.dr = take((size_t)g.M0 * 64 * 2);
   g.total = o;
   return true;
@@ -250,6 +286,7 @@ void* mmnn_encoder_create(int in_channels, const int* block_config, int nblocks,
     return nullptr;
   Plan* pl = new Plan();
   pl->cin_real = in_channels;
+  { const char* e = getenv("MMNN_DETERMINISTIC"); pl->det = !(e != nullptr && e[0] == '0'); }
   int pidx = 0, bidx = 0, foff = 0, boff = 0, lidx = 0;
   size_t pk = 0;
   auto add_param = [&](long long numel) { pl->param_numel.push_back(numel); return pidx++; };
@@ -580,7 +617,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   auto gdot = [&](const BnInfo& bn) { return bstats + BC + bn.bwd_off; };
 
   CUDA_RET(cudaMemsetAsync(bstats, 0, (size_t)BC * 2 * sizeof(double), st));
-  CUDA_RET(cudaMemsetAsync(ws + g.c2scratch, 0, (size_t)pl->num_layers * 27 * GROWTH * BOTT * 4, st));
+  if (!pl->det) CUDA_RET(cudaMemsetAsync(ws + g.wslots, 0, g.wslots_bytes, st));   // atomics accumulate into the 3x3x3 scratch
+  float* const wslots = (float*)(ws + g.wslots);
+  const bool det = pl->det;
   if (pl->side == nullptr) CUDA_RET(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
   // while bench.py's per-kernel profiling is on, everything stays on one stream so that class times are not overlapped
   cudaStream_t sd = prof_state().on ? st : pl->side;
@@ -621,7 +660,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   {
     // table order: [block nb-1 (+n5)] [block nb-2 + its transition] ... [block 0 + its transition] [stem]
     std::vector<BnTableEntry> tab;
-    std::vector<TransposeEntry> tt;
+    std::vector<WReduceEntry> tt;
     auto add_bn_entry = [&](const BnInfo& bn) {
       BnTableEntry e = {};
       e.g_sum = gsum(bn); e.g_dot = gdot(bn);
@@ -629,23 +668,30 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       e.C = bn.C;
       tab.push_back(e);
     };
+    auto add_w_entry = [&](int pidx, int taps, int coci) {
+      WReduceEntry e;
+      e.src = wslots + g.wslot_off[pidx];
+      e.dst_off = (float*)grads[pidx] - gbase;
+      e.numel = (int)pl->param_numel[pidx]; e.S = g.wslot_S[pidx]; e.taps = taps; e.coci = coci;
+      tt.push_back(e);
+    };
     for (int k = 0; k < nb; ++k) {
       const BlockInfo& bi = pl->blocks[nb - 1 - k];
       bn_lo[k] = (int)tab.size(); tt_lo[k] = (int)tt.size();
       for (auto& li : bi.layers) {
         add_bn_entry(li.n1); add_bn_entry(li.n2);
-        TransposeEntry e;
-        e.src = (const float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
-        e.dst_off = (float*)grads[li.conv2_idx] - gbase;
-        tt.push_back(e);
+        add_w_entry(li.conv2_idx, 27, GROWTH * BOTT);
+        if (det) add_w_entry(li.conv1_idx, 0, 0);
       }
       if (bi.has_trans) add_bn_entry(bi.tn); else add_bn_entry(pl->n5);
+      if (bi.has_trans && det) add_w_entry(bi.tconv_idx, 0, 0);
     }
     bn_lo[nb] = (int)tab.size(); tt_lo[nb] = (int)tt.size();
     add_bn_entry(pl->n0);
+    if (det) add_w_entry(pl->conv0_idx, 0, 0);
     bn_lo[nb + 1] = (int)tab.size(); tt_lo[nb + 1] = (int)tt.size();
     RET_IF(upload_table(pl, 2, dtab, tab.data(), tab.size() * sizeof(BnTableEntry), st));
-    RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(TransposeEntry), st));
+    RET_IF(upload_table(pl, 3, dtt, tt.data(), tt.size() * sizeof(WReduceEntry), st));
   }
   while ((int)pl->grad_ev.size() < nb + 1) {
     cudaEvent_t e;
@@ -658,7 +704,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     const int nbn = bn_lo[k + 1] - bn_lo[k], ntt = tt_lo[k + 1] - tt_lo[k];
     ProfScope ps_(PC_TAILS, ts, (nbn > 0) + (ntt > 0));
     if (nbn > 0) bn_param_grad_kernel<<<(unsigned)nbn, 128, 0, ts>>>((const BnTableEntry*)dtab + bn_lo[k], gbase);
-    if (ntt > 0) conv2_grad_transpose_kernel<<<dim3(16, (unsigned)ntt), 256, 0, ts>>>((const TransposeEntry*)dtt + tt_lo[k], gbase, GROWTH, BOTT);
+    if (ntt > 0) wgrad_reduce_kernel<<<dim3(32, (unsigned)ntt), 256, 0, ts>>>((const WReduceEntry*)dtt + tt_lo[k], gbase);
     LAUNCH_RET();
     CUDA_RET(cudaEventRecord(pl->grad_ev[k], ts));
     return 0;
@@ -712,14 +758,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
         w.a_src = bott; w.a_pitch = BOTT; w.bnA = bn2;
         w.b_src = gslice; w.b_pitch = GROWTH;
-        w.dw = (float*)(ws + g.c2scratch) + (size_t)li.index * 27 * GROWTH * BOTT;
+        w.dw = wslots + g.wslot_off[li.conv2_idx];
+        w.slot_stride = det ? pl->param_numel[li.conv2_idx] : 0;
         w.so_a = 1; w.so_b = BOTT; w.so_j = GROWTH * BOTT;
         cudaEvent_t ready = pl->next_event();
         CUDA_RET(cudaEventRecord(ready, st));          // gslice written
         CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
         {
           ProfScope ps_(PC_CONV2_WGRAD, sd);
-          RET_IF(launch_wgrad(w, 1, 0, sd));
+          RET_IF(launch_wgrad(w, 1, det ? g.wslot_S[li.conv2_idx] : 0, sd));
         }
         side_done[parity][0] = pl->next_event();
         CUDA_RET(cudaEventRecord(side_done[parity][0], sd));
@@ -755,14 +802,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
         w.a_src = buf; w.a_pitch = bi.ctot; w.bnA = bn1;
         w.b_src = dA2; w.b_pitch = BOTT;
-        w.dw = (float*)grads[li.conv1_idx];
+        w.dw = det ? wslots + g.wslot_off[li.conv1_idx] : (float*)grads[li.conv1_idx];
+        w.slot_stride = det ? pl->param_numel[li.conv1_idx] : 0;
         w.so_a = 1; w.so_b = li.cin; w.so_j = 0;
         cudaEvent_t ready = pl->next_event();
         CUDA_RET(cudaEventRecord(ready, st));          // dA2 holds dBott
         CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
         {
           ProfScope ps_(PC_CONV1_WGRAD, sd);
-          RET_IF(launch_wgrad(w, 0, 0, sd));
+          RET_IF(launch_wgrad(w, 0, det ? g.wslot_S[li.conv1_idx] : 0, sd));
         }
         side_done[parity][1] = pl->next_event();
         CUDA_RET(cudaEventRecord(side_done[parity][1], sd));
@@ -817,14 +865,15 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
         w.a_src = pooled; w.a_pitch = pv.ctot;
         w.b_src = gout; w.b_pitch = bi.c0;
-        w.dw = (float*)grads[pv.tconv_idx];
+        w.dw = det ? wslots + g.wslot_off[pv.tconv_idx] : (float*)grads[pv.tconv_idx];
+        w.slot_stride = det ? pl->param_numel[pv.tconv_idx] : 0;
         w.so_a = 1; w.so_b = pv.ctot; w.so_j = 0;
         cudaEvent_t ready = pl->next_event();
         CUDA_RET(cudaEventRecord(ready, st));
         CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
         {
           ProfScope ps_(PC_TRANS_WGRAD, sd);
-          RET_IF(launch_wgrad(w, 2, 0, sd));
+          RET_IF(launch_wgrad(w, 2, det ? g.wslot_S[pv.tconv_idx] : 0, sd));
         }
         trans_done = pl->next_event();
         CUDA_RET(cudaEventRecord(trans_done, sd));
@@ -872,10 +921,11 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       w.Dz = g.D0; w.Dy = g.H0; w.Dx = g.W0; w.Sz = g.Sz; w.Sy = g.Sy; w.Sx = g.Sx;
       w.a_src = (const bf16*)(ws + g.xs2d); w.a_pitch = 16;
       w.b_src = q.dr; w.b_pitch = 64;
-      w.dw = (float*)grads[pl->conv0_idx];
+      w.dw = det ? wslots + g.wslot_off[pl->conv0_idx] : (float*)grads[pl->conv0_idx];
+      w.slot_stride = det ? pl->param_numel[pl->conv0_idx] : 0;
       w.cin_real = pl->cin_real;
       ProfScope ps_(PC_STEM_WGRAD, st);
-      RET_IF(launch_wgrad(w, 3, 0, st));
+      RET_IF(launch_wgrad(w, 3, det ? g.wslot_S[pl->conv0_idx] : 0, st));
     }
   }
 

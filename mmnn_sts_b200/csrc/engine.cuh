@@ -620,6 +620,10 @@ struct WgradParams {
   int cin_real;    // stem
   int stages;
   int NP;          // stem: k-block PAIRS handled per CTA (A tile = NP x 128 "channels", NP accumulators); else 1
+  // Ordered reduction of the voxel split (deterministic weight gradients): slot_stride > 0 -> CTA x of the split WRITES its
+  // partial result (plain stores) to dw + x * slot_stride instead of adding it to dw with floating-point atomics, and a tail
+  // kernel sums the slots in index order (encoder.cu, wgrad_reduce_kernel).  0 -> atomics into dw (run-dependent last bits).
+  long long slot_stride;
 };
 
 __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/) {
@@ -1046,6 +1050,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     tc_fence_after();
     const int a = warp * 32 + lane;
     const int nacc = (EMODE == WE_STEM) ? NP : p.NB;
+    const bool slotted = p.slot_stride > 0;
+    float* const dwb = p.dw + (long long)blockIdx.x * p.slot_stride;   // this CTA's slot (== dw when the split is reduced by atomics)
     for (int j = 0; j < nacc; ++j) {
       for (int cc = 0; cc < p.CB / 32; ++cc) {
         float v[32];
@@ -1066,8 +1072,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             for (int i = warp; i < 32; i += 4) {
               if (b0 + i < p.nb_total) {
                 const float4 val = *reinterpret_cast<const float4*>(stg + i * 132 + lane * 4);
-                float* dst = p.dw + (long long)ag4 + (long long)tap * p.so_j + (long long)(b0 + i) * p.so_b;
-                atomicAdd(reinterpret_cast<float4*>(dst), val);
+                float* dst = dwb + (long long)ag4 + (long long)tap * p.so_j + (long long)(b0 + i) * p.so_b;
+                if (slotted) *reinterpret_cast<float4*>(dst) = val;
+                else atomicAdd(reinterpret_cast<float4*>(dst), val);
               }
             }
           }
@@ -1080,7 +1087,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int co = cc * 32 + i;
-              atomicAdd(p.dw + ((((long long)co * p.cin_real + ci) * 7 + kz) * 7 + ky) * 7 + kx, v[i]);
+              float* dst = dwb + ((((long long)co * p.cin_real + ci) * 7 + kz) * 7 + ky) * 7 + kx;
+              if (slotted) *dst = v[i];
+              else atomicAdd(dst, v[i]);
             }
           }
         }
