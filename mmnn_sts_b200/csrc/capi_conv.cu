@@ -153,8 +153,8 @@ int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
 
 // Output-tile grid (gy, gz) of a weight-gradient launch and the voxel split (grid x).  Atomic reduction: as many CTAs as fill the
 // GPU.  Slotted (deterministic) reduction: every CTA of the split writes a full partial copy of its output tile, so the split
-// is additionally capped at one CTA per MMNN_WGRAD_MIN_TILES voxel tiles (default 8): the small late-block layers (32 / 4
-// voxel tiles) then write 4 / 1 partial copies instead of 32 / 4 -- their kernels are latency-bound either way.
+// is additionally capped at one CTA per MMNN_WGRAD_MIN_TILES voxel tiles (default 2; measured on B200 at configs[1]: 1, 2, 3 match the atomic reduction at 1072-1076 volumes/s, 4 -> 1058, 8 -> 1021, 16 -> 935): the small late-block layers (32 / 4
+// voxel tiles) then write 16 / 2 partial copies instead of 32 / 4.
 void wgrad_grid(const WgradParams& p, int kind, int& gy, int& gz) {
   gz = (p.na_total + 127) / 128;
   gy = (p.nb_total + p.CB - 1) / p.CB;
@@ -167,7 +167,7 @@ int wgrad_split(const WgradParams& p, int kind, bool slotted) {
   const int ntiles = (p.M + TILE_ROWS - 1) / TILE_ROWS;
   int split = 148 / (gy * gz);
   if (slotted) {
-    static const int min_tiles = [] { const char* e = getenv("MMNN_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+    static const int min_tiles = [] { const char* e = getenv("MMNN_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     const int cap = (ntiles + min_tiles - 1) / min_tiles;
     if (split > cap) split = cap;
   }

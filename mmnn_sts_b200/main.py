@@ -106,7 +106,8 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
     optimizer = SGD(model.parameters(), args.lr, momentum=args.momentum, nesterov=True, weight_decay=args.weight_decay)
     scheduler = torch.optim.lr_scheduler.OneCycleLR(optimizer, max_lr=args.lr, steps_per_epoch=steps_per_epoch, epochs=args.epochs)
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion) if args.blend else None
-    hist = SimpleNamespace(train_loss=[], val_loss=[], train_c=[], val_c=[], best_loss=math.inf, best_state=None, blender=blender)
+    hist = SimpleNamespace(train_loss=[], val_loss=[], train_c=[], val_c=[], best_loss=math.inf, best_state=None, blender=blender,
+                           step_at=[], lr_trace=[], momentum_trace=[], optimizer=optimizer, scheduler=scheduler)
     for epoch in range(args.epochs):
         model.train()
         losses, c_pred, c_events, c_durations = [], [], [], []
@@ -127,6 +128,8 @@ def train_survival(model, train_batches, val_batches, args, device, grad_sync=No
                 optimizer.step()
                 scheduler.step()
                 optimizer.zero_grad(set_to_none=True)
+                hist.step_at.append((epoch, i))
+                hist.lr_trace.append(optimizer.param_groups[0]["lr"]); hist.momentum_trace.append(optimizer.param_groups[0]["momentum"])
             c_pred.append(outputs.detach()); c_events.append(events); c_durations.append(durations)
         if not c_pred:
             raise ValueError("train_batches yielded no batch in epoch %d: pass a re-iterable (list, DataLoader), not a one-shot generator" % (epoch + 1))

@@ -106,3 +106,28 @@ def test_model_oracle_matches_golden(golden_dir, name):
         key = "image_model.model.backbone.conv0.weight"
         ref = g["grad:" + key]
         assert np.abs(params[key].grad.numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7
+
+
+def test_oracle_train_loop_reproduces_the_reference_trajectory(golden_dir):
+    """oracle/train_loop.py + the oracle's functional network, blender and Cox restatement, driven through two epochs (gradient
+    accumulation, OneCycleLR, blending-weight update), land on the trajectory the UNCHANGED reference classes produced in the same
+    loop (tests/golden/trajectory_mini.npz, tests/golden/make_trajectory_golden.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import cindex, cox, train_loop
+    from oracle.blender import GradientBlenderOracle
+    g = np.load(os.path.join(golden_dir, "trajectory_mini.npz"))
+    args, train, val, sd = train_loop.trajectory_case(mini=True)
+    m = train_loop.OracleMultiModal(sd, blend=True)
+    hist = train_loop.train_survival_loop(m, train, val, args, GradientBlenderOracle(), cox.surv_criterion, cox.CoxPH, cindex.getCIndices)
+    assert [list(x) for x in hist.step_at] == g["step_at"].tolist()
+    assert hist.lr_trace == g["lr_trace"].tolist() and hist.momentum_trace == g["momentum_trace"].tolist()
+    np.testing.assert_allclose(hist.train_loss, g["train_loss"], rtol=1e-5)
+    np.testing.assert_allclose(hist.val_loss, g["val_loss"], rtol=1e-5)
+    assert np.array_equal(np.array(hist.train_c), g["train_c"]) and np.array_equal(np.array(hist.val_c), g["val_c"])
+    np.testing.assert_allclose(np.array(hist.blender_weights), g["blender_weights"], atol=2e-3)
+    for k in train_loop.TRACKED:
+        w0, ref, got = sd[k].double(), torch.tensor(g["final:" + k]).double(), m.sd[k].detach().double()
+        du_ref, du = (ref - w0).flatten(), (got - w0).flatten()
+        assert float((du - du_ref).norm() / du_ref.norm()) < 1e-3, k
