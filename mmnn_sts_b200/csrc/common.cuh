@@ -144,10 +144,14 @@ MMNN_DEVINL uint64_t make_smem_desc_sw(uint32_t addr, uint32_t lbo, uint32_t sbo
 MMNN_DEVINL uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), majors (bits 15,16), N>>3 (17..22), M>>4 (24..28)
 // operand format field: 0 = fp16, 1 = bf16 (both operands the same)
-__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool f16) {
-  const uint32_t fmt = f16 ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+__host__ __device__ inline uint32_t make_idesc_ab(int M, int N, int a_mn_major, int b_mn_major, bool a_f16, bool b_f16) {
+  // the A and B formats are separate fields: an fp16 operand (forward activations) can meet a bf16 one (gradients) in one MMA
+  const uint32_t fa = a_f16 ? 0u : 1u, fb = b_f16 ? 0u : 1u;
+  return (1u << 4) | (fa << 7) | (fb << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, bool f16) {
+  return make_idesc_ab(M, N, a_mn_major, b_mn_major, f16, f16);
 }
 
 // ---------------------------------------------------------------- bf16 helpers

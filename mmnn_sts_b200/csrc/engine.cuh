@@ -729,9 +729,13 @@ MMNN_DEVINL uint32_t load_planes(uint4 (&regs)[2 * MAX_PASSES], int planes, cons
   return okmask;
 }
 
-template <int TRANS, bool IN_F16>
+// OUT_F16: format the tile is written in (the weight-gradient MMA takes an fp16 A operand next to the bf16 gradient operand, so
+// forward activations need no conversion).  IN_F16 && OUT_F16 && BN+ReLU: `scale` points to an H2Coef table (one entry per
+// channel pair) and the transform is the 12-HFMA2 fast path of the forward producers.
+template <int TRANS, bool IN_F16, bool OUT_F16 = false>
 MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okmask, uint32_t sdst, int planes, int warp, int lane,
                               const float* scale, const float* shift) {
+  constexpr bool H2 = TRANS == T_BNRELU && IN_F16 && OUT_F16;
   const int G = planes >= 8 ? 8 : 4;
   const int gshift = planes >= 8 ? 3 : 2;
   const int rsub = lane >> gshift;
@@ -742,7 +746,12 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
     const int chunk = grp * G + (lane & (G - 1));
     if (chunk >= planes) continue;
     float sc[8], sh[8];
-    if (TRANS == T_BNRELU) {
+    H2Coef hc[4];
+    if (H2) {
+      const H2Coef* tab = reinterpret_cast<const H2Coef*>(scale);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hc[i] = tab[chunk * 4 + i];
+    } else if (TRANS == T_BNRELU) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) { sc[e] = scale[chunk * 8 + e]; sh[e] = shift[chunk * 8 + e]; }
     }
@@ -752,8 +761,9 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
         const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
         uint4 v = regs[grp * MAX_PASSES + ps];
         if ((okmask >> (grp * MAX_PASSES + ps)) & 1u) {
-          if (TRANS == T_BNRELU) apply_bnrelu8<IN_F16, false>(v, sc, sh);
-          else convert8<IN_F16, false>(v);
+          if (H2) apply_bnrelu8_h2(v, hc);
+          else if (TRANS == T_BNRELU) apply_bnrelu8<IN_F16, OUT_F16>(v, sc, sh);
+          else convert8<IN_F16, OUT_F16>(v);
         }
         sts16(sdst + chunk * PLANE_BYTES + r * 16, v);
       }
@@ -761,8 +771,16 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
   }
 }
 
+#ifndef MMNN_WGRAD_A_F16
+#define MMNN_WGRAD_A_F16 0
+#endif
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  // NEGATIVE RESULT (round 2, B200): the instruction descriptor of tcgen05 kind::f16 has separate A / B format fields, but an
+  // fp16 A operand (forward activations, no conversion, packed-half BN+ReLU) next to the bf16 B operand (gradients) raises
+  // "illegal instruction" on sm_100a -- both operands must have the same format.  -DMMNN_WGRAD_A_F16=1 builds that variant
+  // (kept to document the experiment); the default converts the activation tile to bf16 in the producers.
+  constexpr bool A_F16 = kActF16 && (MMNN_WGRAD_A_F16 != 0);
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   uint32_t offs[4];
@@ -809,6 +827,29 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   }
   pdl_wait();   // nothing above touches global memory
   if (ATRANS == T_BNRELU) {
+    if (A_F16) {
+      H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // 64 channel pairs x 16 B: same 1 KB as the fp32 scale / shift table
+      for (int j = tid; j < 64; j += ENGINE_THREADS) {
+        float s[2] = {0.f, 0.f}, t[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = ztile * 128 + 2 * j + h;
+          if (ch < p.na_total) {
+            float mean, rstd;
+            bn_mean_rstd(p.bnA, ch, mean, rstd);
+            s[h] = p.bnA.gamma[ch] * rstd;
+            t[h] = p.bnA.beta[ch] - mean * s[h];
+          }
+        }
+        H2Coef c;
+        c.s_hi = __floats2half2_rn(s[0], s[1]);
+        c.t_hi = __floats2half2_rn(t[0], t[1]);
+        const float2 sh = __half22float2(c.s_hi), th = __half22float2(c.t_hi);
+        c.s_lo = __floats2half2_rn(s[0] - sh.x, s[1] - sh.y);
+        c.t_lo = __floats2half2_rn(t[0] - th.x, t[1] - th.y);
+        coefH[j] = c;
+      }
+    } else
     for (int c = tid; c < 128; c += ENGINE_THREADS) {
       const int ch = ztile * 128 + c;
       float s = 0.f, t = 0.f;
@@ -914,7 +955,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       };
       auto finish = [&](int it, const uint4 (&aregs)[2 * MAX_PASSES], uint32_t aok, bool newer_pending) {
         const int s = it % S;
-        store_planes<ATRANS, kActF16>(aregs, aok, stage0 + s * stage_bytes, aplanes, warp, lane, coefA, coefA + 128);
+        store_planes<ATRANS, kActF16, A_F16>(aregs, aok, stage0 + s * stage_bytes, aplanes, warp, lane, coefA, coefA + 128);
         if (newer_pending) cp_async_wait<1>(); else cp_async_wait<0>();
         fence_proxy_async_smem();
         mbar_arrive(bar_full + 8 * s);
@@ -988,7 +1029,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         const uint32_t bok = load_planes<false>(bregs, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0,
                                                 0, p.Dz, p.Dy, p.Dx,
                                                 AMODE == WA_STEM_PAIR ? (long long)(t_begin + it) * TILE_ROWS : -1);
-        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16, A_F16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
         if (AMODE == WA_STEM_PAIR) {
           const int chunk = lane & 7, rsub = lane >> 3;
 #pragma unroll
@@ -998,7 +1039,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
               for (int ps = 0; ps < MAX_PASSES; ++ps) {
                 const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
                 uint4 v = sregs[g][ps];
-                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, false>(v);
+                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, A_F16>(v);
                 sts16(sA + (g * 8 + chunk) * PLANE_BYTES + r * 16, v);
               }
             }
@@ -1024,14 +1065,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             regs[j][ps] = ok ? ldg16(p.b_src + ((long long)ri.x + delta) * p.b_pitch + chunk * 8) : make_uint4(0, 0, 0, 0);
           }
         }
-        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16, A_F16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
 #pragma unroll
         for (int j = 0; j < 9; ++j)
 #pragma unroll
           for (int ps = 0; ps < 2; ++ps)
             sts16(sB + j * bt_bytes + chunk * PLANE_BYTES + ((warp + ps * PRODUCER_WARPS) * 8 + rsub) * 16, regs[j][ps]);
       } else {
-        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16, A_F16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
         for (int j = 0; j < p.NB; ++j) {
           const int tap = ytile * p.NB + j;
           const int dz = -(tap / 9 - 1), dy = -((tap / 3) % 3 - 1), dx = -(tap % 3 - 1);
@@ -1096,7 +1137,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       }
     }
   } else if (warp == MMA_WARP) {
-    const uint32_t idesc = make_idesc(128, p.CB, 1, 1, false);
+    const uint32_t idesc = make_idesc_ab(128, p.CB, 1, 1, A_F16, false);
     for (int it = 0; it < nt; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -1121,7 +1162,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           // the 9 shifted gradient tiles are 36 consecutive chunk planes = ONE MN-major operand of N = 288 columns
           // (column = tap*32 + co, the accumulator layout the epilogue expects): two N = 144 MMAs per K step instead of
           // nine N = 32 ones, so the A tile is read from shared memory 2x instead of 9x per step
-          const uint32_t idesc2 = make_idesc(128, 144, 1, 1, false);
+          const uint32_t idesc2 = make_idesc_ab(128, 144, 1, 1, A_F16, false);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint32_t td = tmem_base + h * 144;
