@@ -131,7 +131,12 @@ def mem_bytes(wl):
     d = [(v - 1) // 2 + 1 for v in d0]
     M0 = B * d0[0] * d0[1] * d0[2]
     by = {"bn_apply": M0 * 64 * 6.0, "maxpool": M0 * 64 * 2.0, "maxpool_bwd": M0 * 64 * 4.0, "extract": 0.0, "avgpool_bwd": 0.0,
-          "trans_pool": 0.0, "s2d": B * wl["cin"] * X * Y * Z * 4.0 + B * (d0[0] + 3) * (d0[1] + 3) * (d0[2] + 3) * 32.0}
+          "trans_pool": 0.0, "s2d": B * wl["cin"] * X * Y * Z * 4.0 + B * (d0[0] + 3) * (d0[1] + 3) * (d0[2] + 3) * 32.0,
+          # the 1x1x1 convolutions sit BELOW the ridge of the machine (arithmetic intensity 128 K / (K + 128) <= 113 FLOP/B against
+          # 1400.9 TF/s / 6547.5 GB/s = 214 FLOP/B): their roofline is HBM.  16-bit tensors, each read / written once:
+          "conv1_fprop": 0.0,    # read M x cin, write M x 128
+          "conv1_dgrad": 0.0,    # read dBott M x 128 and the gating activations M x cin, write M x cin
+          "conv1_wgrad": 0.0}    # read M x cin and M x 128
     c = 64
     for b, nl in enumerate(BLOCKS):
         M = B * d[0] * d[1] * d[2]
@@ -142,6 +147,9 @@ def mem_bytes(wl):
             cin = c + 32 * l
             by["bn_apply"] += M * 128 * 6.0 + M * cin * 12.0
             by["extract"] += M * 32 * 6.0
+            by["conv1_fprop"] += M * (cin + 128) * 2.0
+            by["conv1_dgrad"] += M * (128 + 2 * cin) * 2.0
+            by["conv1_wgrad"] += M * (cin + 128) * 2.0
         c += 32 * nl
         if b < len(BLOCKS) - 1:
             Mo = B * (d[0] // 2) * (d[1] // 2) * (d[2] // 2)
@@ -324,22 +332,42 @@ def run_ours(args):
             e["gbps"] = round(mbytes[k] / (t / nprof / 1e3) / 1e9, 1)
             e["frac_of_hbm_peak"] = round(e["gbps"] / peaks["hbm"], 4)
         kernels[k] = e
-    dom = max((k for k in kernels if k in gemm_classes), key=lambda k: kernels[k]["ms_per_step"])
-    roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                "frac": round(kernels[dom]["tflops"] / peaks["tf_sust"], 4), "traffic": None,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
-                "flops_per_launch": gemm_classes[dom] / max(1, kernels[dom]["launches_per_step"]),
-                "avg_launch_ms": round(kernels[dom]["ms_per_step"] / max(1, kernels[dom]["launches_per_step"]), 5)}
-
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.isfile(tpath):
-        tj = json.load(open(tpath))
-        if dom in tj:        # DRAM bytes of the class's largest launch (ncu --set full), next to that launch's algorithmic bytes
-            roofline["traffic"] = tj[dom]["traffic_bytes"]
-            roofline["traffic_note"] = {k: tj[dom][k] for k in ("launch", "algorithmic_bytes", "duration_us")}
+    # `roofline` = the kernel class that takes the most time of the step, whatever bounds it; `roofline_gemm` = the largest
+    # tensor-core class; `roofline_step` = the whole step's algorithmic FLOPs against the sustained tensor peak.
+    def class_roofline(k):
+        e = kernels[k]
+        hbm_bound = "gbps" in e and (k not in gemm_classes or k.startswith("conv1_"))
+        r = {"kernel": k, "ms_per_step": e["ms_per_step"], "launches_per_step": e["launches_per_step"], "traffic": None}
+        if hbm_bound:
+            r.update({"bound": "hbm", "achieved": e["gbps"], "peak": peaks["hbm"], "unit": "GB/s", "frac": e["frac_of_hbm_peak"],
+                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['src']})",
+                      "bytes_per_launch": mbytes[k] / max(1, e["launches_per_step"])})
+        else:
+            r.update({"bound": "tensor", "achieved": e["tflops"], "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": e["frac_of_sustained_peak"],
+                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                      "flops_per_launch": gemm_classes[k] / max(1, e["launches_per_step"])})
+        r["avg_launch_ms"] = round(e["ms_per_step"] / max(1, e["launches_per_step"]), 5)
+        return r
+    rated = [k for k in kernels if "gbps" in kernels[k] or "tflops" in kernels[k]]
+    dom = max(rated, key=lambda k: kernels[k]["ms_per_step"])
+    dom_gemm = max((k for k in kernels if k in gemm_classes and not k.startswith("conv1_")), key=lambda k: kernels[k]["ms_per_step"])
+    roofline, roofline_gemm = class_roofline(dom), class_roofline(dom_gemm)
+    step_flops = 3.0 * (fl["stem"] + fl["conv1"] + fl["conv2"] + fl["trans"]) - fl["stem"]      # fprop + dgrad + wgrad, no stem dgrad
+    roofline_step = {"bound": "tensor", "achieved": round(step_flops / (ms / args.steps / 1e3) / 1e12, 1), "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                     "frac": round(step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tf_sust"], 4),
+                     "algorithmic_gflop_per_step_per_gpu": round(step_flops / 1e9, 1),
+                     "note": "per GPU; the executed transition GEMMs run on the pooled tensor (8x fewer FLOPs), credited at the un-pooled count"}
+    for tag in ("r02", "r01"):
+        tpath = os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json")
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath))
+            for r in (roofline, roofline_gemm):
+                if r["traffic"] is None and r["kernel"] in tj:   # DRAM bytes of the class's largest launch (ncu --set full), next to that launch's algorithmic bytes
+                    r["traffic"] = tj[r["kernel"]]["traffic_bytes"]
+                    r["traffic_note"] = {k: tj[r["kernel"]][k] for k in ("launch", "algorithmic_bytes", "duration_us")}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_arm(wl, steps=1, warmup=1, sample_batch=2)
+        cpu = cpu_reference_arm(wl, steps=1, warmup=1, sample_batch=wl["batch"])      # the SAME batch of 16 the GPU arm steps on
     if rank == 0:
         in_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
         line = {"metric": "train volumes/sec", "value": round(value, 2), "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
@@ -351,9 +379,30 @@ def run_ours(args):
                            "l2": "inputs (134 MB/batch fp32) and activations (>1 GB) exceed the 126 MB L2; two batches alternate"},
                 "e2e": {"value": round(value_e2e, 2), "unit": "volumes/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_gbps_alone": round(h2d_gbps, 1)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm,
+                "roofline_step": roofline_step, "kernels": kernels}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+    # ---- the other BASELINE configs, measured in the same invocation so the driver's record carries them:
+    # configs[3] (3-D ResNet classification step, N GPUs) and configs[4] (10 000-patient eval forward + 1000-resample bootstrap)
+    extra = {}
+    if not args.no_extras and args.workload == "cfg2":
+        torch.cuda.empty_cache()
+        try:
+            r = resnet_measure(args, rank, world, device, cpu_baseline=False)
+            if r is not None:
+                extra["resnet_cfg4"] = {k: r[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "e2e", "gpu_launches", "roofline", "config", "clocks")}
+        except Exception as ex:    # an extra must never take the headline line down
+            extra["resnet_cfg4"] = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                extra["inference_cfg5"] = inference_measure(args, device)
+            except Exception as ex:
+                extra["inference_cfg5"] = {"error": repr(ex)[:200]}
+    if rank == 0:
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -361,13 +410,16 @@ def run_ours(args):
 
 
 def run_inference(args):
+    print(json.dumps(inference_measure(args, torch.device("cuda", 0))), flush=True)
+
+
+def inference_measure(args, dev):
     """BASELINE.json configs[4]: --inference --bootstrap --no_gradcam on synthetic patients: every patient is forwarded
-    ONCE in eval mode (batched), then 1000 bootstrap resamples of the per-class C-index are counted on the GPU.
-    Extra mode (not the driver's headline line): prints its own JSON line."""
+    ONCE in eval mode (batched), then 1000 bootstrap resamples of the per-class C-index are counted on the GPU
+    (/root/reference/main.py:750-887 re-forwards every patient per resample)."""
     import numpy as np
     from mmnn_sts_b200 import main as M
-    dev = torch.device("cuda", 0)
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS["cfg2" if args.workload == "cfg4" else args.workload]
     model = build_model(wl, dev).eval()
     n, bs, R = args.patients, wl["batch"], args.resamples
     g = torch.Generator(device=dev).manual_seed(7)
@@ -391,9 +443,13 @@ def run_inference(args):
     torch.cuda.synchronize(); e0.record()
     c, mean, std, _ = M.bootstrap_cindices(preds, events, durations, idx)
     e1.record(); torch.cuda.synchronize()
-    print(json.dumps({"mode": "inference+bootstrap", "patients": n, "resamples": R, "forward_volumes_per_s": round(n / (fwd_ms / 1e3), 1),
-                      "forward_ms": round(fwd_ms, 1), "bootstrap_ms": round(e0.elapsed_time(e1), 2), "cindex_mean": [float(v) for v in mean],
-                      "cindex_std": [float(v) for v in std], "workload": wl["name"], "note": "inputs generated on the device per batch (random volumes)"}), flush=True)
+    boot_ms = e0.elapsed_time(e1)
+    return {"mode": "inference+bootstrap", "patients": n, "resamples": R, "forward_volumes_per_s": round(n / (fwd_ms / 1e3), 1),
+            "forward_ms": round(fwd_ms, 1), "bootstrap_ms": round(boot_ms, 2),
+            "patients_per_s_end_to_end": round(n / ((fwd_ms + boot_ms) / 1e3), 1), "cindex_mean": [float(v) for v in mean],
+            "cindex_std": [float(v) for v in std], "workload": wl["name"], "n_gpus": 1,
+            "note": "eval-mode forward of every patient once (batch 16, random volumes generated on the device per batch, inside the timed region), "
+                    "then all resamples counted by one cindex_bootstrap launch per class (exact int64 pair counts)"}
 
 
 def run_preprocess(args):
@@ -463,20 +519,31 @@ def resnet_cpu_arm(wl, steps, warmup, sample_batch, num_classes=2):
 
 
 def run_resnet(args):
-    """SURVEY.md section 8f rank 3 / BASELINE configs[3] (extra mode, prints its own JSON line): image-only classification
-    training step of the 3-D ResNet encoder -- forward, BCEWithLogitsLoss(pos_weight, 'sum') on the sigmoid output (the
-    reference's own call, main.py:208), backward, SGD(nesterov) step -- batch 8 per GPU of 1x256x256x64 volumes."""
     import torch.distributed as dist
-    from mmnn_sts_b200 import _lib as L
-    from mmnn_sts_b200 import ops
-    from mmnn_sts_b200.models.resnet import algorithmic_cost, r3d_18
-    from mmnn_sts_b200.optim import SGD
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    line = resnet_measure(args, rank, world, dev, cpu_baseline=not args.no_cpu_baseline)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def resnet_measure(args, rank, world, dev, cpu_baseline=True):
+    """SURVEY.md section 8f rank 3 / BASELINE configs[3]: image-only classification training step of the 3-D ResNet encoder --
+    forward, BCEWithLogitsLoss(pos_weight, 'sum') on the sigmoid output (the reference's own call, main.py:208), backward,
+    SGD(nesterov) step -- batch 8 per GPU of 1x256x256x64 volumes.  Needs an initialised process group when world > 1.
+    Returns the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    from mmnn_sts_b200 import _lib as L
+    from mmnn_sts_b200 import ops
+    from mmnn_sts_b200.models.resnet import algorithmic_cost, r3d_18
+    from mmnn_sts_b200.optim import SGD
+    local = dev.index or 0
     wl = WORKLOADS["cfg4"]
     B, K = wl["batch"], 2
     torch.manual_seed(42)
@@ -561,7 +628,7 @@ def run_resnet(args):
     prof = L.profile_collect()
     L.lib().mmnn_profile_enable(0)
     if rank != 0:
-        return
+        return None
     peaks = load_peaks()
     cost = algorithmic_cost(m, B, wl["spatial"])
     kernels = {}
@@ -590,11 +657,9 @@ def run_resnet(args):
                          "frac": kernels[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (" + peaks["src"] + ")",
                          "algorithmic_bytes_per_step": cost[top]["bytes"]},
             "kernels": kernels}
-    if not args.no_cpu_baseline:
+    if cpu_baseline:
         line["cpu_baseline"] = resnet_cpu_arm(wl, steps=1, warmup=1, sample_batch=1)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def cpu_reference_arm(wl, steps, warmup, sample_batch):
@@ -632,12 +697,14 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    cpu = cpu_reference_arm(wl, steps=steps, warmup=warmup, sample_batch=2)
+    cpu = cpu_reference_arm(wl, steps=steps, warmup=warmup, sample_batch=wl["batch"])    # the whole batch of 16: same step as the GPU arm
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     line = {"impl": "reference", "metric": "train volumes/sec", "value": cpu["value"], "unit": "volumes/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": round(cpu["sec_per_step"] * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "note": "reference algorithm on the host CPU cores (fp32 torch CPU); each step is a bounded 2-volume sample"},
+            "config": {"workload": wl["name"], "global_batch": wl["batch"], "volume": list(wl["spatial"]), "in_channels": wl["cin"], "optimizer_step": "every batch",
+                       "note": "the reference's algorithm on the host CPU cores (fp32 torch CPU, all host threads): one step = the same batch of "
+                               "16 volumes the GPU arm steps on; under torchrun only rank 0 runs it (it does not scale with N)"},
             "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -650,6 +717,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[3] / configs[4] side measurements of the default run")
     ap.add_argument("--mode", default="train", choices=["train", "inference", "preprocess", "resnet"])
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as one CUDA graph (static shapes)")
     ap.add_argument("--patients", type=int, default=10000)

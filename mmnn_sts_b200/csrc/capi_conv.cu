@@ -8,7 +8,53 @@
 #include "rows_persist.cuh"
 #include "stem.cuh"
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 using namespace mmnn;
+
+namespace mmnn {
+// 5-D TMA tensor map of a channels-last bf16 tensor [N][Dz][Dy][Dx][pitch] with the box (32 channels, bx, by, bz, bn), 64-byte swizzle:
+// the descriptor the weight-gradient kernel's TMA issuer hands to cp.async.bulk.tensor (engine.cuh).  The encoder comes from the
+// driver through cudaGetDriverEntryPoint (no link against libcuda); maps are cached per (pointer, geometry).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+bool make_tmap_ndhwc(CUtensorMap* out, const void* ptr, long long pitch, int N, int Dz, int Dy, int Dx, int bx, int by, int bz, int bn) {
+  typedef std::tuple<const void*, long long, int, int, int, int, int, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key(ptr, pitch, N, Dz, Dy, Dx, bx, by, bz, bn);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || ((uintptr_t)ptr & 15u) != 0 || (pitch * 2) % 16 != 0) return false;
+  const cuuint64_t gdim[5] = {(cuuint64_t)pitch, (cuuint64_t)Dx, (cuuint64_t)Dy, (cuuint64_t)Dz, (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)Dx * pitch * 2, (cuuint64_t)Dy * Dx * pitch * 2,
+                              (cuuint64_t)Dz * Dy * Dx * pitch * 2};
+  const cuuint32_t box[5] = {32u, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bn};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+}  // namespace mmnn
 
 #define MMNN_CHECK_LAUNCH()                      \
   do {                                           \
@@ -31,7 +77,11 @@ int choose_stages(const RowsParams& p, uint32_t budget) {
 template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
 int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   uint32_t offs[6];
-  if (p.stages <= 0) p.stages = choose_stages(p, 100 * 1024);
+  // grids that fill the GPU keep two CTAs per SM (100 KB each); grids of <= 148 tiles (late dense blocks) have an SM to themselves
+  // and are latency chains over their k-blocks, so they take the deepest operand ring that fits (ncu, round 2: with Cin = 992
+  // the 100 KB budget left TWO stages and every k-block exposed its weight fetch: 4 200 cycles per k-block)
+  static const int small_kb = [] { const char* e = getenv("MMNN_ROWS_SMALL_SMEM_KB"); return e ? atoi(e) : 200; }();
+  if (p.stages <= 0) p.stages = choose_stages(p, (PF == 2 ? small_kb : 100) * 1024);
   const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
   static const bool tc_stats_on = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '1'; }();
   if (tc_stats_on) p.stages |= 0x100;    // experiment switch: column statistics on the tensor core (engine.cuh)
@@ -180,17 +230,27 @@ template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream) {
   static const bool piped_on = [] { const char* e = getenv("MMNN_WGRAD_PIPED"); return e != nullptr && e[0] == '1'; }();
   if (piped_on && p.NB == 9) p.NP = -1;   // experiment switch: cp.async-pipelined producer for the 3x3x3 weight gradient (engine.cuh)
+  // gradient (B) operand through the TMA unit when a 128-voxel tile is a box of the volume and the operand needs no transform
+  static const bool tma_on = [] { const char* e = getenv("MMNN_WGRAD_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  CUtensorMap tmb;
+  memset(&tmb, 0, sizeof(tmb));
+  p.tma_b = 0;
+  if (tma_on && BTRANS == T_NONE && p.NP != -1 && wgrad_tma_box(p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) {
+    const long long vps = (long long)p.Dz * p.Dy * p.Dx;
+    const int N = (int)((p.M + vps - 1) / vps);
+    if (make_tmap_ndhwc(&tmb, p.b_src, p.b_pitch, N, p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) p.tma_b = 1;
+  }
   uint32_t offs[4];
   if (p.stages <= 0) {
     p.stages = 1;
     for (int s = 1; s <= 4; ++s)
-      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs) <= 225 * 1024) p.stages = s;
+      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0) <= 225 * 1024) p.stages = s;
   }
-  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs);
+  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0);
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p);
+  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p, tmb);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

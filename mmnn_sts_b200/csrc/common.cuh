@@ -1,6 +1,7 @@
 // Shared device helpers for the sm_100a kernels: PTX wrappers (mbarrier, bulk copy, tcgen05/TMEM), bf16 packing.
 // Everything here is written for compute_100a only (tcgen05.* does not exist elsewhere).
 #pragma once
+#include <cuda.h>        // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -68,6 +69,24 @@ MMNN_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, ui
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// Asynchronous L2 prefetch of a contiguous global range (TMA unit): warms L2 for bulk copies issued later in the kernel.
+MMNN_DEVINL void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// TMA tensor copy global -> shared (cp.async.bulk.tensor, SASS UTMALDG): one box of a 5-D tensor map; coordinates may lie
+// outside the tensor -- those elements arrive as ZEROS, which is exactly the zero padding of a convolution operand that needs
+// no transform (gradient tensors).  Completion is signalled on `bar` with the full box byte count.
+MMNN_DEVINL void tma_load_5d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst_smem),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+MMNN_DEVINL void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
 // One lane of a fully converged warp, chosen by the hardware (elect.sync).  Guarding the tcgen05.mma / commit block

@@ -225,7 +225,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
-  pdl_wait();   // nothing above touches global memory
+  if (PF == 2 && warp == 0 && lane == 0) {
+    // Small grids (late dense blocks) are latency chains: every k-block waits for its weight image (one cp.async.bulk from
+    // wherever it lives -- packed at the start of the forward pass, usually evicted to HBM by now).  The weights do not depend on
+    // the preceding kernel, so the whole image of this CTA's column tile is pulled into L2 right away, in pieces of <= 64 KB.
+    const uint8_t* w = reinterpret_cast<const uint8_t*>(p.b_packed + (size_t)tile_n * KB * (size_t)(planes * p.NT * 8));
+    const uint32_t total = (uint32_t)KB * b_bytes;
+    for (uint32_t o = 0; o < total; o += 65536u) bulk_prefetch_l2(w + o, total - o < 65536u ? total - o : 65536u);
+  }
+  pdl_wait();   // nothing above touches global memory written by the preceding kernel
   H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // fp16 operands: packed per-pair table in place of the fp32 one (same size)
   if (TRANS == T_BNRELU) {
     if (OP_F16) {
@@ -624,17 +632,45 @@ struct WgradParams {
   // partial result (plain stores) to dw + x * slot_stride instead of adding it to dw with floating-point atomics, and a tail
   // kernel sums the slots in index order (encoder.cu, wgrad_reduce_kernel).  0 -> atomics into dw (run-dependent last bits).
   long long slot_stride;
+  // TMA path of the B (gradient) operand: tma_b != 0 -> the kernel's CUtensorMap argument describes b_src as the 5-D tensor
+  // [N][Dz][Dy][Dx][C] and a 128-voxel tile of 32 channels is the box (32 channels, bx, by, bz, bn) -- see wgrad_tma_box() --
+  // written with the 64-byte swizzle: 128 rows of 64 B = the canonical SWIZZLE_64B MN-major tcgen05 operand (K = voxel rows:
+  // 8-row atoms 512 B apart = SBO; the next 32 channels / the next tap: one 8 KB group further = LBO).  A shifted tile (3x3x3
+  // taps) is the same box at shifted coordinates; out-of-volume voxels are zero-filled by the TMA unit.
+  int tma_b;
+  int bx, by, bz, bn;
 };
 
-__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/) {
+constexpr int TMA_GROUP_BYTES = TILE_ROWS * 64;   // one TMA box: 128 voxel rows x 32 bf16 channels
+
+// Box decomposition of a tile of 128 consecutive voxels of an [N][Dz][Dy][Dx] volume (x fastest).  Returns false when a tile is
+// not a box (dims that do not chain-divide 128): the kernel then keeps the register path.
+__host__ __device__ inline bool wgrad_tma_box(int Dz, int Dy, int Dx, int& bx, int& by, int& bz, int& bn) {
+  int rem = TILE_ROWS;
+  if (Dx >= rem) { if (Dx % rem) return false; bx = rem; rem = 1; } else { if (rem % Dx) return false; bx = Dx; rem /= Dx; }
+  if (Dy >= rem) { if (Dy % rem) return false; by = rem; rem = 1; } else { if (rem % Dy) return false; by = Dy; rem /= Dy; }
+  if (Dz >= rem) { if (Dz % rem) return false; bz = rem; rem = 1; } else { if (rem % Dz) return false; bz = Dz; rem /= Dz; }
+  bn = rem;
+  return true;
+}
+
+__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/, bool tma_b = false) {
   uint32_t o = 0;
   offs[0] = o; o += 128;                          // barriers + tmem ptr
   offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
   offs[2] = o; o += 2u * 128 * 4 + 2u * CB * 4;   // coefA (scale, shift) [128], coefB [CB]
   o = (o + 127u) & ~127u;
   offs[3] = o;
-  const uint32_t stage = 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
-  return o + stages * stage;
+  uint32_t stage = 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
+  // TMA mode: [B groups (swizzled, the stage base is 1024-byte aligned at run time)][A planes], stage size a multiple of 1 KB
+  if (tma_b) stage = ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + 16u * NP * PLANE_BYTES + 1023u) & ~1023u;
+  const uint32_t ring = stages * stage + (tma_b ? 1024u : 0u);
+  const uint32_t epi = 32u * 132u * 4u;           // the epilogue's transpose staging reuses the ring
+  return o + (ring > epi ? ring : epi);
+}
+__host__ __device__ inline uint32_t wgrad_stage_bytes(int CB, int NB, int NP, bool tma_b) {
+  if (tma_b) return ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + 16u * NP * PLANE_BYTES + 1023u) & ~1023u;
+  return 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
 }
 
 // Fill `planes` chunk planes of one operand tile. lane -> (chunk within a group of G, row sub-index).
@@ -729,6 +765,33 @@ MMNN_DEVINL uint32_t load_planes(uint4 (&regs)[2 * MAX_PASSES], int planes, cons
   return okmask;
 }
 
+// load_planes for a tile of 128 CONSECUTIVE voxels starting at m0 (no row table: row r is voxel m0 + r, valid while < M)
+MMNN_DEVINL uint32_t load_planes_linear(uint4 (&regs)[2 * MAX_PASSES], int planes, const bf16* src, long long pitch, long long m0,
+                                        long long M, int warp, int lane) {
+  const int G = planes >= 8 ? 8 : 4;
+  const int gshift = planes >= 8 ? 3 : 2;
+  const int rsub = lane >> gshift;
+  const int rpp = 32 >> gshift;
+  const int npass = (TILE_ROWS / rpp) / PRODUCER_WARPS;
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp) {
+    const int chunk = grp * G + (lane & (G - 1));
+#pragma unroll
+    for (int ps = 0; ps < MAX_PASSES; ++ps) {
+      regs[grp * MAX_PASSES + ps] = make_uint4(0, 0, 0, 0);
+      if (ps < npass && chunk < planes) {
+        const long long m = m0 + (warp + ps * PRODUCER_WARPS) * rpp + rsub;
+        if (m < M) {
+          regs[grp * MAX_PASSES + ps] = ldg16(src + m * pitch + chunk * 8);
+          okmask |= 1u << (grp * MAX_PASSES + ps);
+        }
+      }
+    }
+  }
+  return okmask;
+}
+
 // OUT_F16: format the tile is written in (the weight-gradient MMA takes an fp16 A operand next to the bf16 gradient operand, so
 // forward activations need no conversion).  IN_F16 && OUT_F16 && BN+ReLU: `scale` points to an H2Coef table (one entry per
 // channel pair) and the transform is the 12-HFMA2 fast path of the forward producers.
@@ -775,7 +838,8 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
 #define MMNN_WGRAD_A_F16 0
 #endif
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
-__global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p,
+                                                                    const __grid_constant__ CUtensorMap tmb) {
   // NEGATIVE RESULT (round 2, B200): the instruction descriptor of tcgen05 kind::f16 has separate A / B format fields, but an
   // fp16 A operand (forward activations, no conversion, packed-half BN+ReLU) next to the bf16 B operand (gradients) raises
   // "illegal instruction" on sm_100a -- both operands must have the same format.  -DMMNN_WGRAD_A_F16=1 builds that variant
@@ -785,7 +849,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   pdl_trigger();
   uint32_t offs[4];
   const int NP = p.NP < 1 ? 1 : p.NP;
-  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs);
+  const bool tma_b = p.tma_b != 0;
+  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
@@ -796,9 +861,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   float* coefB = coefA + 256;
   const int bplanes = p.CB / 8;
   const uint32_t a_bytes = 16u * NP * PLANE_BYTES;
-  const uint32_t bt_bytes = (uint32_t)bplanes * PLANE_BYTES;
-  const uint32_t stage_bytes = a_bytes + p.NB * bt_bytes;
-  const uint32_t stage0 = sbase + offs[3];
+  const uint32_t bgroups = (uint32_t)p.CB / 32u;                        // TMA mode: 32-channel groups per B tile
+  const uint32_t bt_bytes = tma_b ? bgroups * (uint32_t)TMA_GROUP_BYTES : (uint32_t)bplanes * PLANE_BYTES;
+  const uint32_t stage_bytes = wgrad_stage_bytes(p.CB, p.NB, NP, tma_b);
+  const uint32_t stage0 = tma_b ? ((sbase + offs[3] + 1023u) & ~1023u) : sbase + offs[3];
+  // operand offsets inside a stage: register path [A][B]; TMA path [B][A] (the swizzled B groups need the 1 KB alignment)
+  const uint32_t a_off = tma_b ? p.NB * bt_bytes : 0u, b_off = tma_b ? 0u : a_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
@@ -816,11 +884,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS);
+        mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS + (tma_b ? 1 : 0));   // + the expect_tx arrival of the TMA issuer
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
       fence_mbar_init();
+      if (tma_b) tma_prefetch_desc(&tmb);
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
@@ -894,8 +963,49 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     // MEASURED SLOWER than the register-staged path below in a same-box A/B at configs[1] (3x3x3 weight gradients 2.56 vs
     // 2.37 ms, step 15.17 vs 14.94 ms; 2.63 ms when the copies bypass L1 -- the 9 shifted tiles share their rows), so it
     // is OFF unless MMNN_WGRAD_PIPED=1 (kept as a parity-tested experiment).
-    const bool piped = AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4 && p.NP == -1;   // NP == -1: opt-in experiment switch (MMNN_WGRAD_PIPED=1)
-    if (piped) {
+    const bool piped = !tma_b && AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4 && p.NP == -1;   // NP == -1: opt-in experiment switch (MMNN_WGRAD_PIPED=1)
+    if (tma_b && AMODE == WA_LINEAR) {
+      // ---- TMA mode (default when the tile is a box of the volume): the gradient tiles arrive by cp.async.bulk.tensor, so
+      // the 256 producer threads only build the A tile -- and do it software-pipelined: the 128-bit loads of tile it+1 are in
+      // flight while tile it is transformed and stored (8 loads per thread, no row table, no per-tile barrier).
+      const bf16* asrc = p.a_src + ztile * 128;
+      auto issue_b = [&](int it, int s) {       // one thread: expect_tx + the boxes of this tile
+        const long long m0 = (long long)(t_begin + it) * TILE_ROWS;
+        const int n0 = (int)(m0 / vps);
+        int rem = (int)(m0 - (long long)n0 * vps);
+        const int z0 = rem / (p.Dy * p.Dx);
+        rem -= z0 * p.Dy * p.Dx;
+        const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
+        const uint32_t sBs = stage0 + s * stage_bytes + b_off;
+        mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)p.NB * bt_bytes);
+        for (int j = 0; j < p.NB; ++j) {
+          int dz = 0, dy = 0, dx = 0;
+          if (p.NB > 1) { const int tap = ytile * p.NB + j; dz = -(tap / 9 - 1); dy = -((tap / 3) % 3 - 1); dx = -(tap % 3 - 1); }
+          const int cbase = p.NB == 1 ? ytile * p.CB : 0;
+          for (uint32_t c = 0; c < bgroups; ++c)     // channels beyond the tensor arrive as zeros (their columns are discarded)
+            tma_load_5d(sBs + ((uint32_t)j * bgroups + c) * (uint32_t)TMA_GROUP_BYTES, &tmb, cbase + (int)c * 32, x0 + dx, y0 + dy, z0 + dz, n0,
+                        bar_full + 8 * s);
+        }
+      };
+      uint4 RA[2 * MAX_PASSES], RB[2 * MAX_PASSES];
+      uint32_t okA = load_planes_linear(RA, aplanes, asrc, p.a_pitch, (long long)t_begin * TILE_ROWS, p.M, warp, lane), okB = 0;
+      auto finish = [&](int it, const uint4 (&regs)[2 * MAX_PASSES], uint32_t ok) {
+        const int s = it % S;
+        mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / S) & 1u) ^ 1u, 11);
+        if (tid == 0) issue_b(it, s);
+        store_planes<ATRANS, kActF16, A_F16>(regs, ok, stage0 + s * stage_bytes + a_off, aplanes, warp, lane, coefA, coefA + 128);
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * s);
+      };
+      for (int it = 0; it < nt; it += 2) {
+        if (it + 1 < nt) okB = load_planes_linear(RB, aplanes, asrc, p.a_pitch, (long long)(t_begin + it + 1) * TILE_ROWS, p.M, warp, lane);
+        finish(it, RA, okA);
+        if (it + 1 < nt) {
+          if (it + 2 < nt) okA = load_planes_linear(RA, aplanes, asrc, p.a_pitch, (long long)(t_begin + it + 2) * TILE_ROWS, p.M, warp, lane);
+          finish(it + 1, RB, okB);
+        }
+      }
+    } else if (piped) {
       auto issue = [&](int it, uint4 (&aregs)[2 * MAX_PASSES], uint32_t& aok) {
         const int s = it % S;
         mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / S) & 1u) ^ 1u, 11);
@@ -916,7 +1026,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           rowinfo[tid] = ri;
         }
         named_bar_sync(1, NUM_PRODUCER_THREADS);
-        const uint32_t sB = stage0 + s * stage_bytes + a_bytes;
+        const uint32_t sB = stage0 + s * stage_bytes + b_off;
         aok = load_planes<false>(aregs, aplanes, p.a_src + ztile * 128, p.a_pitch, rowinfo, warp, lane, 0, 0, 0, 0, p.Dz, p.Dy, p.Dx);
         if (p.NB == 1) {
           const int rsub = lane >> 3;
@@ -995,8 +1105,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         rowinfo[tid] = ri;
       }
       named_bar_sync(1, NUM_PRODUCER_THREADS);
-      const uint32_t sA = stage0 + s * stage_bytes;
-      const uint32_t sB = sA + a_bytes;
+      const uint32_t sA = stage0 + s * stage_bytes + a_off;
+      const uint32_t sB = stage0 + s * stage_bytes + b_off;
       uint4 aregs[2 * MAX_PASSES];
       uint32_t aok = 0;
       if (AMODE == WA_LINEAR) {
@@ -1023,7 +1133,43 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           }
         }
       }
-      if (p.NB == 1) {
+      if (tma_b) {
+        // B operand by TMA: one elected thread issues NB x (valid planes) boxes of 128 voxels x 8 channels; rows outside the
+        // volume (taps) or beyond M arrive as zeros.  The 256 producer threads only build the A tile.
+        if (tid == 0) {
+          const long long m0 = (long long)(t_begin + it) * TILE_ROWS;
+          const int n0 = (int)(m0 / vps);
+          int rem = (int)(m0 - (long long)n0 * vps);
+          const int z0 = rem / (p.Dy * p.Dx);
+          rem -= z0 * p.Dy * p.Dx;
+          const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
+          mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)p.NB * bt_bytes);
+          for (int j = 0; j < p.NB; ++j) {
+            int dz = 0, dy = 0, dx = 0;
+            if (p.NB > 1) { const int tap = ytile * p.NB + j; dz = -(tap / 9 - 1); dy = -((tap / 3) % 3 - 1); dx = -(tap % 3 - 1); }
+            const int cbase = p.NB == 1 ? ytile * p.CB : 0;
+            for (uint32_t c = 0; c < bgroups; ++c)     // channels beyond the tensor arrive as zeros (their columns are discarded)
+              tma_load_5d(sB + ((uint32_t)j * bgroups + c) * (uint32_t)TMA_GROUP_BYTES, &tmb, cbase + (int)c * 32, x0 + dx, y0 + dy, z0 + dz, n0,
+                          bar_full + 8 * s);
+          }
+        }
+        if (AMODE == WA_LINEAR) store_planes<ATRANS, kActF16, A_F16>(aregs, aok, sA, aplanes, warp, lane, coefA, coefA + 128);
+        if (AMODE == WA_STEM_PAIR) {
+          const int chunk = lane & 7, rsub = lane >> 3;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < 2 * NP) {
+#pragma unroll
+              for (int ps = 0; ps < MAX_PASSES; ++ps) {
+                const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
+                uint4 v = sregs[g][ps];
+                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, A_F16>(v);
+                sts16(sA + (g * 8 + chunk) * PLANE_BYTES + r * 16, v);
+              }
+            }
+          }
+        }
+      } else if (p.NB == 1) {
         uint4 bregs[2 * MAX_PASSES];
         // stem: the rowinfo index is the space-to-depth row; the B rows are plain output voxels (linear index)
         const uint32_t bok = load_planes<false>(bregs, bplanes_valid, p.b_src + ytile * p.CB, p.b_pitch, rowinfo, warp, lane, 0, 0, 0,
@@ -1144,9 +1290,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       mbar_wait(bar_full + 8 * s, ph, 12);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sA = stage0 + s * stage_bytes;
+        const uint32_t sA = stage0 + s * stage_bytes + a_off;
+        const uint32_t sB = stage0 + s * stage_bytes + b_off;
         const uint64_t ad0 = make_smem_desc(sA, 128, PLANE_BYTES);
-        uint64_t bd0 = make_smem_desc(sA + a_bytes, 128, PLANE_BYTES);
+        // B: register path = SWIZZLE_NONE chunk planes (8-row K groups 128 B apart, 8-channel chunks one plane apart);
+        //    TMA path = SWIZZLE_64B rows of 64 B (8-row atoms 512 B apart, 32-channel groups 8 KB apart)
+        uint64_t bd0 = tma_b ? make_smem_desc_sw(sB, TMA_GROUP_BYTES, 512, 4u) : make_smem_desc(sB, 128, PLANE_BYTES);
+        const uint32_t bk16 = tma_b ? 1024u : 256u;      // byte advance of the B start address per K step of 16 voxel rows
         const uint32_t acc0 = it > 0 ? 1u : 0u;
         if (AMODE == WA_STEM_PAIR) {
           // NP pairs share the B tile; pair pi reads its own 16 A planes and owns accumulator pi
@@ -1156,7 +1306,19 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             tc_mma_bf16(td, ad, bd0, idesc, acc0);
 #pragma unroll
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
-              tc_mma_bf16(td, desc_advance(ad, k16 * 256), desc_advance(bd0, k16 * 256), idesc, 1u);
+              tc_mma_bf16(td, desc_advance(ad, k16 * 256), desc_advance(bd0, k16 * bk16), idesc, 1u);
+          }
+        } else if (p.NB == 9 && p.CB == 32 && tma_b) {
+          // swizzled operand: N must cover whole 32-channel groups -> three N = 96 MMAs (3 taps each) per K step
+          const uint32_t idesc3 = make_idesc_ab(128, 96, 1, 1, A_F16, false);
+#pragma unroll
+          for (int h = 0; h < 3; ++h) {
+            const uint32_t td = tmem_base + h * 96;
+            const uint64_t bd = desc_advance(bd0, h * 3 * TMA_GROUP_BYTES);
+            tc_mma_bf16(td, ad0, bd, idesc3, acc0);
+#pragma unroll
+            for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
+              tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd, k16 * 1024), idesc3, 1u);
           }
         } else if (p.NB == 9 && p.CB == 32) {
           // the 9 shifted gradient tiles are 36 consecutive chunk planes = ONE MN-major operand of N = 288 columns
@@ -1178,7 +1340,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           tc_mma_bf16(td, ad0, bd0, idesc, acc0);
 #pragma unroll
           for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
-            tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd0, k16 * 256), idesc, 1u);
+            tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd0, k16 * bk16), idesc, 1u);
           bd0 = desc_advance(bd0, bt_bytes);
         }
         tc_commit(bar_empty + 8 * s);
