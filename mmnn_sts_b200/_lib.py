@@ -37,7 +37,7 @@ class RowsParams(C.Structure):
                 ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
                 ("b_packed", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_longlong),
                 ("colscale", C.c_void_p), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p),
-                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int)]
+                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int)]
 
 
 class BrickParams(C.Structure):
@@ -105,7 +105,7 @@ class RnConvGeom(C.Structure):
 
 A_LINEAR_CONV, A_STEM = 0, 1
 T_NONE, T_BNRELU = 0, 1
-EP_STORE, EP_STORE_STATS, EP_MASK_STATS = 0, 1, 2
+EP_STORE, EP_STORE_STATS, EP_MASK_STATS, EP_MASK_STATS_ACC = 0, 1, 2, 3
 PACK_GENERIC, PACK_STEM, PACK_STEM_SW32 = 0, 1, 2
 
 

@@ -126,7 +126,7 @@ int launch_rows_t(const RowsParams& p, cudaStream_t stream) {
   // MMNN_ROWS_PERSIST=0 / 1 forces the one-tile-per-CTA / the persistent kernel for both (parity tests run both).
   static const int persist_env = [] { const char* e = getenv("MMNN_ROWS_PERSIST"); return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0); }();
   const bool persist = persist_env == 1 || (persist_env == -1 && !GRAD && EPI == EP_STORE_STATS);
-  if (AMODE == A_LINEAR_CONV && persist && p.ntaps == 1 && p.NT <= 256 && (p.Ncols + p.NT - 1) / p.NT <= 148 && tiles >= 2 * 148)
+  if (AMODE == A_LINEAR_CONV && persist && EPI != EP_MASK_STATS_ACC && p.ntaps == 1 && p.NT <= 256 && (p.Ncols + p.NT - 1) / p.NT <= 148 && tiles >= 2 * 148)
     return launch_rows_persist<TRANS, EPI, GRAD>(p, stream);
   if (tiles <= 148) return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 2>(p, stream);   // latency-bound small grids
   return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 1>(p, stream);
@@ -143,6 +143,7 @@ int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cu
   CASE(A_STEM, T_NONE, EP_STORE_STATS, false)
   CASE(A_LINEAR_CONV, T_NONE, EP_STORE, true)
   CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS, true)
+  CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS_ACC, true)
 #undef CASE
   return -3;
 }

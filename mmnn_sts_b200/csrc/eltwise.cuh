@@ -244,6 +244,7 @@ struct AvgPoolParams {
   const double* g_sum_in;  // pass 2
   const double* g_dot_in;
   float inv_count;
+  int pre_rstd;            // pass 2: write gamma * (v - c1 - xhat c2) (the consumer's finalising pass applies rstd) instead of gamma * rstd * (...)
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
@@ -286,7 +287,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const
 template <int PASS>
 static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
   pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
-  extern __shared__ float coef[];  // [6][C]: s, t, mean, rstd, (pass2) k*c1', k*c2'
+  extern __shared__ float coef[];  // [7][C]: s, t, mean, rstd, (pass2) c1, c2, output factor
   __shared__ float red[PASS == 1 ? EW_THREADS * 16 : 1];
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -296,6 +297,7 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
     if (PASS == 2) {
       coef[4 * p.C + c] = (float)(p.g_sum_in[c] * (double)p.inv_count);
       coef[5 * p.C + c] = (float)(p.g_dot_in[c] * (double)p.inv_count);
+      coef[6 * p.C + c] = p.pre_rstd ? p.bn.gamma[c] : s;
     }
   }
   __syncthreads();
@@ -327,7 +329,7 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
       const float v = act ? g[e] * 0.125f : 0.f;
       const float xh = (f[e] - coef[2 * p.C + c]) * coef[3 * p.C + c];
       if (PASS == 1) { s1[e] += v; s2[e] += v * xh; }
-      else o[e] = coef[c] * (v - coef[4 * p.C + c] - xh * coef[5 * p.C + c]);
+      else o[e] = coef[6 * p.C + c] * (v - coef[4 * p.C + c] - xh * coef[5 * p.C + c]);
     }
     if (PASS == 2) {
       float4* d = reinterpret_cast<float4*>(p.dx + m * p.dx_pitch + chunk * 8);
@@ -361,6 +363,7 @@ struct BnApplyParams {
   int slice_c0;
   const float* slice_scale; // [samples][32] or null
   int vps;
+  int pre_rstd;             // leading factor gamma instead of gamma * rstd (deferred BatchNorm backward: the finalising pass applies rstd)
 };
 
 template <int OUT>
@@ -370,7 +373,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
     bn_mean_rstd(p.bn, c, mean, rstd);
-    const float k = p.bn.gamma[c] * rstd;
+    const float k = p.pre_rstd ? p.bn.gamma[c] : p.bn.gamma[c] * rstd;
     const float c1 = (float)(p.g_sum[c] * (double)p.inv_count);
     const float c2 = (float)(p.g_dot[c] * (double)p.inv_count);
     coef[c] = k;
@@ -450,6 +453,112 @@ static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const _
     m = m1 + sm_;
     chunk = chunk1 + sc_;
     if (chunk >= cpr) { chunk -= cpr; ++m; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- E4b: deferred BN backward
+// Every norm1 of a dense block normalises the SAME tensor (the block buffer) with the SAME batch statistics; only gamma / beta
+// differ per layer (/root/reference/models/densenet.py:76).  So the gradient of buffer channel c,
+//     dX_c = T_c + sum over the layers l reading c of  gamma_lc rstd_c (dA1_lc - mean(dA1_lc) - xhat_c mean(dA1_lc xhat_c)),
+// (T_c = the term of the block's consumer: transition / norm5, a BatchNorm over the same statistics too) factors as
+//     dX_c = rstd_c (G_c - C1_c - xhat_c C2_c),   G_c = T_c / rstd_c + sum_l gamma_lc dA1_lc,
+//     C1_c = sum_l gamma_lc mean(dA1_lc),  C2_c = sum_l gamma_lc mean(dA1_lc xhat_c).
+// G is accumulated by the epilogue of every layer's 1x1x1 data-gradient GEMM (EP_MASK_STATS_ACC, engine.cuh) while the tile
+// is in registers; this pass finalises a channel range once its last contributor has run: instead of one read-modify-write of
+// ALL cin channels per layer (O(L^2) traffic, 12 B per element) each channel is finalised ONCE (O(L)).
+// Eval mode (running statistics differ per layer): G already holds the complete gradient, the pass is the identity + cast.
+struct FinalizeParams {
+  long long M;
+  int c_lo, nch;            // channel range of the block buffer (nch multiple of 8)
+  float* G;                 // [M][g_pitch] fp32 accumulator; the final gradient is written back in place
+  long long g_pitch;
+  const bf16* x;            // block buffer (forward activations), same channel indexing
+  long long x_pitch;
+  BnSrc bn;                 // statistics of the block buffer's channels (any norm of the block: only mean / rstd are used)
+  int nlayers;              // contributing layers (0: the range only holds T)
+  const float* gamma[24];   // per contributing layer: gamma of its norm1, g_sum / g_dot of its backward statistics (channel 0 based)
+  const double* g_sum[24];
+  const double* g_dot[24];
+  float inv_count;
+  int batch;                // 0: eval mode
+  bf16* out;                // optional bf16 copy [M][out_pitch] (the next GEMM's gradient operand), x out_scale[sample][nch]
+  long long out_pitch;
+  const float* out_scale;
+  int vps;
+};
+
+static __global__ void __launch_bounds__(EW_THREADS) grad_finalize_kernel(const __grid_constant__ FinalizeParams p) {
+  pdl_trigger(); pdl_wait();
+  extern __shared__ float coef[];   // [3][nch]: a (on G), b (on x), d;  then double part[2][T][nch] (reduction scratch)
+  // C1 / C2: nlayers x nch independent loads.  T threads share a channel (layers j, j+T, ...), four loads in flight per thread,
+  // partial sums combined in a fixed order -- the serial per-channel loop cost ~0.5 us of L2 latency per contributing layer in
+  // EVERY block of the grid (24 layers: ~10 us per launch).
+  int T = EW_THREADS / p.nch;
+  T = T < 1 ? 1 : (T > 8 ? 8 : T);
+  double* part = reinterpret_cast<double*>(coef + 3 * p.nch + ((3 * p.nch) & 1));
+  if (p.batch) {
+    for (int i = threadIdx.x; i < p.nch * T; i += EW_THREADS) {
+      const int c = i % p.nch, j = i / p.nch;
+      double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+      int l = j;
+      for (; l + 3 * T < p.nlayers; l += 4 * T) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double ga = (double)p.gamma[l + u * T][p.c_lo + c];
+          a1[u] += ga * p.g_sum[l + u * T][p.c_lo + c];
+          a2[u] += ga * p.g_dot[l + u * T][p.c_lo + c];
+        }
+      }
+      for (; l < p.nlayers; l += T) {
+        const double ga = (double)p.gamma[l][p.c_lo + c];
+        a1[0] += ga * p.g_sum[l][p.c_lo + c];
+        a2[0] += ga * p.g_dot[l][p.c_lo + c];
+      }
+      part[(0 * T + j) * p.nch + c] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      part[(1 * T + j) * p.nch + c] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < p.nch; c += EW_THREADS) {
+    float a = 1.f, b = 0.f, d = 0.f;
+    if (p.batch) {
+      float mean, rstd;
+      bn_mean_rstd(p.bn, p.c_lo + c, mean, rstd);
+      double C1 = 0.0, C2 = 0.0;
+      for (int j = 0; j < T; ++j) { C1 += part[(0 * T + j) * p.nch + c]; C2 += part[(1 * T + j) * p.nch + c]; }
+      const float c1 = (float)(C1 * (double)p.inv_count), c2 = (float)(C2 * (double)p.inv_count);
+      a = rstd; b = -rstd * rstd * c2; d = rstd * (-c1 + mean * rstd * c2);
+    }
+    coef[c] = a; coef[p.nch + c] = b; coef[2 * p.nch + c] = d;
+  }
+  __syncthreads();
+  const int cpr = p.nch / 8;
+  const long long total = p.M * cpr;
+  for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {
+    const int chunk = (int)(idx % cpr);
+    const long long m = idx / cpr;
+    float4* gp = reinterpret_cast<float4*>(p.G + m * p.g_pitch + p.c_lo + chunk * 8);
+    const float4 ga = gp[0], gb = gp[1];
+    float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    if (p.batch) {
+      float f[8];
+      unpack8<ACT>(ldg16(p.x + m * p.x_pitch + p.c_lo + chunk * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = chunk * 8 + e;
+        g[e] = fmaf(coef[c], g[e], fmaf(coef[p.nch + c], f[e], coef[2 * p.nch + c]));
+      }
+      gp[0] = make_float4(g[0], g[1], g[2], g[3]);
+      gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+    }
+    if (p.out != nullptr) {
+      if (p.out_scale != nullptr) {
+        const float* cs = p.out_scale + (m / p.vps) * p.nch + chunk * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] *= __ldg(cs + e);
+      }
+      *reinterpret_cast<uint4*>(p.out + m * p.out_pitch + chunk * 8) = pack8<GRD>(g);
+    }
   }
 }
 

@@ -636,9 +636,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   auto bn_apply = [&](int out_mode, long long M, int C, const bf16* v, const float* v32, long long v_pitch, const bf16* x,
                       long long x_pitch, const BnSrc& bn, const double* gs, const double* gd, void* outp,
                       long long out_pitch, bf16* slice_out = nullptr, int slice_c0 = 0, const float* slice_scale = nullptr,
-                      int vps_ = 1) -> int {
+                      int vps_ = 1, int pre_rstd = 0) -> int {
     BnApplyParams a = {};
-    a.slice_out = slice_out; a.slice_c0 = slice_c0; a.slice_scale = slice_scale; a.vps = vps_;
+    a.slice_out = slice_out; a.slice_c0 = slice_c0; a.slice_scale = slice_scale; a.vps = vps_; a.pre_rstd = pre_rstd;
     a.M = M; a.C = C; a.v = v; a.v32 = v32; a.v_pitch = v_pitch; a.x = x; a.x_pitch = x_pitch; a.bn = bn;
     a.g_sum = gs; a.g_dot = gd; a.inv_count = batch ? 1.0f / (float)M : 0.f; a.out = outp; a.out_pitch = out_pitch;
     const int grid = ew_grid(M * (C / 8));
@@ -647,6 +647,39 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     if (out_mode == BA_OUT_BF16) launch_pdl(bn_bwd_apply_kernel<BA_OUT_BF16>, dim3(grid), dim3(EW_THREADS), sm, st, a);
     else if (out_mode == BA_OUT_F32_ADD) launch_pdl(bn_bwd_apply_kernel<BA_OUT_F32_ADD>, dim3(grid), dim3(EW_THREADS), sm, st, a);
     else launch_pdl(bn_bwd_apply_kernel<BA_OUT_F32_STORE>, dim3(grid), dim3(EW_THREADS), sm, st, a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+  };
+
+  // Deferred BatchNorm backward of the dense blocks (eltwise.cuh E4b): dbuf[b] is the fp32 accumulator G.  It is initialised by
+  // the block's consumer (norm5 / the transition's BatchNorm backward, written WITHOUT the rstd factor in batch mode), every
+  // layer's 1x1x1 data-gradient epilogue adds gamma_l * dA1_l, and finalize() turns a channel range into the true gradient
+  // rstd (G - C1 - xhat C2) once its lowest reader has run: layers first_layer .. L-1 of block b contribute.
+  auto finalize = [&](int b, int c_lo, int nch, int first_layer, bf16* outp, long long out_pitch, const float* out_scale) -> int {
+    const BlockInfo& bi = pl->blocks[b];
+    const int L = (int)bi.layers.size();
+    FinalizeParams f = {};
+    f.M = g.M[b]; f.c_lo = c_lo; f.nch = nch;
+    f.G = (float*)(ws + g.dbuf[b]); f.g_pitch = bi.ctot;
+    f.x = (const bf16*)(ws + g.buf[b]); f.x_pitch = bi.ctot;
+    f.bn = make_bn(bi.layers[L - 1].n1, params, buffers, fstats, FC, g.M[b], batch);   // any norm of the block: same statistics
+    f.nlayers = 0;
+    for (int l = first_layer; l < L && batch; ++l) {
+      const LayerInfo& li = bi.layers[l];
+      if (f.nlayers >= 24) return -12;
+      f.gamma[f.nlayers] = (const float*)params[li.n1.param_idx];
+      f.g_sum[f.nlayers] = gsum(li.n1); f.g_dot[f.nlayers] = gdot(li.n1);
+      ++f.nlayers;
+    }
+    f.inv_count = batch ? 1.0f / (float)g.M[b] : 0.f;
+    f.batch = batch ? 1 : 0;
+    f.out = outp; f.out_pitch = out_pitch; f.out_scale = out_scale; f.vps = g.D[b] * g.H[b] * g.W[b];
+    if (!batch && outp == nullptr) return 0;      // eval mode: the accumulator already holds the gradient
+    ProfScope ps_(PC_EXTRACT, st);
+    int T = EW_THREADS / nch;
+    T = T < 1 ? 1 : (T > 8 ? 8 : T);
+    const size_t fsm = (3 * nch + 1) * sizeof(float) + (size_t)2 * T * nch * sizeof(double);
+    launch_pdl(grad_finalize_kernel, dim3(ew_grid(f.M * (nch / 8))), dim3(EW_THREADS), fsm, st, f);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
   };
@@ -722,7 +755,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     { ProfScope ps_(PC_NORM5_BWD, st);
       bn_bwd_stats_f32_kernel<<<blocks, EW_THREADS, 2 * C * sizeof(float), st>>>(grad_out, x, C, bn, M, C, gsum(pl->n5), gdot(pl->n5)); }
     LAUNCH_RET();
-    RET_IF(bn_apply(BA_OUT_F32_STORE, M, C, nullptr, grad_out, C, x, C, bn, gsum(pl->n5), gdot(pl->n5), ws + g.dbuf[nb - 1], C));
+    RET_IF(bn_apply(BA_OUT_F32_STORE, M, C, nullptr, grad_out, C, x, C, bn, gsum(pl->n5), gdot(pl->n5), ws + g.dbuf[nb - 1], C,
+                    nullptr, 0, nullptr, 1, batch ? 1 : 0));
   }
 
   for (int b = nb - 1; b >= 0; --b) {
@@ -745,12 +779,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       // gradient of the layer's 32 new channels (all later consumers have already accumulated into dbuf): for the top
       // layer of a block it is extracted here; for every other layer the previous iteration's BN-backward pass already
       // emitted it while it had the final values in registers (fused slice extraction).
-      if (l == (int)bi.layers.size() - 1) {
-        ProfScope ps_(PC_EXTRACT, st);
-        launch_pdl(extract_slice_kernel, dim3(ew_grid(M * 4)), dim3(EW_THREADS), 0, st, 
-            dbuf + li.cin, bi.ctot, gslice, M, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr, vps);
-        LAUNCH_RET();
-      }
+      if (l == (int)bi.layers.size() - 1)
+        RET_IF(finalize(b, li.cin, GROWTH, (int)bi.layers.size(), gslice, GROWTH, dropmask ? dropmask + (size_t)li.index * B * GROWTH : nullptr));
       // conv2 wgrad -> scratch [tap][co][ci]
       {
         WgradParams w = {};
@@ -815,29 +845,27 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         side_done[parity][1] = pl->next_event();
         CUDA_RET(cudaEventRecord(side_done[parity][1], sd));
       }
-      // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics), then BN1 backward into dbuf[:, :cin]
+      // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics): the masked gradient, scaled by gamma, is ADDED to the
+      // block's fp32 accumulator by the epilogue (deferred BatchNorm backward: no bf16 dA1 tensor, no per-layer pass over cin channels)
       {
         RowsParams p = {};
         p.M = (int)M; p.NT = 128; p.Ncols = li.cin; p.Cin = BOTT; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
         p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
         p.a_src = dA2; p.a_pitch = BOTT;
         p.b_packed = packed + li.pk_c1d;
-        p.out = dA1; p.out_pitch = li.cin;
+        p.out = (bf16*)dbuf; p.out_pitch = bi.ctot; p.acc_rstd = batch ? 0 : 1;
         p.st_sum = gsum(li.n1); p.st_sq = gdot(li.n1);
         p.e_src = buf; p.e_pitch = bi.ctot; p.bnE = bn1;
         ProfScope ps_(PC_CONV1_DGRAD, st);
-        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, 1, st));
+        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS_ACC, 1, st));
       }
       if (l > 0) {
-        // this pass finalises channels [cin-32, cin) = the new channels of layer l-1: emit that layer's gradient slice
-        // into the other parity's buffer (after the side-stream wgrad that last read it has finished)
+        // channels [cin-32, cin) = the new channels of layer l-1 have seen their last reader: finalise them and emit that
+        // layer's gradient slice into the other parity's buffer (after the side-stream wgrad that last read it has finished)
         const LayerInfo& lp = bi.layers[l - 1];
         if (side_done[parity ^ 1][0]) CUDA_RET(cudaStreamWaitEvent(st, side_done[parity ^ 1][0], 0));
         bf16* gnext = (bf16*)(ws + g.gslice) + (size_t)(parity ^ 1) * g.maxM_ * GROWTH;
-        RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot,
-                        gnext, lp.cin, dropmask ? dropmask + (size_t)lp.index * B * GROWTH : nullptr, vps));
-      } else {
-        RET_IF(bn_apply(BA_OUT_F32_ADD, M, li.cin, dA1, nullptr, li.cin, buf, bi.ctot, bn1, gsum(li.n1), gdot(li.n1), dbuf, bi.ctot));
+        RET_IF(finalize(b, lp.cin, GROWTH, l, gnext, GROWTH, dropmask ? dropmask + (size_t)lp.index * B * GROWTH : nullptr));
       }
     }
     {
@@ -856,9 +884,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       bf16* dpooled = (bf16*)(ws + g.dpooled);
       const bf16* pooled = (const bf16*)(ws + g.pooled[b - 1]);
       if (trans_done) CUDA_RET(cudaStreamWaitEvent(st, trans_done, 0));   // previous transition's wgrad still reads gout
-      { ProfScope ps_(PC_EXTRACT, st);
-        launch_pdl(extract_slice_kernel, dim3(ew_grid(M * (bi.c0 / 8))), dim3(EW_THREADS), 0, st, dbuf, bi.ctot, gout, M, bi.c0, nullptr, vps); }
-      LAUNCH_RET();
+      RET_IF(finalize(b, 0, bi.c0, 0, gout, bi.c0, nullptr));     // the block's input channels: every layer of the block read them
       {
         WgradParams w = {};
         w.M = (int)M; w.CB = 128; w.NB = 1; w.na_total = pv.ctot; w.nb_total = bi.c0;
@@ -896,14 +922,16 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       a.dx = (float*)(ws + g.dbuf[b - 1]); a.dx_pitch = pv.ctot;
       a.g_sum = gsum(pv.tn); a.g_dot = gdot(pv.tn); a.g_sum_in = gsum(pv.tn); a.g_dot_in = gdot(pv.tn);
       a.inv_count = batch ? 1.0f / (float)Mp : 0.f;
+      a.pre_rstd = batch ? 1 : 0;                                  // dbuf[b-1] is that block's accumulator G (finalised per channel range)
       const int rows_per_block = EW_THREADS / (pv.ctot / 8);
       int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
       { ProfScope ps_(PC_AVGPOOL_BWD, st, 2);
-        launch_pdl(avgpool_bnrelu_bwd_kernel<1>, dim3(blocks), dim3(EW_THREADS), 6 * pv.ctot * sizeof(float), st, a);
-        launch_pdl(avgpool_bnrelu_bwd_kernel<2>, dim3(blocks), dim3(EW_THREADS), 6 * pv.ctot * sizeof(float), st, a); }
+        launch_pdl(avgpool_bnrelu_bwd_kernel<1>, dim3(blocks), dim3(EW_THREADS), 7 * pv.ctot * sizeof(float), st, a);
+        launch_pdl(avgpool_bnrelu_bwd_kernel<2>, dim3(blocks), dim3(EW_THREADS), 7 * pv.ctot * sizeof(float), st, a); }
       LAUNCH_RET();
     } else {
       // pool0 + relu0 + norm0 + conv0
+      RET_IF(finalize(0, 0, bi.c0, 0, nullptr, 0, nullptr));      // block 1's input channels (the pooled stem output), in place
       PoolBwdParams q = {};
       q.B = B; q.D0 = g.D0; q.H0 = g.H0; q.W0 = g.W0; q.D1 = g.D[0]; q.H1 = g.H[0]; q.W1 = g.W[0];
       q.x = (const bf16*)(ws + g.stem_out);

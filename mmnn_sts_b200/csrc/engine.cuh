@@ -59,7 +59,11 @@ MMNN_DEVINL void bn_mean_rstd(const BnSrc& b, int c, float& mean, float& rstd) {
 
 enum { A_LINEAR_CONV = 0, A_STEM = 1 };
 enum { T_NONE = 0, T_BNRELU = 1 };
-enum { EP_STORE = 0, EP_STORE_STATS = 1, EP_MASK_STATS = 2 };
+// EP_MASK_STATS_ACC (1x1x1 data gradient of a dense layer): like EP_MASK_STATS, but the masked gradient is not stored as a bf16
+// tensor for a separate BatchNorm-backward pass -- it is ADDED, scaled per column by coefG, into the fp32 gradient accumulator
+// of the block buffer (`out` is then a float*, one vector RED per 4 columns; every element has exactly one writer per launch,
+// so the result does not depend on any ordering).  See encoder.cu ("deferred BatchNorm backward") for the algebra.
+enum { EP_STORE = 0, EP_STORE_STATS = 1, EP_MASK_STATS = 2, EP_MASK_STATS_ACC = 3 };
 
 struct RowsParams {
   int M;       // rows (output voxels)
@@ -84,6 +88,8 @@ struct RowsParams {
   long long e_pitch;
   BnSrc bnE;
   int stages;
+  int acc_rstd;       // EP_MASK_STATS_ACC: per-column scale of the accumulated gradient: 0 -> gamma (batch statistics: rstd is
+                      // applied once, by the finalising pass), 1 -> gamma * rstd (running statistics differ per layer)
 };
 
 // 8 elements (16 B): load format IN, BN scale/shift + ReLU in fp32, store format OUT
@@ -150,7 +156,7 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
   offs[0] = o; o += 128;                 // barriers + tmem ptr
   offs[1] = o; o += TILE_ROWS * 16;      // rowinfo
   offs[2] = o; o += 2u * Cin * 4;        // coefA: scale, shift
-  offs[3] = o; o += 4u * NT * 4;         // coefE: scale, shift, mean, rstd
+  offs[3] = o; o += 5u * NT * 4;         // coefE: scale, shift, mean, rstd, accumulate scale
   offs[4] = o; o += 8u * NT * 4;         // red[2][4][NT]
   o = (o + 127u) & ~127u;
   offs[5] = o;
@@ -171,6 +177,8 @@ template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
 __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __grid_constant__ RowsParams p) {
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
+  constexpr bool MASK = EPI == EP_MASK_STATS || EPI == EP_MASK_STATS_ACC;
+  constexpr bool ACC = EPI == EP_MASK_STATS_ACC;
   extern __shared__ __align__(128) uint8_t smem[];
   pdl_trigger();
   uint32_t offs[6];
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   // forward -0.6 %, data gradient +2.4 %): in a one-tile-per-CTA kernel the extra stage -> MMA -> commit -> TMEM-load round
   // trip at the end of the CTA costs what the transposes did.  OFF unless MMNN_TC_STATS=1; the place for it is a
   // persistent kernel where that round trip overlaps the next tile.
-  const bool tcs = (EPI != EP_STORE) && p.NT == 128 && (p.stages & 0x100) != 0;   // bit 8 of `stages`: opt-in switch (MMNN_TC_STATS=1)
+  const bool tcs = (EPI != EP_STORE) && !ACC && p.NT == 128 && (p.stages & 0x100) != 0;   // bit 8 of `stages`: opt-in switch (MMNN_TC_STATS=1)
   const uint32_t sG = stage0, sOnes = stage0 + 16u * PLANE_BYTES;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < p.NT + (tcs ? 32 : 0)) tmem_cols <<= 1;
@@ -261,16 +269,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       }
     }
   }
-  if (EPI == EP_MASK_STATS) {
+  if (MASK) {
     for (int c = tid; c < p.NT; c += ENGINE_THREADS) {
       const int col = tile_n * p.NT + c;
-      float mean = 0.f, rstd = 0.f, s = 0.f, t = -1.f;
+      float mean = 0.f, rstd = 0.f, s = 0.f, t = -1.f, ga = 0.f;
       if (col < p.Ncols) {
         bn_mean_rstd(p.bnE, col, mean, rstd);
-        s = p.bnE.gamma[col] * rstd;
+        ga = p.bnE.gamma[col];
+        s = ga * rstd;
         t = p.bnE.beta[col] - mean * s;
       }
       coefE[c] = s; coefE[p.NT + c] = t; coefE[2 * p.NT + c] = mean; coefE[3 * p.NT + c] = rstd;
+      if (ACC) coefE[4 * p.NT + c] = p.acc_rstd ? s : ga;
     }
   }
   if (tid < TILE_ROWS) {
@@ -429,7 +439,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     // the forward activations that gate the gradient do not depend on the MMA: fetch this row's (up to 128 columns)
     // before waiting for the accumulator so their latency hides behind the tail of the K loop
     uint4 xpre[2][4];
-    if (EPI == EP_MASK_STATS) {
+    if (MASK) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int cc = (warp >> 2) + 2 * k;
@@ -456,7 +466,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(cc * 32), v);
       float q[32];
-      if (EPI == EP_MASK_STATS) {
+      if (MASK) {
         uint4 xv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) xv[i] = xpre[k < 2 ? k : 1][i];
@@ -468,7 +478,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           const float x = (j & 1) ? xhi : xlo;
           const int c = cc * 32 + j;
           const bool act = fmaf(x, coefE[c], coefE[p.NT + c]) > 0.f;
-          const float g = (row_ok && act) ? round16<OP_F16>(v[j]) : 0.f;
+          const float g = (row_ok && act) ? (ACC ? v[j] : round16<OP_F16>(v[j])) : 0.f;   // ACC: the fp32 value itself is accumulated
           v[j] = g;
           q[j] = g * (x - coefE[2 * p.NT + c]) * coefE[3 * p.NT + c];
         }
@@ -485,7 +495,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           q[j] = g * g;
         }
       }
-      {
+      if (ACC) {
+        if (row_ok) {
+          float4* gp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.out_pitch + col0);
+          const float* cg = coefE + 4 * p.NT + cc * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            atomicAdd(gp + i, make_float4(v[4 * i] * cg[4 * i], v[4 * i + 1] * cg[4 * i + 1], v[4 * i + 2] * cg[4 * i + 2], v[4 * i + 3] * cg[4 * i + 3]));
+        }
+      } else {
         uint4* op = reinterpret_cast<uint4*>(p.out + m * p.out_pitch + col0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -501,7 +519,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           const float s1 = warp_transpose_sum32(v, lane);
           red[(0 * 4 + qd) * p.NT + cc * 32 + lane] = s1;
         }
-        if (!tcs || EPI == EP_MASK_STATS) {
+        if (!tcs || MASK) {
           const float s2 = warp_transpose_sum32(q, lane);
           red[(1 * 4 + qd) * p.NT + cc * 32 + lane] = s2;
         }

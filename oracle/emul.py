@@ -74,7 +74,7 @@ def backbone_bf16(sd, x, training, masks=None, prefix="", block_config=(6, 12, 2
     for b, nl in enumerate(block_config):
         for l in range(nl):
             q = f"{p}denseblock{b + 1}.denselayer{l + 1}.layers."
-            a1 = rs(rg(F.relu(_bn(x, sd, q + "norm1", training))))          # dA1 (masked) stored bf16
+            a1 = rs(F.relu(_bn(x, sd, q + "norm1", training)))              # dA1 is never stored: the 1x1x1 dgrad epilogue adds it (fp32) to the block's accumulator
             bott = rb(F.conv3d(a1, rs(sd[q + "conv1.weight"])))             # bott bf16; dBott bf16
             a2 = rs(rg(F.relu(_bn(bott, sd, q + "norm2", training))))       # dA2 (masked) stored bf16
             y = F.conv3d(a2, rs(sd[q + "conv2.weight"]), padding=1)
