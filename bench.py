@@ -143,19 +143,21 @@ def mem_bytes(wl):
         if b == 0:
             by["maxpool"] += M * 64 * 3.0
             by["maxpool_bwd"] += M * 64 * 5.0
+            by["extract"] += M * 64 * 10.0                          # finalize of block 1's input channels in place (read G + x, write G)
         for l in range(nl):
             cin = c + 32 * l
-            by["bn_apply"] += M * 128 * 6.0 + M * cin * 12.0
-            by["extract"] += M * 32 * 6.0
+            last = b == len(BLOCKS) - 1
+            by["bn_apply"] += M * 128 * 6.0                        # BN2 backward in place on dBott (bf16): read dA2 + bott, write dA2
+            by["extract"] += M * 32 * (8.0 + (4.0 if last else 0.0))   # grad_finalize of the layer's slice: read G (fp32) + x, write bf16 (+ fp32 in the last block)
             by["conv1_fprop"] += M * (cin + 128) * 2.0
-            by["conv1_dgrad"] += M * (128 + 2 * cin) * 2.0
+            by["conv1_dgrad"] += M * 128 * 2.0 + M * cin * (2.0 + 8.0)   # read dBott and the gating activations, read-modify-write the fp32 accumulator
             by["conv1_wgrad"] += M * (cin + 128) * 2.0
         c += 32 * nl
         if b < len(BLOCKS) - 1:
             Mo = B * (d[0] // 2) * (d[1] // 2) * (d[2] // 2)
             by["trans_pool"] += M * c * 2.0 + Mo * c * 2.0
-            by["avgpool_bwd"] += 2 * (M * c * 2.0 + Mo * c * 2.0) + M * c * 4.0
-            by["extract"] += Mo * (c // 2) * 6.0
+            by["avgpool_bwd"] += M * c * 2.0 + Mo * c * 2.0 + M * c * 4.0     # ONE pass: read x + dpooled, write gamma*v (fp32)
+            by["extract"] += Mo * (c // 2) * (8.0 + (4.0 if b + 1 == len(BLOCKS) - 1 else 0.0))   # finalize of the next block's input channels
             c //= 2
             d = [v // 2 for v in d]
         else:

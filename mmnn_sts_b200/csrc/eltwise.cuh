@@ -227,6 +227,120 @@ static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(c
   block_channel_reduce(red, s1, s2, 8, p.g_sum, p.g_dot);
 }
 
+// Tiled scatter form of the same pass (the default).  The gather kernel above visits up to 8 windows per INPUT voxel (argmax codes
+// + fp32 gradients re-read 8x, a compare per window and channel): 0.46 ms at configs[1] for 620 MB of algorithmic traffic.  Here a
+// CTA owns an input tile of MPB_TZ x MPB_TY x MPB_TX voxels x 64 channels as an fp32 accumulator in shared memory; every pooling
+// window that overlaps the tile routes its gradient to its arg-max voxel (ONE shared-memory add per window and channel, dropped when
+// the voxel belongs to a neighbouring tile); then the tile is streamed out: mask, round, store dR, BN-backward statistics.
+// Windows of the same parity class (oz & 1, oy & 1, ox & 1) have disjoint 3x3x3 footprints (stride 2), so the eight classes are
+// applied one after the other with plain read-modify-writes: no atomics, a fixed summation order, bit-reproducible.
+constexpr int MPB_TZ = 4, MPB_TY = 8, MPB_TX = 8, MPB_VOX = MPB_TZ * MPB_TY * MPB_TX;
+constexpr int MPB_WZ = MPB_TZ / 2 + 1, MPB_WY = MPB_TY / 2 + 1, MPB_WX = MPB_TX / 2 + 1, MPB_WIN = MPB_WZ * MPB_WY * MPB_WX;   // 75 windows
+constexpr int MPB_SMEM = MPB_VOX * 64 * 4 + MPB_WIN * 64 * 4 + MPB_WIN * 64;   // accumulator 64 KB + staged gradients 19 KB + codes 5 KB: two CTAs per SM
+
+static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_tiled_kernel(const __grid_constant__ PoolBwdParams p) {
+  pdl_trigger(); pdl_wait();
+  extern __shared__ __align__(16) float acc[];          // [MPB_VOX][64]
+  float* wgr = acc + MPB_VOX * 64;                       // [MPB_WIN][64] gradients of the windows overlapping the tile
+  uint8_t* wcd = reinterpret_cast<uint8_t*>(wgr + MPB_WIN * 64);   // [MPB_WIN][64] arg-max codes (255: window outside the volume)
+  __shared__ float red[EW_THREADS * 16];
+  __shared__ float coef[256];
+  for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
+    float mean, rstd;
+    bn_mean_rstd(p.bn, c, mean, rstd);
+    const float s = p.bn.gamma[c] * rstd;
+    coef[c] = s; coef[64 + c] = p.bn.beta[c] - mean * s; coef[128 + c] = mean; coef[192 + c] = rstd;
+  }
+  const int tid = threadIdx.x;
+  const int chunk = tid & 7;
+  const int tz = (p.D0 + MPB_TZ - 1) / MPB_TZ, ty = (p.H0 + MPB_TY - 1) / MPB_TY, tx = (p.W0 + MPB_TX - 1) / MPB_TX;
+  const long long ntiles = (long long)p.B * tz * ty * tx;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    long long r = t;
+    const int x0 = (int)(r % tx) * MPB_TX; r /= tx;
+    const int y0 = (int)(r % ty) * MPB_TY; r /= ty;
+    const int z0 = (int)(r % tz) * MPB_TZ;
+    const int b = (int)(r / tz);
+    __syncthreads();                                     // previous tile fully streamed out (also orders the coef table on the first pass)
+    // ---- stage every overlapping window (o in [i0/2, (i0+T)/2] per axis) in ONE round of loads; zero the accumulator meanwhile
+    for (int i = tid; i < MPB_WIN * 8; i += EW_THREADS) {
+      int w = i >> 3;
+      const int lx = w % MPB_WX, ly = (w / MPB_WX) % MPB_WY, lz = w / (MPB_WX * MPB_WY);
+      const int oz = z0 / 2 + lz, oy = y0 / 2 + ly, ox = x0 / 2 + lx;
+      uint2 cdv = make_uint2(0xffffffffu, 0xffffffffu);
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+      if (oz < p.D1 && oy < p.H1 && ox < p.W1) {
+        const long long o = (((long long)b * p.D1 + oz) * p.H1 + oy) * p.W1 + ox;
+        cdv = *reinterpret_cast<const uint2*>(p.argmax + o * 64 + chunk * 8);
+        ga = *reinterpret_cast<const float4*>(p.dpool + o * p.dpool_pitch + chunk * 8);
+        gb = *reinterpret_cast<const float4*>(p.dpool + o * p.dpool_pitch + chunk * 8 + 4);
+      }
+      *reinterpret_cast<uint2*>(wcd + w * 64 + chunk * 8) = cdv;
+      *reinterpret_cast<float4*>(wgr + w * 64 + chunk * 8) = ga;
+      *reinterpret_cast<float4*>(wgr + w * 64 + chunk * 8 + 4) = gb;
+    }
+    for (int i = tid; i < MPB_VOX * 16; i += EW_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the tile's forward activations: issued now, consumed after the scatter
+    uint4 xr[MPB_VOX * 8 / EW_THREADS];
+#pragma unroll
+    for (int k = 0; k < MPB_VOX * 8 / EW_THREADS; ++k) {
+      const int v = (tid + k * EW_THREADS) >> 3;
+      const int ix = x0 + v % MPB_TX, iy = y0 + (v / MPB_TX) % MPB_TY, iz = z0 + v / (MPB_TX * MPB_TY);
+      xr[k] = make_uint4(0, 0, 0, 0);
+      if (iz < p.D0 && iy < p.H0 && ix < p.W0)
+        xr[k] = ldg16(p.x + ((((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix) * 64 + chunk * 8);
+    }
+    __syncthreads();
+    // ---- scatter, one parity class at a time (disjoint footprints inside a class: plain read-modify-write)
+#pragma unroll 1
+    for (int cls = 0; cls < 8; ++cls) {
+      const int pz = cls >> 2, py = (cls >> 1) & 1, px = cls & 1;
+      const int nz = (MPB_WZ - pz + 1) / 2, ny = (MPB_WY - py + 1) / 2, nx = (MPB_WX - px + 1) / 2;
+      const int items = nz * ny * nx * 64;               // one thread per (window, channel)
+      for (int i = tid; i < items; i += EW_THREADS) {
+        const int c = i & 63;
+        int w = i >> 6;
+        const int lx = (w % nx) * 2 + px; w /= nx;
+        const int ly = (w % ny) * 2 + py;
+        const int lz = (w / ny) * 2 + pz;
+        const int wi = (lz * MPB_WY + ly) * MPB_WX + lx;
+        const int cd = wcd[wi * 64 + c];
+        if (cd == 255) continue;
+        const int dz = cd / 9, dy = (cd / 3) % 3, dx = cd % 3;
+        const int iz = 2 * lz - 1 + dz, iy = 2 * ly - 1 + dy, ix = 2 * lx - 1 + dx;   // tile-local voxel of the arg-max (z0, y0, x0 are even)
+        if ((unsigned)iz < (unsigned)MPB_TZ && (unsigned)iy < (unsigned)MPB_TY && (unsigned)ix < (unsigned)MPB_TX)
+          acc[((iz * MPB_TY + iy) * MPB_TX + ix) * 64 + c] += wgr[wi * 64 + c];
+      }
+      __syncthreads();
+    }
+    // ---- stream the tile out
+#pragma unroll
+    for (int k = 0; k < MPB_VOX * 8 / EW_THREADS; ++k) {
+      const int v = (tid + k * EW_THREADS) >> 3;
+      const int ix = x0 + v % MPB_TX, iy = y0 + (v / MPB_TX) % MPB_TY, iz = z0 + v / (MPB_TX * MPB_TY);
+      if (iz >= p.D0 || iy >= p.H0 || ix >= p.W0) continue;
+      const long long m = (((long long)b * p.D0 + iz) * p.H0 + iy) * p.W0 + ix;
+      float f[8], rr[8];
+      unpack8<ACT>(xr[k], f);
+      const float4 ga = *reinterpret_cast<const float4*>(acc + v * 64 + chunk * 8);
+      const float4 gb = *reinterpret_cast<const float4*>(acc + v * 64 + chunk * 8 + 4);
+      const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = chunk * 8 + e;
+        const bool act = fmaf(f[e], coef[c], coef[64 + c]) > 0.f;
+        rr[e] = act ? round_bf16(g[e]) : 0.f;
+        s1[e] += rr[e];
+        s2[e] += rr[e] * (f[e] - coef[128 + c]) * coef[192 + c];
+      }
+      *reinterpret_cast<uint4*>(p.dr + m * 64 + chunk * 8) = pack8<GRD>(rr);
+    }
+  }
+  __syncthreads();
+  block_channel_reduce(red, s1, s2, 8, p.g_sum, p.g_dot);
+}
+
 // ------------------------------------------------------------------------------------------------- E3: transition pooling
 struct AvgPoolParams {
   int B, D, H, W;   // input dims; output dims = floor(/2)
@@ -284,11 +398,14 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const
 }
 
 // PASS == 1: accumulate sum v, sum v*xhat with v = relu'(bn(x)) * dpooled[parent]/8.   PASS == 2: dx = k (v - c1 - xhat c2)
+// PASS == 3: both in ONE pass with the deferred BatchNorm backward: dx = k v is written while the statistics are accumulated, and the
+//            (c1, c2) terms are applied later by grad_finalize_kernel, which lists this BatchNorm among the channel's contributors
+//            (k = gamma in batch mode; in eval mode k = gamma * rstd and c1 = c2 = 0, so the pass is complete by itself).
 template <int PASS>
 static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
   pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [7][C]: s, t, mean, rstd, (pass2) c1, c2, output factor
-  __shared__ float red[PASS == 1 ? EW_THREADS * 16 : 1];
+  __shared__ float red[PASS != 2 ? EW_THREADS * 16 : 1];
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
     bn_mean_rstd(p.bn, c, mean, rstd);
@@ -297,8 +414,8 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
     if (PASS == 2) {
       coef[4 * p.C + c] = (float)(p.g_sum_in[c] * (double)p.inv_count);
       coef[5 * p.C + c] = (float)(p.g_dot_in[c] * (double)p.inv_count);
-      coef[6 * p.C + c] = p.pre_rstd ? p.bn.gamma[c] : s;
     }
+    if (PASS >= 2) coef[6 * p.C + c] = p.pre_rstd ? p.bn.gamma[c] : s;
   }
   __syncthreads();
   const int cpr = p.C / 8;
@@ -328,16 +445,17 @@ static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(c
       const bool act = fmaf(f[e], coef[c], coef[p.C + c]) > 0.f;
       const float v = act ? g[e] * 0.125f : 0.f;
       const float xh = (f[e] - coef[2 * p.C + c]) * coef[3 * p.C + c];
-      if (PASS == 1) { s1[e] += v; s2[e] += v * xh; }
-      else o[e] = coef[6 * p.C + c] * (v - coef[4 * p.C + c] - xh * coef[5 * p.C + c]);
+      if (PASS != 2) { s1[e] += v; s2[e] += v * xh; }
+      if (PASS == 2) o[e] = coef[6 * p.C + c] * (v - coef[4 * p.C + c] - xh * coef[5 * p.C + c]);
+      if (PASS == 3) o[e] = coef[6 * p.C + c] * v;
     }
-    if (PASS == 2) {
+    if (PASS >= 2) {
       float4* d = reinterpret_cast<float4*>(p.dx + m * p.dx_pitch + chunk * 8);
       d[0] = make_float4(o[0], o[1], o[2], o[3]);
       d[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
-  if (PASS == 1) block_channel_reduce(red, s1, s2, cpr, p.g_sum, p.g_dot);
+  if (PASS != 2) block_channel_reduce(red, s1, s2, cpr, p.g_sum, p.g_dot);
 }
 
 // ------------------------------------------------------------------------------------------------- E4: BN backward apply
@@ -476,15 +594,17 @@ struct FinalizeParams {
   long long x_pitch;
   BnSrc bn;                 // statistics of the block buffer's channels (any norm of the block: only mean / rstd are used)
   int nlayers;              // contributing layers (0: the range only holds T)
-  const float* gamma[24];   // per contributing layer: gamma of its norm1, g_sum / g_dot of its backward statistics (channel 0 based)
-  const double* g_sum[24];
-  const double* g_dot[24];
+  const float* gamma[25];   // per contributor (the reading layers' norm1, + the transition's BatchNorm): gamma, and the g_sum / g_dot
+  const double* g_sum[25];  // of its backward statistics (all indexed from channel 0 of the block buffer)
+  const double* g_dot[25];
   float inv_count;
   int batch;                // 0: eval mode
   bf16* out;                // optional bf16 copy [M][out_pitch] (the next GEMM's gradient operand), x out_scale[sample][nch]
   long long out_pitch;
   const float* out_scale;
   int vps;
+  int write_back;           // store the final fp32 gradient back into G (needed when someone reads G afterwards: the stem's max-pool
+                            // backward, GradCAM); a slice that only feeds the next GEMM through `out` skips the 4 B/element store
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) grad_finalize_kernel(const __grid_constant__ FinalizeParams p) {
@@ -548,8 +668,10 @@ static __global__ void __launch_bounds__(EW_THREADS) grad_finalize_kernel(const 
         const int c = chunk * 8 + e;
         g[e] = fmaf(coef[c], g[e], fmaf(coef[p.nch + c], f[e], coef[2 * p.nch + c]));
       }
-      gp[0] = make_float4(g[0], g[1], g[2], g[3]);
-      gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+      if (p.write_back) {
+        gp[0] = make_float4(g[0], g[1], g[2], g[3]);
+        gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+      }
     }
     if (p.out != nullptr) {
       if (p.out_scale != nullptr) {

@@ -664,9 +664,14 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     f.x = (const bf16*)(ws + g.buf[b]); f.x_pitch = bi.ctot;
     f.bn = make_bn(bi.layers[L - 1].n1, params, buffers, fstats, FC, g.M[b], batch);   // any norm of the block: same statistics
     f.nlayers = 0;
+    if (batch && bi.has_trans) {   // the transition's own BatchNorm reads every channel of the block: its (c1, c2) terms are deferred too
+      f.gamma[0] = (const float*)params[bi.tn.param_idx];
+      f.g_sum[0] = gsum(bi.tn); f.g_dot[0] = gdot(bi.tn);
+      f.nlayers = 1;
+    }
     for (int l = first_layer; l < L && batch; ++l) {
       const LayerInfo& li = bi.layers[l];
-      if (f.nlayers >= 24) return -12;
+      if (f.nlayers >= 25) return -12;
       f.gamma[f.nlayers] = (const float*)params[li.n1.param_idx];
       f.g_sum[f.nlayers] = gsum(li.n1); f.g_dot[f.nlayers] = gdot(li.n1);
       ++f.nlayers;
@@ -674,6 +679,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
     f.inv_count = batch ? 1.0f / (float)g.M[b] : 0.f;
     f.batch = batch ? 1 : 0;
     f.out = outp; f.out_pitch = out_pitch; f.out_scale = out_scale; f.vps = g.D[b] * g.H[b] * g.W[b];
+    // the fp32 gradient itself is read again only by the stem's max-pool backward (block 0 input) and by GradCAM (last block)
+    f.write_back = (outp == nullptr || b == (int)pl->blocks.size() - 1) ? 1 : 0;
     if (!batch && outp == nullptr) return 0;      // eval mode: the accumulator already holds the gradient
     ProfScope ps_(PC_EXTRACT, st);
     int T = EW_THREADS / nch;
@@ -925,9 +932,8 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       a.pre_rstd = batch ? 1 : 0;                                  // dbuf[b-1] is that block's accumulator G (finalised per channel range)
       const int rows_per_block = EW_THREADS / (pv.ctot / 8);
       int blocks = (int)std::min<long long>((Mp + rows_per_block - 1) / rows_per_block, NUM_SMS * 8);
-      { ProfScope ps_(PC_AVGPOOL_BWD, st, 2);
-        launch_pdl(avgpool_bnrelu_bwd_kernel<1>, dim3(blocks), dim3(EW_THREADS), 7 * pv.ctot * sizeof(float), st, a);
-        launch_pdl(avgpool_bnrelu_bwd_kernel<2>, dim3(blocks), dim3(EW_THREADS), 7 * pv.ctot * sizeof(float), st, a); }
+      { ProfScope ps_(PC_AVGPOOL_BWD, st, 1);     // ONE pass: statistics + gamma * v into the block's accumulator (c1 / c2 deferred to finalize)
+        launch_pdl(avgpool_bnrelu_bwd_kernel<3>, dim3(blocks), dim3(EW_THREADS), 7 * pv.ctot * sizeof(float), st, a); }
       LAUNCH_RET();
     } else {
       // pool0 + relu0 + norm0 + conv0
@@ -940,8 +946,16 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       q.argmax = ws + g.argmax;
       q.dr = (bf16*)(ws + g.dr);
       q.g_sum = gsum(pl->n0); q.g_dot = gdot(pl->n0);
-      int blocks = (int)std::min<long long>((g.M0 + 31) / 32, NUM_SMS * 8);
-      { ProfScope ps_(PC_MAXPOOL_BWD, st); launch_pdl(maxpool_bnrelu_bwd_kernel, dim3(blocks), dim3(EW_THREADS), 0, st, q); }
+      static const bool mpb_gather = [] { const char* e = getenv("MMNN_MAXPOOL_BWD_GATHER"); return e != nullptr && e[0] == '1'; }();
+      if (mpb_gather) {   // round-1 gather form (kept for A/B and as the reference of the parity test)
+        int blocks = (int)std::min<long long>((g.M0 + 31) / 32, NUM_SMS * 8);
+        ProfScope ps_(PC_MAXPOOL_BWD, st); launch_pdl(maxpool_bnrelu_bwd_kernel, dim3(blocks), dim3(EW_THREADS), 0, st, q);
+      } else {
+        const long long tiles = (long long)B * ((g.D0 + MPB_TZ - 1) / MPB_TZ) * ((g.H0 + MPB_TY - 1) / MPB_TY) * ((g.W0 + MPB_TX - 1) / MPB_TX);
+        const int blocks = (int)std::min<long long>(tiles, NUM_SMS * 2);
+        CUDA_RET(cudaFuncSetAttribute(maxpool_bnrelu_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MPB_SMEM));
+        ProfScope ps_(PC_MAXPOOL_BWD, st); launch_pdl(maxpool_bnrelu_bwd_tiled_kernel, dim3(blocks), dim3(EW_THREADS), MPB_SMEM, st, q);
+      }
       LAUNCH_RET();
       RET_IF(bn_apply(BA_OUT_BF16, g.M0, 64, q.dr, nullptr, 64, q.x, 64, q.bn, gsum(pl->n0), gdot(pl->n0), q.dr, 64));
       WgradParams w = {};
