@@ -174,7 +174,7 @@ def build_model(wl, device, seed=42):
     return m.to(device).train()
 
 
-def make_batches(wl, n, pinned=False, device=None, seed=1234):
+def make_batches(wl, n, pinned=False, device=None, seed=1234, image_dtype=None):
     """Synthetic batches with the distributions of SURVEY.md section 8d (image U[0,1), 10 N(0,1) + 10 categorical
     clinical columns, Bernoulli events, tie-free integer-day durations)."""
     out = []
@@ -185,6 +185,8 @@ def make_batches(wl, n, pinned=False, device=None, seed=1234):
         cl = torch.cat([torch.randn((B, 10), generator=g), torch.randint(0, 5, (B, 10), generator=g).float()], 1)
         ev = torch.randint(0, 2, (B, 2), generator=g)
         du = torch.stack([torch.randperm(3650, generator=g)[:B] + 1 for _ in range(2)], 1)
+        if image_dtype is not None:
+            im = im.to(image_dtype)
         t = [im, cl, ev, du]
         if pinned:
             t = [x.pin_memory() for x in t]
@@ -212,7 +214,10 @@ def run_ours(args):
     blender = GradientBlender(CoxPH, survival=True, surv_criterion=surv_criterion)
     sync = D.GradientAllReducer(model.parameters(), model=model)
     dev_batches = make_batches(wl, 2, device=device, seed=1234 + 100 * rank)
-    host_batches = make_batches(wl, 2, pinned=True, seed=1234 + 100 * rank)
+    # e2e arm: the loader hands over 16-bit volumes (the stem rounds the image to fp16 first thing, so this changes no result bit
+    # and halves the host->device bytes; --e2e-fp32 ships the reference collate's fp32 tensors instead)
+    e2e_dtype = None if args.e2e_fp32 else torch.float16
+    host_batches = make_batches(wl, 2, pinned=True, seed=1234 + 100 * rank, image_dtype=e2e_dtype)
 
     def step(im, cl, ev, du):
         out = model({"image": im, "clinical": cl})
@@ -304,7 +309,7 @@ def run_ours(args):
     for _ in range(3):
         stage[0][0].copy_(host_batches[0][0], non_blocking=True)
     h1.record(); torch.cuda.synchronize()
-    h2d_gbps = 3 * host_batches[0][0].numel() * 4 / (h0.elapsed_time(h1) / 1e3) / 1e9   # bare pinned-host -> device rate of this box
+    h2d_gbps = 3 * host_batches[0][0].numel() * host_batches[0][0].element_size() / (h0.elapsed_time(h1) / 1e3) / 1e9   # bare pinned-host -> device rate of this box
     vols = wl["batch"] * world * args.steps
     value, value_e2e = vols / (ms / 1e3), vols / (ms_e2e / 1e3)
 
@@ -380,7 +385,8 @@ def run_ours(args):
                            "in_channels": wl["cin"], "parallelism": f"dp{world}", "optimizer_step": "every batch", "cuda_graph": bool(args.graph and world == 1),
                            "l2": "inputs (134 MB/batch fp32) and activations (>1 GB) exceed the 126 MB L2; two batches alternate"},
                 "e2e": {"value": round(value_e2e, 2), "unit": "volumes/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
-                        "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_gbps_alone": round(h2d_gbps, 1)},
+                        "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_gbps_alone": round(h2d_gbps, 1),
+                        "image_dtype": "float32" if args.e2e_fp32 else "float16 (rounded by the stem to fp16 anyway: bit-identical results)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_gemm": roofline_gemm,
                 "roofline_step": roofline_step, "kernels": kernels}
         if cpu is not None:
@@ -719,6 +725,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-fp32", action="store_true", help="end-to-end arm ships fp32 volumes (default: fp16, same results, half the H2D bytes)")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[3] / configs[4] side measurements of the default run")
     ap.add_argument("--mode", default="train", choices=["train", "inference", "preprocess", "resnet"])
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as one CUDA graph (static shapes)")

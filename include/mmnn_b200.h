@@ -38,6 +38,11 @@ int mmnn_encoder_debug_offsets(void* plan, int B, int X, int Y, int Z, long long
 int mmnn_encoder_forward(void* plan, int B, int X, int Y, int Z, const float* image, const void* const* params /*HOST*/,
                          void* const* buffers /*HOST*/, const float* dropmask, void* workspace, float* out, int training,
                          void* stream);
+/* Same forward with the image as IEEE fp16 (a data loader that ships 16-bit volumes: half the host->device bytes per step).  The fp32
+ * entry point rounds the image to the activation format first thing, so both give the same result for fp16-representable inputs. */
+int mmnn_encoder_forward_f16(void* plan, int B, int X, int Y, int Z, const void* image_f16, const void* const* params /*HOST*/,
+                             void* const* buffers /*HOST*/, const float* dropmask, void* workspace, float* out, int training,
+                             void* stream);
 /* grad_out fp32 [B*d*h*w][C];  grads: zero-initialised fp32 tensors shaped like the parameters;  training: the mode of the
  * forward pass that filled `workspace` (batch-statistic or running-statistic BatchNorm is differentiated accordingly) */
 int mmnn_encoder_backward(void* plan, int B, int X, int Y, int Z, const void* const* params /*HOST*/,

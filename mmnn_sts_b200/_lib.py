@@ -140,6 +140,8 @@ def _declare(l):
     l.mmnn_encoder_out_dims.restype = I
     l.mmnn_encoder_forward.argtypes = [VP, I, I, I, I, VP, C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
     l.mmnn_encoder_forward.restype = I
+    l.mmnn_encoder_forward_f16.argtypes = [VP, I, I, I, I, VP, C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
+    l.mmnn_encoder_forward_f16.restype = I
     l.mmnn_encoder_backward.argtypes = [VP, I, I, I, I, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), VP, VP, VP, I, VP]
     l.mmnn_encoder_backward.restype = I
     l.mmnn_encoder_num_grad_groups.argtypes = [VP]

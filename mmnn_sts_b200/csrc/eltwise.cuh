@@ -47,7 +47,10 @@ MMNN_DEVINL void block_channel_reduce(float* red /*[EW_THREADS][16]*/, const flo
 
 // ------------------------------------------------------------------------------------------------- E1: input pack
 // image NCDHW fp32 [B][cin][X][Y][Z]  ->  padded space-to-depth bf16 [B][Sz][Sy][Sx][(pz,py,px,c2)]   (pad 3, stride 2)
-static __global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
+// TIN: float (the reference's collate output, /root/reference/utils/utils.py:98-99) or __half (a loader that ships 16-bit volumes:
+// half the host->device bytes; the values are rounded to the activation format here either way, so the results are identical)
+template <typename TIN>
+static __global__ void s2d_pack_kernel(const TIN* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
                                 int Sz, int Sy, int Sx) {
   const long long total = (long long)B * Sz * Sy * Sx * 2;  // 16-byte cells (pz = cell & 1)
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -65,7 +68,7 @@ static __global__ void s2d_pack_kernel(const float* __restrict__ img, bf16* __re
       const int iy = 2 * qy + py - 3, ix = 2 * qx + px - 3;
       float v = 0.f;
       if (c < cin && iz >= 0 && iz < X && iy >= 0 && iy < Y && ix >= 0 && ix < Z)
-        v = img[((((long long)b * cin + c) * X + iz) * Y + iy) * Z + ix];
+        v = (float)img[((((long long)b * cin + c) * X + iz) * Y + iy) * Z + ix];
       f[e] = v;
     }
     reinterpret_cast<uint4*>(dst)[idx] = pack8<ACT>(f);

@@ -416,9 +416,9 @@ int mmnn_encoder_debug_offsets(void* h, int B, int X, int Y, int Z, long long* o
 // params  : device pointers in backbone.named_parameters() order;  buffers: in backbone.named_buffers() order
 // dropmask: optional fp32 [num_layers][B][32] channel keep-mask already divided by (1-p) (Dropout3d), or null
 // out     : fp32 [M_last][C_last] = norm5 output, NDHWC
-int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image, const void* const* params,
-                         void* const* buffers, const float* dropmask, void* workspace, float* out, int training,
-                         void* stream_) {
+static int encoder_forward_impl(void* h, int B, int X, int Y, int Z, const void* image, int image_f16, const void* const* params,
+                                void* const* buffers, const float* dropmask, void* workspace, float* out, int training,
+                                void* stream_) {
   Plan* pl = (Plan*)h;
   cudaStream_t st = (cudaStream_t)stream_;
   Geo g;
@@ -467,7 +467,8 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
   {
     const long long cells = (long long)B * g.Sz * g.Sy * g.Sx * 2;
     { ProfScope ps_(PC_S2D, st);
-      s2d_pack_kernel<<<ew_grid(cells), EW_THREADS, 0, st>>>(image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
+      if (image_f16) s2d_pack_kernel<__half><<<ew_grid(cells), EW_THREADS, 0, st>>>((const __half*)image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx);
+      else s2d_pack_kernel<float><<<ew_grid(cells), EW_THREADS, 0, st>>>((const float*)image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
     LAUNCH_RET();
     StemBrickParams p = {};
     p.B = B; p.D0 = g.D0; p.H0 = g.H0; p.W0 = g.W0; p.Sz = g.Sz; p.Sy = g.Sy; p.Sx = g.Sx;
@@ -592,6 +593,18 @@ int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image
     LAUNCH_RET();
   }
   return 0;
+}
+
+int mmnn_encoder_forward(void* h, int B, int X, int Y, int Z, const float* image, const void* const* params,
+                         void* const* buffers, const float* dropmask, void* workspace, float* out, int training,
+                         void* stream_) {
+  return encoder_forward_impl(h, B, X, Y, Z, image, 0, params, buffers, dropmask, workspace, out, training, stream_);
+}
+// same with an IEEE fp16 image [B][cin][X][Y][Z] (a loader that ships 16-bit volumes: half the host->device traffic)
+int mmnn_encoder_forward_f16(void* h, int B, int X, int Y, int Z, const void* image_f16, const void* const* params,
+                             void* const* buffers, const float* dropmask, void* workspace, float* out, int training,
+                             void* stream_) {
+  return encoder_forward_impl(h, B, X, Y, Z, image_f16, 1, params, buffers, dropmask, workspace, out, training, stream_);
 }
 
 // grad_out: fp32 [M_last][C_last] gradient w.r.t. the norm5 output (NDHWC)

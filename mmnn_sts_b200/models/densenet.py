@@ -157,7 +157,10 @@ class Backbone(nn.Sequential):
         if not x.is_cuda:
             raise L.MMNNLibraryError("mmnn_sts_b200 has no CPU path: move the model and inputs to a CUDA device")
         plan = self._get_plan()
-        x = x.contiguous().float()
+        # fp16 volumes are consumed as they are (the stem packs the image into the fp16 activation format first thing, so a loader
+        # that ships 16-bit volumes halves the host->device bytes without changing a bit of the result); anything else -> fp32
+        half_in = x.dtype == torch.float16 and bool(L.lib().mmnn_act_is_fp16())
+        x = x.contiguous() if half_in else x.contiguous().float()
         B, cin, X, Y, Z = x.shape
         assert cin == self._cfg[0], f"expected {self._cfg[0]} input channels, got {cin}"
         lib = L.lib()
@@ -178,7 +181,8 @@ class Backbone(nn.Sequential):
         bufs = list(self.buffers())
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.mmnn_encoder_forward(plan, B, X, Y, Z, x.data_ptr(), self._ptr_array(params), self._ptr_array(bufs),
+            fwd = lib.mmnn_encoder_forward_f16 if half_in else lib.mmnn_encoder_forward
+            rc = fwd(plan, B, X, Y, Z, x.data_ptr(), self._ptr_array(params), self._ptr_array(bufs),
                                           mask.data_ptr() if mask is not None else None, ws.tensor.data_ptr(),
                                           out.data_ptr(), int(self.training), stream)
         L.check(rc, "mmnn_encoder_forward")

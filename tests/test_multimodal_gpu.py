@@ -372,3 +372,21 @@ def test_cuda_graph_step_matches_eager():
         cos = float((u1 @ u2).detach() / (u1.norm() * u2.norm()).detach())
         # the stem gradient sits behind all 121 ReLU layers: two runs of 6 chained steps already differ by a few percent
         assert cos > (0.9 if "conv0" in key else 0.98) and 0.9 < float((u1.norm() / u2.norm()).detach()) < 1.1, (key, cos)
+
+
+def test_fp16_volumes_give_bit_identical_results():
+    """A loader that ships 16-bit volumes (mmnn_encoder_forward_f16): the stem rounds the image to the activation format first
+    thing, so fp16 input == fp32 input rounded, bit for bit, in logits and in the stem's weight gradient."""
+    from mmnn_sts_b200.losses.losses import CoxPH
+    from mmnn_sts_b200.utils.utils import surv_criterion
+    from oracle import synth
+    sd = synth.make_state_dict(42, in_channels=2)
+    image, clinical, events, durations = synth.make_batch(31, 4, 2, (64, 64, 32))
+    outs = []
+    for dt in (torch.float32, torch.float16):
+        m = _build([42, 31, 4, 2, 64, 64, 32, 1, 1, 0, 1], sd).train()
+        m.clinical_model.model.dropout_prob = 0.0
+        out = m({"image": image.to(dt).cuda(), "clinical": clinical.cuda()})
+        surv_criterion(CoxPH, out[0], events.cuda(), durations.cuda(), "cuda").backward()
+        outs.append((out.detach().clone(), m.image_model.model.backbone.conv0.weight.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
