@@ -37,7 +37,7 @@ class RowsParams(C.Structure):
                 ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
                 ("b_packed", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_longlong),
                 ("colscale", C.c_void_p), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p),
-                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int)]
+                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int), ("early_ch", C.c_int)]
 
 
 class BrickParams(C.Structure):

@@ -89,7 +89,10 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((p.M + TILE_ROWS - 1) / TILE_ROWS, (p.Ncols + p.NT - 1) / p.NT);
-  launch_pdl(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);
+  static const bool early_on = [] { const char* e = getenv("MMNN_EARLY_START"); return !(e != nullptr && e[0] == '0'); }();
+  if (PF != 2 || !early_on) p.early_ch = 0;
+  if (p.early_ch > 0) launch_pdl_forced(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);   // starts while the previous layer's 3x3x3 conv runs
+  else launch_pdl(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

@@ -504,6 +504,10 @@ static int encoder_forward_impl(void* h, int B, int X, int Y, int Z, const void*
       p.b_packed = packed + li.pk_c1f;
       p.out = bott; p.out_pitch = BOTT;
       p.st_sum = fstats + li.n2.fwd_off; p.st_sq = fstats + FC + li.n2.fwd_off;
+      // every channel but the 32 the previous layer's 3x3x3 conv (the kernel right before this one in the stream) is writing was
+      // final before that conv started: small-grid launches work through them while it runs (engine.cuh, early start).
+      // Not while bench.py's per-class timing is on (classes must not overlap).
+      p.early_ch = (l > 0 && !prof_state().on) ? li.cin - GROWTH : 0;
       { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
       const float* cs = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
       if (true) {  // brick mode for every spatial size: partial tiles only cost idle MMA rows, tiny layers are latency-bound anyway

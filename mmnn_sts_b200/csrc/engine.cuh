@@ -90,6 +90,12 @@ struct RowsParams {
   int stages;
   int acc_rstd;       // EP_MASK_STATS_ACC: per-column scale of the accumulated gradient: 0 -> gamma (batch statistics: rstd is
                       // applied once, by the finalising pass), 1 -> gamma * rstd (running statistics differ per layer)
+  // Early start (1x1x1 forward GEMM of a dense layer, small grids): the first early_ch input channels -- and their BatchNorm
+  // statistics -- were final BEFORE the preceding kernel in the stream (the previous layer's 3x3x3 convolution, which only
+  // appends 32 channels) started.  Launched with the programmatic-dependent-launch attribute, the kernel works through the
+  // k-blocks below early_ch while that convolution is still running and calls griddepcontrol.wait only before the k-blocks
+  // that contain its output.  0: wait first (plain stream order).
+  int early_ch;
 };
 
 // 8 elements (16 B): load format IN, BN scale/shift + ReLU in fp32, store format OUT
@@ -241,11 +247,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     const uint32_t total = (uint32_t)KB * b_bytes;
     for (uint32_t o = 0; o < total; o += 65536u) bulk_prefetch_l2(w + o, total - o < 65536u ? total - o : 65536u);
   }
-  pdl_wait();   // nothing above touches global memory written by the preceding kernel
+  // early start: only the leading `early_ch` channels may be touched before the preceding kernel has completed
+  const bool early = PF == 2 && TRANS == T_BNRELU && OP_F16 && EPI == EP_STORE_STATS && p.ntaps == 1 && p.early_ch >= p.kbw;
+  const int coef_ch = early ? (p.early_ch / p.kbw) * p.kbw : p.Cin;     // channels whose coefficients are computed in the prologue
+  if (!early) pdl_wait();   // nothing above touches global memory written by the preceding kernel
   H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // fp16 operands: packed per-pair table in place of the fp32 one (same size)
   if (TRANS == T_BNRELU) {
     if (OP_F16) {
-      for (int j = tid; j < p.Cin / 2; j += ENGINE_THREADS) {
+      for (int j = tid; j < coef_ch / 2; j += ENGINE_THREADS) {
         float m0, r0, m1, r1;
         bn_mean_rstd(p.bnA, 2 * j, m0, r0);
         bn_mean_rstd(p.bnA, 2 * j + 1, m1, r1);
@@ -408,24 +417,50 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       mbar_arrive(bar_full + 8 * s);
       if (++s == S) { s = 0; ph ^= 1u; }
     };
+    // the k loop runs over [kb0, kb1): once for the whole K, or -- early start -- first over the k-blocks of channels that were
+    // final before the preceding kernel started, then (after griddepcontrol.wait) over the rest
+    auto run_range = [&](int kb0, int kb1) {
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      OK[u] = 0;
-      if (u < KB) { G[u] = next_geom(); load_kb(G[u], R[u], OK[u]); }
-    }
-    for (int kb = 0; kb < KB; kb += PF + 1) {
+      for (int u = 0; u < PF; ++u) {
+        OK[u] = 0;
+        if (kb0 + u < kb1) { G[u] = next_geom(); load_kb(G[u], R[u], OK[u]); }
+      }
+      for (int kb = kb0; kb < kb1; kb += PF + 1) {
 #pragma unroll
-      for (int u = 0; u <= PF; ++u) {
-        const int k = kb + u;
-        if (k < KB) {
-          constexpr int dummy = 0; (void)dummy;
-          if (k + PF < KB) {
-            G[(u + PF) % (PF + 1)] = next_geom();
-            load_kb(G[(u + PF) % (PF + 1)], R[(u + PF) % (PF + 1)], OK[(u + PF) % (PF + 1)]);
+        for (int u = 0; u <= PF; ++u) {
+          const int k = kb + u;
+          if (k < kb1) {
+            if (k + PF < kb1) {
+              G[(u + PF) % (PF + 1)] = next_geom();
+              load_kb(G[(u + PF) % (PF + 1)], R[(u + PF) % (PF + 1)], OK[(u + PF) % (PF + 1)]);
+            }
+            process(k, G[u], R[u], OK[u]);
           }
-          process(k, G[u], R[u], OK[u]);
         }
       }
+    };
+    if (early) {
+      const int kb_early = coef_ch / p.kbw;
+      run_range(0, kb_early);
+      pdl_wait();                                   // the preceding kernel (the previous layer's 3x3x3 conv) is complete and visible
+      for (int j = coef_ch / 2 + tid; j < p.Cin / 2; j += NUM_PRODUCER_THREADS) {
+        float m0, r0, m1, r1;
+        bn_mean_rstd(p.bnA, 2 * j, m0, r0);
+        bn_mean_rstd(p.bnA, 2 * j + 1, m1, r1);
+        const float s0 = p.bnA.gamma[2 * j] * r0, s1 = p.bnA.gamma[2 * j + 1] * r1;
+        const float t0 = p.bnA.beta[2 * j] - m0 * s0, t1 = p.bnA.beta[2 * j + 1] - m1 * s1;
+        H2Coef c;
+        c.s_hi = __floats2half2_rn(s0, s1);
+        c.t_hi = __floats2half2_rn(t0, t1);
+        const float2 sh = __half22float2(c.s_hi), th = __half22float2(c.t_hi);
+        c.s_lo = __floats2half2_rn(s0 - sh.x, s1 - sh.y);
+        c.t_lo = __floats2half2_rn(t0 - th.x, t1 - th.y);
+        coefH[j] = c;
+      }
+      named_bar_sync(1, NUM_PRODUCER_THREADS);
+      run_range(kb_early, KB);
+    } else {
+      run_range(0, KB);
     }
   }
   if (warp < PRODUCER_WARPS) {

@@ -19,6 +19,21 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
+// Launch WITH the attribute regardless of MMNN_PDL: for kernels that are written to do useful work before griddepcontrol.wait
+// (the early-start 1x1x1 GEMMs of the late dense blocks, engine.cuh).  The preceding kernel in the stream must itself have been
+// launched WITHOUT the attribute (so that everything before it is complete when the dependent starts).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_forced(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
