@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(brick_threads(GRAD), 1) conv3_brick_kernel(con
   constexpr int BR_MMA_WARP = NPW, BR_LOAD_WARP = NPW + 1, BR_EPI_WARP0 = NPW + 2;
   static_assert(BR_EPI_WARP0 + NEW == NTHREADS / 32, "warp roles must fill the CTA");
   extern __shared__ __align__(128) uint8_t smem[];
-  pdl_trigger();
   uint32_t offs[6];
   brick_smem_layout(p.CH, p.NT, TP, offs);
   const uint32_t sbase = smem_u32(smem);
@@ -132,6 +131,7 @@ __global__ void __launch_bounds__(brick_threads(GRAD), 1) conv3_brick_kernel(con
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
   pdl_wait();   // nothing above touches global memory
+  pdl_trigger();   // AFTER the wait: a dependent that starts early may rely on everything before THIS kernel being complete
   if (TRANS == T_BNRELU) {
     for (int c = tid; c < p.CH; c += NTHREADS) {
       float mean, rstd;

@@ -100,10 +100,11 @@ MMNN_DEVINL bool elect_one() {
 }
 
 // ---------------------------------------------------------------- programmatic dependent launch
-// Every kernel launched through launch_pdl() (launch.h) calls pdl_trigger() first (the next kernel in the stream may
-// then be scheduled as soon as all CTAs of this one are resident) and pdl_wait() in ALL threads before its first
-// global-memory access (returns when the preceding kernel has completed and its writes are visible), so the launch
-// latency and the prologue (barrier init, TMEM allocation, index tables) overlap the previous kernel's tail.
+// Every kernel launched through launch_pdl() (launch.h) calls pdl_wait() before its first access to global memory that the
+// preceding kernel may write (returns when that kernel has completed and its writes are visible) and pdl_trigger() right AFTER
+// it: the next kernel in the stream may then be scheduled, so its launch latency and pre-wait prologue (barrier init, TMEM
+// allocation, weight prefetch -- or, for the early-start 1x1x1 GEMMs, most of the K loop) overlap this kernel's body.
+// Trigger-after-wait makes the overlap transitive-safe: when a dependent starts, every kernel BEFORE its predecessor is complete.
 // Without the launch attribute (the default, see launch.h) both are no-ops.
 MMNN_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 MMNN_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -88,7 +88,7 @@ struct PoolParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) bnrelu_maxpool_kernel(const __grid_constant__ PoolParams p) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[128];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -170,7 +170,7 @@ struct PoolBwdParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_kernel(const __grid_constant__ PoolBwdParams p) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   __shared__ float red[EW_THREADS * 16];
   __shared__ float coef[256];
   for (int c = threadIdx.x; c < 64; c += EW_THREADS) {
@@ -242,7 +242,7 @@ constexpr int MPB_WZ = MPB_TZ / 2 + 1, MPB_WY = MPB_TY / 2 + 1, MPB_WX = MPB_TX 
 constexpr int MPB_SMEM = MPB_VOX * 64 * 4 + MPB_WIN * 64 * 4 + MPB_WIN * 64;   // accumulator 64 KB + staged gradients 19 KB + codes 5 KB: two CTAs per SM
 
 static __global__ void __launch_bounds__(EW_THREADS) maxpool_bnrelu_bwd_tiled_kernel(const __grid_constant__ PoolBwdParams p) {
-  pdl_trigger(); pdl_wait();
+  pdl_wait(); pdl_trigger();
   extern __shared__ __align__(16) float acc[];          // [MPB_VOX][64]
   float* wgr = acc + MPB_VOX * 64;                       // [MPB_WIN][64] gradients of the windows overlapping the tile
   uint8_t* wcd = reinterpret_cast<uint8_t*>(wgr + MPB_WIN * 64);   // [MPB_WIN][64] arg-max codes (255: window outside the volume)
@@ -365,7 +365,7 @@ struct AvgPoolParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const __grid_constant__ AvgPoolParams p) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [2][C]
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -406,7 +406,7 @@ static __global__ void __launch_bounds__(EW_THREADS) bnrelu_avgpool_kernel(const
 //            (k = gamma in batch mode; in eval mode k = gamma * rstd and c1 = c2 = 0, so the pass is complete by itself).
 template <int PASS>
 static __global__ void __launch_bounds__(EW_THREADS) avgpool_bnrelu_bwd_kernel(const __grid_constant__ AvgPoolParams p) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [7][C]: s, t, mean, rstd, (pass2) c1, c2, output factor
   __shared__ float red[PASS != 2 ? EW_THREADS * 16 : 1];
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
@@ -489,7 +489,7 @@ struct BnApplyParams {
 
 template <int OUT>
 static __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const __grid_constant__ BnApplyParams p) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   extern __shared__ float coef[];  // [3][C]: a (on v), b (on x), d (const):  out = a*v + b*x + d
   for (int c = threadIdx.x; c < p.C; c += EW_THREADS) {
     float mean, rstd;
@@ -611,7 +611,7 @@ struct FinalizeParams {
 };
 
 static __global__ void __launch_bounds__(EW_THREADS) grad_finalize_kernel(const __grid_constant__ FinalizeParams p) {
-  pdl_trigger(); pdl_wait();
+  pdl_wait(); pdl_trigger();
   extern __shared__ float coef[];   // [3][nch]: a (on G), b (on x), d;  then double part[2][T][nch] (reduction scratch)
   // C1 / C2: nlayers x nch independent loads.  T threads share a channel (layers j, j+T, ...), four loads in flight per thread,
   // partial sums combined in a fixed order -- the serial per-channel loop cost ~0.5 us of L2 latency per contributing layer in
@@ -692,7 +692,7 @@ static __global__ void __launch_bounds__(EW_THREADS) grad_finalize_kernel(const 
 static __global__ void __launch_bounds__(EW_THREADS) extract_slice_kernel(const float* __restrict__ src, long long src_pitch,
                                                                    bf16* __restrict__ dst, long long M, int C,
                                                                    const float* __restrict__ colscale, int vps) {
-  pdl_trigger(); pdl_wait();   // launched with launch_pdl (launch.h)
+  pdl_wait(); pdl_trigger();   // launched with launch_pdl (launch.h)
   const int cpr = C / 8;
   const long long total = M * cpr;
   for (long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * EW_THREADS) {

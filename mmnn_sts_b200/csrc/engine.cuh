@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   constexpr bool MASK = EPI == EP_MASK_STATS || EPI == EP_MASK_STATS_ACC;
   constexpr bool ACC = EPI == EP_MASK_STATS_ACC;
   extern __shared__ __align__(128) uint8_t smem[];
-  pdl_trigger();
   uint32_t offs[6];
   rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages & 0xff, offs);
   const uint32_t sbase = smem_u32(smem);
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   // early start: only the leading `early_ch` channels may be touched before the preceding kernel has completed
   const bool early = PF == 2 && TRANS == T_BNRELU && OP_F16 && EPI == EP_STORE_STATS && p.ntaps == 1 && p.early_ch >= p.kbw;
   const int coef_ch = early ? (p.early_ch / p.kbw) * p.kbw : p.Cin;     // channels whose coefficients are computed in the prologue
-  if (!early) pdl_wait();   // nothing above touches global memory written by the preceding kernel
+  if (!early) { pdl_wait(); pdl_trigger(); }   // nothing above touches global memory written by the preceding kernel
   H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // fp16 operands: packed per-pair table in place of the fp32 one (same size)
   if (TRANS == T_BNRELU) {
     if (OP_F16) {
@@ -443,6 +442,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       const int kb_early = coef_ch / p.kbw;
       run_range(0, kb_early);
       pdl_wait();                                   // the preceding kernel (the previous layer's 3x3x3 conv) is complete and visible
+      pdl_trigger();
       for (int j = coef_ch / 2 + tid; j < p.Cin / 2; j += NUM_PRODUCER_THREADS) {
         float m0, r0, m1, r1;
         bn_mean_rstd(p.bnA, 2 * j, m0, r0);
@@ -899,7 +899,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   // (kept to document the experiment); the default converts the activation tile to bf16 in the producers.
   constexpr bool A_F16 = kActF16 && (MMNN_WGRAD_A_F16 != 0);
   extern __shared__ __align__(128) uint8_t smem[];
-  pdl_trigger();
   uint32_t offs[4];
   const int NP = p.NP < 1 ? 1 : p.NP;
   const bool tma_b = p.tma_b != 0;
@@ -948,6 +947,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
   pdl_wait();   // nothing above touches global memory
+  pdl_trigger();   // AFTER the wait: a dependent that starts early may rely on everything before THIS kernel being complete
   if (ATRANS == T_BNRELU) {
     if (A_F16) {
       H2Coef* coefH = reinterpret_cast<H2Coef*>(coefA);   // 64 channel pairs x 16 B: same 1 KB as the fp32 scale / shift table

@@ -1,7 +1,8 @@
-// Host-side launch helper: cudaLaunchKernelEx, optionally with the programmatic-stream-serialization attribute (PDL),
-// see common.cuh pdl_trigger / pdl_wait.  OFF by default: measured on B200 at configs[1] (round 1) the step is bound by
-// kernel time, not by launch gaps -- 15.33 ms with PDL vs 15.35 ms without, and the end-to-end arm (H2D prefetch on a
-// copy stream) got slower -- so plain stream-ordered launches stay the default; MMNN_PDL=1 enables it for experiments.
+// Host-side launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL), see common.cuh
+// pdl_wait / pdl_trigger.  ON by default since round 2 (MMNN_PDL=0 disables it): with every kernel triggering right AFTER its wait the
+// next kernel's launch latency and pre-wait prologue (barrier init, TMEM allocation, weight prefetch) overlap the running kernel's
+// body -- same-box A/B on B200 at configs[1]: 1241 vs 1220 volumes/s device-resident, 1232 vs 1219 end to end, parity and
+// bit-reproducibility tests green under both settings.  (Round 1 triggered at kernel START and measured no gain: 15.33 vs 15.35 ms.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -14,7 +15,7 @@ inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MMNN_PDL");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
 }

@@ -39,7 +39,6 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
-  pdl_trigger();
   // Column statistics on the tensor core (see conv_rows_kernel): here the staged tile of tile t is consumed by the MMA
   // warp AFTER it has issued the main MMAs of tile t+1, and the statistics accumulate in TMEM across all tiles of the
   // CTA -- no transposes and no per-tile read-out for sum / sum of squares (forward) and sum (data gradient).
@@ -87,6 +86,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
   }
   pdl_wait();   // nothing above touches global memory
+  pdl_trigger();   // AFTER the wait: a dependent that starts early may rely on everything before THIS kernel being complete
   if (TRANS == T_BNRELU) {
     if (OP_F16) {
       for (int j = tid; j < p.Cin / 2; j += RP_THREADS) {

@@ -52,7 +52,6 @@ __device__ long long g_stem_dbg[8];
 static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const __grid_constant__ StemBrickParams p) {
   constexpr bool F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  pdl_trigger();
   // swizzle patterns are functions of the shared-memory byte address: work from a 1 KB aligned base
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
@@ -81,6 +80,7 @@ static __global__ void __launch_bounds__(SB_THREADS, 1) stem_brick_kernel(const 
     tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
   }
   pdl_wait();   // nothing above touches global memory
+  pdl_trigger();   // AFTER the wait: a dependent that starts early may rely on everything before THIS kernel being complete
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
