@@ -31,6 +31,16 @@ struct RnConvGeom {
 };
 
 constexpr int THREADS = 256;
+// Deterministic shared-memory accumulation of per-warp partial sums: the warps of the block add their partials one after the other
+// (warp 0 first) with plain read-modify-writes instead of shared-memory atomics, whose arrival order -- and, fp32 addition not being
+// associative, whose result -- changes from run to run.  The BatchNorm statistics of the forward pass decide every ReLU mask: with
+// atomics two runs of the same input differed in the last bit of a statistic, a rounding flipped, and the gradients below moved by
+// 10-25 % (round 1).  `body` must touch each address from at most one lane per warp; all threads of the block must reach the macro.
+#define RN_WARP_ORDERED(nwarps, body)                         \
+  for (int w_ = 0; w_ < (nwarps); ++w_) {                     \
+    if ((int)(threadIdx.x >> 5) == w_) { body }               \
+    __syncthreads();                                          \
+  }
 
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
@@ -177,9 +187,11 @@ __global__ void __launch_bounds__(THREADS) rn_conv_kernel(const RnConvGeom g, co
         s += __shfl_xor_sync(0xffffffffu, s, off);
         q += __shfl_xor_sync(0xffffffffu, q, off);
       }
-      if ((tid & 31) == 0) { atomicAdd(&sstat[c], s); atomicAdd(&sstat[CT + c], q); }
+      ssum[c] = s; ssq[c] = q;
     }
-    __syncthreads();
+    RN_WARP_ORDERED(THREADS / 32, if ((tid & 31) == 0) {
+      _Pragma("unroll") for (int c = 0; c < CT; ++c) { sstat[c] += ssum[c]; sstat[CT + c] += ssq[c]; }
+    })
     if (tid < CT) atomicAdd(&stats[cg * CT + tid], (double)sstat[tid]);
     else if (tid < 2 * CT) atomicAdd(&stats[OC + cg * CT + (tid - CT)], (double)sstat[tid]);
   }
@@ -406,11 +418,10 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
       dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, off); dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, off);
       dsq0 += __shfl_xor_sync(0xffffffffu, dsq0, off); dsq1 += __shfl_xor_sync(0xffffffffu, dsq1, off);
     }
-    if (lane < 4) {
-      atomicAdd(&sstat2[lane * 2], dsum0); atomicAdd(&sstat2[lane * 2 + 1], dsum1);
-      atomicAdd(&sstat2[8 + lane * 2], dsq0); atomicAdd(&sstat2[8 + lane * 2 + 1], dsq1);
-    }
-    __syncthreads();
+    RN_WARP_ORDERED(THREADS / 32, if (lane < 4) {
+      sstat2[lane * 2] += dsum0; sstat2[lane * 2 + 1] += dsum1;
+      sstat2[8 + lane * 2] += dsq0; sstat2[8 + lane * 2 + 1] += dsq1;
+    })
     if (tid < 16) atomicAdd(&stats_ds[tid], (double)sstat2[tid]);
   }
   if (stats != nullptr) {
@@ -419,11 +430,10 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_mma_fwd_kernel(const RnCo
       ssum0 += __shfl_xor_sync(0xffffffffu, ssum0, off); ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, off);
       ssq0 += __shfl_xor_sync(0xffffffffu, ssq0, off); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, off);
     }
-    if (lane < 4) {
-      atomicAdd(&sstat[lane * 2], ssum0); atomicAdd(&sstat[lane * 2 + 1], ssum1);
-      atomicAdd(&sstat[8 + lane * 2], ssq0); atomicAdd(&sstat[8 + lane * 2 + 1], ssq1);
-    }
-    __syncthreads();
+    RN_WARP_ORDERED(THREADS / 32, if (lane < 4) {
+      sstat[lane * 2] += ssum0; sstat[lane * 2 + 1] += ssum1;
+      sstat[8 + lane * 2] += ssq0; sstat[8 + lane * 2 + 1] += ssq1;
+    })
     if (tid < 16) atomicAdd(&stats[tid], (double)sstat[tid]);
   }
 }
@@ -600,11 +610,10 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k8_mma_kernel(const RnCon
       ssum0 += __shfl_xor_sync(0xffffffffu, ssum0, off); ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, off);
       ssq0 += __shfl_xor_sync(0xffffffffu, ssq0, off); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, off);
     }
-    if (lane < 4) {
-      atomicAdd(&sstat[lane * 2], ssum0); atomicAdd(&sstat[lane * 2 + 1], ssum1);
-      atomicAdd(&sstat[8 + lane * 2], ssq0); atomicAdd(&sstat[8 + lane * 2 + 1], ssq1);
-    }
-    __syncthreads();
+    RN_WARP_ORDERED(THREADS / 32, if (lane < 4) {
+      sstat[lane * 2] += ssum0; sstat[lane * 2 + 1] += ssum1;
+      sstat[8 + lane * 2] += ssq0; sstat[8 + lane * 2 + 1] += ssq1;
+    })
     if (tid < 16) atomicAdd(&stats[tid], (double)sstat[tid]);
   }
 }
@@ -1116,9 +1125,7 @@ __global__ void __launch_bounds__(THREADS, 4) rn_stem_mma_fwd_kernel(const RnCon
     }
   }
   if (stats != nullptr) {
-    atomicAdd(&sstat[tid & 63], ssum);
-    atomicAdd(&sstat[64 + (tid & 63)], ssq);
-    __syncthreads();
+    RN_WARP_ORDERED(THREADS / 32, { sstat[tid & 63] += ssum; sstat[64 + (tid & 63)] += ssq; })
     if (tid < 128) atomicAdd(&stats[tid], (double)sstat[tid]);
   }
 }
@@ -1309,15 +1316,13 @@ __global__ void __launch_bounds__(THREADS, 2) rn_conv3_k16_mma_kernel(const RnCo
         ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
       }
     }
-    if (lane < 4) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
+    RN_WARP_ORDERED(THREADS / 32, if (lane < 4) {
+      _Pragma("unroll") for (int k = 0; k < 4; ++k) {
         const int co = (k >> 1) * 8 + lane * 2 + (k & 1);
-        atomicAdd(&sstat[co], ssum[k]);
-        atomicAdd(&sstat[16 + co], ssq[k]);
+        sstat[co] += ssum[k];
+        sstat[16 + co] += ssq[k];
       }
-    }
-    __syncthreads();
+    })
     if (tid < 32) atomicAdd(&stats[tid], (double)sstat[tid]);
   }
 }
@@ -1658,15 +1663,13 @@ __global__ void __launch_bounds__(THREADS) rn_act_bwd_reduce_kernel(const uint4*
       }
     }
   }
-  if ((threadIdx.x & 31) < C / 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&sm[c0 + k], s0[k]);
-      atomicAdd(&sm[C + c0 + k], s1[k]);
-      if (TWO) atomicAdd(&sm[2 * C + c0 + k], s2[k]);
+  RN_WARP_ORDERED(THREADS / 32, if ((int)(threadIdx.x & 31) < C / 8) {
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) {
+      sm[c0 + k] += s0[k];
+      sm[C + c0 + k] += s1[k];
+      if (TWO) sm[2 * C + c0 + k] += s2[k];
     }
-  }
-  __syncthreads();
+  })
   for (int i = threadIdx.x; i < (TWO ? 3 : 2) * C; i += THREADS) atomicAdd(&sums[i], (double)sm[i]);
 }
 
@@ -1726,15 +1729,19 @@ __global__ void __launch_bounds__(128) rn_head_fwd_kernel(const __half* __restri
                                                           const float* __restrict__ W, const float* __restrict__ bias, int K,
                                                           float* __restrict__ pooled, float* __restrict__ out) {
   __shared__ float sp[64];
+  __shared__ float sthr[128];
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < C; i += 128) sp[i] = 0.f;
-  __syncthreads();
   const __half* py = y + (long long)b * V * C;
-  // thread owns channel (tid % C) when 128 % C == 0 (C = 8 / 16 / 64)
-  const int c = threadIdx.x % C;
+  // thread owns channel (tid % C) when 128 % C == 0 (C = 8 / 16 / 64); the 128 / C partial sums of a channel are added in thread order
   float s = 0.f;
   for (long long i = threadIdx.x; i < (long long)V * C; i += 128) s += __half2float(py[i]);
-  atomicAdd(&sp[c], s);
+  sthr[threadIdx.x] = s;
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 128) {
+    float a = 0.f;
+    for (int t = i; t < 128; t += C) a += sthr[t];
+    sp[i] = a;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += 128) { sp[i] *= 1.f / (float)V; pooled[b * C + i] = sp[i]; }
   __syncthreads();
@@ -1754,12 +1761,24 @@ __global__ void __launch_bounds__(128) rn_head_bwd_kernel(const float* __restric
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += 128) {
     const float o = out[b * K + k];
-    const float dl = dout[b * K + k] * o * (1.f - o);
-    sdl[k] = dl;
-    atomicAdd(&db[k], dl);
+    sdl[k] = dout[b * K + k] * o * (1.f - o);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * C; i += 128) atomicAdd(&dW[i], sdl[i / C] * pooled[b * C + (i % C)]);
+  if (b == 0) {
+    // fc gradients: block 0 sums over the samples in index order (B x K x C terms: nothing) -- the per-sample blocks used to add
+    // their terms with global atomics in arrival order.  dW / db are accumulated INTO (the caller passes zeroed or running totals).
+    const int B = gridDim.x;
+    for (int i = threadIdx.x; i < K * C + K; i += 128) {
+      float acc = 0.f;
+      for (int bb = 0; bb < B; ++bb) {
+        const int k = i < K * C ? i / C : i - K * C;
+        const float o = out[bb * K + k];
+        const float dl = dout[bb * K + k] * o * (1.f - o);
+        acc += i < K * C ? dl * pooled[bb * C + (i % C)] : dl;
+      }
+      if (i < K * C) dW[i] += acc; else db[i - K * C] += acc;
+    }
+  }
   for (int c = threadIdx.x; c < C; c += 128) {
     float s = 0.f;
     for (int k = 0; k < K; ++k) s = fmaf(sdl[k], W[k * C + c], s);

@@ -182,7 +182,7 @@ def _train_compare(masks_ncdhw, dropout, batch=BATCH, spatial=SPATIAL, grad_tol=
     assert (out.detach().cpu() - ref.detach()).abs().max() < 5e-3
     assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
     named = dict(m.named_parameters())
-    worst = 0.0
+    worst, worst_cos = 0.0, 1.0
     for k, q in named.items():
         assert q.grad is not None, k
         r = _rel(q.grad, p[k].grad)
@@ -194,19 +194,20 @@ def _train_compare(masks_ncdhw, dropout, batch=BATCH, spatial=SPATIAL, grad_tol=
             # order of the fp32 atomics through flipped fp16 roundings -> absolute floor instead of a relative bound
             assert float((gd - rd).norm()) < 0.05, (k, r, cos)
             continue
-        worst = max(worst, r)
+        worst, worst_cos = max(worst, r), min(worst_cos, cos)
         assert r < grad_tol and cos > cos_tol, (k, r, cos)
     msd = m.state_dict()
     for k in ("stem.1.running_mean", "stem.1.running_var", "layer2.0.downsample.1.running_var", "layer4.1.conv2.1.running_mean"):
         torch.testing.assert_close(msd[k].cpu(), p[k], rtol=2e-2, atol=2e-3)
     assert int(msd["layer3.0.conv1.1.num_batches_tracked"]) == 1
+    print(f"[resnet {tuple(spatial)} dropout={dropout}] worst gradient rel-L2 {worst:.3f}, worst cosine {worst_cos:.4f}")
     return out.detach().cpu(), loss.item(), named, worst
 
 
 def test_train_step_matches_reference_golden_and_oracle():
     # 2x2x2 voxels per sample in layer4: one flipped ReLU there moves every gradient below it -> loose gradient bounds here,
     # the well-conditioned bounds are asserted by test_train_step_larger_volume
-    out, loss, named, worst = _train_compare(None, False, grad_tol=0.5, cos_tol=0.9)
+    out, loss, named, worst = _train_compare(None, False, grad_tol=0.2, cos_tol=0.975)
     gold = np.load(os.path.join(GOLD, "resnet_train.npz"))
     assert np.abs(out.numpy() - gold["out"]).max() < 5e-3
     assert abs(loss - float(gold["loss"])) < 1e-3 * abs(float(gold["loss"]))
@@ -219,17 +220,18 @@ def test_train_step_matches_reference_golden_and_oracle():
 def test_train_step_larger_volume():
     g = torch.Generator().manual_seed(6)
     masks = [(torch.rand(s, generator=g) >= 0.2).float() for s in orn.stage_shapes(4, (20, 96, 64))]
-    # per tensor: 0.45 / cosine 0.9 (run-to-run spread of the worst tensor is 0.10-0.25: fp32 atomics reorder sums, a flipped
-    # fp16 rounding flips a ReLU, the bf16 gradient chain amplifies it); the per-kernel tests above are the tight ones
-    # (weight gradient 1e-4, forward / data gradient one rounding of the output)
-    *_, worst = _train_compare(masks, True, batch=4, spatial=(20, 96, 64), grad_tol=0.45, cos_tol=0.9)
+    # Round 1 had to allow 0.45 / cosine 0.9 here because the worst tensor moved by 0.10-0.25 BETWEEN RUNS of the same input: the
+    # BatchNorm statistics were summed with shared-memory atomics, a last-bit difference flipped an fp16 rounding, that flipped a
+    # ReLU, and the bf16 gradient chain amplified it.  The statistics are now summed in a fixed order (RN_WARP_ORDERED, resnet.cu):
+    # the forward pass is bit-reproducible and this case measures 0.181 every run -> bound 0.25 / cosine 0.96.
+    *_, worst = _train_compare(masks, True, batch=4, spatial=(20, 96, 64), grad_tol=0.25, cos_tol=0.96)
     print(f"worst relative gradient error {worst:.3e}")
 
 
 def test_train_step_with_injected_dropout_masks():
     g = torch.Generator().manual_seed(5)
     masks = [(torch.rand(s, generator=g) >= 0.2).float() for s in orn.stage_shapes(BATCH, SPATIAL)]
-    _train_compare(masks, True, grad_tol=0.5, cos_tol=0.9)
+    _train_compare(masks, True, grad_tol=0.3, cos_tol=0.95)
 
 
 def test_hashed_dropout_statistics():
@@ -269,3 +271,34 @@ def test_train_classification_driver_with_resnet():
     after = m.state_dict()
     assert any(not torch.equal(before[k].to(dev), after[k]) for k in before if k.endswith("0.weight"))
     assert int(after["stem.1.num_batches_tracked"]) == 6
+
+
+def test_forward_is_bit_reproducible_and_gradients_stable():
+    """Two runs of the same training step: sigmoid scores, loss, running statistics and every BatchNorm-parameter gradient are
+    bit-identical (fixed-order statistics); the convolution weight gradients -- still accumulated across thread blocks with fp32
+    atomics on this path -- agree to 1e-5 of their norm (no feedback into the step: only their own last bits move)."""
+    dev = torch.device("cuda", 0)
+    sd = orn.make_state_dict(7, NUM_CLASSES)
+    image, labels = orn.make_batch(13, 4, (20, 96, 64), NUM_CLASSES)
+    g = torch.Generator().manual_seed(6)
+    masks = [(torch.rand(s, generator=g) >= 0.2).float() for s in orn.stage_shapes(4, (20, 96, 64))]
+    runs = []
+    for _ in range(2):
+        m = _model(dev, sd).train()
+        m.dropout.p = 0.2
+        m.injected_masks = [k.permute(0, 2, 3, 4, 1).contiguous().to(torch.uint8) for k in masks]
+        out = m(image.to(dev))
+        loss = F.binary_cross_entropy_with_logits(out, labels.to(dev), reduction="sum")
+        loss.backward()
+        torch.cuda.synchronize()
+        runs.append((out.detach().clone(), loss.detach().clone(), {k: q.grad.clone() for k, q in m.named_parameters()},
+                     {k: v.clone() for k, v in m.state_dict().items() if "running" in k}))
+    a, b = runs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in a[3]:
+        assert torch.equal(a[3][k], b[3][k]), k
+    for k in a[2]:
+        if a[2][k].dim() == 1:
+            assert torch.equal(a[2][k], b[2][k]), k                       # BatchNorm gamma / beta, fc bias
+        else:
+            assert float((a[2][k] - b[2][k]).norm()) <= 1e-5 * float(a[2][k].norm()) + 1e-12, k
