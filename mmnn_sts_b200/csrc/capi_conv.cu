@@ -222,7 +222,9 @@ int wgrad_split(const WgradParams& p, int kind, bool slotted) {
   int split = 148 / (gy * gz);
   if (slotted) {
     static const int min_tiles = [] { const char* e = getenv("MMNN_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
-    const int cap = (ntiles + min_tiles - 1) / min_tiles;
+    static const int small_tiles = [] { const char* e = getenv("MMNN_WGRAD_SMALL_TILES"); return e ? atoi(e) : 0; }();
+    const int mt = (small_tiles > 0 && ntiles <= 64) ? small_tiles : min_tiles;   // experiment: a different cap for the late blocks only
+    const int cap = (ntiles + mt - 1) / mt;
     if (split > cap) split = cap;
   }
   if (split < 1) split = 1;
