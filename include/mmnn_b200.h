@@ -200,6 +200,9 @@ int mmnn_rn_head_bwd(const float* dout, const float* out, const float* pooled, c
 void mmnn_profile_enable(int on);
 long long mmnn_launch_count(void);
 int mmnn_profile_collect(float* ms /*HOST*/, int* counts /*HOST*/);
+/* mmnn_profile_enable(2): records keep the real stream structure (side stream, early start); this returns each launch's class and
+ * its start / end in ms relative to the first record (n = records returned, cleared afterwards) */
+int mmnn_profile_timeline(int* cls /*HOST*/, float* t0 /*HOST*/, float* t1 /*HOST*/, int cap);
 
 #ifdef __cplusplus
 }

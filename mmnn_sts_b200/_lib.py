@@ -37,7 +37,9 @@ class RowsParams(C.Structure):
                 ("a_src", C.c_void_p), ("a_pitch", C.c_longlong), ("bnA", BnSrc),
                 ("b_packed", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_longlong),
                 ("colscale", C.c_void_p), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p),
-                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int), ("early_ch", C.c_int)]
+                ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int), ("early_ch", C.c_int),
+                ("t_src", C.c_void_p), ("t_pitch", C.c_longlong), ("t_gsum", C.c_void_p), ("t_gdot", C.c_void_p),
+                ("t_inv_count", C.c_float), ("t_out", C.c_void_p), ("t_out_pitch", C.c_longlong)]
 
 
 class BrickParams(C.Structure):
@@ -104,7 +106,7 @@ class RnConvGeom(C.Structure):
 
 
 A_LINEAR_CONV, A_STEM = 0, 1
-T_NONE, T_BNRELU = 0, 1
+T_NONE, T_BNRELU, T_BNBWD = 0, 1, 2
 EP_STORE, EP_STORE_STATS, EP_MASK_STATS, EP_MASK_STATS_ACC = 0, 1, 2, 3
 PACK_GENERIC, PACK_STEM, PACK_STEM_SW32 = 0, 1, 2
 
@@ -220,6 +222,16 @@ PROF_CLASSES = ["pack", "s2d", "stem_fprop", "maxpool", "conv1_fprop", "conv2_fp
                 "bn_running", "norm5_bwd", "extract", "conv2_wgrad", "conv2_dgrad", "bn_apply", "conv1_wgrad", "conv1_dgrad",
                 "trans_wgrad", "trans_dgrad", "avgpool_bwd", "maxpool_bwd", "stem_wgrad", "tails", "heads", "sgd", "preprocess",
                 "rn_fprop", "rn_dgrad", "rn_wgrad", "rn_eltwise", "rn_head"]
+
+
+def profile_timeline(cap=4096):
+    """[(class name, start ms, end ms)] of the launches recorded since mmnn_profile_enable(2)."""
+    cls = (C.c_int * cap)(); t0 = (C.c_float * cap)(); t1 = (C.c_float * cap)()
+    f = lib().mmnn_profile_timeline
+    f.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+    f.restype = C.c_int
+    n = f(cls, t0, t1, cap)
+    return [(PROF_CLASSES[cls[i]], float(t0[i]), float(t1[i])) for i in range(n)]
 
 
 def profile_collect():

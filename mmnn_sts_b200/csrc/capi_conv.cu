@@ -147,6 +147,7 @@ int launch_rows(const RowsParams& p, int amode, int trans, int epi, int grad, cu
   CASE(A_LINEAR_CONV, T_NONE, EP_STORE, true)
   CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS, true)
   CASE(A_LINEAR_CONV, T_NONE, EP_MASK_STATS_ACC, true)
+  CASE(A_LINEAR_CONV, T_BNBWD, EP_MASK_STATS_ACC, true)
 #undef CASE
   return -3;
 }
@@ -296,7 +297,32 @@ ProfState& prof_state() {
 
 extern "C" {
 
-void mmnn_profile_enable(int on) { prof_state().on = on != 0; }
+void mmnn_profile_enable(int on) { prof_state().on = on != 0; prof_state().timeline = on == 2; }
+// Timeline of the records taken with mmnn_profile_enable(2): cls[i], start / end in ms relative to the first record's start.
+// Returns the number of records (clears them).  Events sit between kernels of the real streams: a launch's interval includes the
+// time it waited for its stream predecessors / cross-stream events after its start event was reached.
+int mmnn_profile_timeline(int* cls, float* t0, float* t1, int cap) {
+  ProfState& s = prof_state();
+  int n = 0;
+  if (!s.recs.empty()) {
+    cudaEventSynchronize(s.recs.back().b);
+    cudaDeviceSynchronize();
+    for (auto& r : s.recs) {
+      if (n < cap) {
+        float a = 0.f, b = 0.f;
+        cudaError_t ea = cudaEventElapsedTime(&a, s.recs[0].a, r.a);
+        cudaError_t eb = cudaEventElapsedTime(&b, s.recs[0].a, r.b);
+        if (ea != cudaSuccess) a = -(float)ea;
+        if (eb != cudaSuccess) b = -(float)eb;
+        (void)cudaGetLastError();
+        cls[n] = r.cls; t0[n] = a; t1[n] = b; ++n;
+      }
+    }
+    for (auto& r : s.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  }
+  s.recs.clear();
+  return n;
+}
 long long mmnn_launch_count() { return prof_state().launches; }
 // Synchronises, sums the event-timed durations per kernel class, clears the records. ms / counts: PC_COUNT entries.
 int mmnn_profile_collect(float* ms, int* counts) {

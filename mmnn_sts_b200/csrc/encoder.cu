@@ -37,6 +37,9 @@ using namespace mmnn;
 namespace {
 
 constexpr int GROWTH = 32, BOTT = 128, INIT_F = 64, NUM_SMS = 148;
+// Dense blocks of at most this many voxel rows are serial chains of small launches: there the BatchNorm backward of norm2 is
+// applied by the producers of the 1x1x1 data-gradient GEMM (T_BNBWD, engine.cuh) instead of a launch of its own.
+constexpr long long FUSE_BN2_MAX_M = 8192;
 
 struct BnInfo {
   int C;
@@ -146,7 +149,7 @@ struct Geo {
   long long M0;
   int D[8], H[8], W[8];
   long long M[8];
-  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, gslice, gout, dpooled, wslots, dr, total;
+  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, dB2, gslice, gout, dpooled, wslots, dr, total;
   size_t wslots_bytes;
   std::vector<size_t> wslot_off;   // per parameter index: element offset of the weight-gradient slots (convolutions only)
   std::vector<int> wslot_S;        // per parameter index: number of slots == voxel split of that weight-gradient launch
@@ -204,7 +207,8 @@ bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
   g.packed = take(pl.packed_elems_total * 2);
   g.tables = take(1 << 20);
   g.dA2 = take(2 * maxM * BOTT * 2);          // x2: layer parity (the side-stream wgrad of layer l reads it while l+1 runs)
-  g.dA1 = take(maxMC * 2);
+  g.dA1 = take(256);                            // (the bf16 dA1 tensor of round 1 is gone: deferred BatchNorm backward)
+  g.dB2 = take(2 * (size_t)FUSE_BN2_MAX_M * BOTT * 2);   // BN2-backward output of the small blocks (x2: layer parity), see backward
   g.gslice = take(2 * maxM * GROWTH * 2);
   g.gout = take(maxMoutC2 * 2 + 256);
   g.dpooled = take(maxMoutC * 2 + 256);
@@ -507,7 +511,7 @@ static int encoder_forward_impl(void* h, int B, int X, int Y, int Z, const void*
       // every channel but the 32 the previous layer's 3x3x3 conv (the kernel right before this one in the stream) is writing was
       // final before that conv started: small-grid launches work through them while it runs (engine.cuh, early start).
       // Not while bench.py's per-class timing is on (classes must not overlap).
-      p.early_ch = (l > 0 && !prof_state().on) ? li.cin - GROWTH : 0;
+      p.early_ch = (l > 0 && (!prof_state().on || prof_state().timeline)) ? li.cin - GROWTH : 0;
       { ProfScope ps_(PC_CONV1_FPROP, st); RET_IF(launch_rows(p, A_LINEAR_CONV, T_BNRELU, EP_STORE_STATS, 0, st)); }
       const float* cs = (dropmask != nullptr && training) ? dropmask + (size_t)li.index * B * GROWTH : nullptr;
       if (true) {  // brick mode for every spatial size: partial tiles only cost idle MMA rows, tiny layers are latency-bound anyway
@@ -639,7 +643,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
   const bool det = pl->det;
   if (pl->side == nullptr) CUDA_RET(cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
   // while bench.py's per-kernel profiling is on, everything stays on one stream so that class times are not overlapped
-  cudaStream_t sd = prof_state().on ? st : pl->side;
+  cudaStream_t sd = (prof_state().on && !prof_state().timeline) ? st : pl->side;
   pl->ev_next = 0;
   {  // fork: the side stream starts after everything already queued on the caller's stream (zeroed gradients etc.)
     cudaEvent_t e = pl->next_event();
@@ -848,19 +852,25 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         ProfScope ps_(PC_CONV2_DGRAD, st);
         RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS, 1, st));
       }
-      RET_IF(bn_apply(BA_OUT_BF16, M, BOTT, dA2, nullptr, BOTT, bott, BOTT, bn2, gsum(li.n2), gdot(li.n2), dA2, BOTT));
-      // conv1 wgrad: D[ci][co] -> dW1[co][ci]
-      {
+      // NEGATIVE RESULT (round 2, same-box A/B at configs[1]): applying norm2's backward in the producers of the late-block 1x1x1
+      // data-gradient GEMM (T_BNBWD) removes 40 bn_bwd_apply launches (class 0.96 -> 0.63 ms) but lengthens the GEMMs' producer chain
+      // (2.19 -> 2.38 ms) and delays the side-stream weight gradient: 1220 vs 1233 volumes/s.  OFF unless MMNN_FUSE_BN2=1.
+      static const bool fuse_env = [] { const char* e = getenv("MMNN_FUSE_BN2"); return e != nullptr && e[0] == '1'; }();
+      const bool fuse_bn2 = fuse_env && M <= FUSE_BN2_MAX_M;
+      bf16* dB2 = (bf16*)(ws + g.dB2) + (size_t)parity * FUSE_BN2_MAX_M * BOTT;
+      const bf16* dbott = fuse_bn2 ? dB2 : dA2;      // BN2-backward output = gradient of the bottleneck tensor
+      if (!fuse_bn2) RET_IF(bn_apply(BA_OUT_BF16, M, BOTT, dA2, nullptr, BOTT, bott, BOTT, bn2, gsum(li.n2), gdot(li.n2), dA2, BOTT));
+      auto conv1_wgrad = [&]() -> int {              // D[ci][co] -> dW1[co][ci], on the side stream
         WgradParams w = {};
         w.M = (int)M; w.CB = 128; w.NB = 1; w.na_total = li.cin; w.nb_total = BOTT;
         w.Dz = g.D[b]; w.Dy = g.H[b]; w.Dx = g.W[b];
         w.a_src = buf; w.a_pitch = bi.ctot; w.bnA = bn1;
-        w.b_src = dA2; w.b_pitch = BOTT;
+        w.b_src = dbott; w.b_pitch = BOTT;
         w.dw = det ? wslots + g.wslot_off[li.conv1_idx] : (float*)grads[li.conv1_idx];
         w.slot_stride = det ? pl->param_numel[li.conv1_idx] : 0;
         w.so_a = 1; w.so_b = li.cin; w.so_j = 0;
         cudaEvent_t ready = pl->next_event();
-        CUDA_RET(cudaEventRecord(ready, st));          // dA2 holds dBott
+        CUDA_RET(cudaEventRecord(ready, st));          // dBott is final
         CUDA_RET(cudaStreamWaitEvent(sd, ready, 0));
         {
           ProfScope ps_(PC_CONV1_WGRAD, sd);
@@ -868,7 +878,9 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         }
         side_done[parity][1] = pl->next_event();
         CUDA_RET(cudaEventRecord(side_done[parity][1], sd));
-      }
+        return 0;
+      };
+      if (!fuse_bn2) RET_IF(conv1_wgrad());
       // conv1 dgrad (+ ReLU mask of norm1/relu1, + BN1 backward statistics): the masked gradient, scaled by gamma, is ADDED to the
       // block's fp32 accumulator by the epilogue (deferred BatchNorm backward: no bf16 dA1 tensor, no per-layer pass over cin channels)
       {
@@ -880,9 +892,14 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
         p.out = (bf16*)dbuf; p.out_pitch = bi.ctot; p.acc_rstd = batch ? 0 : 1;
         p.st_sum = gsum(li.n1); p.st_sq = gdot(li.n1);
         p.e_src = buf; p.e_pitch = bi.ctot; p.bnE = bn1;
+        if (fuse_bn2) {     // the producers apply BN2's backward to the raw masked gradient and materialise it for the weight gradient
+          p.bnA = bn2; p.t_src = bott; p.t_pitch = BOTT; p.t_gsum = gsum(li.n2); p.t_gdot = gdot(li.n2);
+          p.t_inv_count = batch ? 1.0f / (float)M : 0.f; p.t_out = dB2; p.t_out_pitch = BOTT;
+        }
         ProfScope ps_(PC_CONV1_DGRAD, st);
-        RET_IF(launch_rows(p, A_LINEAR_CONV, T_NONE, EP_MASK_STATS_ACC, 1, st));
+        RET_IF(launch_rows(p, A_LINEAR_CONV, fuse_bn2 ? T_BNBWD : T_NONE, EP_MASK_STATS_ACC, 1, st));
       }
+      if (fuse_bn2) RET_IF(conv1_wgrad());
       if (l > 0) {
         // channels [cin-32, cin) = the new channels of layer l-1 have seen their last reader: finalise them and emit that
         // layer's gradient slice into the other parity's buffer (after the side-stream wgrad that last read it has finished)

@@ -58,7 +58,12 @@ MMNN_DEVINL void bn_mean_rstd(const BnSrc& b, int c, float& mean, float& rstd) {
 }
 
 enum { A_LINEAR_CONV = 0, A_STEM = 1 };
-enum { T_NONE = 0, T_BNRELU = 1 };
+// T_BNBWD (data-gradient GEMMs of small grids): the A operand is the BatchNorm-backward of the raw masked gradient,
+//   a_c * v + b_c * x + d_c   (= gamma rstd (v - mean(v) - xhat mean(v xhat)),  x = the BatchNorm's forward input, from t_src),
+// applied by the producers while the tile passes through registers -- the separate in-place pass (bn_bwd_apply, one more launch
+// in the serial chain of every late dense layer) disappears; the CTAs of column tile 0 also store the transformed tile to t_out
+// (the weight-gradient GEMM on the side stream reads it through TMA).
+enum { T_NONE = 0, T_BNRELU = 1, T_BNBWD = 2 };
 // EP_MASK_STATS_ACC (1x1x1 data gradient of a dense layer): like EP_MASK_STATS, but the masked gradient is not stored as a bf16
 // tensor for a separate BatchNorm-backward pass -- it is ADDED, scaled per column by coefG, into the fp32 gradient accumulator
 // of the block buffer (`out` is then a float*, one vector RED per 4 columns; every element has exactly one writer per launch,
@@ -96,6 +101,14 @@ struct RowsParams {
   // k-blocks below early_ch while that convolution is still running and calls griddepcontrol.wait only before the k-blocks
   // that contain its output.  0: wait first (plain stream order).
   int early_ch;
+  // T_BNBWD
+  const bf16* t_src;       // forward input of the BatchNorm (activation format), same row / channel indexing as a_src
+  long long t_pitch;
+  const double* t_gsum;    // backward statistics of that BatchNorm: sum v, sum v * xhat
+  const double* t_gdot;
+  float t_inv_count;       // 1 / rows in batch mode, 0 in eval mode (then the transform is gamma * rstd * v)
+  bf16* t_out;             // transformed gradient [M][t_out_pitch] (bf16), written by the CTAs with blockIdx.y == 0
+  long long t_out_pitch;
 };
 
 // 8 elements (16 B): load format IN, BN scale/shift + ReLU in fp32, store format OUT
@@ -161,7 +174,7 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
   uint32_t o = 0;
   offs[0] = o; o += 128;                 // barriers + tmem ptr
   offs[1] = o; o += TILE_ROWS * 16;      // rowinfo
-  offs[2] = o; o += 2u * Cin * 4;        // coefA: scale, shift
+  offs[2] = o; o += 3u * Cin * 4;        // coefA: scale, shift (T_BNRELU) / a, b, d (T_BNBWD)
   offs[3] = o; o += 5u * NT * 4;         // coefE: scale, shift, mean, rstd, accumulate scale
   offs[4] = o; o += 8u * NT * 4;         // red[2][4][NT]
   o = (o + 127u) & ~127u;
@@ -275,6 +288,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
         coefA[c] = s;
         coefA[p.Cin + c] = p.bnA.beta[c] - mean * s;
       }
+    }
+  }
+  if (TRANS == T_BNBWD) {
+    for (int c = tid; c < p.Cin; c += ENGINE_THREADS) {
+      float mean, rstd;
+      bn_mean_rstd(p.bnA, c, mean, rstd);
+      const float k = p.bnA.gamma[c] * rstd;
+      const float c1 = (float)(p.t_gsum[c] * (double)p.t_inv_count);
+      const float c2 = (float)(p.t_gdot[c] * (double)p.t_inv_count);
+      coefA[c] = k;
+      coefA[p.Cin + c] = -k * rstd * c2;
+      coefA[2 * p.Cin + c] = -k * c1 + k * rstd * c2 * mean;
     }
   }
   if (MASK) {
@@ -400,6 +425,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           for (int e = 0; e < 8; ++e) { sc[e] = coefA[ch0 + e]; sh[e] = coefA[p.Cin + ch0 + e]; }
         }
       }
+      uint4 xr[MAX_PASSES];
+      if (TRANS == T_BNBWD) {
+        // the BatchNorm's forward input of the same cells: issued together, one L2 round trip per k-block (two k-blocks per launch)
+#pragma unroll
+        for (int ps = 0; ps < MAX_PASSES; ++ps) {
+          xr[ps] = make_uint4(0, 0, 0, 0);
+          if (ps < npass && ((okm >> ps) & 1u)) {
+            const int r = (warp + ps * PRODUCER_WARPS) * rpp + rsub;
+            xr[ps] = ldg16(p.t_src + (long long)rowinfo[r].x * p.t_pitch + ch0);
+          }
+        }
+      }
 #pragma unroll
       for (int ps = 0; ps < MAX_PASSES; ++ps) {
         if (ps < npass) {
@@ -408,6 +445,22 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
           if (TRANS == T_BNRELU && ((okm >> ps) & 1u)) {
             if (OP_F16) apply_bnrelu8_h2(v, hc);     // 12 packed HFMA2 per cell instead of 28 scalar instructions
             else apply_bnrelu8<OP_F16, OP_F16>(v, sc, sh);
+          }
+          if (TRANS == T_BNBWD && ((okm >> ps) & 1u)) {
+            uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xr[ps]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float v0, v1, x0, x1;
+              unpack2<false>(vw[i], v0, v1);
+              unpack2<E_F16>(xw[i], x0, x1);
+              const int c = ch0 + 2 * i;
+              const float o0 = fmaf(coefA[c], v0, fmaf(coefA[p.Cin + c], x0, coefA[2 * p.Cin + c]));
+              const float o1 = fmaf(coefA[c + 1], v1, fmaf(coefA[p.Cin + c + 1], x1, coefA[2 * p.Cin + c + 1]));
+              vw[i] = pack2<false>(o0, o1);
+            }
+            if (tile_n == 0 && p.t_out != nullptr)
+              *reinterpret_cast<uint4*>(p.t_out + (long long)rowinfo[r].x * p.t_out_pitch + ch0) = v;
           }
           sts16(sA + chunk * PLANE_BYTES + r * 16, v);
         }

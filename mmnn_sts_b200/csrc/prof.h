@@ -14,9 +14,11 @@ enum ProfClass {
   PC_RN_FPROP, PC_RN_DGRAD, PC_RN_WGRAD, PC_RN_ELTWISE, PC_RN_HEAD, PC_COUNT
 };
 
-struct ProfRec { int cls; cudaEvent_t a, b; };
+struct ProfRec { int cls; cudaEvent_t a, b; int side; };
 struct ProfState {
   bool on = false;
+  bool timeline = false;   // keep the real stream structure (side stream, early start, PDL) while recording: the records then give
+                           // each launch's start / end on its own stream relative to a base event (mmnn_profile_timeline)
   long long launches = 0;
   std::vector<ProfRec> recs;
 };
@@ -29,7 +31,7 @@ struct ProfScope {
     ProfState& s = prof_state();
     s.launches += nlaunch;
     if (s.on) {
-      ProfRec r; r.cls = cls;
+      ProfRec r; r.cls = cls; r.side = 0;
       cudaEventCreate(&r.a); cudaEventCreate(&r.b);
       cudaEventRecord(r.a, st);
       idx = (int)s.recs.size();
