@@ -81,7 +81,7 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   // and are latency chains over their k-blocks, so they take the deepest operand ring that fits (ncu, round 2: with Cin = 992
   // the 100 KB budget left TWO stages and every k-block exposed its weight fetch: 4 200 cycles per k-block)
   static const int small_kb = [] { const char* e = getenv("MMNN_ROWS_SMALL_SMEM_KB"); return e ? atoi(e) : 200; }();
-  if (p.stages <= 0) p.stages = choose_stages(p, (PF == 2 ? small_kb : 100) * 1024);
+  if (p.stages <= 0) p.stages = choose_stages(p, (PF == 2 ? small_kb : (GRAD ? 112 : 100)) * 1024);
   const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
   static const bool tc_stats_on = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '1'; }();
   if (tc_stats_on) p.stages |= 0x100;    // experiment switch: column statistics on the tensor core (engine.cuh)

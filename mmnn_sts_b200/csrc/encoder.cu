@@ -51,6 +51,8 @@ struct BnInfo {
 
 struct LayerInfo {
   int cin;
+  int nt_d;     // column-tile width of the 1x1x1 data gradient: cin itself for 128 < cin <= 256 (ONE tile: the gradient operand is
+                // read once and no CTA works on a mostly empty second tile), else 128
   BnInfo n1, n2;
   int conv1_idx, conv2_idx;
   size_t pk_c1f, pk_c1d, pk_c2f, pk_c2d;  // packed weight offsets (elements)
@@ -158,6 +160,10 @@ struct Geo {
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+bool nt_cin_enabled() {
+  static const bool on = [] { const char* e = getenv("MMNN_DGRAD_NT_CIN"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
 
 // voxel split of a weight-gradient launch (same rule as launch_wgrad applies: capi_conv.cu)
 int split_for(int kind, long long M, int na_total, int nb_total, int CB, bool slotted) {
@@ -310,12 +316,13 @@ void* mmnn_encoder_create(int in_channels, const int* block_config, int nblocks,
     for (int l = 0; l < block_config[b]; ++l) {
       LayerInfo li;
       li.cin = c + l * GROWTH; li.index = lidx++;
+      li.nt_d = (li.cin > 128 && li.cin <= 256 && nt_cin_enabled()) ? li.cin : 128;
       add_bn(li.n1, li.cin, bi.fwd_off);
       li.conv1_idx = add_param((long long)BOTT * li.cin);
       add_bn(li.n2, BOTT, foff); foff += BOTT;
       li.conv2_idx = add_param((long long)GROWTH * BOTT * 27);
       li.pk_c1f = pk; pk += packed_elems(BOTT, 128, li.cin, 64, 1);
-      li.pk_c1d = pk; pk += packed_elems(li.cin, 128, BOTT, 64, 1);
+      li.pk_c1d = pk; pk += packed_elems(li.cin, li.nt_d, BOTT, 64, 1);
       li.pk_c2f = pk; pk += packed_elems(GROWTH, 32, BOTT, 64, 27);
       li.pk_c2d = pk; pk += packed_elems(BOTT, 128, GROWTH, 32, 27);
       bi.layers.push_back(li);
@@ -450,7 +457,7 @@ static int encoder_forward_impl(void* h, int B, int X, int Y, int Z, const void*
     for (auto& bi : pl->blocks) {
       for (auto& li : bi.layers) {
         add(params[li.conv1_idx], li.pk_c1f, BOTT, 128, li.cin, 64, 1, PACK_GENERIC, li.cin, 1, 0, true);
-        add(params[li.conv1_idx], li.pk_c1d, li.cin, 128, BOTT, 64, 1, PACK_GENERIC, 1, li.cin, 0, false);
+        add(params[li.conv1_idx], li.pk_c1d, li.cin, li.nt_d, BOTT, 64, 1, PACK_GENERIC, 1, li.cin, 0, false);
         add(params[li.conv2_idx], li.pk_c2f, GROWTH, 32, BOTT, 64, 27, PACK_GENERIC, BOTT * 27, 27, 1, true);
         add(params[li.conv2_idx], li.pk_c2d, BOTT, 128, GROWTH, 32, 27, PACK_GENERIC, 27, BOTT * 27, 1, false);
       }
@@ -885,7 +892,7 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       // block's fp32 accumulator by the epilogue (deferred BatchNorm backward: no bf16 dA1 tensor, no per-layer pass over cin channels)
       {
         RowsParams p = {};
-        p.M = (int)M; p.NT = 128; p.Ncols = li.cin; p.Cin = BOTT; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
+        p.M = (int)M; p.NT = li.nt_d; p.Ncols = li.cin; p.Cin = BOTT; p.kbw = 64; p.ntaps = 1; p.tap_sign = 1;
         p.Dz = g.D[b]; p.Dy = g.H[b]; p.Dx = g.W[b];
         p.a_src = dA2; p.a_pitch = BOTT;
         p.b_packed = packed + li.pk_c1d;

@@ -556,8 +556,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       float q[32];
       if (MASK) {
         uint4 xv[4];
+        if (k < 2) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i] = xpre[k < 2 ? k : 1][i];
+          for (int i = 0; i < 4; ++i) xv[i] = xpre[k][i];
+        } else {       // column tiles wider than 128 (single-tile data gradients of 160..256 channels): chunks 4..7 are fetched here
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xv[i] = row_ok ? ldg16(p.e_src + m * p.e_pitch + col0 + i * 8) : make_uint4(0, 0, 0, 0);
+        }
         const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
