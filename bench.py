@@ -46,11 +46,14 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index, self.lines, self.proc = index, [], None
         self.t0 = self.t1 = None
+        self.enabled = enabled     # only rank 0 samples: N concurrent nvidia-smi pollers contend for the driver on a shared host
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -290,7 +293,7 @@ def run_ours(args):
         graphed = GraphedTrainStep(lambda *b: eager_step(*b).detach(), dev_batches[0], warmup=2)
         step = lambda *b: graphed(*b)
     launches0 = L.lib().mmnn_launch_count()
-    with ClockSampler(device.index or 0) as cs:
+    with ClockSampler(device.index or 0, enabled=(rank == 0)) as cs:
         cs.wait_first_sample()
         timed(2, e2e=True)                       # settle the e2e pipeline (staging buffers, events) before anything is timed
         launches0 = L.lib().mmnn_launch_count()
@@ -619,7 +622,7 @@ def resnet_measure(args, rank, world, dev, cpu_baseline=True):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / n
 
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         for i in range(max(3, args.warmup)):
             step(*devb[i % 2])
         clk.wait_first_sample()
