@@ -63,7 +63,8 @@ class WgradParams(C.Structure):
                 ("b_src", C.c_void_p), ("b_pitch", C.c_longlong), ("bnB", BnSrc),
                 ("dw", C.c_void_p), ("so_a", C.c_longlong), ("so_b", C.c_longlong), ("so_j", C.c_longlong),
                 ("cin_real", C.c_int), ("stages", C.c_int), ("NP", C.c_int), ("slot_stride", C.c_longlong),
-                ("tma_b", C.c_int), ("bx", C.c_int), ("by", C.c_int), ("bz", C.c_int), ("bn", C.c_int)]
+                ("tma_b", C.c_int), ("bx", C.c_int), ("by", C.c_int), ("bz", C.c_int), ("bn", C.c_int),
+                ("a_bf16", C.c_int), ("tma_a", C.c_int)]
 
 
 _P6 = C.c_void_p * 6

@@ -54,6 +54,32 @@ bool make_tmap_ndhwc(CUtensorMap* out, const void* ptr, long long pitch, int N, 
   *out = m;
   return true;
 }
+
+// The bf16 space-to-depth image [N][Sz][Sy][Sx][16] seen as [N][Sz][Sy][Sx-3][64]: a "row" is 4 consecutive 16-channel cells and
+// rows advance by one cell (32 B), so consecutive rows overlap -- the operand of the stem weight gradient (engine.cuh, tma_a).
+bool make_tmap_s2d_rows(CUtensorMap* out, const void* ptr, int N, int Sz, int Sy, int Sx, int bx, int by, int bz, int bn) {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key(ptr, N, Sz, Sy, Sx, bx, by, bz, bn);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || ((uintptr_t)ptr & 15u) != 0 || Sx < 4) return false;
+  const cuuint64_t gdim[5] = {64u, (cuuint64_t)(Sx - 3), (cuuint64_t)Sy, (cuuint64_t)Sz, (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {32u, (cuuint64_t)Sx * 32u, (cuuint64_t)Sy * Sx * 32u, (cuuint64_t)Sz * Sy * Sx * 32u};
+  const cuuint32_t box[5] = {32u, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bn};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 256) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
 }  // namespace mmnn
 
 #define MMNN_CHECK_LAUNCH()                      \
@@ -247,6 +273,16 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
     const int N = (int)((p.M + vps - 1) / vps);
     if (make_tmap_ndhwc(&tmb, p.b_src, p.b_pitch, N, p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) p.tma_b = 1;
   }
+  // stem: the space-to-depth operand by TMA too when the caller holds it in bf16 (MMNN_STEM_WGRAD_TMA=0: register path)
+  static const bool tma_a_on = [] { const char* e = getenv("MMNN_STEM_WGRAD_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  CUtensorMap tma;
+  memset(&tma, 0, sizeof(tma));
+  p.tma_a = 0;
+  if (AMODE == WA_STEM_PAIR && tma_a_on && p.tma_b && p.a_bf16 == 1 && p.a_pitch == 16 && p.Sz >= p.Dz + 3 && p.Sy >= p.Dy + 3 && p.Sx >= p.Dx + 3) {
+    const long long vps = (long long)p.Dz * p.Dy * p.Dx;
+    const int N = (int)((p.M + vps - 1) / vps);
+    if (make_tmap_s2d_rows(&tma, p.a_src, N, p.Sz, p.Sy, p.Sx, p.bx, p.by, p.bz, p.bn)) p.tma_a = 1;
+  }
   uint32_t offs[4];
   if (p.stages <= 0) {
     p.stages = 1;
@@ -257,7 +293,7 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p, tmb);
+  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p, tmb, tma);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

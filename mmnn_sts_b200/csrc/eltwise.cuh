@@ -50,8 +50,10 @@ MMNN_DEVINL void block_channel_reduce(float* red /*[EW_THREADS][16]*/, const flo
 // TIN: float (the reference's collate output, /root/reference/utils/utils.py:98-99) or __half (a loader that ships 16-bit volumes:
 // half the host->device bytes; the values are rounded to the activation format here either way, so the results are identical)
 template <typename TIN>
-static __global__ void s2d_pack_kernel(const TIN* __restrict__ img, bf16* __restrict__ dst, int B, int cin, int X, int Y, int Z,
-                                int Sz, int Sy, int Sx) {
+// dst_w (optional): the same image in bf16 (each value = the bf16 rounding of the stored activation-format value), the TMA operand
+// of the stem weight gradient, whose MMA runs in bf16 next to the bf16 gradient tiles
+static __global__ void s2d_pack_kernel(const TIN* __restrict__ img, bf16* __restrict__ dst, bf16* __restrict__ dst_w, int B, int cin,
+                                       int X, int Y, int Z, int Sz, int Sy, int Sx) {
   const long long total = (long long)B * Sz * Sy * Sx * 2;  // 16-byte cells (pz = cell & 1)
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long t = idx;
@@ -71,7 +73,12 @@ static __global__ void s2d_pack_kernel(const TIN* __restrict__ img, bf16* __rest
         v = (float)img[((((long long)b * cin + c) * X + iz) * Y + iy) * Z + ix];
       f[e] = v;
     }
-    reinterpret_cast<uint4*>(dst)[idx] = pack8<ACT>(f);
+    uint4 o = pack8<ACT>(f);
+    reinterpret_cast<uint4*>(dst)[idx] = o;
+    if (dst_w != nullptr) {
+      convert8<kActF16, false>(o);
+      reinterpret_cast<uint4*>(dst_w)[idx] = o;
+    }
   }
 }
 

@@ -151,7 +151,7 @@ struct Geo {
   long long M0;
   int D[8], H[8], W[8];
   long long M[8];
-  size_t xs2d, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, dB2, gslice, gout, dpooled, wslots, dr, total;
+  size_t xs2d, xs2dw, stem_out, argmax, fstats, bstats, packed, tables, dA2, dA1, dB2, gslice, gout, dpooled, wslots, dr, total;
   size_t wslots_bytes;
   std::vector<size_t> wslot_off;   // per parameter index: element offset of the weight-gradient slots (convolutions only)
   std::vector<int> wslot_S;        // per parameter index: number of slots == voxel split of that weight-gradient launch
@@ -189,6 +189,8 @@ bool make_geo(const Plan& pl, int B, int X, int Y, int Z, Geo& g) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   g.xs2d = take((size_t)B * g.Sz * g.Sy * g.Sx * 16 * 2 + 256);
+  // bf16 copy for the stem weight gradient's TMA operand (the image itself when the activation format already is bf16)
+  g.xs2dw = kActF16 ? take((size_t)B * g.Sz * g.Sy * g.Sx * 16 * 2 + 256) : g.xs2d;
   g.stem_out = take((size_t)g.M0 * 64 * 2);
   g.argmax = take((size_t)g.M[0] * 64);
   size_t maxM = 0, maxMC = 0, maxMoutC = 0, maxMoutC2 = 0;
@@ -475,11 +477,12 @@ static int encoder_forward_impl(void* h, int B, int X, int Y, int Z, const void*
 
   // ---- 2. stem
   bf16* xs2d = (bf16*)(ws + g.xs2d);
+  bf16* xs2dw = (kActF16 && training) ? (bf16*)(ws + g.xs2dw) : nullptr;   // eval-mode forward: no weight gradient follows
   {
     const long long cells = (long long)B * g.Sz * g.Sy * g.Sx * 2;
     { ProfScope ps_(PC_S2D, st);
-      if (image_f16) s2d_pack_kernel<__half><<<ew_grid(cells), EW_THREADS, 0, st>>>((const __half*)image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx);
-      else s2d_pack_kernel<float><<<ew_grid(cells), EW_THREADS, 0, st>>>((const float*)image, xs2d, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
+      if (image_f16) s2d_pack_kernel<__half><<<ew_grid(cells), EW_THREADS, 0, st>>>((const __half*)image, xs2d, xs2dw, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx);
+      else s2d_pack_kernel<float><<<ew_grid(cells), EW_THREADS, 0, st>>>((const float*)image, xs2d, xs2dw, B, pl->cin_real, X, Y, Z, g.Sz, g.Sy, g.Sx); }
     LAUNCH_RET();
     StemBrickParams p = {};
     p.B = B; p.D0 = g.D0; p.H0 = g.H0; p.W0 = g.W0; p.Sz = g.Sz; p.Sy = g.Sy; p.Sx = g.Sx;
@@ -1002,7 +1005,10 @@ int mmnn_encoder_backward(void* h, int B, int X, int Y, int Z, const void* const
       WgradParams w = {};
       w.M = (int)g.M0; w.CB = 64; w.NB = 1; w.na_total = 128; w.nb_total = 64;
       w.Dz = g.D0; w.Dy = g.H0; w.Dx = g.W0; w.Sz = g.Sz; w.Sy = g.Sy; w.Sx = g.Sx;
-      w.a_src = (const bf16*)(ws + g.xs2d); w.a_pitch = 16;
+      // after a training-mode forward the workspace holds the bf16 copy (TMA operand); after an eval-mode forward (GradCAM) only
+      // the activation-format image, read by the register path
+      w.a_bf16 = (!kActF16 || batch) ? 1 : 0;
+      w.a_src = (const bf16*)(ws + (w.a_bf16 ? g.xs2dw : g.xs2d)); w.a_pitch = 16;
       w.b_src = q.dr; w.b_pitch = 64;
       w.dw = det ? wslots + g.wslot_off[pl->conv0_idx] : (float*)grads[pl->conv0_idx];
       w.slot_stride = det ? pl->param_numel[pl->conv0_idx] : 0;

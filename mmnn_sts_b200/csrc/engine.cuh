@@ -750,6 +750,14 @@ struct WgradParams {
   // taps) is the same box at shifted coordinates; out-of-volume voxels are zero-filled by the TMA unit.
   int tma_b;
   int bx, by, bz, bn;
+  // Stem (WA_STEM_PAIR): a_bf16 != 0 -> a_src already holds bf16 (1: TMA allowed, 2: register path only -- tests); (the trunk keeps a bf16 copy of the space-to-depth image for
+  // this kernel; otherwise the activation format, converted in the producers).  tma_a != 0 (needs a_bf16 and tma_b) -> the A
+  // operand arrives by TMA as well: the kernel's second CUtensorMap views the image as [N][Sz][Sy][Sx-3][64], dimension x
+  // strided by ONE 16-channel cell (32 B) under a 64-element row -- overlapping rows, so the 128 "channels" of a k-block pair
+  // are four boxes (32 elements, bx, by, bz, bn) at (32 g mod 64, x0, y0 + dy + g / 2, z0 + dz, n0) in the same SWIZZLE_64B
+  // layout as the gradient tiles.  No producer warp touches the data: one thread issues 4 NP + 2 boxes per voxel tile.
+  int a_bf16;
+  int tma_a;
 };
 
 constexpr int TMA_GROUP_BYTES = TILE_ROWS * 64;   // one TMA box: 128 voxel rows x 32 bf16 channels
@@ -950,7 +958,8 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
 #endif
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
 __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p,
-                                                                    const __grid_constant__ CUtensorMap tmb) {
+                                                                    const __grid_constant__ CUtensorMap tmb,
+                                                                    const __grid_constant__ CUtensorMap tma) {
   // NEGATIVE RESULT (round 2, B200): the instruction descriptor of tcgen05 kind::f16 has separate A / B format fields, but an
   // fp16 A operand (forward activations, no conversion, packed-half BN+ReLU) next to the bf16 B operand (gradients) raises
   // "illegal instruction" on sm_100a -- both operands must have the same format.  -DMMNN_WGRAD_A_F16=1 builds that variant
@@ -960,6 +969,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   uint32_t offs[4];
   const int NP = p.NP < 1 ? 1 : p.NP;
   const bool tma_b = p.tma_b != 0;
+  const bool tma_a = AMODE == WA_STEM_PAIR && tma_b && p.tma_a != 0;
   wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
@@ -994,12 +1004,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS + (tma_b ? 1 : 0));   // + the expect_tx arrival of the TMA issuer
+        // producers + the expect_tx arrival of the TMA issuer; all-TMA stem: the issuer alone
+        mbar_init(bar_full + 8 * s, tma_a ? 1 : NUM_PRODUCER_THREADS + (tma_b ? 1 : 0));
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
       fence_mbar_init();
       if (tma_b) tma_prefetch_desc(&tmb);
+      if (tma_a) tma_prefetch_desc(&tma);
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
@@ -1075,7 +1087,31 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     // 2.37 ms, step 15.17 vs 14.94 ms; 2.63 ms when the copies bypass L1 -- the 9 shifted tiles share their rows), so it
     // is OFF unless MMNN_WGRAD_PIPED=1 (kept as a parity-tested experiment).
     const bool piped = !tma_b && AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4 && p.NP == -1;   // NP == -1: opt-in experiment switch (MMNN_WGRAD_PIPED=1)
-    if (tma_b && AMODE == WA_LINEAR) {
+    if (tma_a) {
+      // ---- all-TMA stem: both operands are boxes; one thread feeds the ring, the other producer threads go straight to the epilogue
+      if (tid == 4 * 32) {     // a warp without an epilogue role (the epilogue runs on warps 0-3)
+        for (int it = 0; it < nt; ++it) {
+          const int s = it % S;
+          mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / S) & 1u) ^ 1u, 11);
+          const long long m0 = (long long)(t_begin + it) * TILE_ROWS;
+          const int n0 = (int)(m0 / vps);
+          int rem = (int)(m0 - (long long)n0 * vps);
+          const int z0 = rem / (p.Dy * p.Dx);
+          rem -= z0 * p.Dy * p.Dx;
+          const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
+          const uint32_t sBs = stage0 + s * stage_bytes + b_off, sAs = stage0 + s * stage_bytes + a_off;
+          // (the A region of a stage is sized in padded chunk planes, the boxes fill 4 NP x 8 KB of it)
+          mbar_arrive_expect_tx(bar_full + 8 * s, bt_bytes + 4u * NP * (uint32_t)TMA_GROUP_BYTES);
+          for (uint32_t c = 0; c < bgroups; ++c)
+            tma_load_5d(sBs + c * (uint32_t)TMA_GROUP_BYTES, &tmb, (int)c * 32, x0, y0, z0, n0, bar_full + 8 * s);
+          for (int g = 0; g < 4 * NP; ++g) {     // group g: k-block kb = ztile*2*NP + g/2, elements 32 (g & 1) .. + 32 of its 64
+            const int kb = ztile * 2 * NP + (g >> 1);
+            tma_load_5d(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES, &tma, (g & 1) * 32, x0, y0 + (kb & 3), z0 + (kb >> 2), n0,
+                        bar_full + 8 * s);
+          }
+        }
+      }
+    } else if (tma_b && AMODE == WA_LINEAR) {
       // ---- TMA mode (default when the tile is a box of the volume): the gradient tiles arrive by cp.async.bulk.tensor, so
       // the 256 producer threads only build the A tile -- and do it software-pipelined: the 128-bit loads of tile it+1 are in
       // flight while tile it is transformed and stored (8 loads per thread, no row table, no per-tile barrier).
@@ -1274,7 +1310,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
               for (int ps = 0; ps < MAX_PASSES; ++ps) {
                 const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
                 uint4 v = sregs[g][ps];
-                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, A_F16>(v);
+                if (((sok >> (g * MAX_PASSES + ps)) & 1u) && !p.a_bf16) convert8<kActF16, A_F16>(v);
                 sts16(sA + (g * 8 + chunk) * PLANE_BYTES + r * 16, v);
               }
             }
@@ -1296,7 +1332,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
               for (int ps = 0; ps < MAX_PASSES; ++ps) {
                 const int r = (warp + ps * PRODUCER_WARPS) * 4 + rsub;
                 uint4 v = sregs[g][ps];
-                if ((sok >> (g * MAX_PASSES + ps)) & 1u) convert8<kActF16, A_F16>(v);
+                if (((sok >> (g * MAX_PASSES + ps)) & 1u) && !p.a_bf16) convert8<kActF16, A_F16>(v);
                 sts16(sA + (g * 8 + chunk) * PLANE_BYTES + r * 16, v);
               }
             }
@@ -1403,7 +1439,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       if (elect_one()) {
         const uint32_t sA = stage0 + s * stage_bytes + a_off;
         const uint32_t sB = stage0 + s * stage_bytes + b_off;
-        const uint64_t ad0 = make_smem_desc(sA, 128, PLANE_BYTES);
+        // A: chunk planes, or (all-TMA stem) the same swizzled 32-channel groups as B
+        const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, TMA_GROUP_BYTES, 512, 4u) : make_smem_desc(sA, 128, PLANE_BYTES);
+        const uint32_t ak16 = tma_a ? 1024u : 256u;
         // B: register path = SWIZZLE_NONE chunk planes (8-row K groups 128 B apart, 8-channel chunks one plane apart);
         //    TMA path = SWIZZLE_64B rows of 64 B (8-row atoms 512 B apart, 32-channel groups 8 KB apart)
         uint64_t bd0 = tma_b ? make_smem_desc_sw(sB, TMA_GROUP_BYTES, 512, 4u) : make_smem_desc(sB, 128, PLANE_BYTES);
@@ -1412,12 +1450,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         if (AMODE == WA_STEM_PAIR) {
           // NP pairs share the B tile; pair pi reads its own 16 A planes and owns accumulator pi
           for (int pi = 0; pi < NP; ++pi) {
-            const uint64_t ad = desc_advance(ad0, pi * 16 * PLANE_BYTES);
+            const uint64_t ad = desc_advance(ad0, tma_a ? pi * 4 * TMA_GROUP_BYTES : pi * 16 * PLANE_BYTES);
             const uint32_t td = tmem_base + pi * p.CB;
             tc_mma_bf16(td, ad, bd0, idesc, acc0);
 #pragma unroll
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
-              tc_mma_bf16(td, desc_advance(ad, k16 * 256), desc_advance(bd0, k16 * bk16), idesc, 1u);
+              tc_mma_bf16(td, desc_advance(ad, k16 * ak16), desc_advance(bd0, k16 * bk16), idesc, 1u);
           }
         } else if (p.NB == 9 && p.CB == 32 && tma_b) {
           // swizzled operand: N must cover whole 32-channel groups -> three N = 96 MMAs (3 taps each) per K step

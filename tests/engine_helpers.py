@@ -59,7 +59,7 @@ def rows(M, NT, Ncols, Cin, kbw, ntaps, dims, a_src, a_pitch, b_packed, out, out
 
 
 def wgrad(kind, M, CB, NB, na_total, nb_total, dims, a_src, a_pitch, b_src, b_pitch, dw, so_a, so_b, so_j=0,
-          bnA=None, bnB=None, sdims=(0, 0, 0), cin_real=0, split=0, stages=0):
+          bnA=None, bnB=None, sdims=(0, 0, 0), cin_real=0, split=0, stages=0, a_bf16=0):
     p = L.WgradParams()
     p.M, p.CB, p.NB, p.na_total, p.nb_total = M, CB, NB, na_total, nb_total
     p.Dz, p.Dy, p.Dx = dims
@@ -70,6 +70,7 @@ def wgrad(kind, M, CB, NB, na_total, nb_total, dims, a_src, a_pitch, b_src, b_pi
     p.bnB = bnB if bnB is not None else L.BnSrc()
     p.dw, p.so_a, p.so_b, p.so_j = dw.data_ptr(), so_a, so_b, so_j
     p.cin_real, p.stages = cin_real, stages
+    p.a_bf16 = a_bf16
     L.check(L.lib().mmnn_conv_wgrad(C.byref(p), kind, split, stream_ptr()), "conv_wgrad")
 
 

@@ -315,6 +315,37 @@ def test_wgrad_raw_and_stem():
         assert (dw0 - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw0 - ref).abs().max()
 
 
+@pytest.mark.parametrize("cin,shape,B", [(2, (16, 16, 32), 3), (1, (32, 16, 64), 2), (2, (8, 8, 8), 5)])
+def test_stem_wgrad_all_tma_matches_register_path(cin, shape, B):
+    """Stem weight gradient with BOTH operands by TMA (bf16 space-to-depth image viewed as overlapping 64-element rows,
+    engine.cuh tma_a): volumes whose 128-voxel tiles are boxes, incl. one whose box spans several samples.  Checked against
+    autograd on the same rounded operands and, bit for bit, against the register path fed the same bf16 image."""
+    from tests import engine_helpers as H
+    torch.manual_seed(17)
+    X, Y, Z = shape
+    img = torch.rand(B, cin, X, Y, Z, device="cuda")
+    Dz, Dy, Dx = (X - 1) // 2 + 1, (Y - 1) // 2 + 1, (Z - 1) // 2 + 1
+    Sz, Sy, Sx = Dz + 3, Dy + 3, Dx + 3
+    pad = torch.zeros(B, 2, 2 * Sz, 2 * Sy, 2 * Sx, device="cuda")
+    pad[:, :cin, 3:3 + X, 3:3 + Y, 3:3 + Z] = img
+    s2d = pad.view(B, 2, Sz, 2, Sy, 2, Sx, 2).permute(0, 2, 4, 6, 3, 5, 7, 1).contiguous().to(_actdt()).to(torch.bfloat16)
+    s2d = torch.cat([s2d.view(-1), torch.zeros(64, dtype=torch.bfloat16, device="cuda")])
+    M0 = B * Dz * Dy * Dx
+    dconv = (torch.randn(M0, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    got = []
+    for a_bf16 in (1, 2):      # 1: bf16 image, operand by TMA; 2: bf16 image through the register path
+        dw0 = torch.zeros(64, cin, 7, 7, 7, device="cuda")
+        H.wgrad(3, M0, 64, 1, 128, 64, (Dz, Dy, Dx), s2d, 16, dconv, 64, dw0, 0, 0, sdims=(Sz, Sy, Sx), cin_real=cin,
+                a_bf16=a_bf16, split=1)
+        torch.cuda.synchronize()
+        got.append(dw0)
+    w = torch.zeros(64, cin, 7, 7, 7, device="cuda", requires_grad=True)
+    y = F.conv3d(_bf(_act(img)), w, stride=2, padding=3)
+    (ref,) = torch.autograd.grad(y, w, dconv.float().view(B, Dz, Dy, Dx, 64).permute(0, 4, 1, 2, 3))
+    assert (got[0] - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (got[0] - ref).abs().max()
+    assert torch.equal(got[0], got[1])
+
+
 @pytest.mark.parametrize("dims,B", [((3, 20, 12), 2), ((4, 16, 8), 3), ((2, 32, 16), 40)])
 def test_brick_conv3_fprop(dims, B):
     """Brick-mode 3x3x3 forward (BN+ReLU prologue, dropout scale, statistics) incl. partial tiles and a grid with
