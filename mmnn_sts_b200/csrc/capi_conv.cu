@@ -236,11 +236,15 @@ int launch_stem_brick(const StemBrickParams& p, cudaStream_t stream) {
 // GPU.  Slotted (deterministic) reduction: every CTA of the split writes a full partial copy of its output tile, so the split
 // is additionally capped at one CTA per MMNN_WGRAD_MIN_TILES voxel tiles (default 2; measured on B200 at configs[1]: 1, 2, 3 match the atomic reduction at 1072-1076 volumes/s, 4 -> 1058, 8 -> 1021, 16 -> 935): the small late-block layers (32 / 4
 // voxel tiles) then write 16 / 2 partial copies instead of 32 / 4.
+static int stem_np_default() {   // k-block pairs per CTA of the stem weight gradient (MMNN_STEM_NP=1: 8 z tiles, deeper ring)
+  static const int v = [] { const char* e = getenv("MMNN_STEM_NP"); return (e != nullptr && e[0] == '1') ? 1 : 2; }();
+  return v;
+}
 void wgrad_grid(const WgradParams& p, int kind, int& gy, int& gz) {
   gz = (p.na_total + 127) / 128;
   gy = (p.nb_total + p.CB - 1) / p.CB;
   if (kind == 1) { gy = 3; gz = 1; }
-  if (kind == 3) { const int np = (p.NP == 1 || p.NP == 2) ? p.NP : 2; gy = 1; gz = 8 / np; }
+  if (kind == 3) { const int np = (p.NP == 1 || p.NP == 2) ? p.NP : stem_np_default(); gy = 1; gz = 8 / np; }
 }
 int wgrad_split(const WgradParams& p, int kind, bool slotted) {
   int gy, gz;
@@ -281,15 +285,19 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   if (AMODE == WA_STEM_PAIR && tma_a_on && p.tma_b && p.a_bf16 == 1 && p.a_pitch == 16 && p.Sz >= p.Dz + 3 && p.Sy >= p.Dy + 3 && p.Sx >= p.Dx + 3) {
     const long long vps = (long long)p.Dz * p.Dy * p.Dx;
     const int N = (int)((p.M + vps - 1) / vps);
-    if (make_tmap_s2d_rows(&tma, p.a_src, N, p.Sz, p.Sy, p.Sx, p.bx, p.by, p.bz, p.bn)) p.tma_a = 1;
+    // one (by + 3)-row box per element half when the tile lies in one z slice (engine.cuh, tma_a == 2); MMNN_STEM_WGRAD_HALO=0: four boxes
+    static const bool halo_on = [] { const char* e = getenv("MMNN_STEM_WGRAD_HALO"); return !(e != nullptr && e[0] == '0'); }();
+    const bool halo = halo_on && p.NP == 2 && p.bz == 1 && p.bn == 1 && p.bx % 8 == 0 && p.by + 3 <= 256;
+    if (make_tmap_s2d_rows(&tma, p.a_src, N, p.Sz, p.Sy, p.Sx, p.bx, halo ? p.by + 3 : p.by, p.bz, p.bn)) p.tma_a = halo ? 2 : 1;
   }
+  const uint32_t halo_bytes = p.tma_a == 2 ? wgrad_stem_halo_bytes(p.bx, p.by) : 0u;
   uint32_t offs[4];
   if (p.stages <= 0) {
     p.stages = 1;
     for (int s = 1; s <= 4; ++s)
-      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0) <= 225 * 1024) p.stages = s;
+      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes) <= 225 * 1024) p.stages = s;
   }
-  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0);
+  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes);
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -315,7 +323,7 @@ int launch_wgrad(const WgradParams& p, int kind, int split, cudaStream_t stream)
     case 2: return launch_wgrad_t<WA_LINEAR, T_NONE, T_NONE, WE_STRIDED>(p, split, gy, gz, stream);
     case 3: {
       WgradParams q = p;
-      if (q.NP != 1 && q.NP != 2) q.NP = 2;   // two k-block pairs per CTA share one gradient tile
+      if (q.NP != 1 && q.NP != 2) q.NP = stem_np_default();   // two k-block pairs per CTA share one gradient tile
       return launch_wgrad_t<WA_STEM_PAIR, T_NONE, T_NONE, WE_STEM>(q, split, gy, gz, stream);
     }
   }

@@ -756,11 +756,18 @@ struct WgradParams {
   // strided by ONE 16-channel cell (32 B) under a 64-element row -- overlapping rows, so the 128 "channels" of a k-block pair
   // are four boxes (32 elements, bx, by, bz, bn) at (32 g mod 64, x0, y0 + dy + g / 2, z0 + dz, n0) in the same SWIZZLE_64B
   // layout as the gradient tiles.  No producer warp touches the data: one thread issues 4 NP + 2 boxes per voxel tile.
+  // tma_a == 2 (tile = bx x by voxels of ONE z slice, bx a multiple of 8): the four k-blocks (dz, dy = 0..3) of a CTA read rows
+  // y0 + dy .. of the same slice, so ONE box of by + 3 rows per 32-element half (instead of four boxes of by rows per half) feeds
+  // all of them: k-block dy's operand starts bx rows (bx x 64 B, a multiple of the 512-byte swizzle period) further into the box.
+  // The MMA's M = 128 is then (dy = 0..3) x 32 elements of one half -- LBO = bx x 64 B -- and accumulator j holds half j.
   int a_bf16;
   int tma_a;
 };
 
 constexpr int TMA_GROUP_BYTES = TILE_ROWS * 64;   // one TMA box: 128 voxel rows x 32 bf16 channels
+
+// stem, tma_a == 2: bytes of the two (by + 3)-row boxes of a stage
+__host__ __device__ inline uint32_t wgrad_stem_halo_bytes(int bx, int by) { return 2u * (uint32_t)bx * (uint32_t)(by + 3) * 64u; }
 
 // Box decomposition of a tile of 128 consecutive voxels of an [N][Dz][Dy][Dx] volume (x fastest).  Returns false when a tile is
 // not a box (dims that do not chain-divide 128): the kernel then keeps the register path.
@@ -773,7 +780,8 @@ __host__ __device__ inline bool wgrad_tma_box(int Dz, int Dy, int Dx, int& bx, i
   return true;
 }
 
-__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/, bool tma_b = false) {
+__host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/, bool tma_b = false,
+                                                      uint32_t a_halo_bytes = 0) {
   uint32_t o = 0;
   offs[0] = o; o += 128;                          // barriers + tmem ptr
   offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
@@ -782,13 +790,13 @@ __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages
   offs[3] = o;
   uint32_t stage = 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
   // TMA mode: [B groups (swizzled, the stage base is 1024-byte aligned at run time)][A planes], stage size a multiple of 1 KB
-  if (tma_b) stage = ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + 16u * NP * PLANE_BYTES + 1023u) & ~1023u;
+  if (tma_b) stage = ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
   const uint32_t ring = stages * stage + (tma_b ? 1024u : 0u);
   const uint32_t epi = 32u * 132u * 4u;           // the epilogue's transpose staging reuses the ring
   return o + (ring > epi ? ring : epi);
 }
-__host__ __device__ inline uint32_t wgrad_stage_bytes(int CB, int NB, int NP, bool tma_b) {
-  if (tma_b) return ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + 16u * NP * PLANE_BYTES + 1023u) & ~1023u;
+__host__ __device__ inline uint32_t wgrad_stage_bytes(int CB, int NB, int NP, bool tma_b, uint32_t a_halo_bytes = 0) {
+  if (tma_b) return ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
   return 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
 }
 
@@ -970,7 +978,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const int NP = p.NP < 1 ? 1 : p.NP;
   const bool tma_b = p.tma_b != 0;
   const bool tma_a = AMODE == WA_STEM_PAIR && tma_b && p.tma_a != 0;
-  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b);
+  const bool halo = tma_a && p.tma_a == 2;
+  const uint32_t a_grp = halo ? (uint32_t)p.bx * (uint32_t)(p.by + 3) * 64u : (uint32_t)TMA_GROUP_BYTES;   // one 32-element half / group
+  const uint32_t halo_bytes = halo ? 2u * a_grp : 0u;
+  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b, halo_bytes);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
@@ -983,7 +994,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const uint32_t a_bytes = 16u * NP * PLANE_BYTES;
   const uint32_t bgroups = (uint32_t)p.CB / 32u;                        // TMA mode: 32-channel groups per B tile
   const uint32_t bt_bytes = tma_b ? bgroups * (uint32_t)TMA_GROUP_BYTES : (uint32_t)bplanes * PLANE_BYTES;
-  const uint32_t stage_bytes = wgrad_stage_bytes(p.CB, p.NB, NP, tma_b);
+  const uint32_t stage_bytes = wgrad_stage_bytes(p.CB, p.NB, NP, tma_b, halo_bytes);
   const uint32_t stage0 = tma_b ? ((sbase + offs[3] + 1023u) & ~1023u) : sbase + offs[3];
   // operand offsets inside a stage: register path [A][B]; TMA path [B][A] (the swizzled B groups need the 1 KB alignment)
   const uint32_t a_off = tma_b ? p.NB * bt_bytes : 0u, b_off = tma_b ? 0u : a_bytes;
@@ -1101,9 +1112,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
           const uint32_t sBs = stage0 + s * stage_bytes + b_off, sAs = stage0 + s * stage_bytes + a_off;
           // (the A region of a stage is sized in padded chunk planes, the boxes fill 4 NP x 8 KB of it)
-          mbar_arrive_expect_tx(bar_full + 8 * s, bt_bytes + 4u * NP * (uint32_t)TMA_GROUP_BYTES);
+          mbar_arrive_expect_tx(bar_full + 8 * s, bt_bytes + (halo ? halo_bytes : 4u * NP * (uint32_t)TMA_GROUP_BYTES));
           for (uint32_t c = 0; c < bgroups; ++c)
             tma_load_5d(sBs + c * (uint32_t)TMA_GROUP_BYTES, &tmb, (int)c * 32, x0, y0, z0, n0, bar_full + 8 * s);
+          if (halo) {      // this CTA's k-blocks are (dz = ztile, dy = 0..3): rows y0 .. y0 + by + 2 of slice z0 + ztile, two halves
+            tma_load_5d(sAs, &tma, 0, x0, y0, z0 + ztile, n0, bar_full + 8 * s);
+            tma_load_5d(sAs + a_grp, &tma, 32, x0, y0, z0 + ztile, n0, bar_full + 8 * s);
+          } else
           for (int g = 0; g < 4 * NP; ++g) {     // group g: k-block kb = ztile*2*NP + g/2, elements 32 (g & 1) .. + 32 of its 64
             const int kb = ztile * 2 * NP + (g >> 1);
             tma_load_5d(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES, &tma, (g & 1) * 32, x0, y0 + (kb & 3), z0 + (kb >> 2), n0,
@@ -1414,7 +1429,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           }
         } else {
           // stem: a = (g, c64) with kb = ztile*2 + g, c64 = (dx, pz, py, px, ci); b = output channel
-          const int kb = (ztile * NP + j) * 2 + (a >> 6), c = a & 63;
+          // (halo mode: accumulator j = element half j of the four k-blocks dy = a / 32)
+          const int kb = halo ? ztile * 4 + (a >> 5) : (ztile * NP + j) * 2 + (a >> 6), c = halo ? j * 32 + (a & 31) : (a & 63);
           const int kz = 2 * (kb >> 2) + ((c >> 3) & 1), ky = 2 * (kb & 3) + ((c >> 2) & 1), kx = 2 * (c >> 4) + ((c >> 1) & 1);
           const int ci = c & 1;
           if (kz < 7 && ky < 7 && kx < 7 && ci < p.cin_real) {
@@ -1440,7 +1456,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         const uint32_t sA = stage0 + s * stage_bytes + a_off;
         const uint32_t sB = stage0 + s * stage_bytes + b_off;
         // A: chunk planes, or (all-TMA stem) the same swizzled 32-channel groups as B
-        const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, TMA_GROUP_BYTES, 512, 4u) : make_smem_desc(sA, 128, PLANE_BYTES);
+        const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, halo ? (uint32_t)p.bx * 64u : (uint32_t)TMA_GROUP_BYTES, 512, 4u)
+                                   : make_smem_desc(sA, 128, PLANE_BYTES);
         const uint32_t ak16 = tma_a ? 1024u : 256u;
         // B: register path = SWIZZLE_NONE chunk planes (8-row K groups 128 B apart, 8-channel chunks one plane apart);
         //    TMA path = SWIZZLE_64B rows of 64 B (8-row atoms 512 B apart, 32-channel groups 8 KB apart)
@@ -1450,7 +1467,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         if (AMODE == WA_STEM_PAIR) {
           // NP pairs share the B tile; pair pi reads its own 16 A planes and owns accumulator pi
           for (int pi = 0; pi < NP; ++pi) {
-            const uint64_t ad = desc_advance(ad0, tma_a ? pi * 4 * TMA_GROUP_BYTES : pi * 16 * PLANE_BYTES);
+            const uint64_t ad = desc_advance(ad0, halo ? pi * a_grp : tma_a ? pi * 4 * TMA_GROUP_BYTES : pi * 16 * PLANE_BYTES);
             const uint32_t td = tmem_base + pi * p.CB;
             tc_mma_bf16(td, ad, bd0, idesc, acc0);
 #pragma unroll
