@@ -275,8 +275,12 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   if (tma_on && BTRANS == T_NONE && p.NP != -1 && wgrad_tma_box(p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) {
     const long long vps = (long long)p.Dz * p.Dy * p.Dx;
     const int N = (int)((p.M + vps - 1) / vps);
-    if (make_tmap_ndhwc(&tmb, p.b_src, p.b_pitch, N, p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) p.tma_b = 1;
+    // 3x3x3: one (by + 2)-row box per (dz, dx) when the tile lies in one z slice (engine.cuh, tma_b == 2); MMNN_WGRAD_HALO=0: nine boxes
+    static const bool bhalo_on = [] { const char* e = getenv("MMNN_WGRAD_HALO"); return !(e != nullptr && e[0] == '0'); }();
+    const bool bhalo = bhalo_on && AMODE == WA_LINEAR && p.NB == 9 && p.CB == 32 && p.b_pitch == 32 && p.bz == 1 && p.bn == 1 && p.bx % 8 == 0;
+    if (make_tmap_ndhwc(&tmb, p.b_src, p.b_pitch, N, p.Dz, p.Dy, p.Dx, p.bx, bhalo ? p.by + 2 : p.by, p.bz, p.bn)) p.tma_b = bhalo ? 2 : 1;
   }
+  const uint32_t b_halo_bytes = p.tma_b == 2 ? wgrad_tap_halo_bytes(p.bx, p.by) : 0u;
   // stem: the space-to-depth operand by TMA too when the caller holds it in bf16 (MMNN_STEM_WGRAD_TMA=0: register path)
   static const bool tma_a_on = [] { const char* e = getenv("MMNN_STEM_WGRAD_TMA"); return !(e != nullptr && e[0] == '0'); }();
   CUtensorMap tma;
@@ -295,9 +299,9 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   if (p.stages <= 0) {
     p.stages = 1;
     for (int s = 1; s <= 4; ++s)
-      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes) <= 225 * 1024) p.stages = s;
+      if (wgrad_smem_layout(p.CB, p.NB, s, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes, b_halo_bytes) <= 225 * 1024) p.stages = s;
   }
-  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes);
+  const uint32_t smem = wgrad_smem_layout(p.CB, p.NB, p.stages, p.NP < 1 ? 1 : p.NP, offs, p.tma_b != 0, halo_bytes, b_halo_bytes);
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

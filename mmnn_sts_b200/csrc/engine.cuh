@@ -748,6 +748,9 @@ struct WgradParams {
   // written with the 64-byte swizzle: 128 rows of 64 B = the canonical SWIZZLE_64B MN-major tcgen05 operand (K = voxel rows:
   // 8-row atoms 512 B apart = SBO; the next 32 channels / the next tap: one 8 KB group further = LBO).  A shifted tile (3x3x3
   // taps) is the same box at shifted coordinates; out-of-volume voxels are zero-filled by the TMA unit.
+  // tma_b == 2 (3x3x3, tile = bx x by voxels of ONE z slice, bx a multiple of 8): the three dy taps of a (dz, dx) pair are row
+  // windows of ONE box of by + 2 rows (y0 - 1 .. y0 + by), bx rows = a multiple of the 512-byte swizzle period apart: 3 boxes per
+  // stage instead of 9, so the ring holds 3 stages instead of 2 (this kernel is bound by the fill latency of its ring).
   int tma_b;
   int bx, by, bz, bn;
   // Stem (WA_STEM_PAIR): a_bf16 != 0 -> a_src already holds bf16 (1: TMA allowed, 2: register path only -- tests); (the trunk keeps a bf16 copy of the space-to-depth image for
@@ -766,6 +769,8 @@ struct WgradParams {
 
 constexpr int TMA_GROUP_BYTES = TILE_ROWS * 64;   // one TMA box: 128 voxel rows x 32 bf16 channels
 
+// 3x3x3, tma_b == 2: bytes of the three (by + 2)-row boxes (one per dx) of a stage
+__host__ __device__ inline uint32_t wgrad_tap_halo_bytes(int bx, int by) { return 3u * (uint32_t)bx * (uint32_t)(by + 2) * 64u; }
 // stem, tma_a == 2: bytes of the two (by + 3)-row boxes of a stage
 __host__ __device__ inline uint32_t wgrad_stem_halo_bytes(int bx, int by) { return 2u * (uint32_t)bx * (uint32_t)(by + 3) * 64u; }
 
@@ -781,7 +786,7 @@ __host__ __device__ inline bool wgrad_tma_box(int Dz, int Dy, int Dx, int& bx, i
 }
 
 __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/, bool tma_b = false,
-                                                      uint32_t a_halo_bytes = 0) {
+                                                      uint32_t a_halo_bytes = 0, uint32_t b_halo_bytes = 0) {
   uint32_t o = 0;
   offs[0] = o; o += 128;                          // barriers + tmem ptr
   offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
@@ -790,13 +795,13 @@ __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages
   offs[3] = o;
   uint32_t stage = 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
   // TMA mode: [B groups (swizzled, the stage base is 1024-byte aligned at run time)][A planes], stage size a multiple of 1 KB
-  if (tma_b) stage = ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
+  if (tma_b) stage = ((b_halo_bytes ? b_halo_bytes : (uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES) + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
   const uint32_t ring = stages * stage + (tma_b ? 1024u : 0u);
   const uint32_t epi = 32u * 132u * 4u;           // the epilogue's transpose staging reuses the ring
   return o + (ring > epi ? ring : epi);
 }
-__host__ __device__ inline uint32_t wgrad_stage_bytes(int CB, int NB, int NP, bool tma_b, uint32_t a_halo_bytes = 0) {
-  if (tma_b) return ((uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
+__host__ __device__ inline uint32_t wgrad_stage_bytes(int CB, int NB, int NP, bool tma_b, uint32_t a_halo_bytes = 0, uint32_t b_halo_bytes = 0) {
+  if (tma_b) return ((b_halo_bytes ? b_halo_bytes : (uint32_t)NB * (CB / 32) * TMA_GROUP_BYTES) + (a_halo_bytes ? a_halo_bytes : 16u * NP * PLANE_BYTES) + 1023u) & ~1023u;
   return 16u * NP * PLANE_BYTES + (uint32_t)NB * (CB / 8) * PLANE_BYTES;
 }
 
@@ -981,7 +986,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const bool halo = tma_a && p.tma_a == 2;
   const uint32_t a_grp = halo ? (uint32_t)p.bx * (uint32_t)(p.by + 3) * 64u : (uint32_t)TMA_GROUP_BYTES;   // one 32-element half / group
   const uint32_t halo_bytes = halo ? 2u * a_grp : 0u;
-  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b, halo_bytes);
+  const bool bhalo = tma_b && p.tma_b == 2 && p.NB == 9 && p.CB == 32 && AMODE == WA_LINEAR;
+  const uint32_t b_box = bhalo ? (uint32_t)p.bx * (uint32_t)(p.by + 2) * 64u : 0u;      // one (by + 2)-row box of 32 channels
+  wgrad_smem_layout(p.CB, p.NB, p.stages, NP, offs, tma_b, halo_bytes, 3u * b_box);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
@@ -994,10 +1001,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const uint32_t a_bytes = 16u * NP * PLANE_BYTES;
   const uint32_t bgroups = (uint32_t)p.CB / 32u;                        // TMA mode: 32-channel groups per B tile
   const uint32_t bt_bytes = tma_b ? bgroups * (uint32_t)TMA_GROUP_BYTES : (uint32_t)bplanes * PLANE_BYTES;
-  const uint32_t stage_bytes = wgrad_stage_bytes(p.CB, p.NB, NP, tma_b, halo_bytes);
+  const uint32_t stage_bytes = wgrad_stage_bytes(p.CB, p.NB, NP, tma_b, halo_bytes, 3u * b_box);
   const uint32_t stage0 = tma_b ? ((sbase + offs[3] + 1023u) & ~1023u) : sbase + offs[3];
   // operand offsets inside a stage: register path [A][B]; TMA path [B][A] (the swizzled B groups need the 1 KB alignment)
-  const uint32_t a_off = tma_b ? p.NB * bt_bytes : 0u, b_off = tma_b ? 0u : a_bytes;
+  const uint32_t a_off = bhalo ? 3u * b_box : tma_b ? p.NB * bt_bytes : 0u, b_off = tma_b ? 0u : a_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
@@ -1139,6 +1146,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         rem -= z0 * p.Dy * p.Dx;
         const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
         const uint32_t sBs = stage0 + s * stage_bytes + b_off;
+        if (bhalo) {     // box c = taps (dz of this CTA, dx = 1 - c), rows y0 - 1 .. y0 + by
+          mbar_arrive_expect_tx(bar_full + 8 * s, 3u * b_box);
+          const int dz = -(ytile - 1);
+          for (int c = 0; c < 3; ++c) tma_load_5d(sBs + (uint32_t)c * b_box, &tmb, 0, x0 + 1 - c, y0 - 1, z0 + dz, n0, bar_full + 8 * s);
+          return;
+        }
         mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)p.NB * bt_bytes);
         for (int j = 0; j < p.NB; ++j) {
           int dz = 0, dy = 0, dx = 0;
@@ -1477,10 +1490,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         } else if (p.NB == 9 && p.CB == 32 && tma_b) {
           // swizzled operand: N must cover whole 32-channel groups -> three N = 96 MMAs (3 taps each) per K step
           const uint32_t idesc3 = make_idesc_ab(128, 96, 1, 1, A_F16, false);
+          // halo boxes: MMA h = the taps dy = 1 - h of the three dx boxes (one box apart = LBO), rows (2 - h) * bx .. + 128
+          if (bhalo) bd0 = make_smem_desc_sw(sB, b_box, 512, 4u);
 #pragma unroll
           for (int h = 0; h < 3; ++h) {
             const uint32_t td = tmem_base + h * 96;
-            const uint64_t bd = desc_advance(bd0, h * 3 * TMA_GROUP_BYTES);
+            const uint64_t bd = desc_advance(bd0, bhalo ? (uint32_t)(2 - h) * (uint32_t)p.bx * 64u : (uint32_t)h * 3u * TMA_GROUP_BYTES);
             tc_mma_bf16(td, ad0, bd, idesc3, acc0);
 #pragma unroll
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)

@@ -259,10 +259,17 @@ def test_wgrad_conv1x1():
         assert (dw - ref).abs().max() <= 2e-3 * ref.abs().max() + 1e-3, (dw - ref).abs().max()
 
 
-def test_wgrad_conv3x3x3():
+@pytest.mark.parametrize("B,Dz,Dy,Dx", [
+    (2, 4, 6, 8),       # tiles are not boxes: register path
+    (3, 3, 16, 16),     # box 16 x 8 of one z slice: halo boxes (engine.cuh tma_b == 2), several tiles per slice
+    (2, 5, 16, 8),      # box 8 x 16
+    (2, 2, 4, 32),      # box 32 x 4 = a whole slice: every dy tap leaves the volume on one side
+    (5, 4, 8, 4),       # box spans z slices: nine boxes per stage (tma_b == 1)
+])
+def test_wgrad_conv3x3x3(B, Dz, Dy, Dx):
     from tests import engine_helpers as H
     torch.manual_seed(6)
-    B, Dz, Dy, Dx, Cb, Cg = 2, 4, 6, 8, 128, 32
+    Cb, Cg = 128, 32
     M = B * Dz * Dy * Dx
     bott = torch.randn(M, Cb, device="cuda").to(_actdt())
     g = (torch.randn(M, Cg, device="cuda") * 0.1).to(torch.bfloat16)
