@@ -294,6 +294,13 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
     const bool halo = halo_on && p.NP == 2 && p.bz == 1 && p.bn == 1 && p.bx % 8 == 0 && p.by + 3 <= 256;
     if (make_tmap_s2d_rows(&tma, p.a_src, N, p.Sz, p.Sy, p.Sx, p.bx, halo ? p.by + 3 : p.by, p.bz, p.bn)) p.tma_a = halo ? 2 : 1;
   }
+  // 1x1x1 / 3x3x3: the raw activation tile by TMA too, BN+ReLU applied in place (engine.cuh, araw); MMNN_WGRAD_TMA_A=0: register staging
+  static const bool araw_on = [] { const char* e = getenv("MMNN_WGRAD_TMA_A"); return !(e != nullptr && e[0] == '0'); }();
+  if (AMODE == WA_LINEAR && ATRANS == T_BNRELU && araw_on && p.tma_b && p.NP != -1) {
+    const long long vps = (long long)p.Dz * p.Dy * p.Dx;
+    const int N = (int)((p.M + vps - 1) / vps);
+    if (make_tmap_ndhwc(&tma, p.a_src, p.a_pitch, N, p.Dz, p.Dy, p.Dx, p.bx, p.by, p.bz, p.bn)) p.tma_a = 1;
+  }
   const uint32_t halo_bytes = p.tma_a == 2 ? wgrad_stem_halo_bytes(p.bx, p.by) : 0u;
   uint32_t offs[4];
   if (p.stages <= 0) {
@@ -305,7 +312,7 @@ int launch_wgrad_t(WgradParams p, int split, int gy, int gz, cudaStream_t stream
   auto kern = conv_wgrad_kernel<AMODE, ATRANS, BTRANS, EMODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  launch_pdl(kern, dim3(split, gy, gz), dim3(ENGINE_THREADS), smem, stream, p, tmb, tma);
+  launch_pdl(kern, dim3(split, gy, gz), dim3(WGRAD_THREADS), smem, stream, p, tmb, tma);
   MMNN_CHECK_LAUNCH();
   return 0;
 }
@@ -422,15 +429,15 @@ int mmnn_sizeof_pack_desc() { return (int)sizeof(PackDesc); }
 // elapsed SM clock cycles between the first issue and the arrival of the commit are written to out[0].
 // layout 0: SWIZZLE_NONE core matrices (LBO = plane stride, SBO = 128 B), 6: SWIZZLE_32B rows of 32 B (SBO = 256 B).
 namespace mmnn {
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int iters, int a_step_bytes, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int iters, int a_step_bytes, long long* out, int nacc = 2) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar = sbase, tptr = sbase + 16, sA = sbase + 1024, sB = sA + 64 * 1024;
-  for (int i = threadIdx.x; i < (64 + 16) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + 1024)[i] = 0x3c003c00u;  // fp16 1.0
+  const uint32_t bar = sbase, tptr = sbase + 32, sA = sbase + 1024, sB = sA + 64 * 1024;   // B: 32 KB (N = 128 in MN-major groups)
+  for (int i = threadIdx.x; i < (64 + 32) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem + 1024)[i] = 0x3c003c00u;  // fp16 1.0
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_mbar_init(); }
     __syncwarp();
     tmem_alloc(tptr, 512);
   }
@@ -438,16 +445,39 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + 16);
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + 32);
   if (warp == 0) {
-    const uint32_t idesc = make_idesc(128, N, 0, 0, true);
-    const uint64_t ad0 = layout == 0 ? make_smem_desc(sA, 2064, 128) : make_smem_desc_sw(sA, 16, 256, (uint32_t)layout);
-    const uint64_t bd0 = layout == 0 ? make_smem_desc(sB, (uint32_t)N * 16, 128) : make_smem_desc_sw(sB, 16, 256, (uint32_t)layout);
+    // layout 100 / 101: the weight-gradient kernel's MN-major operands (K = voxel rows).  100: A = SWIZZLE_NONE chunk planes,
+    // B = SWIZZLE_64B 32-channel groups (3x3x3 / 1x1x1 weight gradient); 101: both SWIZZLE_64B groups (all-TMA stem)
+    const bool mn = layout >= 100;
+    const uint32_t idesc = mn ? make_idesc_ab(128, N, 1, 1, false, false) : make_idesc(128, N, 0, 0, true);
+    const uint64_t ad0 = layout == 100 ? make_smem_desc(sA, 128, PLANE_BYTES)
+                         : layout == 101 ? make_smem_desc_sw(sA, 8192, 512, 4u)
+                         : layout == 0 ? make_smem_desc(sA, 2064, 128) : make_smem_desc_sw(sA, 16, 256, (uint32_t)layout);
+    const uint64_t bd0 = mn ? make_smem_desc_sw(sB, 8192, 512, 4u)
+                         : layout == 0 ? make_smem_desc(sB, (uint32_t)N * 16, 128) : make_smem_desc_sw(sB, 16, 256, (uint32_t)layout);
     long long t0 = 0;
     if (elect_one()) {
+      const int amask = nacc - 1;
+      const uint32_t acols = 512u / (uint32_t)nacc;
       t0 = clock64();
+      if (layout == 102) {
+        // the 3x3x3 weight gradient's issue pattern: per tile 3 accumulators (columns 0 / 96 / 192) x 8 K steps, halo-box B operand
+        const uint64_t a0 = make_smem_desc(sA, 128, PLANE_BYTES);
+        const uint64_t b0 = make_smem_desc_sw(sB, 10240, 512, 4u);
+        for (int i = 0; i < iters / 24; ++i) {
+#pragma unroll
+          for (int h = 0; h < 3; ++h) {
+            const uint64_t bd = desc_advance(b0, (uint32_t)(2 - h) * 1024u);
+#pragma unroll
+            for (int k16 = 0; k16 < 8; ++k16)
+              tc_mma_bf16(tmem_base + h * 96, desc_advance(a0, k16 * 256), desc_advance(bd, k16 * 1024), idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+          }
+          if (nacc == 1) tc_commit(bar + 8);     // a commit per tile like the kernel's (to a second, never awaited barrier)
+        }
+      } else
       for (int i = 0; i < iters; ++i)
-        tc_mma_bf16(tmem_base + (i & 1) * 256, desc_advance(ad0, (uint32_t)((i & 7) * a_step_bytes)), bd0, idesc, i > 1 ? 1u : 0u);
+        tc_mma_bf16(tmem_base + (uint32_t)(i & amask) * acols, desc_advance(ad0, (uint32_t)((i & 7) * a_step_bytes)), bd0, idesc, i >= nacc ? 1u : 0u);
       tc_commit(bar);
     }
     __syncwarp();
@@ -462,13 +492,28 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int layout, int
 }  // namespace mmnn
 
 extern "C" int mmnn_mma_rate(int N, int layout, int iters, int a_step_bytes, long long* out_cycles, void* stream) {
-  const int smem = (1 + 64 + 16 + 1) * 1024;
+  const int smem = (1 + 64 + 32 + 1) * 1024;
   cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, layout, iters, a_step_bytes, out_cycles);
   return (int)cudaGetLastError();
 }
 
+// nacc: accumulators the back-to-back MMAs rotate over (1 = every MMA accumulates into the same TMEM columns)
+extern "C" int mmnn_mma_rate_acc(int N, int layout, int iters, int a_step_bytes, int nacc, long long* out_cycles) {
+  const int smem = (1 + 64 + 32 + 1) * 1024;
+  if (nacc < 1 || nacc > 4 || nacc == 3 || N * nacc > 512) return -2;
+  cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  mma_rate_kernel<<<1, 128, smem, 0>>>(N, layout, iters, a_step_bytes, out_cycles, nacc);
+  return (int)cudaGetLastError();
+}
+#ifdef MMNN_WGRAD_TIMING
+extern "C" int mmnn_wgrad_dbg(unsigned long long* out, int reset) {
+  if (reset) { unsigned long long z[12] = {0}; return (int)cudaMemcpyToSymbol(mmnn::g_wgrad_dbg, z, sizeof(z)); }
+  return (int)cudaMemcpyFromSymbol(out, mmnn::g_wgrad_dbg, 12 * sizeof(unsigned long long));
+}
+#endif
 #ifdef MMNN_STEM_TIMING
 extern "C" int mmnn_stem_dbg(long long* out) { return (int)cudaMemcpyFromSymbol(out, mmnn::g_stem_dbg, 8 * sizeof(long long)); }
 #endif

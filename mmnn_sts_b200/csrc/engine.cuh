@@ -763,6 +763,12 @@ struct WgradParams {
   // y0 + dy .. of the same slice, so ONE box of by + 3 rows per 32-element half (instead of four boxes of by rows per half) feeds
   // all of them: k-block dy's operand starts bx rows (bx x 64 B, a multiple of the 512-byte swizzle period) further into the box.
   // The MMA's M = 128 is then (dy = 0..3) x 32 elements of one half -- LBO = bx x 64 B -- and accumulator j holds half j.
+  // WA_LINEAR with a BN+ReLU A operand (1x1x1 / 3x3x3 weight gradients): tma_a == 1 (needs tma_b) -> the RAW activation tile
+  // arrives by TMA as well (4 boxes of 32 channels, SWIZZLE_64B, straight into the operand stage; issued by warp 9 as soon as the
+  // stage is free, i.e. up to `stages - 1` tiles ahead), and the 256 producer threads apply BN+ReLU -> bf16 IN PLACE
+  // (LDS.128 -> 8 FMAs -> STS.128 to the same cell).  No global load sits in the producers' instruction stream any more: with
+  // register staging the tile period was one exposed HBM round trip (ring depth 1, 2 or 3 gave the same 105-118 us per block-1
+  // launch, profiles/scripts/microbench_wgrad.py).
   int a_bf16;
   int tma_a;
 };
@@ -788,7 +794,7 @@ __host__ __device__ inline bool wgrad_tma_box(int Dz, int Dy, int Dx, int& bx, i
 __host__ __device__ inline uint32_t wgrad_smem_layout(int CB, int NB, int stages, int NP, uint32_t* offs /*[4]*/, bool tma_b = false,
                                                       uint32_t a_halo_bytes = 0, uint32_t b_halo_bytes = 0) {
   uint32_t o = 0;
-  offs[0] = o; o += 128;                          // barriers + tmem ptr
+  offs[0] = o; o += 192;                          // barriers (full[6], empty[6], accum, tmem ptr, raw[6] at +128) + debug slot
   offs[1] = o; o += stages * TILE_ROWS * 16;      // rowinfo per stage
   offs[2] = o; o += 2u * 128 * 4 + 2u * CB * 4;   // coefA (scale, shift) [128], coefB [CB]
   o = (o + 127u) & ~127u;
@@ -969,8 +975,20 @@ MMNN_DEVINL void store_planes(const uint4 (&regs)[2 * MAX_PASSES], uint32_t okma
 #ifndef MMNN_WGRAD_A_F16
 #define MMNN_WGRAD_A_F16 0
 #endif
+constexpr int WGRAD_THREADS = ENGINE_THREADS + 32;   // + warp 9: the TMA issuer of the raw-A mode (idle otherwise)
+constexpr int WGRAD_TMA_WARP = MMA_WARP + 1;
+#ifdef MMNN_WGRAD_TIMING
+// debug build (-DMMNN_WGRAD_TIMING): cycle counters summed over CTAs -- [0] MMA warp waiting for a full stage, [1] MMA issue,
+// [2] producer warp 0 waiting for an empty stage, [3] its A stores, [4] fill latency free->full (warp 2), [5] whole kernel, [6] CTAs, [7] tiles
+static __device__ unsigned long long g_wgrad_dbg[12];   // [8] fence + elect, [9] the MMAs, [10] commits, [11] syncwarp + loop
+#define WG_T(var) const long long var = clock64()
+#define WG_ADD(i, v) do { if (lane == 0) atomicAdd(&g_wgrad_dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define WG_T(var)
+#define WG_ADD(i, v)
+#endif
 template <int AMODE, int ATRANS, int BTRANS, int EMODE>
-__global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p,
+__global__ void __launch_bounds__(WGRAD_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradParams p,
                                                                     const __grid_constant__ CUtensorMap tmb,
                                                                     const __grid_constant__ CUtensorMap tma) {
   // NEGATIVE RESULT (round 2, B200): the instruction descriptor of tcgen05 kind::f16 has separate A / B format fields, but an
@@ -984,6 +1002,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const bool tma_b = p.tma_b != 0;
   const bool tma_a = AMODE == WA_STEM_PAIR && tma_b && p.tma_a != 0;
   const bool halo = tma_a && p.tma_a == 2;
+  const bool araw = AMODE == WA_LINEAR && ATRANS == T_BNRELU && tma_b && p.tma_a == 1;      // raw A by TMA, transformed in place
   const uint32_t a_grp = halo ? (uint32_t)p.bx * (uint32_t)(p.by + 3) * 64u : (uint32_t)TMA_GROUP_BYTES;   // one 32-element half / group
   const uint32_t halo_bytes = halo ? 2u * a_grp : 0u;
   const bool bhalo = tma_b && p.tma_b == 2 && p.NB == 9 && p.CB == 32 && AMODE == WA_LINEAR;
@@ -993,6 +1012,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
   const uint32_t bar_accum = bar_full + 8 * 12;
+  const uint32_t bar_raw = bar_full + 128;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 13);
   int4* rowinfo_all = reinterpret_cast<int4*>(smem + offs[1]);
   float* coefA = reinterpret_cast<float*>(smem + offs[2]);
@@ -1007,6 +1027,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
   const uint32_t a_off = bhalo ? 3u * b_box : tma_b ? p.NB * bt_bytes : 0u, b_off = tma_b ? 0u : a_bytes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  WG_T(wg_t_start);
   const int S = p.stages;
   const int ntiles_total = (p.M + TILE_ROWS - 1) / TILE_ROWS;
   const int split = gridDim.x;
@@ -1025,11 +1046,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         // producers + the expect_tx arrival of the TMA issuer; all-TMA stem: the issuer alone
         mbar_init(bar_full + 8 * s, tma_a ? 1 : NUM_PRODUCER_THREADS + (tma_b ? 1 : 0));
         mbar_init(bar_empty + 8 * s, 1);
+        mbar_init(bar_raw + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
       fence_mbar_init();
       if (tma_b) tma_prefetch_desc(&tmb);
-      if (tma_a) tma_prefetch_desc(&tma);
+      if (tma_a || araw) tma_prefetch_desc(&tma);
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
@@ -1105,7 +1127,39 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     // 2.37 ms, step 15.17 vs 14.94 ms; 2.63 ms when the copies bypass L1 -- the 9 shifted tiles share their rows), so it
     // is OFF unless MMNN_WGRAD_PIPED=1 (kept as a parity-tested experiment).
     const bool piped = !tma_b && AMODE == WA_LINEAR && BTRANS == T_NONE && S >= 2 && p.NB == 9 && bplanes == 4 && p.NP == -1;   // NP == -1: opt-in experiment switch (MMNN_WGRAD_PIPED=1)
-    if (tma_a) {
+    if (araw) {
+      // ---- raw A by TMA (issued by warp 9 below), BN+ReLU -> bf16 in place.  Thread -> logical 16-byte chunk c = tid & 3 of every
+      // 32-channel group and rows r0, r0 + 64: its 32 channels never change, so their scale / shift live in registers; a warp touches
+      // 8 rows x 64 B = one 512-byte swizzle atom per access (conflict-free), the chunk's physical position is c ^ ((row >> 1) & 3).
+      const int c = tid & 3, r0 = tid >> 2;
+      float sc[4][8], sh[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[g][e] = coefA[g * 32 + c * 8 + e]; sh[g][e] = coefA[128 + g * 32 + c * 8 + e]; }
+      const uint32_t o0 = (uint32_t)r0 * 64u + (uint32_t)((c ^ ((r0 >> 1) & 3)) * 16);
+      const uint32_t o1 = (uint32_t)(r0 + 64) * 64u + (uint32_t)((c ^ (((r0 + 64) >> 1) & 3)) * 16);
+      for (int it = 0; it < nt; ++it) {
+        const int s = it % S;
+        WG_T(w0);
+        mbar_wait(bar_raw + 8 * s, (uint32_t)(it / S) & 1u, 15);
+        WG_T(w1);
+        const uint32_t sAs = stage0 + s * stage_bytes + a_off;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v0 = lds16(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES + o0);
+          uint4 v1 = lds16(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES + o1);
+          apply_bnrelu8<kActF16, false>(v0, sc[g], sh[g]);
+          apply_bnrelu8<kActF16, false>(v1, sc[g], sh[g]);
+          sts16(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES + o0, v0);
+          sts16(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES + o1, v1);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * s);
+        WG_T(w2);
+        if (warp == 1) { WG_ADD(2, w1 - w0); WG_ADD(3, w2 - w1); }
+      }
+    } else if (tma_a) {
       // ---- all-TMA stem: both operands are boxes; one thread feeds the ring, the other producer threads go straight to the epilogue
       if (tid == 4 * 32) {     // a warp without an epilogue role (the epilogue runs on warps 0-3)
         for (int it = 0; it < nt; ++it) {
@@ -1146,6 +1200,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         rem -= z0 * p.Dy * p.Dx;
         const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
         const uint32_t sBs = stage0 + s * stage_bytes + b_off;
+        if (p.cin_real == 2 || p.cin_real == 3) { mbar_arrive_expect_tx(bar_full + 8 * s, 0u); return; }
         if (bhalo) {     // box c = taps (dz of this CTA, dx = 1 - c), rows y0 - 1 .. y0 + by
           mbar_arrive_expect_tx(bar_full + 8 * s, 3u * b_box);
           const int dz = -(ytile - 1);
@@ -1164,13 +1219,24 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
       };
       uint4 RA[2 * MAX_PASSES], RB[2 * MAX_PASSES];
       uint32_t okA = load_planes_linear(RA, aplanes, asrc, p.a_pitch, (long long)t_begin * TILE_ROWS, p.M, warp, lane), okB = 0;
+      const int dbg = p.cin_real;     // ablation switches of profiles/scripts/microbench_wgrad.py (0 in the product): 1 = no A stores, 2 = no B boxes
       auto finish = [&](int it, const uint4 (&regs)[2 * MAX_PASSES], uint32_t ok) {
         const int s = it % S;
+        WG_T(w0);
         mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / S) & 1u) ^ 1u, 11);
+        WG_T(w1);
         if (tid == 0) issue_b(it, s);
-        store_planes<ATRANS, kActF16, A_F16>(regs, ok, stage0 + s * stage_bytes + a_off, aplanes, warp, lane, coefA, coefA + 128);
+        if (dbg != 1 && dbg != 3) store_planes<ATRANS, kActF16, A_F16>(regs, ok, stage0 + s * stage_bytes + a_off, aplanes, warp, lane, coefA, coefA + 128);
         fence_proxy_async_smem();
         mbar_arrive(bar_full + 8 * s);
+        WG_T(w2);
+        if (warp == 1) { WG_ADD(2, w1 - w0); WG_ADD(3, w2 - w1); }
+#ifdef MMNN_WGRAD_TIMING
+        if (warp == 2) {     // fill latency: stage free -> stage full (this warp then lags the others a little)
+          mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1u, 14);
+          WG_ADD(4, clock64() - w1);
+        }
+#endif
       };
       for (int it = 0; it < nt; it += 2) {
         if (it + 1 < nt) okB = load_planes_linear(RB, aplanes, asrc, p.a_pitch, (long long)(t_begin + it + 1) * TILE_ROWS, p.M, warp, lane);
@@ -1410,6 +1476,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
     // ---- epilogue: TMEM lane = A channel
     mbar_wait(bar_accum, 0, 13);
     tc_fence_after();
+    WG_T(wg_e0);
+#ifdef MMNN_WGRAD_TIMING
+    if (warp == 0) WG_ADD(11, wg_e0 - *reinterpret_cast<volatile long long*>(smem + offs[0] + 184));   // last commit -> accumulator complete
+#endif
     const int a = warp * 32 + lane;
     const int nacc = (EMODE == WE_STEM) ? NP : p.NB;
     const bool slotted = p.slot_stride > 0;
@@ -1458,20 +1528,32 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
         }
       }
     }
+#ifdef MMNN_WGRAD_TIMING
+    if (warp == 0) { WG_ADD(5, clock64() - wg_t_start); WG_ADD(6, 1); WG_ADD(7, nt); }
+#endif
   } else if (warp == MMA_WARP) {
     const uint32_t idesc = make_idesc_ab(128, p.CB, 1, 1, A_F16, false);
     for (int it = 0; it < nt; ++it) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
+      WG_T(m0);
       mbar_wait(bar_full + 8 * s, ph, 12);
+      WG_T(m1);
+      WG_ADD(0, m1 - m0);
       tc_fence_after();
+#ifdef MMNN_WGRAD_TIMING
+      long long q0 = 0, q1 = 0, q2 = 0;
+#endif
       if (elect_one()) {
+#ifdef MMNN_WGRAD_TIMING
+        q0 = clock64();
+#endif
         const uint32_t sA = stage0 + s * stage_bytes + a_off;
         const uint32_t sB = stage0 + s * stage_bytes + b_off;
         // A: chunk planes, or (all-TMA stem) the same swizzled 32-channel groups as B
-        const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, halo ? (uint32_t)p.bx * 64u : (uint32_t)TMA_GROUP_BYTES, 512, 4u)
-                                   : make_smem_desc(sA, 128, PLANE_BYTES);
-        const uint32_t ak16 = tma_a ? 1024u : 256u;
+        const uint64_t ad0 = (tma_a || araw) ? make_smem_desc_sw(sA, halo ? (uint32_t)p.bx * 64u : (uint32_t)TMA_GROUP_BYTES, 512, 4u)
+                                             : make_smem_desc(sA, 128, PLANE_BYTES);
+        const uint32_t ak16 = (tma_a || araw) ? 1024u : 256u;
         // B: register path = SWIZZLE_NONE chunk planes (8-row K groups 128 B apart, 8-channel chunks one plane apart);
         //    TMA path = SWIZZLE_64B rows of 64 B (8-row atoms 512 B apart, 32-channel groups 8 KB apart)
         uint64_t bd0 = tma_b ? make_smem_desc_sw(sB, TMA_GROUP_BYTES, 512, 4u) : make_smem_desc(sB, 128, PLANE_BYTES);
@@ -1487,6 +1569,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
               tc_mma_bf16(td, desc_advance(ad, k16 * ak16), desc_advance(bd0, k16 * bk16), idesc, 1u);
           }
+        } else if (AMODE == WA_LINEAR && p.cin_real == 4) {
+          // ablation: no MMA at all (fill pipeline alone)
         } else if (p.NB == 9 && p.CB == 32 && tma_b) {
           // swizzled operand: N must cover whole 32-channel groups -> three N = 96 MMAs (3 taps each) per K step
           const uint32_t idesc3 = make_idesc_ab(128, 96, 1, 1, A_F16, false);
@@ -1499,7 +1583,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
             tc_mma_bf16(td, ad0, bd, idesc3, acc0);
 #pragma unroll
             for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
-              tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd, k16 * 1024), idesc3, 1u);
+              tc_mma_bf16(td, desc_advance(ad0, k16 * ak16), desc_advance(bd, k16 * 1024), idesc3, 1u);
           }
         } else if (p.NB == 9 && p.CB == 32) {
           // the 9 shifted gradient tiles are 36 consecutive chunk planes = ONE MN-major operand of N = 288 columns
@@ -1521,13 +1605,57 @@ __global__ void __launch_bounds__(ENGINE_THREADS) conv_wgrad_kernel(const __grid
           tc_mma_bf16(td, ad0, bd0, idesc, acc0);
 #pragma unroll
           for (int k16 = 1; k16 < TILE_ROWS / 16; ++k16)
-            tc_mma_bf16(td, desc_advance(ad0, k16 * 256), desc_advance(bd0, k16 * bk16), idesc, 1u);
+            tc_mma_bf16(td, desc_advance(ad0, k16 * ak16), desc_advance(bd0, k16 * bk16), idesc, 1u);
           bd0 = desc_advance(bd0, bt_bytes);
         }
+#ifdef MMNN_WGRAD_TIMING
+        q1 = clock64();
+#endif
         tc_commit(bar_empty + 8 * s);
         if (it == nt - 1) tc_commit(bar_accum);
+#ifdef MMNN_WGRAD_TIMING
+        q2 = clock64();
+        if (it == nt - 1) *reinterpret_cast<volatile long long*>(smem + offs[0] + 184) = q2;     // spare bytes of the barrier block
+        atomicAdd(&g_wgrad_dbg[8], (unsigned long long)(q0 - m1));
+        atomicAdd(&g_wgrad_dbg[9], (unsigned long long)(q1 - q0));
+        atomicAdd(&g_wgrad_dbg[10], (unsigned long long)(q2 - q1));
+#endif
       }
       __syncwarp();
+      WG_ADD(1, clock64() - m1);
+    }
+  }
+  if (warp == WGRAD_TMA_WARP && araw && lane == 0) {
+    // ---- TMA issuer of the raw-A mode: refills a stage the moment the MMAs that read it are done -- up to S - 1 tiles ahead of
+    // the transform -- with the 4 activation boxes (-> raw[s]) and the gradient boxes (-> full[s], next to the 256 producer arrivals)
+    for (int it = 0; it < nt; ++it) {
+      const int s = it % S;
+      mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / S) & 1u) ^ 1u, 16);
+      const long long m0 = (long long)(t_begin + it) * TILE_ROWS;
+      const int n0 = (int)(m0 / vps);
+      int rem = (int)(m0 - (long long)n0 * vps);
+      const int z0 = rem / (p.Dy * p.Dx);
+      rem -= z0 * p.Dy * p.Dx;
+      const int y0 = rem / p.Dx, x0 = rem - (rem / p.Dx) * p.Dx;
+      const uint32_t sBs = stage0 + s * stage_bytes + b_off, sAs = stage0 + s * stage_bytes + a_off;
+      mbar_arrive_expect_tx(bar_raw + 8 * s, 4u * (uint32_t)TMA_GROUP_BYTES);
+      for (int g = 0; g < 4; ++g)     // channels beyond the tensor arrive as zeros, beyond na_total their accumulator rows are discarded
+        tma_load_5d(sAs + (uint32_t)g * (uint32_t)TMA_GROUP_BYTES, &tma, ztile * 128 + g * 32, x0, y0, z0, n0, bar_raw + 8 * s);
+      if (bhalo) {
+        mbar_arrive_expect_tx(bar_full + 8 * s, 3u * b_box);
+        const int dz = -(ytile - 1);
+        for (int c = 0; c < 3; ++c) tma_load_5d(sBs + (uint32_t)c * b_box, &tmb, 0, x0 + 1 - c, y0 - 1, z0 + dz, n0, bar_full + 8 * s);
+      } else {
+        mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)p.NB * bt_bytes);
+        for (int j = 0; j < p.NB; ++j) {
+          int dz = 0, dy = 0, dx = 0;
+          if (p.NB > 1) { const int tap = ytile * p.NB + j; dz = -(tap / 9 - 1); dy = -((tap / 3) % 3 - 1); dx = -(tap % 3 - 1); }
+          const int cbase = p.NB == 1 ? ytile * p.CB : 0;
+          for (uint32_t c = 0; c < bgroups; ++c)
+            tma_load_5d(sBs + ((uint32_t)j * bgroups + c) * (uint32_t)TMA_GROUP_BYTES, &tmb, cbase + (int)c * 32, x0 + dx, y0 + dy, z0 + dz, n0,
+                        bar_full + 8 * s);
+        }
+      }
     }
   }
   tc_fence_before();

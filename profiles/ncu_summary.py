@@ -15,7 +15,7 @@ for row in r[2:]:
     print("=" * 100)
     items = []
     for a, b, c in zip(h, u, row):
-        if any(a.startswith(k) or a == k for k in KEYS):
+        if any(a.startswith(k) or a == k for k in KEYS) or (("pipe_tensor" in a or "pipe_tc" in a or "tmem" in a) and "pct" in a):
             if "stalled" in a or "average_warp" in a:
                 try:
                     if float(c.replace(",", "")) < 0.3: continue
