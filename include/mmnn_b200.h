@@ -149,6 +149,22 @@ int mmnn_sgd_max_tensors(void);
 int mmnn_preprocess_volumes(const float* src, float* dst, void* scratch, int B, int C, int X, int Y, int Z, int ox, int oy,
                             int oz, float mean, float std, void* stream);
 
+/* mmnn_augment_resample / mmnn_augment_intensity : the RANDOM part of train_transforms (/root/reference/main.py:64-85; MONAI 1.2
+ *                     RandRotate / RandAxisFlip / RandZoom composed into ONE affine map and fused with Resize; RandShiftIntensity,
+ *                     RandAdjustContrast, RandGaussianSmooth, RandGaussianSharpen, RandHistogramShift, RandGaussianNoise) with
+ *                     EXPLICIT per-sample parameters drawn by the caller (mmnn_sts_b200/data/transforms.py TrainTransformsGPU).
+ *                     Parity unpinned: the reference as shipped never executes these transforms.
+ *                     sp: device array of B {float a[9]; float t[3]} (source = A (grid - centre) + centre + t, voxel units);
+ *                     prm: device array of B AugIntensity (csrc/augment.cu); smooth_sigma [B][3]; sharpen = sigma1 [B][3],
+ *                     sigma2 [B][3], alpha [B]; tmp = 3 volumes of v's size; scratch 2*B uint32. */
+int mmnn_preprocess_minmax(const float* src, void* scratch, int B, long long per_image, void* stream);
+int mmnn_augment_resample(const float* src, float* dst, void* scratch, const void* sp, int B, int C, int X, int Y, int Z, int ox, int oy,
+                          int oz, float mean, float std, void* stream);
+int mmnn_augment_intensity(float* v, float* tmp, void* scratch, const void* prm, const float* smooth_sigma, const float* sharpen, int B,
+                           int C, int ox, int oy, int oz, int any_smooth, int any_sharpen, void* stream);
+int mmnn_sizeof_aug_spatial(void);
+int mmnn_sizeof_aug_intensity(void);
+
 /* ------------------------------------------------------------------------------------------------ 3-D ResNet encoder
  * The image-only classification encoder of BASELINE configs[3] (/root/reference/models/resnet.py) as
  * direct convolutions on channels-last (NDHWC) bf16 tensors; parameters / statistics fp32 / fp64.  RnConvGeom:

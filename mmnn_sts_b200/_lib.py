@@ -112,6 +112,18 @@ EP_STORE, EP_STORE_STATS, EP_MASK_STATS, EP_MASK_STATS_ACC = 0, 1, 2, 3
 PACK_GENERIC, PACK_STEM, PACK_STEM_SW32 = 0, 1, 2
 
 
+AUG_HIST_POINTS = 10
+
+
+class AugSpatial(C.Structure):        # csrc/augment.cu
+    _fields_ = [("a", C.c_float * 9), ("t", C.c_float * 3)]
+
+
+class AugIntensity(C.Structure):      # csrc/augment.cu
+    _fields_ = [("shift", C.c_float), ("gamma", C.c_float), ("noise_std", C.c_float), ("hist_on", C.c_int),
+                ("hist_ref", C.c_float * AUG_HIST_POINTS), ("hist_flt", C.c_float * AUG_HIST_POINTS), ("seed", C.c_ulonglong)]
+
+
 def _declare(l):
     l.mmnn_conv_rows.argtypes = [C.POINTER(RowsParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     l.mmnn_act_is_fp16.restype = C.c_int
@@ -174,6 +186,12 @@ def _declare(l):
     l.mmnn_bce_logits.restype = I
     l.mmnn_preprocess_volumes.argtypes = [VP, VP, VP, I, I, I, I, I, I, I, I, C.c_float, C.c_float, VP]
     l.mmnn_preprocess_volumes.restype = I
+    l.mmnn_augment_resample.argtypes = [VP, VP, VP, VP, I, I, I, I, I, I, I, I, C.c_float, C.c_float, VP]
+    l.mmnn_augment_resample.restype = I
+    l.mmnn_augment_intensity.argtypes = [VP, VP, VP, VP, VP, VP, I, I, I, I, I, I, I, VP]
+    l.mmnn_augment_intensity.restype = I
+    l.mmnn_sizeof_aug_spatial.restype = I
+    l.mmnn_sizeof_aug_intensity.restype = I
     D, F, ULL, GP = C.c_double, C.c_float, C.c_ulonglong, C.POINTER(RnConvGeom)
     l.mmnn_sizeof_rn_conv_geom.restype = I
     assert l.mmnn_sizeof_rn_conv_geom() == C.sizeof(RnConvGeom), (l.mmnn_sizeof_rn_conv_geom(), C.sizeof(RnConvGeom))

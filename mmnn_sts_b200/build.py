@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmmnn_b200.so")
-SOURCES = ["capi_conv.cu", "encoder.cu", "heads.cu", "optim.cu", "preprocess.cu", "resnet.cu"]
+SOURCES = ["capi_conv.cu", "encoder.cu", "heads.cu", "optim.cu", "preprocess.cu", "augment.cu", "resnet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math" if False else "-DMMNN_NO_FAST_MATH"]
 

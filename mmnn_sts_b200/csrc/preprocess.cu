@@ -103,6 +103,18 @@ __global__ void __launch_bounds__(256) preproc_resize_kernel(const __grid_consta
 }  // namespace mmnn
 
 extern "C" {
+// pass 1 alone (per-patient extremes into scratch[2*B]); shared with the training chain (augment.cu)
+int mmnn_preprocess_minmax(const float* src, void* scratch, int B, long long per_image, void* stream) {
+  using namespace mmnn;
+  if (B <= 0 || per_image <= 0) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * 2 * B, st);
+  if (e != cudaSuccess) return (int)e;
+  int gx = (int)((per_image / 4 + 255) / 256);
+  gx = gx < 1 ? 1 : (gx > 148 * 8 / (B < 8 ? B : 8) ? 148 * 8 / (B < 8 ? B : 8) : gx);
+  preproc_minmax_kernel<<<dim3(gx, B), 256, 0, st>>>(src, per_image, (uint32_t*)scratch);
+  return (int)cudaGetLastError();
+}
 // src fp32 [B][C][X][Y][Z] (device), dst fp32 [B][C][ox][oy][oz], scratch: 2*B uint32 (device).  Stream-ordered.
 int mmnn_preprocess_volumes(const float* src, float* dst, void* scratch, int B, int C, int X, int Y, int Z, int ox, int oy,
                             int oz, float mean, float std, void* stream) {
