@@ -39,7 +39,7 @@ class RowsParams(C.Structure):
                 ("colscale", C.c_void_p), ("st_sum", C.c_void_p), ("st_sq", C.c_void_p),
                 ("e_src", C.c_void_p), ("e_pitch", C.c_longlong), ("bnE", BnSrc), ("stages", C.c_int), ("acc_rstd", C.c_int), ("early_ch", C.c_int),
                 ("t_src", C.c_void_p), ("t_pitch", C.c_longlong), ("t_gsum", C.c_void_p), ("t_gdot", C.c_void_p),
-                ("t_inv_count", C.c_float), ("t_out", C.c_void_p), ("t_out_pitch", C.c_longlong)]
+                ("t_inv_count", C.c_float), ("t_out", C.c_void_p), ("t_out_pitch", C.c_longlong), ("tma_a", C.c_int)]
 
 
 class BrickParams(C.Structure):

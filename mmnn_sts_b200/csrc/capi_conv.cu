@@ -80,6 +80,32 @@ bool make_tmap_s2d_rows(CUtensorMap* out, const void* ptr, int N, int Sz, int Sy
   *out = m;
   return true;
 }
+
+// [M][pitch] 2-byte elements as a 2-D tensor, box = 64 channels x 128 rows, SWIZZLE_128B: the canonical K-major tcgen05 operand of a
+// 1x1x1 GEMM k-block (engine.cuh, RowsParams::tma_a)
+bool make_tmap_rows_kmajor(CUtensorMap* out, const void* ptr, long long pitch, long long M) {
+  typedef std::tuple<const void*, long long, long long> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  const Key key(ptr, pitch, M);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || ((uintptr_t)ptr & 15u) != 0 || (pitch * 2) % 16 != 0 || pitch < 64) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)M};
+  const cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)TILE_ROWS};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 1024) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
 }  // namespace mmnn
 
 #define MMNN_CHECK_LAUNCH()                      \
@@ -107,8 +133,25 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   // and are latency chains over their k-blocks, so they take the deepest operand ring that fits (ncu, round 2: with Cin = 992
   // the 100 KB budget left TWO stages and every k-block exposed its weight fetch: 4 200 cycles per k-block)
   static const int small_kb = [] { const char* e = getenv("MMNN_ROWS_SMALL_SMEM_KB"); return e ? atoi(e) : 200; }();
-  if (p.stages <= 0) p.stages = choose_stages(p, (PF == 2 ? small_kb : (GRAD ? 112 : 100)) * 1024);
-  const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs);
+  // small-grid forward launches: raw activation k-blocks by TMA, BN+ReLU in place (MMNN_ROWS_TMA=0: register staging)
+  static const bool rows_tma_on = [] { const char* e = getenv("MMNN_ROWS_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  p.tma_a = 0;
+  if (PF == 2 && rows_tma_on && AMODE == A_LINEAR_CONV && TRANS == T_BNRELU && !GRAD && kActF16 && p.ntaps == 1 && p.kbw == 64 &&
+      make_tmap_rows_kmajor(&tmap, p.a_src, p.a_pitch, p.M))
+    p.tma_a = 1;
+  if (p.stages <= 0) {
+    if (p.tma_a) {
+      const int KB = (p.Cin + p.kbw - 1) / p.kbw;
+      p.stages = 1;
+      for (int s = 1; s <= 6 && s <= (KB > 1 ? KB : 1); ++s)
+        if (rows_smem_layout(p.Cin, p.NT, p.kbw, s, offs, true) <= (uint32_t)small_kb * 1024) p.stages = s;
+    } else {
+      p.stages = choose_stages(p, (PF == 2 ? small_kb : (GRAD ? 112 : 100)) * 1024);
+    }
+  }
+  const uint32_t smem = rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages, offs, p.tma_a != 0);
   static const bool tc_stats_on = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '1'; }();
   if (tc_stats_on) p.stages |= 0x100;    // experiment switch: column statistics on the tensor core (engine.cuh)
   auto kern = conv_rows_kernel<AMODE, TRANS, EPI, GRAD, PF>;
@@ -116,9 +159,9 @@ int launch_rows_pf(RowsParams p, cudaStream_t stream) {
   if (e != cudaSuccess) return (int)e;
   dim3 grid((p.M + TILE_ROWS - 1) / TILE_ROWS, (p.Ncols + p.NT - 1) / p.NT);
   static const bool early_on = [] { const char* e = getenv("MMNN_EARLY_START"); return !(e != nullptr && e[0] == '0'); }();
-  if (PF != 2 || !early_on) p.early_ch = 0;
-  if (p.early_ch > 0) launch_pdl_forced(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);   // starts while the previous layer's 3x3x3 conv runs
-  else launch_pdl(kern, grid, dim3(ENGINE_THREADS), smem, stream, p);
+  if (PF < 2 || !early_on) p.early_ch = 0;
+  if (p.early_ch > 0) launch_pdl_forced(kern, grid, dim3(ENGINE_THREADS), smem, stream, p, tmap);   // starts while the previous layer's 3x3x3 conv runs
+  else launch_pdl(kern, grid, dim3(ENGINE_THREADS), smem, stream, p, tmap);
   MMNN_CHECK_LAUNCH();
   return 0;
 }
@@ -157,6 +200,7 @@ int launch_rows_t(const RowsParams& p, cudaStream_t stream) {
   const bool persist = persist_env == 1 || (persist_env == -1 && !GRAD && EPI == EP_STORE_STATS);
   if (AMODE == A_LINEAR_CONV && persist && EPI != EP_MASK_STATS_ACC && p.ntaps == 1 && p.NT <= 256 && (p.Ncols + p.NT - 1) / p.NT <= 148 && tiles >= 2 * 148)
     return launch_rows_persist<TRANS, EPI, GRAD>(p, stream);
+  // (a deeper register prefetch, PF = 4, spills under the 2-CTA register cap: 1343 vs 1423 volumes/s)
   if (tiles <= 148) return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 2>(p, stream);   // latency-bound small grids
   return launch_rows_pf<AMODE, TRANS, EPI, GRAD, 1>(p, stream);
 }

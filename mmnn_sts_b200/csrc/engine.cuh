@@ -109,6 +109,11 @@ struct RowsParams {
   float t_inv_count;       // 1 / rows in batch mode, 0 in eval mode (then the transform is gamma * rstd * v)
   bf16* t_out;             // transformed gradient [M][t_out_pitch] (bf16), written by the CTAs with blockIdx.y == 0
   long long t_out_pitch;
+  // Small-grid 1x1x1 forward GEMM (late dense blocks): tma_a != 0 -> the RAW activation k-block (128 rows x 64 channels) arrives by
+  // TMA (2-D map of [M][a_pitch], box 64 x 128, SWIZZLE_128B = the canonical K-major operand) up to stages - 2 k-blocks ahead, and
+  // the producers apply BN+ReLU in place in shared memory: no global load in their instruction stream (the register prefetch kept at
+  // most 2 k-blocks in flight; a depth of 4 spills under the 2-CTA register cap).
+  int tma_a;
 };
 
 // 8 elements (16 B): load format IN, BN scale/shift + ReLU in fp32, store format OUT
@@ -170,17 +175,21 @@ struct EngineSmem {
 };
 
 // dynamic smem carve-up shared by host (size) and device (offsets)
-__host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, int stages, uint32_t* offs /*[6]*/) {
+__host__ __device__ inline uint32_t rows_stage_bytes(int NT, int kbw, bool tma) {
+  const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
+  return tma ? (stage + 1023u) & ~1023u : stage;      // TMA mode: [A 16 KB swizzled, 1 KB aligned][B]
+}
+__host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, int stages, uint32_t* offs /*[6]*/, bool tma = false) {
   uint32_t o = 0;
-  offs[0] = o; o += 128;                 // barriers + tmem ptr
+  offs[0] = o; o += 192;                 // barriers + tmem ptr (+128: raw[6] of the TMA mode)
   offs[1] = o; o += TILE_ROWS * 16;      // rowinfo
   offs[2] = o; o += 3u * Cin * 4;        // coefA: scale, shift (T_BNRELU) / a, b, d (T_BNBWD)
   offs[3] = o; o += 5u * NT * 4;         // coefE: scale, shift, mean, rstd, accumulate scale
   offs[4] = o; o += 8u * NT * 4;         // red[2][4][NT]
   o = (o + 127u) & ~127u;
   offs[5] = o;
-  const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
-  const uint32_t ring = stages * stage;
+  const uint32_t stage = rows_stage_bytes(NT, kbw, tma);
+  const uint32_t ring = stages * stage + (tma ? 1024u : 0u);
   // the operand ring is reused by the epilogue to stage the rounded output tile (16 chunk planes) + 512 B of ones for the
   // tensor-core column statistics (NT == 128 launches)
   const uint32_t tcstats = 16u * PLANE_BYTES + 512u;
@@ -193,19 +202,23 @@ __host__ __device__ inline uint32_t rows_smem_layout(int Cin, int NT, int kbw, i
 // PF = register prefetch distance in k-blocks: 1 for grids of many tiles (registers -> occupancy), 2 for grids that do not
 // fill the GPU (tiny late-block layers are bound by the serial chain of K iterations, not by occupancy).
 template <int AMODE, int TRANS, int EPI, bool GRAD, int PF>
-__global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __grid_constant__ RowsParams p,
+                                                                      const __grid_constant__ CUtensorMap tma) {
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
   constexpr bool MASK = EPI == EP_MASK_STATS || EPI == EP_MASK_STATS_ACC;
   constexpr bool ACC = EPI == EP_MASK_STATS_ACC;
   extern __shared__ __align__(128) uint8_t smem[];
   uint32_t offs[6];
-  rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages & 0xff, offs);
+  // raw activation k-blocks by TMA, BN+ReLU in place (small-grid forward launches; RowsParams::tma_a)
+  const bool tma_a = PF == 2 && AMODE == A_LINEAR_CONV && TRANS == T_BNRELU && OP_F16 && !GRAD && p.ntaps == 1 && p.kbw == 64 && p.tma_a != 0;
+  rows_smem_layout(p.Cin, p.NT, p.kbw, p.stages & 0xff, offs, tma_a);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + offs[0];
   const uint32_t bar_empty = bar_full + 8 * 6;
   const uint32_t bar_accum = bar_full + 8 * 12;
   const uint32_t bar_staged = bar_full + 8 * 14, bar_stats = bar_full + 8 * 15;
+  const uint32_t bar_raw = bar_full + 128;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + offs[0] + 8 * 13);
   int4* rowinfo = reinterpret_cast<int4*>(smem + offs[1]);
   float* coefA = reinterpret_cast<float*>(smem + offs[2]);
@@ -214,8 +227,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
   const int planes = p.kbw / 8;
   const uint32_t a_bytes = planes * PLANE_BYTES;
   const uint32_t b_bytes = planes * p.NT * 16;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t stage0 = sbase + offs[5];
+  const uint32_t stage_bytes = rows_stage_bytes(p.NT, p.kbw, tma_a);
+  const uint32_t stage0 = tma_a ? ((sbase + offs[5] + 1023u) & ~1023u) : sbase + offs[5];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
@@ -242,7 +255,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_full + 8 * s, NUM_PRODUCER_THREADS + 1);
         mbar_init(bar_empty + 8 * s, 1);
+        mbar_init(bar_raw + 8 * s, 1);
       }
+      if (tma_a) tma_prefetch_desc(&tma);
       mbar_init(bar_accum, 1);
       mbar_init(bar_staged, NUM_PRODUCER_THREADS);
       mbar_init(bar_stats, 1);
@@ -471,7 +486,52 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
     };
     // the k loop runs over [kb0, kb1): once for the whole K, or -- early start -- first over the k-blocks of channels that were
     // final before the preceding kernel started, then (after griddepcontrol.wait) over the rest
+    // TMA mode: thread 0 feeds the ring LA = S - 2 k-blocks ahead (raw activation box -> raw[s], weight image -> full[s]); waiting
+    // for the stage of k-block j - S cannot deadlock: that k-block was handed to the MMA warp two iterations ago.  Every thread
+    // then transforms its 4 cells of the swizzled tile in place: logical 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 j, at
+    // physical chunk c ^ (row & 7); rows beyond M stay the zeros the TMA unit delivered.
+    const int LA = S > 2 ? S - 2 : 1;
+    auto tma_issue = [&](int j) {
+      const int sj = j % S;
+      mbar_wait(bar_empty + 8 * sj, ((uint32_t)(j / S) & 1u) ^ 1u, 1);
+      const uint32_t sAj = stage0 + sj * stage_bytes;
+      mbar_arrive_expect_tx(bar_raw + 8 * sj, (uint32_t)TILE_ROWS * 128u);
+      tma_load_2d(sAj, &tma, j * 64, tile_m * TILE_ROWS, bar_raw + 8 * sj);
+      mbar_arrive_expect_tx(bar_full + 8 * sj, b_bytes);
+      bulk_g2s(sAj + (uint32_t)TILE_ROWS * 128u, p.b_packed + ((size_t)tile_n * KB + j) * (size_t)(planes * p.NT * 8), b_bytes, bar_full + 8 * sj);
+    };
+    auto run_range_tma = [&](int kb0, int kb1) {
+      if (tid == 0)
+        for (int j = kb0; j < kb1 && j < kb0 + LA; ++j) tma_issue(j);
+      const int c = tid & 7, rb = tid >> 3;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (tid == 0 && kb + LA < kb1) tma_issue(kb + LA);
+        const int s2 = kb % S;
+        mbar_wait(bar_raw + 8 * s2, (uint32_t)(kb / S) & 1u, 3);
+        const uint32_t sA = stage0 + s2 * stage_bytes;
+        int cpl = (p.Cin - kb * 64) / 8;
+        cpl = cpl > 8 ? 8 : cpl;
+        if (c < cpl) {
+          H2Coef hc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hc[i] = coefH[(kb * 64 + c * 8) / 2 + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = rb + 32 * j;
+            if ((long long)tile_m * TILE_ROWS + r < p.M) {
+              const uint32_t addr = sA + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+              uint4 v = lds16(addr);
+              apply_bnrelu8_h2(v, hc);
+              sts16(addr, v);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * s2);
+      }
+    };
     auto run_range = [&](int kb0, int kb1) {
+      if (tma_a) { run_range_tma(kb0, kb1); return; }
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         OK[u] = 0;
@@ -669,9 +729,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 2) conv_rows_kernel(const __gr
         int cpl = (p.Cin - cb * p.kbw) / 8;
         cpl = cpl > planes ? planes : cpl;
         const uint32_t sA = stage0 + s * stage_bytes;
-        const uint64_t ad0 = make_smem_desc(sA, PLANE_BYTES, 128);
-        const uint64_t bd0 = make_smem_desc(sA + a_bytes, p.NT * 16, 128);
-        const uint32_t a_step = 2 * PLANE_BYTES, b_step = 2 * p.NT * 16;
+        // A: SWIZZLE_NONE chunk planes, or (TMA mode) 128-byte rows with the 128-byte swizzle: 8-row atoms 1 KB apart, a K step of
+        // 16 channels = 32 B inside the row
+        const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, 16, 1024, 2u) : make_smem_desc(sA, PLANE_BYTES, 128);
+        const uint64_t bd0 = make_smem_desc(sA + (tma_a ? (uint32_t)TILE_ROWS * 128u : a_bytes), p.NT * 16, 128);
+        const uint32_t a_step = tma_a ? 32u : 2 * PLANE_BYTES, b_step = 2 * p.NT * 16;
         tc_mma_bf16(tmem_base, ad0, bd0, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
         for (int k16 = 1; k16 < 4; ++k16)
