@@ -172,10 +172,15 @@ int launch_rows_persist(RowsParams p, cudaStream_t stream) {
   uint32_t offs[6];
   static const bool tc_stats_off = [] { const char* e = getenv("MMNN_TC_STATS"); return e != nullptr && e[0] == '0'; }();
   const bool tcs = EPI != EP_STORE && p.NT == 128 && !tc_stats_off;   // persistent kernel: tensor-core statistics by default
+  static const bool rows_tma_on = [] { const char* e = getenv("MMNN_ROWS_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  p.tma_a = 0;
+  if (rows_tma_on && TRANS == T_BNRELU && !GRAD && kActF16 && p.kbw == 64 && make_tmap_rows_kmajor(&tmap, p.a_src, p.a_pitch, p.M)) p.tma_a = 1;
   int stages = 1;
   for (int s = 1; s <= 6; ++s)
-    if (rowsp_smem_layout(p.Cin, p.NT, p.kbw, s, tcs, offs) <= 220 * 1024) stages = s;
-  const uint32_t smem = rowsp_smem_layout(p.Cin, p.NT, p.kbw, stages, tcs, offs);
+    if (rowsp_smem_layout(p.Cin, p.NT, p.kbw, s, tcs, offs, p.tma_a != 0) <= 220 * 1024) stages = s;
+  const uint32_t smem = rowsp_smem_layout(p.Cin, p.NT, p.kbw, stages, tcs, offs, p.tma_a != 0);
   p.stages = stages | (tcs ? 0x100 : 0);
   auto kern = conv1_persist_kernel<TRANS, EPI, GRAD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -184,7 +189,7 @@ int launch_rows_persist(RowsParams p, cudaStream_t stream) {
   int per_n = 148 / ntn;
   if (per_n > tiles_m) per_n = tiles_m;
   if (per_n < 1) return -2;
-  launch_pdl(kern, dim3(per_n * ntn), dim3(RP_THREADS), smem, stream, p);
+  launch_pdl(kern, dim3(per_n * ntn), dim3(RP_THREADS), smem, stream, p, tmap);
   MMNN_CHECK_LAUNCH();
   return 0;
 }

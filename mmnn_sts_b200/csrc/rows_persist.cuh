@@ -18,16 +18,16 @@ constexpr int RP_THREADS = (RP_EPI_WARP0 + RP_NEW) * 32;   // 544
 
 // offs[5]: two staging buffers of the rounded output tile (16 chunk planes each) + 512 B of ones for the tensor-core
 // column statistics (NT == 128 launches with statistics; size 0 otherwise)
-__host__ __device__ inline uint32_t rowsp_smem_layout(int Cin, int NT, int kbw, int stages, bool tcs, uint32_t* offs /*[6]*/) {
+__host__ __device__ inline uint32_t rowsp_smem_layout(int Cin, int NT, int kbw, int stages, bool tcs, uint32_t* offs /*[6]*/, bool tma = false) {
   uint32_t o = 0;
-  offs[0] = o; o += 256;                 // barriers: full[6] empty[6] acc_full[2] acc_empty[2] staged[2] gfree[2] stats_final + tmem ptr
+  offs[0] = o; o += 256;                 // barriers: full[6] empty[6] acc_full[2] acc_empty[2] staged[2] gfree[2] stats_final + tmem ptr, raw[6] at +192
   offs[1] = o; o += 2u * Cin * 4;        // coefA: fp32 scale / shift or packed half2 table (same size)
   offs[2] = o; o += 4u * NT * 4;         // coefE: scale, shift, mean, rstd
   offs[3] = o; o += 8u * NT * 4;         // red[2][4][NT]
   o = (o + 127u) & ~127u;
   offs[4] = o;
-  const uint32_t stage = (uint32_t)(kbw / 8) * PLANE_BYTES + (uint32_t)(kbw / 8) * NT * 16;
-  o += stages * stage;
+  const uint32_t stage = rows_stage_bytes(NT, kbw, tma);      // TMA mode (RowsParams::tma_a): 1 KB multiples behind a 1 KB aligned base
+  o += stages * stage + (tma ? 1024u : 0u);
   o = (o + 127u) & ~127u;
   offs[5] = o;
   if (tcs) o += 2u * 16u * PLANE_BYTES + 512u;
@@ -35,7 +35,8 @@ __host__ __device__ inline uint32_t rowsp_smem_layout(int Cin, int NT, int kbw, 
 }
 
 template <int TRANS, int EPI, bool GRAD>
-__global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __grid_constant__ RowsParams p,
+                                                                      const __grid_constant__ CUtensorMap tma) {
   constexpr bool OP_F16 = !GRAD && kActF16;   // MMA operand + output format of this launch
   constexpr bool E_F16 = kActF16;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -45,9 +46,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   const bool tcs = (EPI != EP_STORE) && p.NT == 128 && (p.stages & 0x100) != 0;
   const int S = p.stages & 0xff;
   uint32_t offs[6];
-  rowsp_smem_layout(p.Cin, p.NT, p.kbw, S, tcs, offs);
+  // raw activation k-blocks by TMA (SWIZZLE_128B K-major rows), BN+ReLU applied in place: see conv_rows_kernel / RowsParams::tma_a
+  const bool tma_a = TRANS == T_BNRELU && OP_F16 && !GRAD && p.kbw == 64 && p.tma_a != 0;
+  rowsp_smem_layout(p.Cin, p.NT, p.kbw, S, tcs, offs, tma_a);
   const uint32_t sbase = smem_u32(smem);
-  constexpr int FULL = 0, EMPTY = 6, AF = 12, AE = 14, STAGED = 16, GFREE = 18, SFINAL = 20;
+  constexpr int FULL = 0, EMPTY = 6, AF = 12, AE = 14, STAGED = 16, GFREE = 18, SFINAL = 20, RAW = 24;
   const uint32_t sG0 = sbase + offs[5], sOnes = sG0 + 2u * 16u * PLANE_BYTES;
   constexpr uint32_t D1_COL = 256, D2_COL = 288;   // statistics accumulators in TMEM (main accumulators: 0..255)
   auto BAR = [&](int i) { return sbase + offs[0] + 8u * i; };
@@ -59,8 +62,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
   const int planes = p.kbw / 8;
   const uint32_t a_bytes = planes * PLANE_BYTES;
   const uint32_t b_bytes = planes * p.NT * 16;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t stage0 = sbase + offs[4];
+  const uint32_t stage_bytes = rows_stage_bytes(p.NT, p.kbw, tma_a);
+  const uint32_t stage0 = tma_a ? ((sbase + offs[4] + 1023u) & ~1023u) : sbase + offs[4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KB = (p.Cin + p.kbw - 1) / p.kbw;
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
 
   if (warp == RP_MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(BAR(FULL + s), RP_NPT + 1); mbar_init(BAR(EMPTY + s), 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(BAR(FULL + s), RP_NPT + 1); mbar_init(BAR(EMPTY + s), 1); mbar_init(BAR(RAW + s), 1); }
+      if (tma_a) tma_prefetch_desc(&tma);
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(AF + i), 1); mbar_init(BAR(AE + i), RP_NET); }
       for (int i = 0; i < 2; ++i) { mbar_init(BAR(STAGED + i), RP_NET); mbar_init(BAR(GFREE + i), 1); }
       mbar_init(BAR(SFINAL), 1);
@@ -208,6 +212,50 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
       fence_proxy_async_smem();
       mbar_arrive(BAR(FULL + s));
     };
+    if (tma_a) {
+      // thread 0 feeds the ring LA = S - 2 k-blocks ahead, across tile boundaries; all threads transform their 4 cells in place
+      const int LA = S > 2 ? S - 2 : 1;
+      auto tma_issue = [&](long long j) {
+        const int sj = (int)(j % S);
+        mbar_wait(BAR(EMPTY + sj), ((uint32_t)(j / S) & 1u) ^ 1u, 61);
+        const int itj = (int)(j / KB), cbj = (int)(j - (long long)itj * KB);
+        const uint32_t sAj = stage0 + sj * stage_bytes;
+        mbar_arrive_expect_tx(BAR(RAW + sj), (uint32_t)TILE_ROWS * 128u);
+        tma_load_2d(sAj, &tma, cbj * 64, (m_first + itj * m_step) * TILE_ROWS, BAR(RAW + sj));
+        mbar_arrive_expect_tx(BAR(FULL + sj), b_bytes);
+        bulk_g2s(sAj + (uint32_t)TILE_ROWS * 128u, p.b_packed + ((size_t)tile_n * KB + cbj) * (size_t)(planes * p.NT * 8), b_bytes, BAR(FULL + sj));
+      };
+      if (tid == 0)
+        for (long long j = 0; j < total && j < LA; ++j) tma_issue(j);
+      const int c = tid & 7, rb = tid >> 3;
+      int cbq = 0, itq = 0;
+      for (long long g = 0; g < total; ++g) {
+        if (tid == 0 && g + LA < total) tma_issue(g + LA);
+        const int s2 = (int)(g % S);
+        mbar_wait(BAR(RAW + s2), (uint32_t)(g / S) & 1u, 68);
+        const uint32_t sA = stage0 + s2 * stage_bytes;
+        const int cpl = geom_cpl(cbq);
+        if (c < cpl) {
+          H2Coef hc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hc[i] = coefH[(cbq * 64 + c * 8) / 2 + i];
+          const long long row0 = (long long)(m_first + itq * m_step) * TILE_ROWS;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = rb + 32 * j;
+            if (row0 + r < p.M) {
+              const uint32_t addr = sA + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+              uint4 v = lds16(addr);
+              apply_bnrelu8_h2(v, hc);
+              sts16(addr, v);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(BAR(FULL + s2));
+        if (++cbq == KB) { cbq = 0; ++itq; }
+      }
+    } else {
     if (total > 0) next_load(R0, ok0);
     int cb = 0;
     for (long long g = 0; g < total; g += 2) {
@@ -219,6 +267,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
         process(g + 1, cb, R1, ok1);
         if (++cb == KB) cb = 0;
       }
+    }
     }
   } else if (warp == RP_MMA_WARP) {
     // ================= MMA issuer
@@ -258,9 +307,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv1_persist_kernel(const __gr
           int cpl = (p.Cin - kb * p.kbw) / 8;
           cpl = cpl > planes ? planes : cpl;
           const uint32_t sA = stage0 + s * stage_bytes;
-          const uint64_t ad0 = make_smem_desc(sA, PLANE_BYTES, 128);
-          const uint64_t bd0 = make_smem_desc(sA + a_bytes, p.NT * 16, 128);
-          const uint32_t a_step = 2 * PLANE_BYTES, b_step = 2 * p.NT * 16;
+          const uint64_t ad0 = tma_a ? make_smem_desc_sw(sA, 16, 1024, 2u) : make_smem_desc(sA, PLANE_BYTES, 128);
+          const uint64_t bd0 = make_smem_desc(sA + (tma_a ? (uint32_t)TILE_ROWS * 128u : a_bytes), p.NT * 16, 128);
+          const uint32_t a_step = tma_a ? 32u : 2 * PLANE_BYTES, b_step = 2 * p.NT * 16;
           tc_mma_bf16(td, ad0, bd0, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
           for (int k16 = 1; k16 < 4; ++k16)
