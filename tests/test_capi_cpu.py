@@ -35,6 +35,8 @@ def test_struct_sizes_match(lib):
     assert lib.mmnn_sizeof_mlp_args() == ctypes.sizeof(L.MlpArgs)
     assert lib.mmnn_sizeof_cox_args() == ctypes.sizeof(L.CoxArgs)
     assert lib.mmnn_sizeof_cindex_args() == ctypes.sizeof(L.CindexArgs)
+    assert lib.mmnn_sizeof_aug_spatial() == ctypes.sizeof(L.AugSpatial)
+    assert lib.mmnn_sizeof_aug_intensity() == ctypes.sizeof(L.AugIntensity)
 
 
 def test_encoder_plan_tables(lib):
