@@ -57,9 +57,9 @@ def test_affine_composition():
     assert np.allclose(TrainTransformsGPU.affine(NEUTRAL), np.eye(3))
 
 
-def _raw(B, C, shape, seed):
+def _raw(B, C, shape, seed, device="cuda"):
     g = torch.Generator().manual_seed(seed)
-    return (torch.rand(B, C, *shape, generator=g) * 1500.0 + 20.0).cuda()
+    return (torch.rand(B, C, *shape, generator=g) * 1500.0 + 20.0).to(device)
 
 
 def _normalized(raw):      # Normalize -> ScaleIntensity over the whole multi-channel image of one patient
@@ -75,13 +75,14 @@ def _spatial_ref(raw, params, out_size):
     n = _normalized(raw)
     B, C, X, Y, Z = n.shape
     res = []
-    ctr = torch.tensor([(X - 1) / 2, (Y - 1) / 2, (Z - 1) / 2], dtype=torch.float64, device="cuda")
-    gx, gy, gz = torch.meshgrid(torch.arange(X, device="cuda"), torch.arange(Y, device="cuda"), torch.arange(Z, device="cuda"), indexing="ij")
+    dev = raw.device
+    ctr = torch.tensor([(X - 1) / 2, (Y - 1) / 2, (Z - 1) / 2], dtype=torch.float64, device=dev)
+    gx, gy, gz = torch.meshgrid(torch.arange(X, device=dev), torch.arange(Y, device=dev), torch.arange(Z, device=dev), indexing="ij")
     g = torch.stack([gx, gy, gz], -1).double() - ctr
     for b, q in enumerate(params):
-        A = torch.tensor(TrainTransformsGPU.affine(q), dtype=torch.float64, device="cuda")
+        A = torch.tensor(TrainTransformsGPU.affine(q), dtype=torch.float64, device=dev)
         src = g @ A.T + ctr                                   # voxel coordinates in the source volume
-        lim = torch.tensor([X - 1, Y - 1, Z - 1], dtype=torch.float64, device="cuda")
+        lim = torch.tensor([X - 1, Y - 1, Z - 1], dtype=torch.float64, device=dev)
         src = torch.minimum(torch.maximum(src, torch.zeros_like(lim)), lim)
         # grid_sample: last dim (x, y, z) = (W, H, D) = (Z, Y, X) order, align_corners=True maps -1..1 to 0..N-1
         norm = torch.stack([src[..., 2] / max(Z - 1, 1), src[..., 1] / max(Y - 1, 1), src[..., 0] / max(X - 1, 1)], -1) * 2 - 1
@@ -117,9 +118,9 @@ def test_spatial_transforms_match_the_torch_restatement(q):
         assert torch.allclose(got[0], plain[0].flip(1 + q["flip_axis"]), atol=1e-4)
 
 
-def _gauss1d(sigma):
+def _gauss1d(sigma, device="cuda"):
     tail = int(max(sigma * 4.0, 0.5) + 0.5)
-    x = torch.arange(-tail, tail + 1, dtype=torch.float32, device="cuda")
+    x = torch.arange(-tail, tail + 1, dtype=torch.float32, device=device)
     t = 0.70710678 / abs(sigma)
     return (0.5 * ((t * (x + 0.5)).erf() - (t * (x - 0.5)).erf())).clamp(min=0)
 
@@ -127,7 +128,7 @@ def _gauss1d(sigma):
 def _blur(v, sigmas):      # v [C][x][y][z], separable, zero padding
     out = v[None]
     for ax, s in enumerate(sigmas):
-        k = _gauss1d(s)
+        k = _gauss1d(s, v.device)
         shape = [1, 1, 1, 1, 1]
         shape[2 + ax] = k.numel()
         pad = [0, 0, 0]
@@ -195,3 +196,57 @@ def test_random_call_runs_and_stays_finite():
     raw = _raw(6, 2, (40, 36, 20), 5)
     out = TrainTransformsGPU(seed=0)(raw)
     assert out.shape == (6, 2, 64, 64, 64) and torch.isfinite(out).all()
+
+
+# ---------------------------------------------------------------------------------------------------------- oracle (CPU)
+def test_oracle_restatement_properties():
+    """oracle/augment.py (numpy restatement of the published MONAI algorithms, parity unpinned) against exact identities."""
+    from oracle import augment as OA
+    from oracle import preprocess as OP
+    rng = np.random.RandomState(0)
+    q = _q(rotate=0.7, flip_axis=2, zoom=1.07)
+    assert np.allclose(OA.affine_matrix(q["rotate"], q["flip_axis"], q["zoom"]), TrainTransformsGPU.affine(q))
+    img = rng.rand(2, 12, 10, 8)
+    # identity map: the resampling is the area resize alone
+    ident = OA.resample(img, np.eye(3), (6, 5, 4))
+    assert np.allclose(ident, OP.resize(img.astype(np.float32), (6, 5, 4)), atol=1e-6)
+    # a pure flip commutes with the area resize
+    flip = OA.resample(img, OA.affine_matrix(flip_axis=1), (6, 5, 4))
+    assert np.allclose(flip, ident[:, :, ::-1, :], atol=1e-12)
+    # Gaussian kernel: symmetric, non-negative, mass = erf of the truncation point; a constant stays constant away from the border
+    for s in (0.25, 0.8, 1.5):
+        k = OA.gaussian_1d(s)
+        assert k.size == 2 * int(max(4 * s, 0.5) + 0.5) + 1 and np.allclose(k, k[::-1]) and (k >= 0).all() and 0.99 < k.sum() <= 1.0 + 1e-12
+    const = OA.gaussian_smooth(np.ones((1, 16, 16, 16)), [1.0, 0.5, 1.5])
+    assert np.allclose(const[0, 7:9, 7:9, 7:9], 1.0, atol=1e-3) and const[0, 0, 0, 0] < 0.5          # zero padding at the corner
+    # contrast: the extremes are fixed points, gamma = 1 is the identity up to the 1e-7 guard
+    v = rng.rand(1, 6, 6, 6) * 3 - 1
+    c = OA.adjust_contrast(v, 2.0)
+    assert abs(c.min() - v.min()) < 1e-6 and abs(c.max() - v.max()) < 1e-5 and np.allclose(OA.adjust_contrast(v, 1.0), v, atol=1e-6)
+    # histogram shift: identical control points = identity; any increasing floating set keeps the order and the extremes
+    ref = np.linspace(0, 1, 10)
+    assert np.allclose(OA.histogram_shift(v, ref, ref), v, atol=1e-12)
+    flt = np.array([0.0, 0.05, 0.3, 0.32, 0.5, 0.52, 0.7, 0.9, 0.95, 1.0])
+    h = OA.histogram_shift(v, ref, flt)
+    order = np.argsort(v.ravel())
+    assert (np.diff(h.ravel()[order]) >= -1e-12).all() and abs(h.min() - v.min()) < 1e-12 and abs(h.max() - v.max()) < 1e-12
+    # sharpen with alpha = 0 is the first blur
+    assert np.allclose(OA.gaussian_sharpen(v, [0.6] * 3, [0.5] * 3, 0.0), OA.gaussian_smooth(v, [0.6] * 3))
+
+
+def test_torch_restatement_of_the_gpu_tests_equals_the_oracle():
+    """The GPU tests above check the CUDA path against torch restatements (`_spatial_ref`, `_blur`); this CPU test ties those to
+    oracle/augment.py: same formulas, float64 numpy."""
+    from oracle import augment as OA
+    raw = _raw(2, 2, (16, 12, 8), 9, device="cpu")
+    params = [_q(rotate=0.3), _q(rotate=-14.2, flip_axis=1, zoom=1.05)]
+    ref = _spatial_ref(raw, params, (8, 6, 4)).numpy()
+    n = _normalized(raw).numpy().astype(np.float64)
+    for b, q in enumerate(params):
+        o = OA.resample(n[b], OA.affine_matrix(q["rotate"], q["flip_axis"], q["zoom"]), (8, 6, 4))
+        assert np.abs(o - ref[b]).max() < 1e-6
+    v = torch.rand(2, 16, 16, 16, generator=torch.Generator().manual_seed(3))
+    assert np.abs(OA.gaussian_smooth(v.numpy(), [0.4, 1.2, 0.8]) - _blur(v, [0.4, 1.2, 0.8]).numpy()).max() < 1e-6
+    b1 = _blur(v, [0.6, 0.9, 0.7])
+    sharp = (b1 + 17.0 * (b1 - _blur(b1, [0.5, 0.6, 0.55]))).numpy()
+    assert np.abs(OA.gaussian_sharpen(v.numpy(), [0.6, 0.9, 0.7], [0.5, 0.6, 0.55], 17.0) - sharp).max() < 2e-5
